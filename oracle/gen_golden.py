@@ -1,0 +1,290 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (the reference lives at /root/reference, which
+does not exist on the GPU box):
+
+    python oracle/gen_golden.py
+
+Every fixture stores the inputs next to the reference's outputs, so nothing at
+test time depends on torch's RNG.  Seeds follow the reference (235,
+pyscripts/train/train.py:34-35).  Two CPU-only shims are applied from outside
+(never by editing the reference): ``device.index`` is None on CPU
+(hsg/utils/segsort/common.py:376) and ``scatter_gather.gather`` asserts CUDA
+(hsg/models/utils.py:56,172-178).
+"""
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get('HSG_REFERENCE', '/root/reference')
+sys.path.insert(0, REF)
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
+
+import hsg.utils.general.common as g_common          # noqa: E402
+import hsg.utils.segsort.common as s_common          # noqa: E402
+import hsg.utils.segsort.loss as s_loss              # noqa: E402
+import hsg.models.utils as m_utils                   # noqa: E402
+
+
+def _np(t):
+  return t.detach().cpu().numpy()
+
+
+def save(name, **arrays):
+  os.makedirs(OUT, exist_ok=True)
+  path = os.path.join(OUT, name + '.npz')
+  np.savez_compressed(path, **arrays)
+  print('%-28s %8.1f KB' % (name, os.path.getsize(path) / 1024.0))
+
+
+def segment_by_kmeans_cpu(*args, **kwargs):
+  """Reference segment_by_kmeans with the CPU shim `device.index or 0`
+  (hsg/utils/segsort/common.py:376: `.device.index` is None on CPU and
+  `N * None` raises).  The reference source is re-compiled in memory with that
+  one expression patched; nothing is written anywhere."""
+  import inspect
+  text = inspect.getsource(s_common.segment_by_kmeans)
+  patched = text.replace('cur_cluster_indices.device.index',
+                         '(cur_cluster_indices.device.index or 0)')
+  assert patched != text
+  scope = dict(s_common.__dict__)
+  exec(compile(patched, '<segment_by_kmeans+cpu-shim>', 'exec'), scope)
+  return scope['segment_by_kmeans'](*args, **kwargs)
+
+
+def main():
+  torch.set_num_threads(8)
+
+  # ---------------------------------------------------------------- a2
+  torch.manual_seed(235)
+  grids = [((16, 16), (448, 448)), ((6, 6), (14, 14)), ((4, 4), (28, 28)),
+           ((6, 6), (512, 512)), ((12, 24), (1024, 2048)), ((2, 3), (4, 6)),
+           ((3, 3), (12, 12)), ((5, 5), (7, 9)), ((1, 1), (14, 14)), ((3, 2), (10, 14))]
+  arrays = {}
+  for i, (k, hw) in enumerate(grids):
+    lab = s_common.initialize_cluster_labels(list(k), hw, 'cpu')
+    arrays['k%d' % i] = np.asarray(k)
+    arrays['hw%d' % i] = np.asarray(hw)
+    # store as row/col vectors (labels = y + (ymax+1)*x is rank-1 separable)
+    arrays['lab_col0_%d' % i] = _np(lab[:, 0])
+    arrays['lab_row0_%d' % i] = _np(lab[0, :])
+    arrays['lab_sum_%d' % i] = np.asarray(int(lab.sum()))
+  loc = s_common.generate_location_features((7, 9), 'cpu', 'float')
+  arrays['loc_7_9'] = _np(loc)
+  loc = s_common.generate_location_features((448, 448), 'cpu', 'float')
+  arrays['loc_448_y'] = _np(loc[:, 0, 0])
+  arrays['loc_448_x'] = _np(loc[0, :, 1])
+  save('init_and_loc', n=np.asarray(len(grids)), **arrays)
+
+  # ---------------------------------------------------------------- a1
+  torch.manual_seed(235)
+  x = torch.randn(64, 5, 34)
+  x[3, 2] = 0.0                       # zero vector -> stays zero (eps branch)
+  x[7, 1] = 1e-14                     # below eps
+  save('normalize', x=_np(x), y=_np(g_common.normalize_embedding(x)))
+
+  # ---------------------------------------------------------------- a4/a5/a6 KAT1
+  torch.manual_seed(235)
+  x = g_common.normalize_embedding(torch.randn(4096, 66))
+  l0 = torch.randint(0, 16, (4096,))
+  labs = [l0]
+  protos = []
+  lab = l0
+  for _ in range(10):
+    p = s_common.calculate_prototypes_from_labels(x, lab, 16)
+    lab = s_common.find_nearest_prototypes(x, p)
+    protos.append(p)
+    labs.append(lab)
+  final = s_common.kmeans_with_initial_labels(x, l0, 16, 10)
+  assert torch.equal(final, lab)
+  pf = s_common.calculate_prototypes_from_labels(x, final, 16)
+  # torch CPU scatter_add_ visits rows in ascending order == np.add.at
+  chk = np.zeros((16, 66), np.float32)
+  np.add.at(chk, _np(final), _np(x))
+  ref_sum = torch.zeros(16, 66).scatter_add_(0, final.view(-1, 1).expand(-1, 66), x)
+  assert np.array_equal(chk, _np(ref_sum)), 'scatter order assumption broken'
+  save('kmeans_flat_kat1', x=_np(x), labels=np.stack([_np(l) for l in labs]),
+       prototypes=np.stack([_np(p) for p in protos]), final_prototypes=_np(pf))
+
+  # well separated flat case: every implementation must agree exactly
+  torch.manual_seed(235)
+  centres = g_common.normalize_embedding(torch.randn(12, 40))
+  assign = torch.randint(0, 12, (3000,))
+  x = g_common.normalize_embedding(centres[assign] + 0.05 * torch.randn(3000, 40))
+  l0 = torch.randint(0, 12, (3000,))
+  labs = [l0]
+  lab = l0
+  for _ in range(8):
+    p = s_common.calculate_prototypes_from_labels(x, lab, 12)
+    lab = s_common.find_nearest_prototypes(x, p)
+    labs.append(lab)
+  save('kmeans_flat_separated', x=_np(x), labels=np.stack([_np(l) for l in labs]),
+       prototypes=_np(s_common.calculate_prototypes_from_labels(x, lab, 12)))
+
+  # prototypes with empty bins and explicit max_label, 4-D input
+  torch.manual_seed(235)
+  x = torch.randn(2, 6, 5, 18)
+  lab = torch.randint(0, 9, (2, 6, 5))
+  lab[lab == 4] = 5
+  save('prototypes_empty_bins', x=_np(x), labels=_np(lab),
+       p12=_np(s_common.calculate_prototypes_from_labels(x, lab, 12)),
+       pauto=_np(s_common.calculate_prototypes_from_labels(x, lab)))
+
+  # ---------------------------------------------------------------- a7 / a8
+  torch.manual_seed(235)
+  sem = torch.randint(0, 5, (500,))
+  inst = torch.randint(0, 7, (500,)) * 3
+  pl, ul = s_common.prepare_prototype_labels(sem, inst, 5)
+  pl2, ul2 = s_common.prepare_prototype_labels(sem, inst)
+  x = torch.randn(500, 10)
+  idx = torch.randint(0, 9, (500,))
+  idx[idx == 2] = 3
+  save('labels_and_segment_mean', sem=_np(sem), inst=_np(inst), proto_labels=_np(pl),
+       unique_inst=_np(ul), proto_labels_256=_np(pl2), unique_inst_256=_np(ul2),
+       x=_np(x), idx=_np(idx), mean=_np(g_common.segment_mean(x, idx)))
+
+  # ---------------------------------------------------------------- a3 KAT2
+  torch.manual_seed(235)
+  emb = torch.randn(2, 32, 12, 12)
+  labels = torch.zeros(2, 12, 12, dtype=torch.long)
+  for by in range(2):
+    for bx in range(2):
+      labels[:, by * 6:(by + 1) * 6, bx * 6:(bx + 1) * 6] = by * 2 + bx
+  labels[0, :2, :] = 99
+  res = segment_by_kmeans_cpu(emb, labels, [3, 3], ignore_index=99, iterations=5)
+  save('segment_by_kmeans_kat2', emb=_np(emb), labels=_np(labels),
+       out_emb=_np(res[0]), out_emb_loc=_np(res[1]), out_labels=_np(res[2]),
+       out_cluster=_np(res[3]), out_batch=_np(res[4]))
+
+  # no labels, model-style local features (location only), odd sizes, one iter more
+  torch.manual_seed(235)
+  emb = torch.randn(3, 16, 10, 14)
+  loc = s_common.generate_location_features((10, 14), 'cpu', 'float') - 0.5
+  loc = loc.unsqueeze(0).expand(3, 10, 14, 2)
+  res = segment_by_kmeans_cpu(emb, None, [3, 2], local_features=loc, iterations=4)
+  res0 = segment_by_kmeans_cpu(emb, None, [3, 2], iterations=4)
+  for a, b in zip(res, res0):
+    assert torch.equal(a, b)
+  # 4 local-feature channels (location + colour-like), labels, ignore
+  loc4 = torch.cat([loc, 0.3 * torch.randn(3, 10, 14, 2)], -1)
+  labels = torch.randint(0, 3, (3, 10, 14)) * 2048 + torch.randint(0, 2, (3, 10, 14))
+  labels[1, 4:, 5:] = 7000
+  labels[2] = 7000                  # a whole image ignored
+  res4 = segment_by_kmeans_cpu(emb, labels, [2, 3], local_features=loc4,
+                               ignore_index=7000, iterations=3)
+  save('segment_by_kmeans_misc', emb=_np(emb),
+       a_emb=_np(res[0]), a_emb_loc=_np(res[1]), a_labels=_np(res[2]),
+       a_cluster=_np(res[3]), a_batch=_np(res[4]),
+       loc4=_np(loc4), labels4=_np(labels),
+       b_emb=_np(res4[0]), b_emb_loc=_np(res4[1]), b_labels=_np(res4[2]),
+       b_cluster=_np(res4[3]), b_batch=_np(res4[4]))
+
+  # ---------------------------------------------------------------- a14 KAT3 (+ grads)
+  torch.manual_seed(235)
+  n, p_, d = 2048, 64, 32
+  e = g_common.normalize_embedding(torch.randn(n, d))
+  inst = torch.randint(0, p_, (n,))
+  protos = s_common.calculate_prototypes_from_labels(e, inst, p_)
+  psem = torch.randint(0, 20, (p_,))
+  sem = psem[inst]
+  loss = s_loss.SegSortLoss(16)(e, sem, inst, protos, psem)
+  none = s_loss.SegSortLoss(16, reduction='none')(e, sem, inst, protos, psem)
+  e_g = e.clone().requires_grad_(True)
+  p_g = protos.clone().requires_grad_(True)
+  s_loss.SegSortLoss(16)(e_g, sem, inst, p_g, psem).backward()
+  plain = s_loss.SegSortLoss(16, group_mode='segsort', reduction='none')(e, sem, inst, protos, psem)
+  save('nce_kat3', e=_np(e), inst=_np(inst), protos=_np(protos), psem=_np(psem), sem=_np(sem),
+       loss=_np(loss), per_pixel=_np(none), de=_np(e_g.grad), dp=_np(p_g.grad),
+       per_pixel_plain=_np(plain))
+
+  # every prototype its own class -> every pixel takes the fallback branch;
+  # prototypes NOT derived from the pixels; concentration 10
+  torch.manual_seed(236)
+  n, p_, d = 700, 37, 24
+  e = g_common.normalize_embedding(torch.randn(n, d))
+  protos = g_common.normalize_embedding(torch.randn(p_, d))
+  inst = torch.randint(0, p_, (n,))
+  psem = torch.arange(p_)
+  psem[30:] = 5                      # a few shared classes
+  sem = psem[inst]
+  e_g = e.clone().requires_grad_(True)
+  p_g = protos.clone().requires_grad_(True)
+  w = torch.randn(n, 1)
+  ll = s_loss.SegSortLoss(10, reduction='none')(e_g, sem, inst, p_g, psem)
+  (ll * w).sum().backward()
+  save('nce_fallback', e=_np(e), inst=_np(inst), protos=_np(protos), psem=_np(psem), sem=_np(sem),
+       w=_np(w), per_pixel=_np(ll), de=_np(e_g.grad), dp=_np(p_g.grad))
+
+  # ---------------------------------------------------------------- pooling backward
+  torch.manual_seed(235)
+  x = torch.randn(300, 12, requires_grad=True)
+  lab = torch.randint(0, 11, (300,))
+  lab[lab == 6] = 7
+  g = torch.randn(14, 12)
+  p = s_common.calculate_prototypes_from_labels(x, lab, 14)
+  (p * g).sum().backward()
+  dx_proto = x.grad.clone()
+  x.grad = None
+  gm = torch.randn(11, 12)
+  m = g_common.segment_mean(x, lab)
+  (m * gm).sum().backward()
+  dx_mean = x.grad.clone()
+  x.grad = None
+  gn = torch.randn(300, 12)
+  (g_common.normalize_embedding(x) * gn).sum().backward()
+  save('pool_backward', x=_np(x), labels=_np(lab), g=_np(g), p=_np(p), dx_proto=_np(dx_proto),
+       gm=_np(gm), mean=_np(m), dx_mean=_np(dx_mean), gn=_np(gn), dx_norm=_np(x.grad))
+
+  # ---------------------------------------------------------------- a9 per-image(-pair) prototypes
+  from hsg.models.embeddings.resnet_fcn_hsg import MultiviewResnetFcn, ResnetFcn
+  torch.manual_seed(235)
+  emb = torch.randn(4, 16, 8, 8)
+  labels = torch.randint(0, 3, (4, 8, 8)) * 2048 + torch.randint(0, 2, (4, 8, 8))
+  e_, el_, lab_, cidx_, bidx_ = segment_by_kmeans_cpu(emb, labels, [2, 2], iterations=3)
+  pos = torch.randn(e_.shape[0], 16)
+  fake_self = types.SimpleNamespace(label_divisor=2048, max_num_clusters=256)
+  image_indices = torch.tensor([0, 0, 1, 1])
+  mv = MultiviewResnetFcn._calculate_kmeans_prototypes(fake_self, e_, cidx_, bidx_, pos, lab_, image_indices)
+  sv = ResnetFcn._calculate_kmeans_prototypes(fake_self, e_, cidx_, bidx_, pos, lab_)
+  save('kmeans_prototypes', emb=_np(e_), cluster=_np(cidx_), batch=_np(bidx_), pos=_np(pos),
+       labels=_np(lab_), image_indices=_np(image_indices),
+       **{'mv%d' % i: _np(t) for i, t in enumerate(mv)},
+       **{'sv%d' % i: _np(t) for i, t in enumerate(sv)})
+
+  # ---------------------------------------------------------------- a13 cross-GPU gather (2 "GPUs")
+  m_utils.scatter_gather.gather = lambda xs, dev, dim=0: torch.cat(list(xs), dim)
+  torch.manual_seed(235)
+  ranks = []
+  for r in range(2):
+    emb = torch.randn(2, 16, 8, 8)
+    labels = torch.randint(0, 3, (2, 8, 8)) * 2048 + torch.randint(0, 2, (2, 8, 8))
+    e_, el_, lab_, cidx_, bidx_ = segment_by_kmeans_cpu(emb, labels, [2, 2], iterations=3)
+    ranks.append((e_, el_, cidx_, bidx_ + 2 * r, lab_ // 2048, lab_ % 2048))
+  outs = m_utils.gather_clustering_and_update_prototypes(
+      [r[0] for r in ranks], [r[1] for r in ranks], [r[2] for r in ranks],
+      [r[3] for r in ranks], [r[4] for r in ranks], [r[5] for r in ranks])
+  fine = [torch.randint(0, 5, r[2].shape) for r in ranks]
+  # mapping needs a function of ids: make level-2 ids a function of level-1 ids
+  fine = [(o * 7 + 3) % 5 for o in outs[5]]
+  mapping = m_utils.gather_and_update_cluster_mappings(list(outs[5]), fine)
+  img = [torch.tensor([5, 5, 9, 2]), torch.tensor([9, 7, 7, 2])]
+  reord = m_utils.gather_and_reorder_image_indices(img)
+  arrays = {}
+  for r in range(2):
+    for j, nm in enumerate(['emb', 'emb_loc', 'cluster', 'batch', 'sem', 'inst']):
+      arrays['r%d_%s' % (r, nm)] = _np(ranks[r][j])
+    arrays['r%d_updated' % r] = _np(outs[5][r])
+    arrays['r%d_fine' % r] = _np(fine[r])
+    arrays['r%d_img' % r] = _np(img[r])
+    arrays['r%d_img_reordered' % r] = _np(reord[r])
+  save('gather_prototypes', prototypes=_np(outs[0][0]), prototypes_loc=_np(outs[1][0]),
+       proto_sem=_np(outs[2][0]), proto_inst=_np(outs[3][0]), proto_batch=_np(outs[4][0]),
+       mapping=_np(mapping[0]), **arrays)
+
+
+if __name__ == '__main__':
+  main()
