@@ -1,0 +1,54 @@
+"""hsg_b200 -- B200-native (sm_100a) implementation of HSG's per-step dense-embedding
+clustering + contrastive hot path, behind the reference's own operator signatures.
+
+    import hsg_b200
+    hsg_b200.patch()        # rebinds hsg.utils.* / hsg.models.utils attributes
+
+The arithmetic lives in libhsgb200.so (hand-written CUDA behind the C ABI in
+include/hsg_b200.h); this package is the thin Python mirror of the reference's
+operator interface.  There is no CPU or stock-PyTorch fallback: without the
+built library every operator raises.
+"""
+
+from . import _lib
+from ._lib import HsgError, load as load_library
+
+__all__ = ['patch', 'unpatch', 'load_library', 'HsgError']
+
+_PATCHED = {}
+
+# reference module -> (our module, names rebound)
+_TARGETS = {
+    'hsg.utils.segsort.common': ('hsg_b200.utils.segsort.common', [
+        'calculate_prototypes_from_labels', 'find_nearest_prototypes', 'kmeans_with_initial_labels',
+        'kmeans', 'prepare_prototype_labels', 'segment_by_kmeans', 'find_majority_label_index']),
+    'hsg.utils.general.common': ('hsg_b200.utils.general.common', [
+        'normalize_embedding', 'segment_mean']),
+    'hsg.utils.segsort.loss': ('hsg_b200.utils.segsort.loss', [
+        '_calculate_log_likelihood', 'SegSortLoss']),
+    'hsg.models.utils': ('hsg_b200.models.utils', [
+        'gather_clustering_and_update_prototypes', 'gather_and_update_cluster_mappings',
+        'gather_and_reorder_image_indices', 'gather_and_update_datas']),
+}
+
+
+def patch():
+  """Rebind the reference's hot-path operators to this package.  The reference
+  resolves them late through module attributes (e.g. segsort_common.segment_by_kmeans
+  in hsg/models/embeddings/resnet_fcn_hsg.py:206), so nothing else changes."""
+  import importlib
+  load_library()                       # fail loudly before touching anything
+  for ref_name, (our_name, names) in _TARGETS.items():
+    ref = importlib.import_module(ref_name)
+    ours = importlib.import_module(our_name)
+    for n in names:
+      if (ref_name, n) not in _PATCHED:
+        _PATCHED[(ref_name, n)] = getattr(ref, n)
+      setattr(ref, n, getattr(ours, n))
+
+
+def unpatch():
+  import importlib
+  for (ref_name, n), orig in list(_PATCHED.items()):
+    setattr(importlib.import_module(ref_name), n, orig)
+    del _PATCHED[(ref_name, n)]

@@ -1,0 +1,474 @@
+// K1: spherical k-means (kmeans_with_initial_labels, hsg/utils/segsort/common.py:67-97)
+// batched over independent segments (the per-image loop of segment_by_kmeans,
+// :337-372), plus the single-step and segmented-reduction entry points.
+//
+// M-step: deterministic segmented sum + normalise (segreduce.cu).
+// E-step: a cheap pass (fp32 CUDA cores here, fp16 tcgen05 in tc_estep.cu)
+//         finds the best centroid and the gap to the runner-up; pixels whose gap
+//         is inside that pass's rigorous error bound go to a float64 re-decision
+//         (estep_fixup), so the label is always the arg-max of the float64 dot
+//         products of the fp32 inputs, ties to the lowest index -- whichever
+//         pass produced it.
+#include "kmeans.cuh"
+
+#include <float.h>
+
+namespace hsg {
+
+// ---------------------------------------------------------------- SIMT E-step
+constexpr int ES_TP = 64;     // pixels per CTA
+constexpr int ES_TK = 64;     // centroids per k-block
+constexpr int ES_DC = 32;     // feature chunk
+constexpr int ES_THREADS = 256;
+
+__device__ __forceinline__ void merge_best(float& bv, int& bi, float& sv, float ov, int oi, float osv) {
+  if (ov > bv || (ov == bv && oi < bi)) {
+    sv = fmaxf(bv, fmaxf(sv, osv));
+    bv = ov;
+    bi = oi;
+  } else {
+    sv = fmaxf(ov, fmaxf(sv, osv));
+  }
+}
+
+__global__ void __launch_bounds__(ES_THREADS) estep_simt_kernel(const EStepArgs a, const float thr) {
+  __shared__ float Xs[ES_TP][ES_DC + 1];
+  __shared__ float Cs[ES_TK][ES_DC + 1];
+  __shared__ float best_v[ES_TP], second_v[ES_TP];
+  __shared__ int best_i[ES_TP];
+
+  const int ti = blockIdx.x;
+  if (ti >= *a.tiles.count) return;
+  const int64_t p0 = a.tiles.begin[ti] + (int64_t)blockIdx.y * ES_TP;
+  const int64_t pe = a.tiles.end[ti];
+  if (p0 >= pe) return;
+  const int np = (int)min((int64_t)ES_TP, pe - p0);
+  const int seg = a.tiles.seg[ti];
+  const int K = a.seg_k ? a.seg_k[seg] : a.kmax;
+  const float* cbase = a.centroids + (int64_t)seg * a.kmax * a.dim;
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  if (tid < ES_TP) { best_v[tid] = -FLT_MAX; second_v[tid] = -FLT_MAX; best_i[tid] = 0x7fffffff; }
+
+  for (int kb = 0; kb < K; kb += ES_TK) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int d0 = 0; d0 < a.dim; d0 += ES_DC) {
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < (ES_TP * ES_DC) / ES_THREADS; ++r) {
+        const int idx = tid + ES_THREADS * r;
+        const int row = idx >> 5, dd = idx & 31;
+        const int d = d0 + dd;
+        Xs[row][dd] = (row < np && d < a.dim) ? a.x[(p0 + row) * a.dim + d] : 0.f;
+        const int k = kb + row;
+        Cs[row][dd] = (k < K && d < a.dim) ? cbase[(int64_t)k * a.dim + d] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int dd = 0; dd < ES_DC; ++dd) {
+        float xa[4], cb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xa[i] = Xs[ty + 16 * i][dd];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cb[j] = Cs[tx + 16 * j][dd];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], cb[j], acc[i][j]);
+      }
+    }
+    // per pixel: best / runner-up over this thread's 4 centroids, then over the 16 tx lanes
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float bv = -FLT_MAX, sv = -FLT_MAX;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = kb + tx + 16 * j;
+        if (k < K) merge_best(bv, bi, sv, acc[i][j], k, -FLT_MAX);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULL, bv, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        const float osv = __shfl_xor_sync(FULL, sv, o);
+        merge_best(bv, bi, sv, ov, oi, osv);
+      }
+      if (tx == 0) {
+        const int px = ty + 16 * i;
+        float rb = best_v[px], rs = second_v[px];
+        int ri = best_i[px];
+        merge_best(rb, ri, rs, bv, bi, sv);
+        best_v[px] = rb; second_v[px] = rs; best_i[px] = ri;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < np) {
+    const int64_t pix = p0 + tid;
+    a.keys_out[pix] = seg * a.kmax + best_i[tid];
+    if (best_v[tid] - second_v[tid] <= thr) {
+      const int slot = atomicAdd(a.fix.count, 1);
+      if (slot < a.fix.capacity) {
+        a.fix.pixels[slot] = (int32_t)pix;
+        if (a.fix.cand) a.fix.cand[(int64_t)slot * FIX_MAX_CAND] = 0xFFFF;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- float64 re-decision
+constexpr int FIX_WARPS = 8;
+
+__device__ __forceinline__ int upper_bound_off(const int64_t* a, int n, int64_t v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(FIX_WARPS * 32) estep_fixup_kernel(const EStepArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int total = min((int64_t)*a.fix.count, a.fix.capacity);
+  const int warps = gridDim.x * FIX_WARPS;
+  for (int e = blockIdx.x * FIX_WARPS + (threadIdx.x >> 5); e < total; e += warps) {
+    const int64_t pix = a.fix.pixels[e];
+    const int seg = upper_bound_off(a.seg_offsets, a.S + 1, pix) - 1;
+    const int K = a.seg_k ? a.seg_k[seg] : a.kmax;
+    const float* xr = a.x + pix * a.dim;
+    const float* cbase = a.centroids + (int64_t)seg * a.kmax * a.dim;
+    const uint16_t* cand = a.fix.cand ? a.fix.cand + (int64_t)e * FIX_MAX_CAND : nullptr;
+    const bool all = !cand || cand[0] == 0xFFFF;
+    const int n = all ? K : FIX_MAX_CAND;
+    double bv = -DBL_MAX;
+    int bi = 0x7fffffff;
+    for (int c = 0; c < n; ++c) {
+      int k = c;
+      if (!all) {
+        k = cand[c];
+        if (k == 0xFFFF) break;
+      }
+      const float* cr = cbase + (int64_t)k * a.dim;
+      double s = 0.0;
+      for (int d = lane; d < a.dim; d += 32) s = fma((double)xr[d], (double)cr[d], s);
+      s = warp_sum(s);
+      if (s > bv || (s == bv && k < bi)) { bv = s; bi = k; }
+    }
+    if (lane == 0) a.keys_out[pix] = seg * a.kmax + bi;
+  }
+}
+
+int estep_simt(const EStepArgs& a, cudaStream_t st) {
+  // |fl(dot) - dot| <= gamma_dim * sum|x_d c_d| <= dim*2^-24*(1+tiny) for unit rows;
+  // two such errors can reorder a pair, so re-decide below twice that (plus slack).
+  const float thr = 2.f * (a.dim + 2) * 5.9604645e-8f * 1.02f + 1e-7f;
+  dim3 grid((unsigned)a.tiles.bound, (unsigned)ceil_div64(a.tiles.tile, ES_TP));
+  estep_simt_kernel<<<grid, ES_THREADS, 0, st>>>(a, thr);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+int estep_fixup(const EStepArgs& a, cudaStream_t st) {
+  estep_fixup_kernel<<<num_sms() * 4, FIX_WARPS * 32, 0, st>>>(a);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+__global__ void copy_count_kernel(const int32_t* c, int64_t* out) { *out = *c; }
+
+// ---------------------------------------------------------------- orchestration
+struct KmPlan {
+  SegReducePlan sr;
+  float* centroids;      // [S*kmax*dim]
+  FixList fix;
+  TcState tc;
+};
+
+static void km_carve(Carver& c, KmPlan& p, int64_t N, int dim, int S, int kmax, int64_t max_seg_len,
+                     int d16) {
+  sr_carve(c, p.sr, N, dim, S, kmax, max_seg_len);
+  p.centroids = c.take<float>((int64_t)S * kmax * dim);
+  p.fix.count = c.take<int32_t>(1);
+  p.fix.capacity = N;
+  p.fix.pixels = c.take<int32_t>(N);
+  p.fix.cand = c.take<uint16_t>(N * FIX_MAX_CAND);
+  tc_carve(c, p.tc, S, kmax, d16 > 0 ? d16 : 64);
+}
+
+static int check_common(const float* x, int64_t N, int dim, const int64_t* seg_offsets, int S,
+                        int64_t max_seg_len, int kmax) {
+  HSG_REQUIRE(N >= 0 && N < (1ll << 31), HSG_E_UNSUPPORTED, "kmeans: N=%lld rows (max 2^31-1)", (long long)N);
+  HSG_REQUIRE(dim > 0 && S > 0 && kmax > 0, HSG_E_INVALID, "kmeans: bad shape dim=%d S=%d kmax=%d", dim, S, kmax);
+  HSG_REQUIRE(max_seg_len >= 0 && max_seg_len <= N, HSG_E_INVALID, "kmeans: max_seg_len %lld outside [0,N]", (long long)max_seg_len);
+  HSG_REQUIRE(kmax <= SR_MAX_KEYS, HSG_E_UNSUPPORTED, "kmeans: kmax=%d (max %d)", kmax, SR_MAX_KEYS);
+  HSG_REQUIRE((int64_t)S * kmax < (1ll << 31), HSG_E_UNSUPPORTED, "kmeans: S*kmax overflows int32");
+  HSG_REQUIRE(N == 0 || (x && seg_offsets), HSG_E_INVALID, "kmeans: null pointer");
+  return HSG_OK;
+}
+
+static int run_estep(EStepArgs& ea, KmPlan& p, bool use_tc, cudaStream_t st) {
+  HSG_CUDA(cudaMemsetAsync(p.fix.count, 0, sizeof(int32_t), st));
+  if (use_tc) {
+    int rc = tc_convert_centroids(ea, p.tc, st);
+    if (rc) return rc;
+    rc = estep_tc(ea, p.tc, st);
+    if (rc) return rc;
+  } else {
+    int rc = estep_simt(ea, st);
+    if (rc) return rc;
+  }
+  return estep_fixup(ea, st);
+}
+
+static int decide_tc(int flags, int dim, const void* xh, int d16, const float* xerr, int kmax, bool* use_tc) {
+  const bool possible = xh && xerr && tc_shape_supported(dim, d16, kmax);
+  if (flags == HSG_KMEANS_FORCE_TC) {
+    HSG_REQUIRE(possible, HSG_E_UNSUPPORTED,
+                "kmeans: tensor-core E-step needs the fp16 copy, d16 in {64,128,256}, kmax*d16*2 <= 128 KiB "
+                "(got dim=%d d16=%d kmax=%d, xh=%p)", dim, d16, kmax, xh);
+    *use_tc = true;
+  } else if (flags == HSG_KMEANS_FORCE_SIMT) {
+    *use_tc = false;
+  } else {
+    *use_tc = possible;
+  }
+  return HSG_OK;
+}
+
+}  // namespace hsg
+
+using namespace hsg;
+
+extern "C" {
+
+size_t hsg_kmeans_workspace_bytes(int64_t N, int dim, int S, int kmax, int64_t max_seg_len) {
+  Carver c(nullptr);
+  KmPlan p;
+  km_carve(c, p, N, dim, S, kmax, max_seg_len, 256);
+  return c.used() + 1024;
+}
+
+int hsg_kmeans_f32(const float* x, int64_t N, int dim, const void* xh, int d16, const float* xerr,
+                   const int64_t* seg_offsets, int S, int64_t max_seg_len, const int32_t* seg_k,
+                   int kmax, const int64_t* init_labels, int iterations, int64_t* labels_out,
+                   float* centroids_out, int flags, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  int rc = check_common(x, N, dim, seg_offsets, S, max_seg_len, kmax);
+  if (rc) return rc;
+  HSG_REQUIRE(iterations >= 0, HSG_E_INVALID, "kmeans: iterations=%d", iterations);
+  if (N == 0) return HSG_OK;
+  HSG_REQUIRE(init_labels && labels_out, HSG_E_INVALID, "kmeans: null labels");
+  HSG_REQUIRE(workspace && workspace_bytes >= hsg_kmeans_workspace_bytes(N, dim, S, kmax, max_seg_len),
+              HSG_E_WORKSPACE, "kmeans: workspace too small (%zu < %zu)", workspace_bytes,
+              hsg_kmeans_workspace_bytes(N, dim, S, kmax, max_seg_len));
+  bool use_tc = false;
+  rc = decide_tc(flags, dim, xh, d16, xerr, kmax, &use_tc);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c(workspace);
+  KmPlan p;
+  km_carve(c, p, N, dim, S, kmax, max_seg_len, d16);
+  if (use_tc) {
+    p.tc.xh = (const __half*)xh; p.tc.xerr = xerr; p.tc.d16 = d16;
+    rc = tc_prepare(p.tc, N, S);
+    if (rc) return rc;
+  }
+  if ((rc = sr_build_tiles(p.sr, seg_offsets, st))) return rc;
+  if ((rc = sr_labels_to_keys(p.sr, init_labels, nullptr, st))) return rc;
+
+  EStepArgs ea;
+  ea.x = x; ea.N = N; ea.dim = dim; ea.centroids = p.centroids; ea.seg_offsets = seg_offsets;
+  ea.S = S; ea.seg_k = seg_k; ea.kmax = kmax; ea.tiles = p.sr.tiles; ea.keys_out = p.sr.keys;
+  ea.fix = p.fix;
+
+  for (int it = 0; it < iterations; ++it) {
+    if ((rc = sr_sort_and_sum(p.sr, x, seg_offsets, st))) return rc;
+    if ((rc = sr_combine(p.sr, p.sr.bins, nullptr, HSG_REDUCE_NORMALIZE, p.centroids, nullptr, nullptr, st))) return rc;
+    if ((rc = run_estep(ea, p, use_tc, st))) return rc;
+  }
+  if ((rc = sr_keys_to_labels(p.sr, p.sr.keys, labels_out, st))) return rc;
+  if (centroids_out && iterations > 0)
+    HSG_CUDA(cudaMemcpyAsync(centroids_out, p.centroids, sizeof(float) * S * kmax * dim,
+                             cudaMemcpyDeviceToDevice, st));
+  return HSG_OK;
+}
+
+int hsg_kmeans_mstep_f32(const float* x, int64_t N, int dim, const int64_t* seg_offsets, int S,
+                         int64_t max_seg_len, const int32_t* seg_k, int kmax, const int64_t* labels,
+                         float* centroids_out, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)seg_k;
+  int rc = check_common(x, N, dim, seg_offsets, S, max_seg_len, kmax);
+  if (rc) return rc;
+  HSG_REQUIRE(centroids_out, HSG_E_INVALID, "mstep: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) {
+    HSG_CUDA(cudaMemsetAsync(centroids_out, 0, sizeof(float) * S * kmax * dim, st));
+    return HSG_OK;
+  }
+  HSG_REQUIRE(labels, HSG_E_INVALID, "mstep: null labels");
+  HSG_REQUIRE(workspace && workspace_bytes >= sr_workspace_bytes(N, dim, S, kmax, max_seg_len),
+              HSG_E_WORKSPACE, "mstep: workspace too small");
+  Carver c(workspace);
+  SegReducePlan p;
+  sr_carve(c, p, N, dim, S, kmax, max_seg_len);
+  if ((rc = sr_build_tiles(p, seg_offsets, st))) return rc;
+  if ((rc = sr_labels_to_keys(p, labels, nullptr, st))) return rc;
+  if ((rc = sr_sort_and_sum(p, x, seg_offsets, st))) return rc;
+  return sr_combine(p, p.bins, nullptr, HSG_REDUCE_NORMALIZE, centroids_out, nullptr, nullptr, st);
+}
+
+int hsg_kmeans_estep_f32(const float* x, int64_t N, int dim, const void* xh, int d16,
+                         const float* xerr, const int64_t* seg_offsets, int S, int64_t max_seg_len,
+                         const int32_t* seg_k, int kmax, const float* centroids, int64_t* labels_out,
+                         int64_t* num_rechecked_out, int flags, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  int rc = check_common(x, N, dim, seg_offsets, S, max_seg_len, kmax);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) {
+    if (num_rechecked_out) HSG_CUDA(cudaMemsetAsync(num_rechecked_out, 0, sizeof(int64_t), st));
+    return HSG_OK;
+  }
+  HSG_REQUIRE(centroids && labels_out, HSG_E_INVALID, "estep: null pointer");
+  HSG_REQUIRE(workspace && workspace_bytes >= hsg_kmeans_workspace_bytes(N, dim, S, kmax, max_seg_len),
+              HSG_E_WORKSPACE, "estep: workspace too small");
+  bool use_tc = false;
+  rc = decide_tc(flags, dim, xh, d16, xerr, kmax, &use_tc);
+  if (rc) return rc;
+  Carver c(workspace);
+  KmPlan p;
+  km_carve(c, p, N, dim, S, kmax, max_seg_len, d16);
+  if (use_tc) {
+    p.tc.xh = (const __half*)xh; p.tc.xerr = xerr; p.tc.d16 = d16;
+    rc = tc_prepare(p.tc, N, S);
+    if (rc) return rc;
+  }
+  if ((rc = sr_build_tiles(p.sr, seg_offsets, st))) return rc;
+  EStepArgs ea;
+  ea.x = x; ea.N = N; ea.dim = dim; ea.centroids = centroids; ea.seg_offsets = seg_offsets;
+  ea.S = S; ea.seg_k = seg_k; ea.kmax = kmax; ea.tiles = p.sr.tiles; ea.keys_out = p.sr.keys;
+  ea.fix = p.fix;
+  if ((rc = run_estep(ea, p, use_tc, st))) return rc;
+  if (num_rechecked_out) {
+    copy_count_kernel<<<1, 1, 0, st>>>(p.fix.count, num_rechecked_out);
+    HSG_LAUNCH_CHECK();
+  }
+  return sr_keys_to_labels(p.sr, p.sr.keys, labels_out, st);
+}
+
+// ---------------------------------------------------------------- K3 segmented reduction
+size_t hsg_segment_reduce_workspace_bytes(int64_t N, int dim, int64_t P, int S, int kmax,
+                                          int64_t max_seg_len) {
+  (void)P;
+  return sr_workspace_bytes(N, dim, S > 0 ? S : 1, kmax, max_seg_len) + 1024;
+}
+
+int hsg_segment_reduce_f32(const float* x, int64_t N, int dim, const int64_t* labels, int64_t P,
+                           const int64_t* seg_offsets, int S, int64_t max_seg_len,
+                           const int64_t* seg_base, int kmax, int mode, float* out, float* sums_out,
+                           float* counts_out, void* workspace, size_t workspace_bytes, void* stream) {
+  HSG_REQUIRE(P >= 0 && dim > 0 && N >= 0, HSG_E_INVALID, "segment_reduce: bad shape");
+  HSG_REQUIRE(mode >= 0 && mode <= 2, HSG_E_INVALID, "segment_reduce: bad mode %d", mode);
+  HSG_REQUIRE(seg_offsets && seg_base && S > 0, HSG_E_INVALID,
+              "segment_reduce: seg_offsets/seg_base are required (one segment: offsets {0,N}, base {0}, kmax=P)");
+  if (P == 0) return HSG_OK;
+  HSG_REQUIRE(out, HSG_E_INVALID, "segment_reduce: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) {
+    HSG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * P * dim, st));
+    if (sums_out) HSG_CUDA(cudaMemsetAsync(sums_out, 0, sizeof(float) * P * dim, st));
+    if (counts_out) HSG_CUDA(cudaMemsetAsync(counts_out, 0, sizeof(float) * P, st));
+    return HSG_OK;
+  }
+  int rc = check_common(x, N, dim, seg_offsets, S, max_seg_len, kmax);
+  if (rc) return rc;
+  HSG_REQUIRE(labels, HSG_E_INVALID, "segment_reduce: null labels");
+  HSG_REQUIRE(workspace && workspace_bytes >= hsg_segment_reduce_workspace_bytes(N, dim, P, S, kmax, max_seg_len),
+              HSG_E_WORKSPACE, "segment_reduce: workspace too small");
+  Carver c(workspace);
+  SegReducePlan p;
+  sr_carve(c, p, N, dim, S, kmax, max_seg_len);
+  if ((rc = sr_build_tiles(p, seg_offsets, st))) return rc;
+  if ((rc = sr_labels_to_keys(p, labels, seg_base, st))) return rc;
+  if ((rc = sr_sort_and_sum(p, x, seg_offsets, st))) return rc;
+  return sr_combine(p, P, seg_base, mode, out, sums_out, counts_out, st);
+}
+
+}  // extern "C"
+
+// backward: per-bin gradient of the finishing step, then a row gather
+namespace hsg {
+
+__global__ void segreduce_bin_grad_kernel(const float* __restrict__ g, const float* __restrict__ out,
+                                          const float* __restrict__ sums, const float* __restrict__ counts,
+                                          int64_t P, int dim, int mode, float* __restrict__ gs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= P) return;
+  const float* gr = g + p * dim;
+  float* o = gs + p * dim;
+  if (mode == HSG_REDUCE_SUM) {
+    for (int d = lane; d < dim; d += 32) o[d] = gr[d];
+  } else if (mode == HSG_REDUCE_MEAN) {
+    const float c = counts[p] > 0.f ? counts[p] : 1.f;
+    for (int d = lane; d < dim; d += 32) o[d] = gr[d] / c;
+  } else {
+    const float* sr = sums + p * dim;
+    const float* pr = out + p * dim;
+    float ss = 0.f, dot = 0.f;
+    for (int d = lane; d < dim; d += 32) {
+      ss = fmaf(sr[d], sr[d], ss);
+      dot = fmaf(pr[d], gr[d], dot);
+    }
+    ss = warp_sum(ss);
+    dot = warp_sum(dot);
+    const float n = sqrtf(ss);
+    if (n >= 1e-12f) {
+      for (int d = lane; d < dim; d += 32) o[d] = (gr[d] - pr[d] * dot) / n;
+    } else {
+      for (int d = lane; d < dim; d += 32) o[d] = gr[d] / 1e-12f;
+    }
+  }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
+                                   int64_t N, int dim, int64_t P, float* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= N) return;
+  int64_t k = idx[i];
+  k = k < 0 ? 0 : (k >= P ? P - 1 : k);
+  const float* s = src + k * dim;
+  float* d = dst + i * dim;
+  for (int j = lane; j < dim; j += 32) d[j] = s[j];
+}
+
+}  // namespace hsg
+
+extern "C" int hsg_segment_reduce_bwd_f32(const float* grad_out, const float* out, const float* sums,
+                                          const float* counts, const int64_t* labels, int64_t N,
+                                          int dim, int64_t P, int mode, float* grad_x,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+  HSG_REQUIRE(P >= 0 && dim > 0 && N >= 0 && mode >= 0 && mode <= 2, HSG_E_INVALID, "segment_reduce_bwd: bad argument");
+  if (N == 0 || P == 0) return HSG_OK;
+  HSG_REQUIRE(grad_out && labels && grad_x, HSG_E_INVALID, "segment_reduce_bwd: null pointer");
+  HSG_REQUIRE(mode != HSG_REDUCE_NORMALIZE || (out && sums), HSG_E_INVALID, "segment_reduce_bwd: NORMALIZE needs out and sums");
+  HSG_REQUIRE(mode != HSG_REDUCE_MEAN || counts, HSG_E_INVALID, "segment_reduce_bwd: MEAN needs counts");
+  HSG_REQUIRE(workspace && workspace_bytes >= sizeof(float) * P * dim, HSG_E_WORKSPACE,
+              "segment_reduce_bwd: workspace needs P*dim floats");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* gs = (float*)workspace;
+  segreduce_bin_grad_kernel<<<(unsigned)ceil_div64(P, 8), 256, 0, st>>>(grad_out, out, sums, counts, P, dim, mode, gs);
+  HSG_LAUNCH_CHECK();
+  gather_rows_kernel<<<(unsigned)ceil_div64(N, 8), 256, 0, st>>>(gs, labels, N, dim, P, grad_x);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}

@@ -1,0 +1,340 @@
+// K0: front half of segment_by_kmeans as one pass over the embedding tensor.
+//
+// Reference (hsg/utils/segsort/common.py:305-365 + general/common.py:101-120):
+// permute NCHW->NHWC + contiguous, normalise, per image cat(loc) + normalise
+// again, then nonzero/index_select to drop ignore pixels: >= 5 full-tensor
+// temporaries.  Here: one read of the NCHW tensor (transposed through shared
+// memory), one write each of x, x_with_loc and the optional fp16 side copy,
+// with the compaction offsets coming from a small count + scan pre-pass.
+#include "common.cuh"
+
+namespace hsg {
+
+constexpr int PREP_TPX = 32;       // pixels per CTA tile
+constexpr int PREP_THREADS = 256;  // 8 warps
+
+// ------------------------------------------------------------ normalize (a1)
+__global__ void normalize_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                 int64_t rows, int dim) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * dim;
+  float ss = 0.f;
+  for (int d = lane; d < dim; d += 32) {
+    float v = xr[d];
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float n = safe_norm(ss);
+  float* yr = y + row * dim;
+  for (int d = lane; d < dim; d += 32) yr[d] = xr[d] / n;
+}
+
+__global__ void normalize_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                     float* __restrict__ gx, int64_t rows, int dim) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * dim;
+  const float* gr = gy + row * dim;
+  float ss = 0.f, dot = 0.f;
+  for (int d = lane; d < dim; d += 32) {
+    float v = xr[d];
+    ss = fmaf(v, v, ss);
+    dot = fmaf(v, gr[d], dot);
+  }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float n = sqrtf(ss);
+  float* out = gx + row * dim;
+  if (n >= 1e-12f) {
+    const float inv = 1.f / n;
+    const float proj = dot * inv * inv;   // <xhat, g> / ||x||
+    for (int d = lane; d < dim; d += 32) out[d] = (gr[d] - xr[d] * proj) * inv;
+  } else {
+    for (int d = lane; d < dim; d += 32) out[d] = gr[d] / 1e-12f;
+  }
+}
+
+// ------------------------------------------------------------ half copy
+__global__ void half_copy_kernel(const float* __restrict__ x, int64_t rows, int dim, int d16,
+                                 __half* __restrict__ xh, float* __restrict__ xerr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * dim;
+  float e2 = 0.f;
+  for (int d = lane; d < d16; d += 32) {
+    const float v = xr[d];
+    const __half h = __float2half_rn(v);
+    const float r = v - __half2float(h);
+    e2 = fmaf(r, r, e2);
+    xh[row * d16 + d] = h;
+  }
+  e2 = warp_sum(e2);
+  if (lane == 0 && xerr) xerr[row] = sqrtf(e2) * 1.0001f + 1e-30f;
+}
+
+// ------------------------------------------------------------ compaction pre-pass
+__global__ void prep_count_kernel(const int64_t* __restrict__ labels, int64_t ignore_index,
+                                  int HW, int tiles_per_image, int64_t n_tiles,
+                                  int32_t* __restrict__ tile_count) {
+  // one warp per tile of 32 pixels
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile >= n_tiles) return;
+  const int64_t b = tile / tiles_per_image;
+  const int t = (int)(tile % tiles_per_image);
+  const int p = t * PREP_TPX + lane;
+  bool valid = false;
+  if (p < HW) valid = labels[b * HW + p] != ignore_index;
+  const unsigned m = __ballot_sync(FULL, valid);
+  if (lane == 0) tile_count[tile] = __popc(m);
+}
+
+// exclusive scan of tile counts (single CTA, 1024 threads, chunked)
+__global__ void prep_scan_kernel(const int32_t* __restrict__ tile_count, int64_t n_tiles,
+                                 int tiles_per_image, int B, int64_t* __restrict__ tile_base,
+                                 int64_t* __restrict__ seg_offsets) {
+  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n_tiles; base += blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    const int v = i < n_tiles ? tile_count[i] : 0;
+    const int incl = warp_scan_incl(v, lane);
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int64_t w = warp_tot[lane];
+      // inclusive scan of 32 warp totals
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int64_t t = __shfl_up_sync(FULL, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const int64_t before = carry + (warp ? warp_tot[warp - 1] : 0) + (incl - v);
+    if (i < n_tiles) {
+      tile_base[i] = before;
+      if (i % tiles_per_image == 0) seg_offsets[i / tiles_per_image] = before;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warp_tot[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) seg_offsets[B] = carry;
+}
+
+__global__ void fill_dense_offsets_kernel(int64_t* seg_offsets, int B, int64_t HW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= B) seg_offsets[i] = (int64_t)i * HW;
+}
+
+// ------------------------------------------------------------ main pass
+struct PrepArgs {
+  const float* emb;
+  int B, D, HW;
+  const float* loc;
+  int L;
+  int64_t loc_image_stride;
+  const int64_t* labels;
+  int use_ignore;
+  int64_t ignore_index;
+  const int64_t* init;
+  int64_t init_image_stride;
+  int64_t batch_base;
+  float* x;
+  float* xloc;
+  __half* xh;
+  float* xerr;
+  int64_t* labels_out;
+  int64_t* clusters_out;
+  int64_t* batch_out;
+  int64_t* pixel_out;         // optional: flat source pixel b*HW+p of each row
+  const int64_t* tile_base;   // NULL when nothing is dropped
+  int tiles_per_image;
+};
+
+__global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs a) {
+  extern __shared__ float tile[];                 // [D][33]
+  __shared__ int64_t rows[PREP_TPX];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int t = blockIdx.x;
+  const int p0 = t * PREP_TPX;
+  const int p = p0 + lane;
+  const bool inb = p < a.HW;
+
+  // NCHW read: one channel row of 32 pixels per warp-iteration (coalesced)
+  const float* src = a.emb + (int64_t)b * a.D * a.HW;
+  for (int d = warp; d < a.D; d += PREP_THREADS / 32)
+    tile[d * 33 + lane] = inb ? ld_stream(src + (int64_t)d * a.HW + p) : 0.f;
+
+  if (warp == 0) {
+    int64_t lab = 0;
+    if (inb && a.labels) lab = a.labels[(int64_t)b * a.HW + p];
+    const bool valid = inb && !(a.use_ignore && lab == a.ignore_index);
+    const unsigned m = __ballot_sync(FULL, valid);
+    const int64_t base = a.tile_base ? a.tile_base[(int64_t)b * a.tiles_per_image + t]
+                                     : (int64_t)b * a.HW + p0;
+    const int64_t row = valid ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+    rows[lane] = row;
+    if (valid) {
+      a.labels_out[row] = lab;
+      a.clusters_out[row] = a.init[(int64_t)b * a.init_image_stride + p];
+      a.batch_out[row] = a.batch_base + b;
+      if (a.pixel_out) a.pixel_out[row] = (int64_t)b * a.HW + p;
+    }
+  }
+  __syncthreads();
+
+  const int Dp = a.D + a.L;
+  for (int i = 0; i < PREP_TPX / (PREP_THREADS / 32); ++i) {
+    const int px = warp * (PREP_TPX / (PREP_THREADS / 32)) + i;
+    const int64_t row = rows[px];
+    if (row < 0) continue;                          // warp-uniform
+    float ss = 0.f;
+    for (int d = lane; d < a.D; d += 32) {
+      const float v = tile[d * 33 + px];
+      ss = fmaf(v, v, ss);
+    }
+    const float n1 = safe_norm(warp_sum(ss));
+    // second normalisation over cat(normalised embedding, local features)
+    float ss2 = 0.f;
+    for (int d = lane; d < a.D; d += 32) {
+      const float y = tile[d * 33 + px] / n1;
+      ss2 = fmaf(y, y, ss2);
+    }
+    float lv = 0.f;
+    if (lane < a.L) {
+      lv = a.loc[(int64_t)b * a.loc_image_stride + (int64_t)(p0 + px) * a.L + lane];
+      ss2 = fmaf(lv, lv, ss2);
+    }
+    const float n2 = safe_norm(warp_sum(ss2));
+    float* xr = a.x + row * a.D;
+    float* xl = a.xloc + row * Dp;
+    float e2 = 0.f;
+    for (int d = lane; d < a.D; d += 32) {
+      const float y = tile[d * 33 + px] / n1;
+      const float z = y / n2;
+      xr[d] = y;
+      xl[d] = z;
+      if (a.xh) {
+        const __half h = __float2half_rn(z);
+        const float r = z - __half2float(h);
+        e2 = fmaf(r, r, e2);
+        a.xh[row * a.D + d] = h;
+      }
+    }
+    if (lane < a.L) xl[a.D + lane] = lv / n2;
+    if (a.xh && a.xerr) {
+      e2 = warp_sum(e2);
+      if (lane == 0) a.xerr[row] = sqrtf(e2) * 1.0001f + 1e-30f;
+    }
+  }
+}
+
+}  // namespace hsg
+
+using namespace hsg;
+
+extern "C" {
+
+int hsg_normalize_f32(const float* x, float* y, int64_t rows, int dim, void* stream) {
+  HSG_REQUIRE(rows >= 0 && dim > 0, HSG_E_INVALID, "normalize: bad shape rows=%lld dim=%d", (long long)rows, dim);
+  if (rows == 0) return HSG_OK;
+  HSG_REQUIRE(x && y, HSG_E_INVALID, "normalize: null pointer");
+  const int rpb = 8;
+  normalize_kernel<<<(unsigned)ceil_div64(rows, rpb), rpb * 32, 0, (cudaStream_t)stream>>>(x, y, rows, dim);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+int hsg_normalize_bwd_f32(const float* x, const float* gy, float* gx, int64_t rows, int dim, void* stream) {
+  HSG_REQUIRE(rows >= 0 && dim > 0, HSG_E_INVALID, "normalize_bwd: bad shape");
+  if (rows == 0) return HSG_OK;
+  HSG_REQUIRE(x && gy && gx, HSG_E_INVALID, "normalize_bwd: null pointer");
+  const int rpb = 8;
+  normalize_bwd_kernel<<<(unsigned)ceil_div64(rows, rpb), rpb * 32, 0, (cudaStream_t)stream>>>(x, gy, gx, rows, dim);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+int hsg_make_half_copy_f32(const float* x, int64_t rows, int dim, int d16, void* xh_out,
+                           float* xerr_out, void* stream) {
+  HSG_REQUIRE(rows >= 0 && dim > 0 && d16 > 0 && d16 <= dim, HSG_E_INVALID, "half_copy: bad shape");
+  if (rows == 0) return HSG_OK;
+  HSG_REQUIRE(x && xh_out, HSG_E_INVALID, "half_copy: null pointer");
+  const int rpb = 8;
+  half_copy_kernel<<<(unsigned)ceil_div64(rows, rpb), rpb * 32, 0, (cudaStream_t)stream>>>(
+      x, rows, dim, d16, (__half*)xh_out, xerr_out);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+size_t hsg_prep_workspace_bytes(int B, int H, int W) {
+  const int64_t tpi = ceil_div64((int64_t)H * W, PREP_TPX);
+  return align_up((size_t)B * tpi * sizeof(int32_t), 256) + align_up((size_t)B * tpi * sizeof(int64_t), 256) + 512;
+}
+
+int hsg_prep_f32(const float* emb_nchw, int B, int D, int H, int W,
+                 const float* loc, int L, int64_t loc_image_stride,
+                 const int64_t* labels, int use_ignore, int64_t ignore_index,
+                 const int64_t* init_clusters, int64_t init_image_stride,
+                 int64_t batch_index_base,
+                 float* x_out, float* xloc_out, void* xh_out, float* xerr_out,
+                 int64_t* labels_out, int64_t* clusters_out, int64_t* batch_out,
+                 int64_t* pixel_out, int64_t* seg_offsets, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  HSG_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, HSG_E_INVALID, "prep: bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
+  HSG_REQUIRE(L >= 0 && L <= 32, HSG_E_UNSUPPORTED, "prep: %d local-feature channels (max 32)", L);
+  HSG_REQUIRE(emb_nchw && (loc || L == 0) && init_clusters && x_out && xloc_out && labels_out &&
+              clusters_out && batch_out && seg_offsets, HSG_E_INVALID, "prep: null pointer");
+  HSG_REQUIRE(!use_ignore || labels, HSG_E_INVALID, "prep: ignore_index without labels");
+  HSG_REQUIRE((int64_t)H * W < (1ll << 31) && B <= 65535, HSG_E_UNSUPPORTED, "prep: image too large");
+  const size_t smem = (size_t)D * 33 * sizeof(float);
+  HSG_REQUIRE(smem <= 200 * 1024, HSG_E_UNSUPPORTED, "prep: embedding_dim %d too large", D);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = H * W;
+  const int tpi = (HW + PREP_TPX - 1) / PREP_TPX;
+
+  const int64_t* tile_base = nullptr;
+  if (use_ignore) {
+    HSG_REQUIRE(workspace && workspace_bytes >= hsg_prep_workspace_bytes(B, H, W), HSG_E_WORKSPACE,
+                "prep: workspace too small");
+    Carver c(workspace);
+    int32_t* cnt = c.take<int32_t>((size_t)B * tpi);
+    int64_t* base = c.take<int64_t>((size_t)B * tpi);
+    const int64_t n_tiles = (int64_t)B * tpi;
+    prep_count_kernel<<<(unsigned)ceil_div64(n_tiles, 8), 256, 0, st>>>(
+        labels, ignore_index, HW, tpi, n_tiles, cnt);
+    HSG_LAUNCH_CHECK();
+    prep_scan_kernel<<<1, 1024, 0, st>>>(cnt, n_tiles, tpi, B, base, seg_offsets);
+    HSG_LAUNCH_CHECK();
+    tile_base = base;
+  } else {
+    fill_dense_offsets_kernel<<<(B + 256) / 256, 256, 0, st>>>(seg_offsets, B, HW);
+    HSG_LAUNCH_CHECK();
+  }
+
+  PrepArgs a;
+  a.emb = emb_nchw; a.B = B; a.D = D; a.HW = HW; a.loc = loc; a.L = L;
+  a.loc_image_stride = loc_image_stride; a.labels = labels; a.use_ignore = use_ignore;
+  a.ignore_index = ignore_index; a.init = init_clusters; a.init_image_stride = init_image_stride;
+  a.batch_base = batch_index_base; a.x = x_out; a.xloc = xloc_out; a.xh = (__half*)xh_out;
+  a.xerr = xerr_out; a.labels_out = labels_out; a.clusters_out = clusters_out;
+  a.batch_out = batch_out; a.pixel_out = pixel_out; a.tile_base = tile_base; a.tiles_per_image = tpi;
+  if (smem > 48 * 1024)
+    HSG_CUDA(cudaFuncSetAttribute(prep_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prep_main_kernel<<<dim3(tpi, B), PREP_THREADS, smem, st>>>(a);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+}  // extern "C"

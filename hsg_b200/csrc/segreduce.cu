@@ -1,0 +1,431 @@
+// Deterministic segmented row sums (see segreduce.cuh for the scheme).
+#include "segreduce.cuh"
+
+namespace hsg {
+
+// ---------------------------------------------------------------- helpers
+__device__ __forceinline__ int upper_bound_i64(const int64_t* a, int n, int64_t v) {
+  // first index with a[idx] > v
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// exclusive scan over one value per thread of a 1024-thread CTA (int64)
+__device__ __forceinline__ int64_t block_scan_excl_1024(int64_t v, int64_t* warp_tot, int64_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int64_t w = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t t = __shfl_up_sync(FULL, w, o);
+      if (lane >= o) w += t;
+    }
+    warp_tot[lane] = w;
+  }
+  __syncthreads();
+  const int64_t res = (warp ? warp_tot[warp - 1] : 0) + incl - v;
+  *total = warp_tot[(blockDim.x >> 5) - 1];
+  __syncthreads();
+  return res;
+}
+
+// ---------------------------------------------------------------- tiles
+__global__ void __launch_bounds__(1024) build_tiles_kernel(const int64_t* __restrict__ off, int S,
+                                                           Tiles t) {
+  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < S; base += 1024) {
+    const int s = base + threadIdx.x;
+    int64_t nt = 0;
+    if (s < S) nt = (off[s + 1] - off[s] + t.tile - 1) / t.tile;
+    int64_t total;
+    const int64_t first = carry_s + block_scan_excl_1024(nt, warp_tot, &total);
+    if (s < S) {
+      t.seg_first[s] = (int32_t)min(first, t.bound);
+      for (int64_t j = 0; j < nt; ++j) {
+        const int64_t idx = first + j;
+        if (idx < t.bound) {
+          t.seg[idx] = s;
+          const int64_t b = off[s] + j * t.tile;
+          t.begin[idx] = b;
+          t.end[idx] = min(off[s + 1], b + t.tile);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    t.seg_first[S] = (int32_t)min(carry_s, t.bound);
+    *t.count = (int32_t)min(carry_s, t.bound);
+  }
+}
+
+// rows [r0,r1) of segment `seg` handled by this CTA (grid = (tiles.bound, tile/chunk_rows))
+__device__ __forceinline__ bool cta_rows(const Tiles& t, int chunk_rows, int64_t& r0, int64_t& r1, int& seg) {
+  const int ti = blockIdx.x;
+  if (ti >= *t.count) return false;
+  r0 = t.begin[ti] + (int64_t)blockIdx.y * chunk_rows;
+  const int64_t e = t.end[ti];
+  if (r0 >= e) return false;
+  r1 = min(e, r0 + chunk_rows);
+  seg = t.seg[ti];
+  return true;
+}
+
+__global__ void labels_to_keys_kernel(Tiles t, const int64_t* __restrict__ labels,
+                                      const int64_t* __restrict__ seg_base, int kmax,
+                                      int32_t* __restrict__ keys) {
+  int64_t r0, r1; int seg;
+  if (!cta_rows(t, SR_TILE_MIN, r0, r1, seg)) return;
+  const int64_t base = seg_base ? seg_base[seg] : 0;
+  for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+    int64_t k = labels[i] - base;
+    k = k < 0 ? 0 : (k >= kmax ? kmax - 1 : k);      // out-of-range ids are clamped, never scattered out of bounds
+    keys[i] = seg * kmax + (int)k;
+  }
+}
+
+__global__ void keys_to_labels_kernel(Tiles t, const int32_t* __restrict__ keys, int kmax,
+                                      int64_t* __restrict__ labels) {
+  int64_t r0, r1; int seg;
+  if (!cta_rows(t, SR_TILE_MIN, r0, r1, seg)) return;
+  for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+    labels[i] = (int64_t)(keys[i] - seg * kmax);
+}
+
+// ---------------------------------------------------------------- hist / scan / scatter
+__global__ void __launch_bounds__(512) hist_kernel(Tiles t, const int32_t* __restrict__ keys, int kmax,
+                                                   uint32_t* __restrict__ tile_hist) {
+  extern __shared__ uint32_t hist[];
+  const int ti = blockIdx.x;
+  if (ti >= *t.count) return;
+  for (int k = threadIdx.x; k < kmax; k += blockDim.x) hist[k] = 0;
+  __syncthreads();
+  const int seg = t.seg[ti];
+  const int64_t b = t.begin[ti], e = t.end[ti];
+  const int kbase = seg * kmax;
+  for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) atomicAdd(&hist[keys[i] - kbase], 1u);
+  __syncthreads();
+  for (int k = threadIdx.x; k < kmax; k += blockDim.x) tile_hist[(int64_t)ti * kmax + k] = hist[k];
+}
+
+__global__ void __launch_bounds__(1024) scan_kernel(Tiles t, const int64_t* __restrict__ off, int kmax,
+                                                    uint32_t* __restrict__ tile_hist,
+                                                    int64_t* __restrict__ bin_start,
+                                                    int32_t* __restrict__ bin_count) {
+  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t carry_s;
+  const int s = blockIdx.x;
+  const int t0 = t.seg_first[s], t1 = t.seg_first[s + 1];
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < kmax; base += 1024) {
+    const int k = base + threadIdx.x;
+    int64_t run = 0;
+    if (k < kmax) {
+      for (int ti = t0; ti < t1; ++ti) {
+        const int64_t idx = (int64_t)ti * kmax + k;
+        const uint32_t v = tile_hist[idx];
+        tile_hist[idx] = (uint32_t)run;
+        run += v;
+      }
+    }
+    int64_t total;
+    const int64_t before = carry_s + block_scan_excl_1024(run, warp_tot, &total);
+    if (k < kmax) {
+      bin_start[(int64_t)s * kmax + k] = off[s] + before;
+      bin_count[(int64_t)s * kmax + k] = (int32_t)run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s += total;
+    __syncthreads();
+  }
+}
+
+template <int SCATTER_WARPS>
+__global__ void __launch_bounds__(SCATTER_WARPS * 32) scatter_kernel(
+    Tiles t, const int64_t* __restrict__ off, const int32_t* __restrict__ keys, int kmax,
+    const uint32_t* __restrict__ tile_hist, const int64_t* __restrict__ bin_start,
+    uint32_t* __restrict__ perm) {
+  extern __shared__ uint32_t cursors[];          // [SCATTER_WARPS][kmax]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ti = blockIdx.x * SCATTER_WARPS + warp;
+  if (ti >= *t.count) return;                    // only __syncwarp below
+  uint32_t* cur = cursors + (size_t)warp * kmax;
+  const int seg = t.seg[ti];
+  const int64_t so = off[seg];
+  const int kbase = seg * kmax;
+  for (int k = lane; k < kmax; k += 32)
+    cur[k] = (uint32_t)(bin_start[(int64_t)kbase + k] - so) + tile_hist[(int64_t)ti * kmax + k];
+  __syncwarp();
+  const int64_t b = t.begin[ti], e = t.end[ti];
+  const unsigned lt = (1u << lane) - 1u;
+  for (int64_t base = b; base < e; base += 32) {
+    const int64_t i = base + lane;
+    const bool valid = i < e;
+    const int kl = valid ? keys[i] - kbase : -1 - lane;
+    const unsigned m = __match_any_sync(FULL, kl);
+    uint32_t pos = 0;
+    if (valid) pos = cur[kl] + __popc(m & lt);
+    __syncwarp();
+    if (valid) {
+      perm[so + pos] = (uint32_t)(i - so);
+      if ((m & lt) == 0) cur[kl] += __popc(m);   // lowest lane of the group advances the cursor
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- gather-sum
+constexpr int GATHER_WARPS = 8;
+
+template <int NV>
+__global__ void __launch_bounds__(GATHER_WARPS * 32) gather_sum_kernel(
+    const float* __restrict__ x, int dim, int64_t N, const int64_t* __restrict__ off, int S,
+    const int32_t* __restrict__ keys, const uint32_t* __restrict__ perm,
+    float* __restrict__ pieces, int32_t* __restrict__ piece_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t run = (int64_t)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
+  const int64_t j0 = run * SR_RUN;
+  if (j0 >= N) return;
+  const int n = (int)min((int64_t)SR_RUN, N - j0);
+
+  int64_t pix[2];
+  int key[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int64_t j = j0 + h * 32 + lane;
+    pix[h] = 0; key[h] = -1;
+    if (j < j0 + n) {
+      const int s = upper_bound_i64(off, S + 1, j) - 1;
+      pix[h] = off[s] + perm[j];
+      key[h] = keys[pix[h]];
+    }
+  }
+
+  float acc[NV];
+#pragma unroll
+  for (int m = 0; m < NV; ++m) acc[m] = 0.f;
+  int cur = -1, cnt = 0;
+
+  auto flush = [&]() {
+    const int64_t id = run + cur;
+    float* dst = pieces + id * dim;
+#pragma unroll
+    for (int m = 0; m < NV; ++m) {
+      const int d = lane + 32 * m;
+      if (d < dim) dst[d] = acc[m];
+    }
+    if (lane == 0) piece_cnt[id] = cnt;
+  };
+
+  constexpr int U = 4;
+  for (int e0 = 0; e0 < n; e0 += U) {
+    float v[U][NV];
+    int kk[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u;
+      const int src = e & 31;
+      const int64_t p = __shfl_sync(FULL, e < 32 ? pix[0] : pix[1], src);
+      kk[u] = __shfl_sync(FULL, e < 32 ? key[0] : key[1], src);
+      if (e < n) {
+        const float* row = x + p * dim;
+#pragma unroll
+        for (int m = 0; m < NV; ++m) {
+          const int d = lane + 32 * m;
+          v[u][m] = d < dim ? ld_stream(row + d) : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (e0 + u < n) {
+        if (kk[u] != cur) {
+          if (cur >= 0) flush();
+          cur = kk[u];
+          cnt = 0;
+#pragma unroll
+          for (int m = 0; m < NV; ++m) acc[m] = 0.f;
+        }
+#pragma unroll
+        for (int m = 0; m < NV; ++m) acc[m] += v[u][m];
+        ++cnt;
+      }
+    }
+  }
+  if (cur >= 0) flush();
+}
+
+// ---------------------------------------------------------------- combine
+constexpr int COMBINE_WARPS = 8;
+
+__global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_kernel(
+    int64_t P, int dim, int S, int kmax, const int64_t* __restrict__ seg_base,
+    const int64_t* __restrict__ bin_start, const int32_t* __restrict__ bin_count,
+    const float* __restrict__ pieces, int mode, float* __restrict__ out,
+    float* __restrict__ sums_out, float* __restrict__ counts_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p = (int64_t)blockIdx.x * COMBINE_WARPS + (threadIdx.x >> 5);
+  if (p >= P) return;
+  int64_t key = p;
+  bool covered = true;
+  if (seg_base) {
+    const int s = upper_bound_i64(seg_base, S, p) - 1;
+    const int64_t k = s >= 0 ? p - seg_base[s] : kmax;
+    covered = s >= 0 && k < kmax;
+    key = covered ? (int64_t)s * kmax + k : 0;
+  }
+  const int cnt = covered ? bin_count[key] : 0;
+  const int64_t start = covered ? bin_start[key] : 0;
+  const int64_t r0 = start / SR_RUN, r1 = cnt > 0 ? (start + cnt - 1) / SR_RUN : r0 - 1;
+  float* o = out + p * dim;
+  float ss = 0.f;
+  for (int d = lane; d < dim; d += 32) {
+    float a = 0.f;
+    for (int64_t r = r0; r <= r1; ++r) a += pieces[(r + key) * dim + d];
+    if (sums_out) sums_out[p * dim + d] = a;
+    o[d] = a;
+    ss = fmaf(a, a, ss);
+  }
+  if (counts_out && lane == 0) counts_out[p] = (float)cnt;
+  if (mode == HSG_REDUCE_NORMALIZE) {
+    const float n = safe_norm(warp_sum(ss));
+    for (int d = lane; d < dim; d += 32) o[d] = o[d] / n;
+  } else if (mode == HSG_REDUCE_MEAN) {
+    const float c = cnt > 0 ? (float)cnt : 1.f;
+    for (int d = lane; d < dim; d += 32) o[d] = o[d] / c;
+  }
+}
+
+// ---------------------------------------------------------------- host side
+int64_t sr_tile_size(int64_t max_seg_len) {
+  int64_t tile = SR_TILE_MIN;
+  while (ceil_div64(max_seg_len, tile) > 1024) tile *= 2;
+  return tile;
+}
+
+int64_t sr_tiles_bound(int64_t N, int S, int64_t tile) { return N / tile + S + 1; }
+
+static int64_t sr_num_pieces(int64_t N, int64_t bins) { return ceil_div64(N, SR_RUN) + bins + 2; }
+
+void sr_carve(Carver& c, SegReducePlan& p, int64_t N, int dim, int S, int kmax, int64_t max_seg_len) {
+  p.N = N; p.dim = dim; p.S = S; p.kmax = kmax; p.bins = (int64_t)S * kmax;
+  p.tiles.tile = sr_tile_size(max_seg_len);
+  p.tiles.bound = sr_tiles_bound(N, S, p.tiles.tile);
+  p.tiles.seg = c.take<int32_t>(p.tiles.bound);
+  p.tiles.begin = c.take<int64_t>(p.tiles.bound);
+  p.tiles.end = c.take<int64_t>(p.tiles.bound);
+  p.tiles.seg_first = c.take<int32_t>(S + 1);
+  p.tiles.count = c.take<int32_t>(1);
+  p.keys = c.take<int32_t>(N);
+  p.perm = c.take<uint32_t>(N);
+  p.tile_hist = c.take<uint32_t>(p.tiles.bound * kmax);
+  p.bin_start = c.take<int64_t>(p.bins);
+  p.bin_count = c.take<int32_t>(p.bins);
+  const int64_t np = sr_num_pieces(N, p.bins);
+  p.pieces = c.take<float>(np * dim);
+  p.piece_cnt = c.take<int32_t>(np);
+}
+
+size_t sr_workspace_bytes(int64_t N, int dim, int S, int kmax, int64_t max_seg_len) {
+  Carver c(nullptr);
+  SegReducePlan p;
+  sr_carve(c, p, N, dim, S, kmax, max_seg_len);
+  return c.used() + 256;
+}
+
+int sr_build_tiles(const SegReducePlan& p, const int64_t* seg_offsets, cudaStream_t st) {
+  build_tiles_kernel<<<1, 1024, 0, st>>>(seg_offsets, p.S, p.tiles);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+static dim3 row_grid(const Tiles& t, int chunk) {
+  return dim3((unsigned)t.bound, (unsigned)ceil_div64(t.tile, chunk));
+}
+
+int sr_labels_to_keys(const SegReducePlan& p, const int64_t* labels, const int64_t* seg_base,
+                      cudaStream_t st) {
+  labels_to_keys_kernel<<<row_grid(p.tiles, SR_TILE_MIN), 256, 0, st>>>(p.tiles, labels, seg_base,
+                                                                         p.kmax, p.keys);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+int sr_keys_to_labels(const SegReducePlan& p, const int32_t* keys, int64_t* labels, cudaStream_t st) {
+  keys_to_labels_kernel<<<row_grid(p.tiles, SR_TILE_MIN), 256, 0, st>>>(p.tiles, keys, p.kmax, labels);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+template <int NV>
+static int launch_gather(const SegReducePlan& p, const float* x, const int64_t* off, cudaStream_t st) {
+  const int64_t runs = ceil_div64(p.N, SR_RUN);
+  gather_sum_kernel<NV><<<(unsigned)ceil_div64(runs, GATHER_WARPS), GATHER_WARPS * 32, 0, st>>>(
+      x, p.dim, p.N, off, p.S, p.keys, p.perm, p.pieces, p.piece_cnt);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+int sr_sort_and_sum(const SegReducePlan& p, const float* x, const int64_t* off, cudaStream_t st) {
+  HSG_REQUIRE(p.kmax <= SR_MAX_KEYS, HSG_E_UNSUPPORTED, "segment reduce: %d keys per segment (max %d)", p.kmax, SR_MAX_KEYS);
+  HSG_REQUIRE(p.dim <= 32 * 20, HSG_E_UNSUPPORTED, "segment reduce: dim %d (max 640)", p.dim);
+  const size_t hist_smem = (size_t)p.kmax * sizeof(uint32_t);
+  if (hist_smem > 48 * 1024)
+    HSG_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+  hist_kernel<<<(unsigned)p.tiles.bound, 512, hist_smem, st>>>(p.tiles, p.keys, p.kmax, p.tile_hist);
+  HSG_LAUNCH_CHECK();
+  scan_kernel<<<p.S, 1024, 0, st>>>(p.tiles, off, p.kmax, p.tile_hist, p.bin_start, p.bin_count);
+  HSG_LAUNCH_CHECK();
+  if (p.kmax <= 8192) {
+    const size_t sc_smem = (size_t)4 * p.kmax * sizeof(uint32_t);
+    if (sc_smem > 48 * 1024)
+      HSG_CUDA(cudaFuncSetAttribute(scatter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+    scatter_kernel<4><<<(unsigned)ceil_div64(p.tiles.bound, 4), 128, sc_smem, st>>>(
+        p.tiles, off, p.keys, p.kmax, p.tile_hist, p.bin_start, p.perm);
+  } else {
+    const size_t sc_smem = (size_t)p.kmax * sizeof(uint32_t);
+    HSG_CUDA(cudaFuncSetAttribute(scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+    scatter_kernel<1><<<(unsigned)p.tiles.bound, 32, sc_smem, st>>>(
+        p.tiles, off, p.keys, p.kmax, p.tile_hist, p.bin_start, p.perm);
+  }
+  HSG_LAUNCH_CHECK();
+  const int nv = (p.dim + 31) / 32;
+  if (nv <= 1) return launch_gather<1>(p, x, off, st);
+  if (nv <= 2) return launch_gather<2>(p, x, off, st);
+  if (nv <= 3) return launch_gather<3>(p, x, off, st);
+  if (nv <= 5) return launch_gather<5>(p, x, off, st);
+  if (nv <= 9) return launch_gather<9>(p, x, off, st);
+  if (nv <= 12) return launch_gather<12>(p, x, off, st);
+  if (nv <= 17) return launch_gather<17>(p, x, off, st);
+  return launch_gather<20>(p, x, off, st);
+}
+
+int sr_combine(const SegReducePlan& p, int64_t P, const int64_t* seg_base, int mode, float* out,
+               float* sums_out, float* counts_out, cudaStream_t st) {
+  if (P == 0) return HSG_OK;
+  combine_kernel<<<(unsigned)ceil_div64(P, COMBINE_WARPS), COMBINE_WARPS * 32, 0, st>>>(
+      P, p.dim, p.S, p.kmax, seg_base, p.bin_start, p.bin_count, p.pieces, mode, out, sums_out,
+      counts_out);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+}  // namespace hsg

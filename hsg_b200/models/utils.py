@@ -1,0 +1,186 @@
+"""Drop-in operators for hsg/models/utils.py -- the cross-GPU step.
+
+The reference (single process, one thread per GPU) concatenates EVERY pixel
+embedding of every GPU on one anchor GPU, re-ranks the clusters there, pools
+the prototypes and copies them back (hsg/models/utils.py:127-217): N*(D+D')*4
+bytes through one device, three times per step.  Here each GPU pools the
+prototypes of its own images (complete locally, because images never straddle
+GPUs and batch indices are rank-major) and only the [P_r, D] prototypes and
+their labels travel.  SURVEY.md A.3b: the results are identical.
+
+Two call styles:
+  * the reference's own list-of-per-GPU-tensors signatures (one process, any
+    number of devices) -- what pyscripts/train/train.py calls;
+  * ``dist_*`` variants for one process per GPU (torchrun): NCCL all-gather of
+    the prototypes (backward = all-reduce of their gradients) and an all-reduce
+    of the centroid sums inside flat k-means.
+"""
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from .._lib import REDUCE_NORMALIZE, REDUCE_SUM
+
+_PACK = 1 << 31   # order-preserving packing of (semantic, instance) pairs
+
+
+# ---------------------------------------------------------------- local stage (per GPU)
+def _local_rank_and_pool(embeddings, embeddings_with_loc, cluster_indices, batch_indices,
+                         semantic_labels, instance_labels):
+  """Dense ids of the distinct (batch, cluster, sem, inst) tuples on this GPU
+  (lexicographic, as utils.py:181-194 ranks them), the pooled prototypes and
+  their labels."""
+  dev = embeddings.device
+  packed = semantic_labels.long() * _PACK + instance_labels.long()
+  # host-side scalars, like the reference's .max() calls
+  b0, b1 = int(batch_indices.min()), int(batch_indices.max())
+  kmax = int(cluster_indices.max()) + 1
+  label_values = torch.unique(packed)
+  ids, pl, pb, _, npro = ops.relabel(batch_indices.long().contiguous(), cluster_indices.long().contiguous(),
+                                     packed.contiguous(), b0, b1 - b0 + 1, kmax, label_values)
+  n = int(npro)
+  protos = ops.segment_reduce(embeddings, ids, n, REDUCE_NORMALIZE)
+  protos_loc = ops.segment_reduce(embeddings_with_loc, ids, n, REDUCE_NORMALIZE)
+  pl = pl[:n]
+  return ids, protos, protos_loc, pl // _PACK, pl % _PACK, pb[:n], (b0, b1)
+
+
+def _check_rank_major(ranges):
+  for (a0, a1), (c0, c1) in zip(ranges, ranges[1:]):
+    if c0 <= a1:
+      raise RuntimeError('batch indices of different GPUs overlap or are not rank-major '
+                         '(%d..%d then %d..%d): images must not straddle GPUs' % (a0, a1, c0, c1))
+
+
+# ---------------------------------------------------------------- reference (list) signatures
+def gather_clustering_and_update_prototypes(embeddings, embeddings_with_loc, cluster_indices,
+                                            batch_indices, semantic_labels, instance_labels,
+                                            anchor_device=None):
+  """Reference utils.py:127-217, same lists in / lists out."""
+  devices = [c.device for c in cluster_indices]
+  local = [_local_rank_and_pool(*args) for args in zip(embeddings, embeddings_with_loc, cluster_indices,
+                                                       batch_indices, semantic_labels, instance_labels)]
+  _check_rank_major([l[6] for l in local])
+  offsets, total = [], 0
+  for l in local:
+    offsets.append(total)
+    total += l[1].shape[0]
+
+  def everywhere(k):
+    return [torch.cat([l[k].to(d) for l in local], 0) for d in devices]
+
+  prototypes, prototypes_with_loc = everywhere(1), everywhere(2)
+  proto_sem, proto_inst, proto_batch = everywhere(3), everywhere(4), everywhere(5)
+  updated = [l[0] + off for l, off in zip(local, offsets)]
+  return prototypes, prototypes_with_loc, proto_sem, proto_inst, proto_batch, updated
+
+
+def gather_and_update_cluster_mappings(cluster_indices_1, cluster_indices_2, anchor_device=None):
+  """Reference utils.py:78-124: table level-1 id -> level-2 id, on every GPU."""
+  devices = [c.device for c in cluster_indices_1]
+  size = max(int(c.max()) for c in cluster_indices_1) + 1
+  table = torch.zeros((size,), dtype=torch.long, device=devices[0])
+  for c1, c2 in zip(cluster_indices_1, cluster_indices_2):
+    # the reference keeps, per level-1 id, the LARGEST level-2 id (its sorted unique() writes last)
+    table.scatter_reduce_(0, c1.to(devices[0]), c2.to(devices[0]), reduce='amax', include_self=True)
+  return [table.to(d) for d in devices]
+
+
+def gather_and_reorder_image_indices(image_indices, anchor_device=None):
+  """Reference utils.py:41-74: image ids renumbered by first occurrence; every
+  GPU receives the whole vector."""
+  devices = [i.device for i in image_indices]
+  ids = torch.cat([i.to(devices[0]) for i in image_indices], 0)
+  _, inv = torch.unique(ids, return_inverse=True)
+  first = torch.full((int(inv.max()) + 1,), inv.numel(), dtype=torch.long, device=devices[0])
+  first.scatter_reduce_(0, inv, torch.arange(inv.numel(), device=devices[0]), reduce='amin', include_self=True)
+  _, out = torch.unique(first[inv], return_inverse=True)
+  return [out.to(d) for d in devices]
+
+
+def gather_and_update_datas(datas, anchor_device=None):
+  """Reference utils.py:220-240."""
+  devices = [d.device for d in datas]
+  return [torch.cat([x.to(d) for x in datas], 0) for d in devices]
+
+
+# ---------------------------------------------------------------- one process per GPU
+class _AllGatherVarlen(torch.autograd.Function):
+  """Concatenate a [n_r, ...] tensor over ranks (n_r may differ).  Backward:
+  all-reduce(sum) of the gradient, then this rank's slice -- every rank's loss
+  sees every prototype."""
+
+  @staticmethod
+  def forward(ctx, t, sizes, rank, group):
+    world = len(sizes)
+    cap = max(sizes) if sizes else 0
+    padded = t.new_zeros((cap,) + tuple(t.shape[1:]))
+    padded[:t.shape[0]] = t
+    bufs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(bufs, padded, group=group)
+    ctx.sizes, ctx.rank, ctx.group = sizes, rank, group
+    return torch.cat([b[:n] for b, n in zip(bufs, sizes)], 0)
+
+  @staticmethod
+  def backward(ctx, g):
+    g = g.contiguous().clone()
+    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+    start = sum(ctx.sizes[:ctx.rank])
+    return g[start:start + ctx.sizes[ctx.rank]], None, None, None
+
+
+def all_gather_sizes(n, device, group=None):
+  world = dist.get_world_size(group)
+  mine = torch.tensor([n], dtype=torch.long, device=device)
+  outs = [torch.empty_like(mine) for _ in range(world)]
+  dist.all_gather(outs, mine, group=group)
+  return [int(o) for o in outs]
+
+
+def all_gather_varlen(t, group=None, sizes=None):
+  if sizes is None:
+    sizes = all_gather_sizes(t.shape[0], t.device, group)
+  return _AllGatherVarlen.apply(t, sizes, dist.get_rank(group), group)
+
+
+def exchange_prototypes(local_ids, prototypes, prototypes_with_loc, proto_sem, proto_inst, proto_batch,
+                        group=None):
+  """All-gather the per-rank prototypes and labels (rank order == the
+  reference's global order) and shift this rank's pixel -> prototype ids by the
+  number of prototypes on lower ranks.  Pure torch.distributed (gloo or nccl)."""
+  sizes = all_gather_sizes(prototypes.shape[0], prototypes.device, group)
+  rank = dist.get_rank(group)
+  out = [all_gather_varlen(t, group, sizes)
+         for t in (prototypes, prototypes_with_loc, proto_sem, proto_inst, proto_batch)]
+  return out[0], out[1], out[2], out[3], out[4], local_ids + sum(sizes[:rank])
+
+
+def dist_gather_clustering_and_update_prototypes(embeddings, embeddings_with_loc, cluster_indices,
+                                                 batch_indices, semantic_labels, instance_labels,
+                                                 group=None):
+  """Per-rank form of gather_clustering_and_update_prototypes: tensors of THIS
+  rank in, global prototypes + this rank's updated ids out."""
+  ids, protos, protos_loc, psem, pinst, pbat, _ = _local_rank_and_pool(
+      embeddings, embeddings_with_loc, cluster_indices, batch_indices, semantic_labels, instance_labels)
+  return exchange_prototypes(ids, protos, protos_loc, psem, pinst, pbat, group)
+
+
+def dist_kmeans_with_initial_labels(embeddings, initial_labels, max_label, iterations=10, group=None):
+  """Flat spherical k-means over rows sharded across ranks: each iteration
+  all-reduces the [K,D] centroid sums (the one real exchange step of the path),
+  every rank normalises identically, then assigns its own rows."""
+  x = embeddings.reshape(-1, embeddings.shape[-1]).detach()
+  labels = initial_labels.reshape(-1).long()
+  d16 = ops.tc_d16(x.shape[1], max_label)
+  xh = xerr = None
+  if d16 and x.shape[0] >= 16384:
+    xh, xerr = ops.make_half_copy(x, d16)
+  with torch.no_grad():
+    for _ in range(int(iterations)):
+      sums = ops.segment_reduce(x, labels, int(max_label), REDUCE_SUM)
+      if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+      centroids = ops.normalize(sums)
+      labels = ops.kmeans_estep(x, centroids.view(1, int(max_label), -1), xh=xh, xerr=xerr)
+  return labels

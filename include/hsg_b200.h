@@ -1,0 +1,214 @@
+/* hsg_b200 -- C ABI of the B200-native (sm_100a) implementation of HSG's
+ * clustering + contrastive hot path.
+ *
+ * This header is the drop-in boundary.  The reference (twke18/HSG) is pure
+ * Python/PyTorch and has no FFI of its own; each entry point below replaces a
+ * Python operator of the reference (cited per function, paths relative to the
+ * reference root) and is what a maintainer binds with ctypes (see
+ * INTEGRATION.md; hsg_b200/_lib.py is that binding).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch types.
+ *  - every pointer is DEVICE memory unless the name ends in _host;
+ *    all tensors are contiguous, row-major; floats are fp32, labels int64
+ *    (the reference's dtypes).
+ *  - the caller owns every buffer, including outputs and the workspace
+ *    (size it with the matching hsg_*_workspace_bytes()).  The library keeps
+ *    no pointer after a call returns and allocates nothing on the device.
+ *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it and
+ *    the call returns without synchronising.  The device is the current one.
+ *  - return value: HSG_OK (0) or a negative HSG_E_* code; the message is in
+ *    hsg_last_error() (thread-local).  No C++ exception crosses the boundary.
+ *  - re-entrant: may be called concurrently from one host thread per GPU
+ *    (the reference's DataParallel threading model).
+ */
+#ifndef HSG_B200_H_
+#define HSG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define HSG_API __attribute__((visibility("default")))
+#else
+#define HSG_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSG_OK 0
+#define HSG_E_INVALID (-1)     /* bad argument */
+#define HSG_E_CUDA (-2)        /* CUDA runtime / launch error */
+#define HSG_E_WORKSPACE (-3)   /* workspace too small */
+#define HSG_E_UNSUPPORTED (-4) /* shape outside what the kernels cover */
+#define HSG_E_COMM (-5)        /* collective error */
+
+/* flags for the k-means entry points */
+#define HSG_KMEANS_AUTO 0        /* tensor-core E-step when the shape allows it */
+#define HSG_KMEANS_FORCE_SIMT 1  /* fp32 CUDA-core E-step (any shape) */
+#define HSG_KMEANS_FORCE_TC 2    /* fail with HSG_E_UNSUPPORTED instead of falling back */
+
+/* modes of hsg_segment_reduce_f32 */
+#define HSG_REDUCE_SUM 0
+#define HSG_REDUCE_NORMALIZE 1 /* sum then L2-normalise: calculate_prototypes_from_labels */
+#define HSG_REDUCE_MEAN 2      /* sum / max(count,1): segment_mean */
+
+HSG_API const char* hsg_last_error(void);
+HSG_API int hsg_version(void);
+/* number of SMs of the current device, or a negative error code */
+HSG_API int hsg_device_sms(void);
+
+/* ---- a1: normalize_embedding  (hsg/utils/general/common.py:101-120) -------
+ * y[r,:] = x[r,:] / max(||x[r,:]||_2, 1e-12).  x may alias y. */
+HSG_API int hsg_normalize_f32(const float* x, float* y, int64_t rows, int dim, void* stream);
+/* gx = (gy - y <y,gy>) / ||x||   (gy/1e-12 when ||x|| < 1e-12) */
+HSG_API int hsg_normalize_bwd_f32(const float* x, const float* gy, float* gx, int64_t rows, int dim,
+                          void* stream);
+
+/* ---- K0 prep: front half of segment_by_kmeans
+ *      (hsg/utils/segsort/common.py:305-365: NCHW->NHWC, normalise, concat the
+ *      local features, re-normalise, drop ignore pixels; :376-381 batch index)
+ * emb_nchw      [B,D,H,W]
+ * loc           [.,H,W,L] local features; image b starts at loc + b*loc_image_stride
+ *               (stride 0 = one map shared by all images, the reference's expand())
+ * labels        [B,H,W] or NULL (-> all zero); pixels with labels == ignore_index
+ *               are dropped when use_ignore != 0
+ * init_clusters [.,H,W] dense initial cluster ids (already passed through
+ *               unique(return_inverse), :341); image stride like loc
+ * outputs, each with room for B*H*W rows; valid rows are [0, seg_offsets[B]):
+ *   x_out [N,D], xloc_out [N,D+L], labels_out [N], clusters_out [N],
+ *   batch_out [N] (= b + batch_index_base), seg_offsets [B+1] (device, int64).
+ *   xh_out   (optional, may be NULL) [N,D] fp16 copy of xloc_out[:, :D]
+ *   xerr_out (optional, with xh_out) [N] ||xloc[:, :D] - fp16(xloc[:, :D])||_2
+ *   pixel_out (optional) [N] flat source pixel b*H*W + y*W + x of each kept row
+ */
+HSG_API size_t hsg_prep_workspace_bytes(int B, int H, int W);
+HSG_API int hsg_prep_f32(const float* emb_nchw, int B, int D, int H, int W,
+                 const float* loc, int L, int64_t loc_image_stride,
+                 const int64_t* labels, int use_ignore, int64_t ignore_index,
+                 const int64_t* init_clusters, int64_t init_image_stride,
+                 int64_t batch_index_base,
+                 float* x_out, float* xloc_out, void* xh_out, float* xerr_out,
+                 int64_t* labels_out, int64_t* clusters_out, int64_t* batch_out,
+                 int64_t* pixel_out, int64_t* seg_offsets, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* fp16 side copy used by the tensor-core E-step, for callers that did not go
+ * through hsg_prep_f32: xh[r, :d16] = fp16(x[r, :d16]), xerr[r] = rounding norm */
+HSG_API int hsg_make_half_copy_f32(const float* x, int64_t rows, int dim, int d16, void* xh_out,
+                           float* xerr_out, void* stream);
+
+/* ---- K1: spherical k-means
+ *      kmeans_with_initial_labels (hsg/utils/segsort/common.py:67-97), batched
+ *      over S independent segments (the per-image loop of segment_by_kmeans,
+ *      :337-372) or S == 1 for the flat problem.
+ * x            [N,dim] unit rows (embedding with location features)
+ * seg_offsets  [S+1] device int64, segment s = rows [seg_offsets[s], seg_offsets[s+1])
+ * max_seg_len  host upper bound on any segment length (sizes the grids; no sync)
+ * seg_k        [S] device int32 clusters per segment, or NULL (= kmax everywhere)
+ * init_labels  [N] int64 in [0, k_s)
+ * labels_out   [N] int64
+ * centroids_out optional [S,kmax,dim]: the centroids the last E-step used
+ * xh, xerr     optional fp16 copy (see prep); enables the tcgen05 E-step when
+ *              d16 in {64,128,256} and kmax*d16*2 <= 128 KiB
+ * Each iteration = M-step (deterministic segmented sum + normalise; empty
+ * cluster -> zero row) then E-step (arg-max of <x,c>, ties -> lowest index).
+ * The E-step result is the arg-max of the float64 dot products of the fp32
+ * inputs: cheap fp32/fp16 passes only prune, every pixel whose top-2 gap is
+ * inside the pass's rigorous error bound is re-decided in float64.
+ */
+HSG_API size_t hsg_kmeans_workspace_bytes(int64_t N, int dim, int S, int kmax, int64_t max_seg_len);
+HSG_API int hsg_kmeans_f32(const float* x, int64_t N, int dim,
+                   const void* xh, int d16, const float* xerr,
+                   const int64_t* seg_offsets, int S, int64_t max_seg_len,
+                   const int32_t* seg_k, int kmax,
+                   const int64_t* init_labels, int iterations,
+                   int64_t* labels_out, float* centroids_out, int flags,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* single steps, for per-iteration (teacher-forced) parity:
+ * M-step == calculate_prototypes_from_labels per segment (common.py:11-41),
+ * E-step == find_nearest_prototypes per segment (common.py:44-64). */
+HSG_API int hsg_kmeans_mstep_f32(const float* x, int64_t N, int dim,
+                         const int64_t* seg_offsets, int S, int64_t max_seg_len,
+                         const int32_t* seg_k, int kmax, const int64_t* labels,
+                         float* centroids_out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+HSG_API int hsg_kmeans_estep_f32(const float* x, int64_t N, int dim,
+                         const void* xh, int d16, const float* xerr,
+                         const int64_t* seg_offsets, int S, int64_t max_seg_len,
+                         const int32_t* seg_k, int kmax, const float* centroids,
+                         int64_t* labels_out, int64_t* num_rechecked_out, int flags,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K3: segmented reduction by label
+ *      calculate_prototypes_from_labels (common.py:11-41, mode NORMALIZE),
+ *      segment_mean (hsg/utils/general/common.py:123-147, mode MEAN).
+ * labels [N] int64 in [0,P).  When seg_offsets != NULL the labels of segment s
+ * must lie in [seg_base[s], seg_base[s] + kmax) (true for prototype ids made by
+ * segment_by_kmeans: they are ranked by image first); with seg_offsets == NULL
+ * the call is one segment with kmax = P.  Deterministic: rows of one label are
+ * added in a fixed order that depends only on the shapes.
+ * out [P,dim]; counts_out optional [P] float.
+ * The backward pass is a row gather: gx[i,:] = gs[labels[i],:] with
+ *   NORMALIZE: gs_k = (g_k - p_k <p_k,g_k>)/||s_k||  (g_k/1e-12 below eps)
+ *   MEAN:      gs_k = g_k / max(count_k,1)           SUM: gs_k = g_k
+ */
+HSG_API size_t hsg_segment_reduce_workspace_bytes(int64_t N, int dim, int64_t P, int S, int kmax,
+                                          int64_t max_seg_len);
+HSG_API int hsg_segment_reduce_f32(const float* x, int64_t N, int dim, const int64_t* labels, int64_t P,
+                           const int64_t* seg_offsets, int S, int64_t max_seg_len,
+                           const int64_t* seg_base, int kmax, int mode,
+                           float* out, float* sums_out, float* counts_out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+HSG_API int hsg_segment_reduce_bwd_f32(const float* grad_out, const float* out, const float* sums,
+                               const float* counts, const int64_t* labels, int64_t N, int dim,
+                               int64_t P, int mode, float* grad_x, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
+/* ---- K4: pixel-to-prototype NCE ("SegSort+") loss
+ *      _calculate_log_likelihood (hsg/utils/segsort/loss.py:15-82).
+ * e [N,dim], prototypes [P,dim], inst [N] (own prototype id), n_sets label
+ * sets evaluated in ONE pass over e x prototypes (Hsg.losses calls the loss 3x
+ * on the same (e, prototypes), hsg/models/predictions/hsg.py:105,130,149):
+ *   sem  [n_sets,N]  psem [n_sets,P]   group_plus[n_sets] (1 = 'segsort+')
+ * per_pixel_out [n_sets,N] = -log(num/den);  stats_out [n_sets,N,4] =
+ * (num, den, own, flags) saved for the backward pass (may be NULL).
+ * Backward for L = sum_s sum_i w[s,i] * l[s,i]:
+ *   grad_e [N,dim], grad_p [P,dim]  (SURVEY.md A.1 closed form).
+ */
+HSG_API size_t hsg_nce_workspace_bytes(int64_t N, int64_t P, int dim, int n_sets);
+HSG_API int hsg_nce_fwd_f32(const float* e, const float* prototypes, int64_t N, int64_t P, int dim,
+                    const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets,
+                    const int32_t* group_plus_host, float concentration,
+                    float* per_pixel_out, float* stats_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+HSG_API int hsg_nce_bwd_f32(const float* e, const float* prototypes, int64_t N, int64_t P, int dim,
+                    const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets,
+                    const int32_t* group_plus_host, float concentration,
+                    const float* stats, const float* w, float* grad_e, float* grad_p,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K2: dense relabel  (segment_by_kmeans tail, common.py:397-405;
+ *      prepare_prototype_labels :192-218)
+ * ids_out[i] = rank of the triple (batch[i], cluster[i], label[i]) among the
+ * distinct triples present, in lexicographic order.  label_values must be a
+ * sorted list of the distinct label values (n_label_values of them, device).
+ * proto_label_out/proto_batch_out/proto_cluster_out [>= n_protos] describe each
+ * id; n_protos_out is a device int64.  batch values are in [batch_base,
+ * batch_base + B), cluster in [0,kmax).
+ */
+HSG_API size_t hsg_relabel_workspace_bytes(int B, int kmax, int64_t n_label_values);
+HSG_API int hsg_relabel_i64(const int64_t* batch, const int64_t* cluster, const int64_t* label, int64_t N,
+                    int64_t batch_base, int B, int kmax,
+                    const int64_t* label_values, int64_t n_label_values,
+                    int64_t* ids_out, int64_t* proto_label_out, int64_t* proto_batch_out,
+                    int64_t* proto_cluster_out, int64_t* n_protos_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSG_B200_H_ */

@@ -1,0 +1,73 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every
+symbol include/hsg_b200.h declares, the ctypes table matches the header, and
+argument errors come back as codes + messages (no compute, no GPU needed)."""
+
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import hsg_b200
+from hsg_b200 import _lib
+
+
+@pytest.fixture(scope='module')
+def lib():
+  if not os.path.exists(_lib.LIB_PATH):
+    from hsg_b200 import build
+    build.build()
+  return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(lib):
+  declared = _lib.declared_symbols()
+  assert len(declared) >= 20
+  for name in declared:
+    assert hasattr(lib, name), 'libhsgb200.so does not export %s' % name
+  assert sorted(_lib.SIGNATURES) == declared, 'ctypes table and header disagree'
+
+
+def test_header_is_plain_c_abi():
+  text = open(_lib.HEADER_PATH).read()
+  assert 'extern "C"' in text
+  assert '#include <torch' not in text and 'at::Tensor' not in text and 'c10::' not in text
+  # every entry point cites the reference operator it replaces
+  assert len(re.findall(r'common\.py:|loss\.py:|hsg/models/', text)) >= 8
+
+
+def test_argument_errors_are_codes_not_crashes(lib):
+  assert lib.hsg_version() >= 100
+  rc = lib.hsg_normalize_f32(None, None, -1, 8, None)
+  assert rc == _lib.HSG_E_INVALID
+  assert b'normalize' in lib.hsg_last_error()
+  with pytest.raises(ValueError):
+    _lib.check(rc, 'normalize')
+  rc = lib.hsg_kmeans_f32(None, 10, 8, None, 0, None, None, 1, 10, None, 4, None, 3, None, None, 0,
+                          None, 0, None)
+  assert rc == _lib.HSG_E_INVALID
+  assert lib.hsg_kmeans_workspace_bytes(1000, 34, 2, 9, 600) > 1000 * 8
+  assert lib.hsg_segment_reduce_workspace_bytes(1000, 34, 18, 2, 9, 600) > 0
+  assert lib.hsg_nce_workspace_bytes(1000, 64, 32, 3) > 0
+  plus = (ctypes.c_int32 * 5)(1, 1, 1, 1, 1)
+  rc = lib.hsg_nce_fwd_f32(None, None, 0, 4, 8, None, None, None, 5, plus, 16.0, None, None, None, 0, None)
+  assert rc == _lib.HSG_E_UNSUPPORTED
+
+
+def test_cpu_tensors_are_refused_not_emulated():
+  from hsg_b200.utils.general import common as g
+  from hsg_b200.utils.segsort import common as s
+  with pytest.raises(hsg_b200.HsgError):
+    g.normalize_embedding(torch.randn(4, 8))
+  with pytest.raises(hsg_b200.HsgError):
+    s.segment_by_kmeans(torch.randn(1, 8, 4, 4))
+  with pytest.raises(hsg_b200.HsgError):
+    s.calculate_prototypes_from_labels(torch.randn(4, 8), torch.zeros(4, dtype=torch.long), 2)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+  monkeypatch.setattr(_lib, '_lib', None)
+  monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
+  with pytest.raises(hsg_b200.HsgError):
+    _lib.load()

@@ -1,0 +1,307 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the
+committed golden fixtures of the reference.
+
+Bars (north_star / SURVEY.md section 8c):
+  * integer outputs (labels, ids, batch indices) bit-exact.  For arg-max labels
+    the contract is stronger than the reference's own: the label is the arg-max
+    of the float64 dot products of the fp32 inputs (ties -> lowest index), so
+    against the float64 oracle it must match EXACTLY, and against the fp32
+    reference it may differ only where the float64 top-2 gap is below the
+    reference's own fp32 rounding error (tau = 2e-5).
+  * fp32 values within 1e-5 relative (written next to each check).
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as o_ops, loss as o_loss, protos as o_protos
+
+pytestmark = pytest.mark.gpu
+
+TAU = 2e-5
+
+
+def dev():
+  return torch.device('cuda:0')
+
+
+def t(a, dtype=None):
+  x = torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+  return x if dtype is None else x.to(dtype)
+
+
+def n(x):
+  return x.detach().cpu().numpy()
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+  np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def labels_match_certified(mine, ref, x, protos):
+  """`mine` must equal the float64 arg-max everywhere, and equal `ref` except
+  where the float64 gap is below TAU."""
+  best, _, gap = o_ops.argmax_margins(x, protos)
+  tie = gap <= 1e-12
+  assert np.array_equal(mine[~tie], best[~tie]), 'not the float64 arg-max'
+  bad = np.nonzero(mine != ref)[0]
+  if bad.size:
+    assert gap[bad].max() < TAU, 'differs from the reference outside near-ties'
+  return bad.size
+
+
+@pytest.fixture(scope='module')
+def S():
+  from hsg_b200.utils.segsort import common
+  return common
+
+
+@pytest.fixture(scope='module')
+def G():
+  from hsg_b200.utils.general import common
+  return common
+
+
+def test_library_loaded_and_device():
+  from hsg_b200 import _lib
+  lib = _lib.load()
+  assert lib.hsg_device_sms() > 0
+
+
+def test_normalize(golden, G):
+  g = golden('normalize')
+  y = G.normalize_embedding(t(g['x']))
+  close(n(y), g['y'], rtol=1e-5, atol=1e-7)
+  assert np.all(n(y)[3, 2] == 0)
+
+
+def test_prototypes_and_segment_mean(golden, S, G):
+  g = golden('prototypes_empty_bins')
+  p12 = S.calculate_prototypes_from_labels(t(g['x']), t(g['labels']), 12)
+  close(n(p12), g['p12'], atol=1e-7)
+  assert np.all(n(p12)[4] == 0) and np.all(n(p12)[9:] == 0)
+  close(n(S.calculate_prototypes_from_labels(t(g['x']), t(g['labels']))), g['pauto'], atol=1e-7)
+  g = golden('labels_and_segment_mean')
+  m = G.segment_mean(t(g['x']), t(g['idx']))
+  assert m.dtype == torch.float32
+  close(n(m), g['mean'], atol=1e-7)
+  pl, ul = S.prepare_prototype_labels(t(g['sem']), t(g['inst']), 5)
+  assert np.array_equal(n(pl), g['proto_labels']) and np.array_equal(n(ul), g['unique_inst'])
+
+
+def test_pool_backward(golden, S, G):
+  g = golden('pool_backward')
+  x = t(g['x']).requires_grad_(True)
+  p = S.calculate_prototypes_from_labels(x, t(g['labels']), 14)
+  close(n(p), g['p'], atol=1e-7)
+  (p * t(g['g'])).sum().backward()
+  close(n(x.grad), g['dx_proto'], rtol=1e-4, atol=1e-6)
+  x.grad = None
+  m = G.segment_mean(x, t(g['labels']))
+  (m * t(g['gm'])).sum().backward()
+  close(n(x.grad), g['dx_mean'], rtol=1e-5, atol=1e-7)
+  x.grad = None
+  (G.normalize_embedding(x) * t(g['gn'])).sum().backward()
+  close(n(x.grad), g['dx_norm'], rtol=1e-4, atol=1e-6)
+
+
+def test_kmeans_kat1_teacher_forced(golden, S):
+  from hsg_b200 import ops
+  g = golden('kmeans_flat_kat1')
+  x = t(g['x'])
+  flips = 0
+  for it in range(10):
+    cent = ops.kmeans_mstep(x, t(g['labels'][it]), 16)[0]
+    close(n(cent), g['prototypes'][it], rtol=1e-5, atol=1e-7)          # fp32 centroids, 1e-5
+    new = S.find_nearest_prototypes(x, t(g['prototypes'][it]))
+    assert new.dtype == torch.int64
+    flips += labels_match_certified(n(new), g['labels'][it + 1], g['x'], g['prototypes'][it])
+  assert flips <= 4
+  final = S.kmeans_with_initial_labels(x, t(g['labels'][0]), 16, 10)
+  agree = np.mean(n(final) == g['labels'][10])
+  assert agree > 0.995, agree
+
+
+def test_kmeans_separated_end_to_end(golden, S):
+  g = golden('kmeans_flat_separated')
+  x = t(g['x'])
+  final = S.kmeans_with_initial_labels(x, t(g['labels'][0]), None, 8)
+  assert np.array_equal(n(final), g['labels'][8])
+  close(n(S.calculate_prototypes_from_labels(x, final, 12)), g['prototypes'], atol=1e-7)
+
+
+def _check_segment(res, g, prefix, exact_clusters=True):
+  emb, emb_loc, lab, clu, bat = [n(r) for r in res]
+  close(emb, g[prefix + 'emb'], rtol=1e-5, atol=1e-7)
+  close(emb_loc, g[prefix + 'emb_loc'], rtol=1e-5, atol=1e-6)
+  assert np.array_equal(lab, g[prefix + 'labels'])
+  assert np.array_equal(bat, g[prefix + 'batch'])
+  if exact_clusters:
+    assert np.array_equal(clu, g[prefix + 'cluster'])
+  for r in res[2:]:
+    assert r.dtype == torch.int64
+
+
+def test_segment_by_kmeans_kat2(golden, S):
+  g = golden('segment_by_kmeans_kat2')
+  res = S.segment_by_kmeans(t(g['emb']), t(g['labels']), [3, 3], ignore_index=99, iterations=5)
+  _check_segment(res, g, 'out_')
+  assert res[1].shape == (264, 34)
+
+
+def test_segment_by_kmeans_misc(golden, S):
+  g = golden('segment_by_kmeans_misc')
+  res = S.segment_by_kmeans(t(g['emb']), None, [3, 2], iterations=4)
+  _check_segment(res, g, 'a_')
+  res = S.segment_by_kmeans(t(g['emb']), t(g['labels4']), [2, 3], local_features=t(g['loc4']),
+                            ignore_index=torch.tensor(7000, device=dev()), iterations=3)
+  _check_segment(res, g, 'b_')
+
+
+def test_segment_by_kmeans_backward(golden, S):
+  """gradient w.r.t. the NCHW embeddings through the two float outputs, against
+  finite differences of the oracle (float64)."""
+  rng = np.random.RandomState(235)
+  emb = rng.randn(2, 6, 4, 5).astype(np.float32)
+  labels = np.zeros((2, 4, 5), np.int64)
+  labels[0, 0, :2] = 9
+  w1 = rng.randn(38, 6).astype(np.float32)
+  w2 = rng.randn(38, 8).astype(np.float32)
+  e = t(emb).requires_grad_(True)
+  x, xl, _, _, _ = S.segment_by_kmeans(e, t(labels), [2, 2], ignore_index=9, iterations=1)
+  ((x * t(w1)).sum() + (xl * t(w2)).sum()).backward()
+
+  def f(a):
+    a = a.astype(np.float64)
+    nhwc = np.transpose(a, (0, 2, 3, 1)).reshape(-1, 6)
+    keep = np.nonzero(labels.reshape(-1) != 9)[0]
+    y = nhwc / np.maximum(np.linalg.norm(nhwc, axis=1, keepdims=True), 1e-12)
+    loc = (o_ops.generate_location_features((4, 5), 'float').astype(np.float64) - 0.5).reshape(-1, 2)
+    cat = np.concatenate([y, np.tile(loc, (2, 1))], 1)
+    z = cat / np.linalg.norm(cat, axis=1, keepdims=True)
+    return (y[keep] * w1).sum() + (z[keep] * w2).sum()
+
+  num = np.zeros_like(emb, np.float64)
+  for idx in np.ndindex(emb.shape):
+    d = np.zeros_like(emb, np.float64)
+    d[idx] = 1e-5
+    num[idx] = (f(emb + d) - f(emb - d)) / 2e-5
+  close(n(e.grad), num, rtol=2e-3, atol=2e-4)
+
+
+def test_relabel_matches_oracle():
+  from hsg_b200 import ops
+  rng = np.random.RandomState(3)
+  nn = 5000
+  bat = np.sort(rng.randint(4, 8, nn)).astype(np.int64)
+  clu = rng.randint(0, 6, nn).astype(np.int64)
+  lab = (rng.randint(0, 3, nn) * 2048 + rng.randint(0, 2, nn)).astype(np.int64)
+  ids, pl, pb, pc, npro = ops.relabel(t(bat), t(clu), t(lab), 4, 4, 6, t(np.unique(lab)))
+  _, first = np.unique(bat * 6 + clu, return_inverse=True)
+  plab, ref = o_ops.prepare_prototype_labels(lab, first.reshape(-1), int(lab.max()) + 1)
+  assert np.array_equal(n(ids), ref)
+  k = int(npro)
+  assert k == plab.shape[0]
+  assert np.array_equal(n(pl)[:k], plab)
+
+
+def test_estep_random_is_exact_float64_argmax(S):
+  """size-independent property at a moderate size: every label is the float64
+  arg-max, including planted near-ties and duplicated / empty centroids."""
+  from hsg_b200 import ops
+  rng = np.random.RandomState(235)
+  nn, d, k = 60000, 66, 37
+  x = o_ops.normalize_embedding(rng.randn(nn, d).astype(np.float32))
+  c = o_ops.normalize_embedding(rng.randn(k, d).astype(np.float32))
+  c[5] = c[3]                       # exact duplicate -> ties go to the lower index
+  c[11] = 0                         # empty cluster: zero centroid competes with similarity 0
+  c[20] = c[19] + 1e-7 * rng.randn(d).astype(np.float32)     # near duplicate
+  lab, nre = ops.kmeans_estep(t(x), t(c).view(1, k, d), return_rechecked=True)
+  best, _, gap = o_ops.argmax_margins(x, c)
+  lab = n(lab)
+  assert not np.any(lab == 5)
+  sel = gap > 1e-12
+  assert np.array_equal(lab[sel], best[sel])
+  assert 0 < int(nre) < nn // 10
+
+
+def test_nce_forward_backward(golden):
+  from hsg_b200.utils.segsort import loss as L
+  for name, conc in (('nce_kat3', 16), ('nce_fallback', 10)):
+    g = golden(name)
+    e = t(g['e']).requires_grad_(True)
+    p = t(g['protos']).requires_grad_(True)
+    args = (g['e'], g['sem'], g['inst'], g['protos'], g['psem'])
+    pp = L.SegSortLoss(conc, reduction='none')(e, t(g['sem']), t(g['inst']), p, t(g['psem']))
+    assert pp.shape == (g['e'].shape[0], 1) and pp.dtype == torch.float32
+    kappa = o_loss.nce_condition(*args, conc).reshape(-1, 1)
+    err = np.abs(n(pp) - g['per_pixel'])
+    assert np.all(err <= 1e-5 * np.abs(g['per_pixel']) + 1e-6 * kappa)        # 1e-5 rel (+ reference's own cancellation)
+    w = g['w'] if 'w' in g else np.full((g['e'].shape[0], 1), 1.0 / g['e'].shape[0], np.float32)
+    (pp * t(w)).sum().backward()
+    row_ref = np.abs(g['de']).max(1, keepdims=True)
+    assert np.all(np.abs(n(e.grad) - g['de']) <= row_ref * (1e-5 + 2e-6 * kappa) + 1e-12)
+    assert np.abs(n(p.grad) - g['dp']).max() <= 1e-3 * np.abs(g['dp']).max()
+  g = golden('nce_kat3')
+  loss = L.SegSortLoss(16)(t(g['e']), t(g['sem']), t(g['inst']), t(g['protos']), t(g['psem']))
+  assert abs(float(loss) - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))    # scalar loss, 1e-5 rel
+  plain = L.SegSortLoss(16, group_mode='segsort', reduction='none')(
+      t(g['e']), t(g['sem']), t(g['inst']), t(g['protos']), t(g['psem']))
+  close(n(plain), g['per_pixel_plain'], rtol=2e-5)
+  # three label sets in one pass == three separate calls
+  sem2 = (g['sem'] // 2).astype(np.int64)
+  psem2 = (g['psem'] // 2).astype(np.int64)
+  multi = L.segsort_loss_multi(t(g['e']), t(g['inst']), [t(g['sem']), t(sem2), t(g['inst'])],
+                               t(g['protos']), [t(g['psem']), t(psem2), t(np.arange(64))], 16)
+  singles = [L.SegSortLoss(16)(t(g['e']), t(s), t(g['inst']), t(g['protos']), t(ps))
+             for s, ps in ((g['sem'], g['psem']), (sem2, psem2), (g['inst'], np.arange(64)))]
+  for a, b in zip(multi, singles):
+    assert float(a) == float(b)
+
+
+def test_gather_prototypes_single_process_lists(golden):
+  from hsg_b200.models import utils as mu
+  g = golden('gather_prototypes')
+  ranks = [[t(g['r%d_%s' % (r, nm)]) for nm in ('emb', 'emb_loc', 'cluster', 'batch', 'sem', 'inst')]
+           for r in range(2)]
+  out = mu.gather_clustering_and_update_prototypes(*[[rk[j] for rk in ranks] for j in range(6)])
+  close(n(out[0][0]), g['prototypes'], atol=1e-7)
+  close(n(out[1][1]), g['prototypes_loc'], atol=1e-7)
+  assert np.array_equal(n(out[2][0]), g['proto_sem'])
+  assert np.array_equal(n(out[3][0]), g['proto_inst'])
+  assert np.array_equal(n(out[4][0]), g['proto_batch'])
+  for r in range(2):
+    assert np.array_equal(n(out[5][r]), g['r%d_updated' % r])
+  table = mu.gather_and_update_cluster_mappings([t(g['r0_updated']), t(g['r1_updated'])],
+                                                [t(g['r0_fine']), t(g['r1_fine'])])
+  assert np.array_equal(n(table[0]), g['mapping'])
+  re = mu.gather_and_reorder_image_indices([t(g['r0_img']), t(g['r1_img'])])
+  assert np.array_equal(n(re[1]), g['r1_img_reordered'])
+
+
+def test_kmeans_moderate_segments_property(S):
+  """ragged segments, K not a multiple of anything, per-iteration objective
+  non-decreasing and labels equal to an oracle E-step on the kernel's own centroids."""
+  from hsg_b200 import ops
+  rng = np.random.RandomState(7)
+  lens = [5000, 1, 0, 12345, 777]
+  d, k = 130, 36
+  x = o_ops.normalize_embedding(rng.randn(sum(lens), d).astype(np.float32))
+  off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+  init = np.concatenate([rng.randint(0, k, l) for l in lens]).astype(np.int64)
+  lab, cent = ops.kmeans(t(x), t(init), k, 3, seg_offsets=t(off), max_seg_len=max(lens), return_centroids=True)
+  lab, cent = n(lab), n(cent)
+  for s, l in enumerate(lens):
+    if l == 0:
+      continue
+    xs = x[off[s]:off[s + 1]]
+    best, _, gap = o_ops.argmax_margins(xs, cent[s])
+    sel = gap > 1e-12
+    assert np.array_equal(lab[off[s]:off[s + 1]][sel], best[sel])
+  # the M-step alone reproduces the oracle's centroids for the final labels
+  c2 = n(ops.kmeans_mstep(t(x), t(lab), k, seg_offsets=t(off), max_seg_len=max(lens)))
+  for s, l in enumerate(lens):
+    if l:
+      close(c2[s], o_ops.calculate_prototypes_from_labels(x[off[s]:off[s + 1]], lab[off[s]:off[s + 1]], k),
+            rtol=1e-5, atol=1e-6)
