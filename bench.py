@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the HSG clustering + contrastive hot path on B200.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3            # our CUDA path
+    python bench.py --impl reference --steps 2 --warmup 1    # CPU restatement of the reference
+
+One "step" = one pass of the hot path over one synthetic batch:
+    segment_by_kmeans (prep -> T x (M-step, E-step) -> dense relabel)
+    -> prototype pooling -> [all-gather of prototypes over ranks] -> NCE loss (forward)
+on BASELINE.json configs[1]: 48 images of 448x448 embeddings, D=256, k-means grid
+16x16 (K=256), 10 iterations.  Prints ONE JSON line (see the keys below).
+
+value   : pixel-embeddings/s with the input embeddings already resident in HBM.
+e2e     : the same metric through the reference-facing Python operators with HOST
+          (pinned) input, the host->device copy and the loss read-back inside the
+          timed region.
+roofline: the spherical k-means iteration (its E-step + M-step kernels), CUDA-event
+          timed inside the timed region through the library's phase profiler;
+          algorithmic bytes N*(4*(D+2)+8) per iteration.
+"""
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+PHASES = ['prep', 'mstep_sort', 'mstep_gather', 'mstep_combine', 'estep', 'estep_fixup', 'relabel',
+          'pool', 'nce_fwd', 'nce_bwd', 'convert']
+
+
+def parse():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=5)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--images', type=int, default=48)
+  ap.add_argument('--size', type=int, default=448)
+  ap.add_argument('--dim', type=int, default=256)
+  ap.add_argument('--grid', type=int, default=16)
+  ap.add_argument('--iters', type=int, default=10)
+  ap.add_argument('--concentration', type=float, default=16.0)
+  ap.add_argument('--dist', default='iid', choices=['iid', 'planted'])
+  ap.add_argument('--no-e2e', action='store_true')
+  ap.add_argument('--no-cpu', action='store_true')
+  ap.add_argument('--cpu-images', type=int, default=1)
+  return ap.parse_args()
+
+
+def peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    with open(path) as f:
+      p = json.load(f)
+    return p, 'measured'
+  return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler(object):
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+       'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.index = index
+    self.proc = None
+    self.lines = []
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                    '--format=csv,noheader,nounits', '-lms', '100'],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    for line in self.lines:
+      f = [x.strip() for x in line.split(',')]
+      if len(f) < 9:
+        continue
+      try:
+        sm.append(float(f[1]))
+        mx.append(float(f[2]))
+      except ValueError:
+        continue
+      for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+        if v.lower().startswith('active'):
+          reasons.add(name)
+    if not sm:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+    load = sorted(sm)[len(sm) // 2:]            # upper half = samples taken under load
+    return {'sm_mhz': float(np.median(load)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+            'samples': len(sm)}
+
+
+# ------------------------------------------------------------------ synthetic input
+def make_embeddings(torch, args, device, seed):
+  g = torch.Generator(device=device)
+  g.manual_seed(seed)
+  b, d, s = args.images, args.dim, args.size
+  if args.dist == 'iid':
+    return torch.randn((b, d, s, s), generator=g, device=device, dtype=torch.float32)
+  # planted: per image 64 unit centres on an 8x8 block layout + noise
+  out = torch.empty((b, d, s, s), device=device, dtype=torch.float32)
+  blk = (s + 7) // 8
+  for i in range(b):
+    c = torch.randn((64, d), generator=g, device=device)
+    c = c / c.norm(dim=1, keepdim=True)
+    yy = torch.arange(s, device=device) // blk
+    idx = (yy.view(-1, 1) * 8 + yy.view(1, -1)).reshape(-1)
+    e = c[idx] + 0.5 * torch.randn((s * s, d), generator=g, device=device) / d ** 0.5
+    out[i] = e.t().reshape(d, s, s)
+  return out
+
+
+# ------------------------------------------------------------------ our arm
+def hot_path(torch, S, L, MU, emb, args, world, group):
+  """The reference-facing call sequence for one batch (what train.py does between the
+  embedding model and the loss, restricted to the operators of the path)."""
+  ex = S.segment_by_kmeans_ex(emb, None, [args.grid, args.grid], iterations=args.iters,
+                              count_prototypes=True)
+  x, ids, bat = ex['embeddings'], ex['cluster_indices'], ex['batch_indices']
+  protos = S.pool_prototypes(ex)
+  pbatch = ex['proto_batch']
+  if world > 1:       # all-gather of the prototypes (replaces hsg/models/utils.py:127-217)
+    res = MU.exchange_prototypes(ids, protos, protos, pbatch, pbatch, pbatch, group)
+    protos, pbatch, ids = res[0], res[2], res[5]
+  # two label sets in one pass over E x P: image-level positives ("img_sim",
+  # hsg/models/predictions/hsg.py:97-110) and prototype-level positives
+  pid = torch.arange(protos.shape[0], device=emb.device, dtype=torch.int64)
+  losses = L.segsort_loss_multi(x, ids, [bat, ids], protos, [pbatch, pid], args.concentration)
+  return losses[0] + losses[1], x.shape[0]
+
+
+def run_ours(args):
+  import torch
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local_rank)
+  device = torch.device('cuda', local_rank)
+  group = None
+  if world > 1:
+    torch.distributed.init_process_group('nccl', device_id=device)
+  import hsg_b200
+  from hsg_b200 import _lib
+  from hsg_b200.utils.segsort import common as S, loss as L
+  from hsg_b200.models import utils as MU
+  lib = hsg_b200.load_library()
+
+  n_pix = args.images * args.size * args.size
+  dp = args.dim + 2
+  # two resident input batches (each 9.9 GB >> 126 MB L2), alternated between steps
+  embs = [make_embeddings(torch, args, device, 235 + rank * 7 + i) for i in range(2)]
+
+  def barrier():
+    if world > 1:
+      torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+  def step(i):
+    with torch.no_grad():
+      loss, n = hot_path(torch, S, L, MU, embs[i % 2], args, world, group)
+    return loss
+
+  for i in range(args.warmup):
+    step(i)
+  barrier()
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  lib.hsg_profile_enable(1)
+  launches0 = lib.hsg_launch_count()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  ev0.record()
+  for i in range(args.steps):
+    loss = step(i)
+  ev1.record()
+  barrier()
+  ms = ev0.elapsed_time(ev1)
+  launches = lib.hsg_launch_count() - launches0
+  tot = (ctypes.c_double * len(PHASES))()
+  cnt = (ctypes.c_longlong * len(PHASES))()
+  lib.hsg_profile_collect(tot, cnt, len(PHASES))
+  lib.hsg_profile_enable(0)
+  clocks = sampler.stop() if rank == 0 else None
+  t = torch.tensor([ms], device=device, dtype=torch.float64)
+  if world > 1:
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+  ms = float(t)
+  value = world * n_pix * args.steps / (ms * 1e-3)
+
+  # ---- end to end: pinned host input, H2D + loss read-back inside the timed region
+  e2e = None
+  if not args.no_e2e:
+    host = torch.empty(embs[0].shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(embs[0])
+    dev_in = embs[1]                       # reuse a resident buffer as the H2D target
+
+    def e2e_step():
+      dev_in.copy_(host, non_blocking=True)
+      with torch.no_grad():
+        loss, _ = hot_path(torch, S, L, MU, dev_in, args, world, group)
+      return float(loss)                  # device -> host read of the result
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e_steps = max(2, min(args.steps, 3))
+    for _ in range(e_steps):
+      e2e_step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+      torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
+    e2e = {'value': world * n_pix * e_steps / float(dt), 'unit': 'pixel-embeddings/s',
+           'h2d_bytes_per_step': int(host.numel() * 4), 'd2h_bytes_per_step': 4, 'steps': e_steps}
+
+  if rank != 0:
+    if world > 1:
+      torch.distributed.destroy_process_group()
+    return
+
+  pk, pk_src = peaks()
+  phase_ms = {PHASES[i]: tot[i] for i in range(len(PHASES))}
+  phase_n = {PHASES[i]: int(cnt[i]) for i in range(len(PHASES))}
+  iters = max(1, args.steps * args.iters)
+  kmeans_ms = (phase_ms['mstep_sort'] + phase_ms['mstep_gather'] + phase_ms['mstep_combine'] +
+               phase_ms['estep'] + phase_ms['estep_fixup'] + phase_ms['convert']) / iters
+  alg_bytes = n_pix * (4.0 * dp + 8.0)
+  achieved = alg_bytes / (kmeans_ms * 1e-3) / 1e9 if kmeans_ms > 0 else 0.0
+  roofline = {'kernel': 'spherical k-means iteration (E-step + M-step kernels)', 'bound': 'hbm',
+              'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / pk['hbm_gbs'],
+              'peak_source': pk_src + ' (burst copy bandwidth)', 'traffic': None,
+              'algorithmic_bytes_per_launch': alg_bytes, 'ms_per_launch': kmeans_ms}
+  per_phase = {k: {'ms_per_step': phase_ms[k] / args.steps, 'ranges': phase_n[k]} for k in PHASES if phase_n[k]}
+
+  cpu = None if args.no_cpu else cpu_baseline(args)
+  out = {
+      'metric': 'pixel-embeddings/sec spherical-kmeans+NCE (448^2, D=256, K=256)',
+      'value': value, 'unit': 'pixel-embeddings/s', 'n_gpus': world, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': 'configs[1]: %d images x %dx%d embeddings, D=%d, k-means grid %dx%d (K=%d), '
+                             '%d iterations + prototype pooling + NCE fwd (2 label sets, P=%d/GPU); %s values; '
+                             'inputs %.1f GB per step (> L2), two batches alternated'
+                             % (args.images, args.size, args.size, args.dim, args.grid, args.grid,
+                                args.grid ** 2, args.iters, args.images * args.grid ** 2, args.dist,
+                                n_pix * args.dim * 4 / 1e9),
+                 'images_per_gpu': args.images, 'embedding_grid': [args.size, args.size], 'dim': args.dim,
+                 'k': args.grid ** 2, 'iterations': args.iters, 'parallelism': 'images sharded over %d GPU(s)' % world},
+      'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+      'roofline': roofline, 'phases': per_phase, 'cpu_baseline': cpu, 'loss': float(loss),
+  }
+  print(json.dumps(out))
+  if world > 1:
+    torch.distributed.destroy_process_group()
+
+
+# ------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_workload(args, images):
+  """The same path on the host cores through the numpy restatement of the
+  reference (oracle/), on a bounded sample: `images` images for the k-means +
+  pooling part, 4096 pixels against all prototypes for the NCE part."""
+  from oracle import ops as o_ops, loss as o_loss
+  rng = np.random.RandomState(235)
+  s, d, g = args.size, args.dim, args.grid
+  emb = rng.standard_normal((images, d, s, s)).astype(np.float32)
+  t0 = time.perf_counter()
+  x, xloc, lab, ids, bat = o_ops.segment_by_kmeans(emb, None, (g, g), iterations=args.iters)
+  protos = o_ops.calculate_prototypes_from_labels(x, ids)
+  t_cluster = time.perf_counter() - t0
+  p_total = args.images * g * g
+  pr = o_ops.normalize_embedding(rng.standard_normal((p_total, d)).astype(np.float32))
+  pr[:protos.shape[0]] = protos
+  pb = np.arange(p_total) // (g * g)
+  n_s = 4096
+  t0 = time.perf_counter()
+  o_loss.calculate_log_likelihood(x[:n_s], bat[:n_s], ids[:n_s], pr, pb, args.concentration)
+  o_loss.calculate_log_likelihood(x[:n_s], ids[:n_s], ids[:n_s], pr, np.arange(p_total), args.concentration)
+  t_nce = time.perf_counter() - t0
+  per_pixel = t_cluster / (images * s * s) + t_nce / n_s
+  return 1.0 / per_pixel, t_cluster, t_nce
+
+
+def cpu_baseline(args):
+  import torch
+  value, t_c, t_n = cpu_workload(args, args.cpu_images)
+  return {'value': value, 'unit': 'pixel-embeddings/s', 'cores': os.cpu_count(), 'kind': 'port',
+          'threads': torch.get_num_threads(),
+          'sample': 'oracle (numpy restatement of the reference, BLAS threads = host cores): k-means+pooling on '
+                    '%d image(s) of the workload (%.1f s), NCE (2 label sets) on 4096 pixels x %d prototypes '
+                    '(%.1f s); per-pixel times added' % (args.cpu_images, t_c, args.images * args.grid ** 2, t_n)}
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  vals = []
+  for i in range(args.warmup + args.steps):
+    t0 = time.perf_counter()
+    v, t_c, t_n = cpu_workload(args, args.cpu_images)
+    if i >= args.warmup:
+      vals.append((v, time.perf_counter() - t0, t_c, t_n))
+  value = float(np.mean([v[0] for v in vals]))
+  ms = float(np.mean([v[1] for v in vals])) * 1e3
+  n_pix = args.images * args.size * args.size
+  cpu = {'value': value, 'unit': 'pixel-embeddings/s', 'cores': os.cpu_count(), 'kind': 'port',
+         'sample': 'each step = oracle k-means+pooling on %d image(s) + NCE on 4096 pixels x %d prototypes; '
+                   'per-pixel times added' % (args.cpu_images, args.images * args.grid ** 2)}
+  out = {
+      'impl': 'reference',
+      'metric': 'pixel-embeddings/sec spherical-kmeans+NCE (448^2, D=256, K=256)',
+      'value': value, 'unit': 'pixel-embeddings/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', '1')),
+      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': 'configs[1] sampled: see cpu_baseline.sample', 'images_per_gpu': args.images,
+                 'embedding_grid': [args.size, args.size], 'dim': args.dim, 'k': args.grid ** 2,
+                 'iterations': args.iters, 'full_batch_pixels': n_pix},
+      'cpu_baseline': cpu,
+      'e2e': {'value': value, 'unit': 'pixel-embeddings/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+      'gpu_launches': 0,
+  }
+  print(json.dumps(out))
+
+
+if __name__ == '__main__':
+  a = parse()
+  if a.impl == 'reference':
+    run_reference(a)
+  else:
+    run_ours(a)

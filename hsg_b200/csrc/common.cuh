@@ -36,6 +36,7 @@ void set_error(const char* fmt, ...);
 
 #define HSG_LAUNCH_CHECK()                                                    \
   do {                                                                        \
+    ::hsg::count_launch();                                                    \
     cudaError_t e__ = cudaGetLastError();                                     \
     if (e__ != cudaSuccess) {                                                 \
       ::hsg::set_error("kernel launch failed: %s (%s:%d)",                    \
@@ -45,6 +46,23 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 int num_sms();   // SM count of the current device (cached per device)
+void count_launch();
+
+// optional per-phase device timing (hsg_profile_* in the C ABI): records a pair
+// of CUDA events on the launching stream around a phase when enabled
+enum ProfPhase { PROF_PREP = 0, PROF_MSTEP_SORT, PROF_MSTEP_GATHER, PROF_MSTEP_COMBINE,
+                 PROF_ESTEP, PROF_ESTEP_FIXUP, PROF_RELABEL, PROF_POOL, PROF_NCE_FWD,
+                 PROF_NCE_BWD, PROF_CONVERT, PROF_NUM };
+struct ProfSuppress {   // inner ranges are skipped while one of these is alive (per thread)
+  ProfSuppress();
+  ~ProfSuppress();
+};
+struct ProfRange {
+  int slot;
+  cudaStream_t st;
+  ProfRange(int phase, cudaStream_t stream);
+  ~ProfRange();
+};
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }

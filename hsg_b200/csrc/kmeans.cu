@@ -146,21 +146,29 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) estep_fixup_kernel(const EStep
     const float* xr = a.x + pix * a.dim;
     const float* cbase = a.centroids + (int64_t)seg * a.kmax * a.dim;
     const uint16_t* cand = a.fix.cand ? a.fix.cand + (int64_t)e * FIX_MAX_CAND : nullptr;
-    const bool all = !cand || cand[0] == 0xFFFF;
-    const int n = all ? K : FIX_MAX_CAND;
+    bool all = !cand || cand[0] == 0xFFFF;
     double bv = -DBL_MAX;
     int bi = 0x7fffffff;
-    for (int c = 0; c < n; ++c) {
-      int k = c;
-      if (!all) {
-        k = cand[c];
-        if (k == 0xFFFF) break;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int n = all ? K : FIX_MAX_CAND;
+      bv = -DBL_MAX;
+      bi = 0x7fffffff;
+      for (int c = 0; c < n; ++c) {
+        int k = c;
+        if (!all) {
+          k = cand[c];
+          if (k == 0xFFFF) break;
+          if (k >= K) continue;
+        }
+        const float* cr = cbase + (int64_t)k * a.dim;
+        double s = 0.0;
+        for (int d = lane; d < a.dim; d += 32) s = fma((double)xr[d], (double)cr[d], s);
+        s = warp_sum(s);
+        if (s > bv || (s == bv && k < bi)) { bv = s; bi = k; }
       }
-      const float* cr = cbase + (int64_t)k * a.dim;
-      double s = 0.0;
-      for (int d = lane; d < a.dim; d += 32) s = fma((double)xr[d], (double)cr[d], s);
-      s = warp_sum(s);
-      if (s > bv || (s == bv && k < bi)) { bv = s; bi = k; }
+      // a candidate list is only conclusive when its winner beats everything outside it
+      if (all || !a.fix.bound || bv > (double)a.fix.bound[e]) break;
+      all = true;
     }
     if (lane == 0) a.keys_out[pix] = seg * a.kmax + bi;
   }
@@ -200,6 +208,7 @@ static void km_carve(Carver& c, KmPlan& p, int64_t N, int dim, int S, int kmax, 
   p.fix.capacity = N;
   p.fix.pixels = c.take<int32_t>(N);
   p.fix.cand = c.take<uint16_t>(N * FIX_MAX_CAND);
+  p.fix.bound = c.take<float>(N);
   tc_carve(c, p.tc, S, kmax, d16 > 0 ? d16 : 64);
 }
 
@@ -217,14 +226,21 @@ static int check_common(const float* x, int64_t N, int dim, const int64_t* seg_o
 static int run_estep(EStepArgs& ea, KmPlan& p, bool use_tc, cudaStream_t st) {
   HSG_CUDA(cudaMemsetAsync(p.fix.count, 0, sizeof(int32_t), st));
   if (use_tc) {
-    int rc = tc_convert_centroids(ea, p.tc, st);
+    int rc;
+    {
+      ProfRange prof(PROF_CONVERT, st);
+      rc = tc_convert_centroids(ea, p.tc, st);
+    }
     if (rc) return rc;
+    ProfRange prof(PROF_ESTEP, st);
     rc = estep_tc(ea, p.tc, st);
     if (rc) return rc;
   } else {
+    ProfRange prof(PROF_ESTEP, st);
     int rc = estep_simt(ea, st);
     if (rc) return rc;
   }
+  ProfRange prof(PROF_ESTEP_FIXUP, st);
   return estep_fixup(ea, st);
 }
 
@@ -396,6 +412,8 @@ int hsg_segment_reduce_f32(const float* x, int64_t N, int dim, const int64_t* la
   Carver c(workspace);
   SegReducePlan p;
   sr_carve(c, p, N, dim, S, kmax, max_seg_len);
+  ProfRange prof(PROF_POOL, st);
+  ProfSuppress inner;
   if ((rc = sr_build_tiles(p, seg_offsets, st))) return rc;
   if ((rc = sr_labels_to_keys(p, labels, seg_base, st))) return rc;
   if ((rc = sr_sort_and_sum(p, x, seg_offsets, st))) return rc;

@@ -11,6 +11,8 @@ struct FixList {
   int32_t* pixels;     // [capacity]
   uint16_t* cand;      // [capacity * FIX_MAX_CAND] candidate local ids, 0xFFFF-terminated;
                        // first entry 0xFFFF = "all clusters"; NULL = always all
+  float* bound;        // [capacity] with a candidate list: upper bound on the true similarity of every
+                       // centroid NOT in the list; if the float64 winner does not clear it, all are scanned
   int64_t capacity;
 };
 constexpr int FIX_MAX_CAND = 4;

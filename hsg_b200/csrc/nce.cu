@@ -312,6 +312,7 @@ int hsg_nce_fwd_f32(const float* e, const float* prototypes, int64_t N, int64_t 
   HSG_REQUIRE(per_pixel_out, HSG_E_INVALID, "nce_fwd: null output");
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)ceil_div64(N, NC_T);
+  ProfRange prof(PROF_NCE_FWD, st);
   switch (n_sets) {
     case 1: nce_fwd_kernel<1><<<grid, NC_THREADS, 0, st>>>(a, per_pixel_out, stats_out); break;
     case 2: nce_fwd_kernel<2><<<grid, NC_THREADS, 0, st>>>(a, per_pixel_out, stats_out); break;
@@ -337,6 +338,7 @@ int hsg_nce_bwd_f32(const float* e, const float* prototypes, int64_t N, int64_t 
   HSG_REQUIRE(workspace && workspace_bytes >= hsg_nce_workspace_bytes(N, P, dim, n_sets), HSG_E_WORKSPACE,
               "nce_bwd: workspace too small");
   float* G = (float*)workspace;
+  ProfRange prof(PROF_NCE_BWD, st);
   const int64_t chunk = nce_chunk_pixels(N, P);
   for (int64_t i0 = 0; i0 < N; i0 += chunk) {
     const int64_t i1 = i0 + chunk < N ? i0 + chunk : N;

@@ -304,6 +304,7 @@ int hsg_prep_f32(const float* emb_nchw, int B, int D, int H, int W,
   const int HW = H * W;
   const int tpi = (HW + PREP_TPX - 1) / PREP_TPX;
 
+  ProfRange prof(PROF_PREP, st);
   const int64_t* tile_base = nullptr;
   if (use_ignore) {
     HSG_REQUIRE(workspace && workspace_bytes >= hsg_prep_workspace_bytes(B, H, W), HSG_E_WORKSPACE,

@@ -123,6 +123,7 @@ int hsg_relabel_i64(const int64_t* batch, const int64_t* cluster, const int64_t*
   a.B = B; a.kmax = kmax; a.label_values = label_values; a.nl = (int)n_label_values; a.T = T;
   a.flags = c.take<int32_t>(T);
   a.rank = c.take<int32_t>(T);
+  ProfRange prof(PROF_RELABEL, st);
   HSG_CUDA(cudaMemsetAsync(a.flags, 0, sizeof(int32_t) * T, st));
   const int blocks = num_sms() * 8;
   if (N > 0) {

@@ -387,6 +387,9 @@ static int launch_gather(const SegReducePlan& p, const float* x, const int64_t* 
 int sr_sort_and_sum(const SegReducePlan& p, const float* x, const int64_t* off, cudaStream_t st) {
   HSG_REQUIRE(p.kmax <= SR_MAX_KEYS, HSG_E_UNSUPPORTED, "segment reduce: %d keys per segment (max %d)", p.kmax, SR_MAX_KEYS);
   HSG_REQUIRE(p.dim <= 32 * 20, HSG_E_UNSUPPORTED, "segment reduce: dim %d (max 640)", p.dim);
+  int rc;
+  {
+  ProfRange prof(PROF_MSTEP_SORT, st);
   const size_t hist_smem = (size_t)p.kmax * sizeof(uint32_t);
   if (hist_smem > 48 * 1024)
     HSG_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
@@ -407,20 +410,24 @@ int sr_sort_and_sum(const SegReducePlan& p, const float* x, const int64_t* off, 
         p.tiles, off, p.keys, p.kmax, p.tile_hist, p.bin_start, p.perm);
   }
   HSG_LAUNCH_CHECK();
+  }
+  ProfRange prof(PROF_MSTEP_GATHER, st);
   const int nv = (p.dim + 31) / 32;
-  if (nv <= 1) return launch_gather<1>(p, x, off, st);
-  if (nv <= 2) return launch_gather<2>(p, x, off, st);
-  if (nv <= 3) return launch_gather<3>(p, x, off, st);
-  if (nv <= 5) return launch_gather<5>(p, x, off, st);
-  if (nv <= 9) return launch_gather<9>(p, x, off, st);
-  if (nv <= 12) return launch_gather<12>(p, x, off, st);
-  if (nv <= 17) return launch_gather<17>(p, x, off, st);
-  return launch_gather<20>(p, x, off, st);
+  if (nv <= 1) rc = launch_gather<1>(p, x, off, st);
+  else if (nv <= 2) rc = launch_gather<2>(p, x, off, st);
+  else if (nv <= 3) rc = launch_gather<3>(p, x, off, st);
+  else if (nv <= 5) rc = launch_gather<5>(p, x, off, st);
+  else if (nv <= 9) rc = launch_gather<9>(p, x, off, st);
+  else if (nv <= 12) rc = launch_gather<12>(p, x, off, st);
+  else if (nv <= 17) rc = launch_gather<17>(p, x, off, st);
+  else rc = launch_gather<20>(p, x, off, st);
+  return rc;
 }
 
 int sr_combine(const SegReducePlan& p, int64_t P, const int64_t* seg_base, int mode, float* out,
                float* sums_out, float* counts_out, cudaStream_t st) {
   if (P == 0) return HSG_OK;
+  ProfRange prof(PROF_MSTEP_COMBINE, st);
   combine_kernel<<<(unsigned)ceil_div64(P, COMBINE_WARPS), COMBINE_WARPS * 32, 0, st>>>(
       P, p.dim, p.S, p.kmax, seg_base, p.bin_start, p.bin_count, p.pieces, mode, out, sums_out,
       counts_out);

@@ -1,18 +1,489 @@
-// Tensor-core (tcgen05) E-step of the spherical k-means -- placeholder build.
-// The real kernel lands in the next commit; until then the shape test says
-// "unsupported" so every call takes the fp32 CUDA-core E-step.
+// Tensor-core E-step of the spherical k-means (tcgen05 + TMEM + TMA, sm_100a).
+//
+// Replaces find_nearest_prototypes (hsg/utils/segsort/common.py:44-64: fp32
+// cuBLAS mm -> [n,K] matrix in HBM -> argmax) for the shapes that matter at full
+// resolution (D in {64,128,256}, K <= 256).  Per 128-pixel tile:
+//
+//   TMA        : fp16 pixel tile, one [128 x 64] slab (128B-swizzled) per stage
+//   tcgen05.mma: D[128 x K] (TMEM, fp32) += A[128 x 64] * C[K x 64]^T, the fp16
+//                centroids of the image resident in shared memory (<= 128 KiB)
+//   epilogue   : 8 warps read the accumulator back (tcgen05.ld), add the exact
+//                fp32 contribution of the location features, and keep per pixel
+//                the best and second-best value with the centroid index packed
+//                into the low mantissa bits (one FMNMX pair per value)
+//
+// The similarity matrix never leaves the SM.  A pixel whose gap is below twice
+// the rigorous error bound of this pass (fp16 rounding of x and c measured at
+// conversion time + accumulation + packing) is appended to the re-decision list
+// with its two candidates and an upper bound on everything else; the float64
+// kernel (kmeans.cu) settles it.  HBM traffic: 2*D bytes/pixel for the fp16
+// copy + 4*L for the location features + 4 (error norm) + 4 (label).
 #include "kmeans.cuh"
+
+#include <cuda.h>
+#include <float.h>
 
 namespace hsg {
 
-bool tc_shape_supported(int, int, int) { return false; }
-size_t tc_workspace_bytes(int, int, int) { return 0; }
-void tc_carve(Carver&, TcState& t, int, int, int) { t.enabled = false; }
-int tc_prepare(TcState&, int64_t, int) { return HSG_OK; }
-int tc_convert_centroids(const EStepArgs&, const TcState&, cudaStream_t) { return HSG_OK; }
-int estep_tc(const EStepArgs&, const TcState&, cudaStream_t) {
-  set_error("tensor-core E-step not built");
-  return HSG_E_UNSUPPORTED;
+constexpr int TC_BM = 128;              // pixels per tile (UMMA M)
+constexpr int TC_BK = 64;               // fp16 per slab row (128 bytes, one swizzle atom)
+constexpr int TC_STAGE_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_THREADS = 384;         // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
+constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_LMAX = 8;              // location-feature channels handled in the epilogue
+constexpr int TC_TMEM_COLS = 512;
+constexpr float TC_EPS_CONST = 7e-5f;   // accumulation (3e-5) + index packing (2^-15 * 1.2)
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must trap (launch failure), never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
+  d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+  return d;
+}
+
+struct TcParams {
+  const float* x;            // [N,dim] fp32 rows (location features live at [d16, dim))
+  int dim, d16, L;
+  const float* centroids;    // [S,kmax,dim]
+  const int32_t* seg_k;
+  int kmax, kpad;
+  const float* xerr;
+  const float* cerr_max;
+  Tiles tiles;
+  int sub;                   // 128-pixel sub-tiles per tile
+  long long items;           // tiles.bound * sub
+  int32_t* keys_out;
+  FixList fix;
+  int nst;                   // pipeline stages
+  float* dbg_sims;           // optional [N,kmax] dump of the screening values
+};
+
+__device__ __forceinline__ bool item_rows(const TcParams& p, long long item, int count, int& seg,
+                                          int64_t& row0, int& np) {
+  const int ti = (int)(item / p.sub);
+  if (ti >= count) return false;
+  const int64_t b = p.tiles.begin[ti] + (int64_t)(item % p.sub) * TC_BM;
+  const int64_t e = p.tiles.end[ti];
+  if (b >= e) return false;
+  seg = p.tiles.seg[ti];
+  row0 = b;
+  np = (int)min((int64_t)TC_BM, e - b);
+  return true;
+}
+
+__device__ __forceinline__ void upd2(float& m, float& s, float v) {
+  s = fmaxf(s, fminf(m, v));
+  m = fmaxf(m, v);
+}
+
+template <int LT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_c,
+                const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve (the dynamic segment is 1024-aligned by the attribute + the launch size)
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nslab = p.d16 / TC_BK;
+  const uint32_t slab_b_bytes = (uint32_t)p.kpad * 128u;
+  const uint32_t sB = base;
+  const uint32_t sA = sB + nslab * slab_b_bytes;
+  const uint32_t sMisc = sA + p.nst * TC_STAGE_BYTES;
+  uint8_t* misc = smem_raw + (sMisc - smem_u32(smem_raw));
+  float* cloc = reinterpret_cast<float*>(misc);                         // [kpad][TC_LMAX]
+  float* ex_m = cloc + 256 * TC_LMAX;                                   // [2][128]
+  float* ex_s = ex_m + 2 * TC_BM;                                       // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ex_s + 2 * TC_BM);       // full[nst], empty[nst], bfull, tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * 8 + 5);
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8 * 8;
+  const uint32_t bar_bfull = bar_empty + 8 * 8;
+  const uint32_t bar_tfull = bar_bfull + 8;
+  const uint32_t bar_tempty = bar_tfull + 16;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.nst; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_bfull, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_c) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int count = *p.tiles.count;
+  const long long i_begin = p.items * blockIdx.x / gridDim.x;
+  const long long i_end = p.items * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0, cur_seg = -1, last_stage = 0;
+      uint32_t phase = 0, last_phase = 0;
+      for (long long item = i_begin; item < i_end; ++item) {
+        int seg, np; int64_t row0;
+        if (!item_rows(p, item, count, seg, row0, np)) continue;
+        if (seg != cur_seg) {
+          if (cur_seg >= 0) mbar_wait(bar_empty + 8 * last_stage, last_phase);   // every MMA reading the old centroids is done
+          mbar_expect_tx(bar_bfull, nslab * slab_b_bytes);
+          for (int j = 0; j < nslab; ++j)
+            tma_load_2d(sB + j * slab_b_bytes, &tmap_c, j * TC_BK, seg * p.kpad, bar_bfull);
+          cur_seg = seg;
+        }
+        for (int j = 0; j < nslab; ++j) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
+          tma_load_2d(sA + stage * TC_STAGE_BYTES, &tmap_x, j * TC_BK, (int)row0, bar_full + 8 * stage);
+          last_stage = stage; last_phase = phase;
+          if (++stage == p.nst) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=f16, both K-major, N=kpad, M=128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.kpad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0, cur_seg = -1, acc = 0;
+      uint32_t phase = 0, bcount = 0, acc_phase[2] = {0, 0};
+      for (long long item = i_begin; item < i_end; ++item) {
+        int seg, np; int64_t row0;
+        if (!item_rows(p, item, count, seg, row0, np)) continue;
+        if (seg != cur_seg) {
+          mbar_wait(bar_bfull, bcount & 1);
+          ++bcount;
+          cur_seg = seg;
+        }
+        mbar_wait(bar_tempty + 8 * acc, acc_phase[acc] ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int j = 0; j < nslab; ++j) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a0 = sA + stage * TC_STAGE_BYTES, b0 = sB + j * slab_b_bytes;
+#pragma unroll
+          for (int k4 = 0; k4 < TC_BK / 16; ++k4)
+            tc_mma_f16(d_tmem, umma_desc(a0 + k4 * 32), umma_desc(b0 + k4 * 32), idesc, (j | k4) ? 1u : 0u);
+          tc_commit(bar_empty + 8 * stage);
+          if (++stage == p.nst) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_tfull + 8 * acc);
+        acc_phase[acc] ^= 1;
+        acc ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int et = threadIdx.x - 128;              // 0..255
+    const int q = warp & 3;                        // TMEM lane quadrant of this warp
+    const int h = (warp - 4) >> 2;                 // column half
+    const int r = 32 * q + lane;                   // accumulator row = pixel within the tile
+    const int nchunk = p.kpad >> 4;
+    const int c_begin = h == 0 ? 0 : (nchunk + 1) / 2;
+    const int c_end = h == 0 ? (nchunk + 1) / 2 : nchunk;
+    int cur_seg = -1, acc = 0, K = p.kmax, par = 0;
+    uint32_t acc_phase[2] = {0, 0};
+    float cerrmax = 0.f;
+    for (long long item = i_begin; item < i_end; ++item) {
+      int seg, np; int64_t row0;
+      if (!item_rows(p, item, count, seg, row0, np)) continue;
+      if (seg != cur_seg) {
+        // all 256 epilogue threads finished the previous tile (they passed its exchange barrier)
+        for (int idx = et; idx < p.kpad * TC_LMAX; idx += TC_EPI_THREADS) {
+          const int k = idx / TC_LMAX, l = idx % TC_LMAX;
+          cloc[idx] = (k < p.kmax && l < p.L)
+                          ? p.centroids[((int64_t)seg * p.kmax + k) * p.dim + p.d16 + l] : 0.f;
+        }
+        K = p.seg_k ? p.seg_k[seg] : p.kmax;
+        cerrmax = p.cerr_max[seg];
+        cur_seg = seg;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      const int64_t pix = row0 + r;
+      const bool inb = r < np;
+      float lv[TC_LMAX];
+#pragma unroll
+      for (int l = 0; l < TC_LMAX; ++l)
+        lv[l] = (inb && l < p.L && (LT < 0 || l < LT)) ? p.x[pix * p.dim + p.d16 + l] : 0.f;
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase[acc]);
+      tc_fence_after();
+      float m = -FLT_MAX, s = -FLT_MAX;
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t v[16];
+        tc_ld16(tmem_base + acc * 256 + c * 16 + ((uint32_t)(32 * q) << 16), v);
+        tc_ld_wait();
+        if (c * 16 >= K) continue;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = c * 16 + j;
+          float val = __uint_as_float(v[j]);
+          if (LT < 0) {
+            for (int l = 0; l < p.L; ++l) val = fmaf(lv[l], cloc[k * TC_LMAX + l], val);
+          } else {
+#pragma unroll
+            for (int l = 0; l < LT; ++l) val = fmaf(lv[l], cloc[k * TC_LMAX + l], val);
+          }
+          if (p.dbg_sims && inb && k < K) p.dbg_sims[pix * p.kmax + k] = val;
+          const float packed = __uint_as_float((__float_as_uint(val) & 0xFFFFFF00u) | (uint32_t)(255 - k));
+          if (k < K) upd2(m, s, packed);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      acc_phase[acc] ^= 1;
+      acc ^= 1;
+
+      if (h == 1) { ex_m[par * TC_BM + r] = m; ex_s[par * TC_BM + r] = s; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (h == 0 && inb) {
+        const float m2 = ex_m[par * TC_BM + r], s2 = ex_s[par * TC_BM + r];
+        const float S2 = fmaxf(fmaxf(s, s2), fminf(m, m2));
+        const float M = fmaxf(m, m2);
+        const int kb = 255 - (int)(__float_as_uint(M) & 0xFFu);
+        p.keys_out[pix] = seg * p.kmax + kb;
+        const float eps = p.xerr[pix] * 1.001f + cerrmax * 1.001f + TC_EPS_CONST;
+        if (M - S2 <= 2.f * eps) {
+          const int slot = atomicAdd(p.fix.count, 1);
+          if (slot < p.fix.capacity) {
+            p.fix.pixels[slot] = (int32_t)pix;
+            uint16_t* cd = p.fix.cand + (int64_t)slot * FIX_MAX_CAND;
+            cd[0] = (uint16_t)kb;
+            cd[1] = S2 > -FLT_MAX ? (uint16_t)(255 - (int)(__float_as_uint(S2) & 0xFFu)) : (uint16_t)0xFFFF;
+            cd[2] = 0xFFFF;
+            p.fix.bound[slot] = S2 + eps;      // no centroid outside {kb, ks} can have a true similarity above this
+          }
+        }
+      }
+      par ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+  }
+}
+
+// ---------------------------------------------------------------- centroid conversion
+__global__ void tc_convert_kernel(const float* __restrict__ cent, int S, int kmax, int kpad, int dim, int d16,
+                                  __half* __restrict__ ch, float* __restrict__ cerr, float* __restrict__ cerr_max) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (int64_t)S * kpad) return;
+  const int s = (int)(row / kpad), k = (int)(row % kpad);
+  __half* dst = ch + row * d16;
+  if (k >= kmax) {
+    for (int d = lane; d < d16; d += 32) dst[d] = __float2half_rn(0.f);
+    return;
+  }
+  const float* src = cent + ((int64_t)s * kmax + k) * dim;
+  float e2 = 0.f;
+  for (int d = lane; d < d16; d += 32) {
+    const float v = src[d];
+    const __half hv = __float2half_rn(v);
+    const float rr = v - __half2float(hv);
+    e2 = fmaf(rr, rr, e2);
+    dst[d] = hv;
+  }
+  e2 = warp_sum(e2);
+  if (lane == 0) {
+    const float e = sqrtf(e2) * 1.0001f + 1e-30f;
+    cerr[(int64_t)s * kmax + k] = e;
+    atomicMax(reinterpret_cast<int*>(cerr_max + s), __float_as_int(e));   // non-negative floats order like ints
+  }
+}
+
+// ---------------------------------------------------------------- host side
+bool tc_shape_supported(int dim, int d16, int kmax) {
+  if (!(d16 == 64 || d16 == 128 || d16 == 256)) return false;
+  if (dim < d16 || dim - d16 > TC_LMAX) return false;
+  if (kmax < 1 || kmax > 256) return false;
+  const int kpad = (kmax + 15) / 16 * 16;
+  return (size_t)kpad * d16 * 2 <= 128 * 1024;
+}
+
+void tc_carve(Carver& c, TcState& t, int S, int kmax, int d16) {
+  t.enabled = false;
+  t.kpad = (kmax + 15) / 16 * 16;
+  t.d16 = d16;
+  t.ch = c.take<__half>((size_t)S * t.kpad * d16);
+  t.cerr = c.take<float>((size_t)S * kmax);
+  t.cerr_max = c.take<float>(S);
+}
+
+size_t tc_workspace_bytes(int S, int kmax, int d16) {
+  Carver c(nullptr);
+  TcState t;
+  tc_carve(c, t, S, kmax, d16);
+  return c.used();
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int encode_2d_f16(void* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  HSG_REQUIRE(fn, HSG_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {TC_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HSG_REQUIRE(r == CUDA_SUCCESS, HSG_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box=%u",
+              (int)r, (unsigned long long)rows, (unsigned long long)cols, box_rows);
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  memcpy(out, &m, sizeof(m));
+  return HSG_OK;
+}
+
+int tc_prepare(TcState& t, int64_t N, int S) {
+  HSG_REQUIRE(((uintptr_t)t.xh & 15) == 0, HSG_E_INVALID, "tensor-core E-step: fp16 copy must be 16-byte aligned");
+  int rc = encode_2d_f16(t.tmap_x, t.xh, (uint64_t)N, (uint64_t)t.d16, TC_BM);
+  if (rc) return rc;
+  rc = encode_2d_f16(t.tmap_c, t.ch, (uint64_t)S * t.kpad, (uint64_t)t.d16, (uint32_t)t.kpad);
+  if (rc) return rc;
+  t.enabled = true;
+  return HSG_OK;
+}
+
+int tc_convert_centroids(const EStepArgs& a, const TcState& t, cudaStream_t st) {
+  HSG_CUDA(cudaMemsetAsync(t.cerr_max, 0, sizeof(float) * a.S, st));
+  const int64_t rows = (int64_t)a.S * t.kpad;
+  tc_convert_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(a.centroids, a.S, a.kmax, t.kpad, a.dim, t.d16,
+                                                                  t.ch, t.cerr, t.cerr_max);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+float* g_tc_debug_sims = nullptr;   // set by hsg_debug_set_tc_dump (tests only)
+
+int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
+  HSG_REQUIRE(t.enabled, HSG_E_INVALID, "tensor-core E-step used before tc_prepare");
+  TcParams p;
+  p.x = a.x; p.dim = a.dim; p.d16 = t.d16; p.L = a.dim - t.d16; p.centroids = a.centroids;
+  p.seg_k = a.seg_k; p.kmax = a.kmax; p.kpad = t.kpad; p.xerr = t.xerr; p.cerr_max = t.cerr_max;
+  p.tiles = a.tiles; p.sub = (int)(a.tiles.tile / TC_BM); p.items = (long long)a.tiles.bound * p.sub;
+  p.keys_out = a.keys_out; p.fix = a.fix; p.dbg_sims = g_tc_debug_sims;
+  const int nslab = t.d16 / TC_BK;
+  const size_t b_bytes = (size_t)nslab * t.kpad * 128;
+  const size_t misc = 256 * TC_LMAX * 4 + 4 * TC_BM * 4 + (2 * 8 + 5) * 8 + 64;
+  const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - b_bytes - misc;
+  int nst = (int)(budget / TC_STAGE_BYTES);
+  if (nst > 8) nst = 8;
+  HSG_REQUIRE(nst >= 2, HSG_E_UNSUPPORTED, "tensor-core E-step: shared memory budget (kpad=%d d16=%d)", t.kpad, t.d16);
+  p.nst = nst;
+  const size_t smem = 1024 + b_bytes + (size_t)nst * TC_STAGE_BYTES + misc;
+  CUtensorMap mx, mc;
+  memcpy(&mx, t.tmap_x, sizeof(mx));
+  memcpy(&mc, t.tmap_c, sizeof(mc));
+  long long grid = num_sms();
+  if (grid > p.items) grid = p.items;
+  if (grid < 1) grid = 1;
+  if (p.L == 0) {
+    HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    estep_tc_kernel<0><<<(unsigned)grid, TC_THREADS, smem, st>>>(mx, mc, p);
+  } else if (p.L == 2) {
+    HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    estep_tc_kernel<2><<<(unsigned)grid, TC_THREADS, smem, st>>>(mx, mc, p);
+  } else {
+    HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    estep_tc_kernel<-1><<<(unsigned)grid, TC_THREADS, smem, st>>>(mx, mc, p);
+  }
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
 }
 
 }  // namespace hsg
+
+// test hook: dump the screening similarities of the next tensor-core E-steps into
+// a caller buffer [N,kmax] (NULL switches it off)
+extern "C" int hsg_debug_set_tc_dump(float* sims) {
+  hsg::g_tc_debug_sims = sims;
+  return HSG_OK;
+}

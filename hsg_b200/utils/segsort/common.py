@@ -151,6 +151,15 @@ def segment_by_kmeans(embeddings, labels=None, num_clusters=[5, 5], cluster_indi
   cluster_indices [N], batch_indices [N]) with the reference's ordering
   contract: pixels image by image in raster order with ignore pixels removed;
   cluster ids are the ranks of the distinct (image, cluster, label) triples."""
+  ex = segment_by_kmeans_ex(embeddings, labels, num_clusters, cluster_indices, local_features,
+                            ignore_index, iterations)
+  return ex['embeddings'], ex['embeddings_with_loc'], ex['labels'], ex['cluster_indices'], ex['batch_indices']
+
+
+def segment_by_kmeans_ex(embeddings, labels=None, num_clusters=[5, 5], cluster_indices=None,
+                         local_features=None, ignore_index=None, iterations=10, count_prototypes=False):
+  """segment_by_kmeans plus the by-products the next stages can reuse (image
+  offsets, per-prototype descriptions) so they need no sort / unique of their own."""
   if not embeddings.is_cuda:
     raise ops._lib.HsgError('segment_by_kmeans: CUDA tensors only (no CPU fallback)')
   b, c, h, w = embeddings.shape
@@ -206,9 +215,33 @@ def segment_by_kmeans(embeddings, labels=None, num_clusters=[5, 5], cluster_indi
       label_values = torch.zeros((1,), dtype=torch.int64, device=dev)
     else:
       label_values = torch.unique(lab)
-    ids = ops.relabel(bat, clusters, lab, b * gpu_id, b, kmax, label_values)[0]     # :397-405
+    ids, pl, pb, pc, npro = ops.relabel(bat, clusters, lab, b * gpu_id, b, kmax, label_values)   # :397-405
 
   if embeddings.requires_grad and torch.is_grad_enabled():
     loc_rows = loc.reshape(-1, n_loc).index_select(0, pix % (h * w) if loc_stride == 0 else pix)
     x, xloc = _PrepOutputs.apply(embeddings, x, xloc, pix, loc_rows)
-  return x, xloc, lab, ids, bat
+  ex = {'embeddings': x, 'embeddings_with_loc': xloc, 'labels': lab, 'cluster_indices': ids,
+        'batch_indices': bat, 'seg_offsets': buf['seg_offsets'], 'max_seg_len': h * w,
+        'num_images': b, 'batch_base': b * gpu_id, 'kmeans_labels': clusters,
+        'slots_per_image': kmax * int(label_values.numel()),
+        'num_prototypes_device': npro, 'proto_label': pl, 'proto_batch': pb, 'proto_cluster': pc}
+  if count_prototypes:
+    p = int(npro)                                                         # the one host sync of this stage
+    ex['num_prototypes'] = p
+    ex['proto_label'], ex['proto_batch'], ex['proto_cluster'] = pl[:p], pb[:p], pc[:p]
+  return ex
+
+
+def pool_prototypes(ex, embeddings=None):
+  """calculate_prototypes_from_labels(embeddings, cluster_indices) for the output
+  of segment_by_kmeans_ex, using the image structure (ids are ranked by image) so
+  the reduction needs no global sort.  Differentiable in the embeddings."""
+  if 'num_prototypes' not in ex:
+    raise ValueError('pool_prototypes needs segment_by_kmeans_ex(..., count_prototypes=True)')
+  x = ex['embeddings'] if embeddings is None else embeddings
+  dev = x.device
+  images = torch.arange(ex['num_images'], device=dev, dtype=torch.int64) + ex['batch_base']
+  seg_base = torch.searchsorted(ex['proto_batch'], images).contiguous()   # first prototype id of each image
+  return ops.segment_reduce(x, ex['cluster_indices'], ex['num_prototypes'], REDUCE_NORMALIZE,
+                            seg_offsets=ex['seg_offsets'], max_seg_len=ex['max_seg_len'],
+                            seg_base=seg_base, kmax=ex['slots_per_image'])

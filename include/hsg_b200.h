@@ -60,6 +60,19 @@ HSG_API int hsg_version(void);
 /* number of SMs of the current device, or a negative error code */
 HSG_API int hsg_device_sms(void);
 
+/* instrumentation used by bench.py: number of kernels launched by this library
+ * so far (process-wide), and optional CUDA-event timing of the phases of the
+ * path on the launching stream (phase ids: 0 prep, 1 M-step sort, 2 M-step
+ * gather, 3 M-step combine, 4 E-step, 5 E-step float64 re-decision, 6 relabel,
+ * 7 pooling, 8 NCE fwd, 9 NCE bwd, 10 centroid fp16 conversion). */
+HSG_API long long hsg_launch_count(void);
+HSG_API int hsg_profile_enable(int on);
+HSG_API int hsg_profile_collect(double* total_ms_host, long long* counts_host, int n_phases);
+
+/* test hook: the next tensor-core E-steps also write their screening
+ * similarities to sims [N,kmax] (device); NULL switches the dump off. */
+HSG_API int hsg_debug_set_tc_dump(float* sims);
+
 /* ---- a1: normalize_embedding  (hsg/utils/general/common.py:101-120) -------
  * y[r,:] = x[r,:] / max(||x[r,:]||_2, 1e-12).  x may alias y. */
 HSG_API int hsg_normalize_f32(const float* x, float* y, int64_t rows, int dim, void* stream);

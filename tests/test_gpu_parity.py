@@ -305,3 +305,96 @@ def test_kmeans_moderate_segments_property(S):
     if l:
       close(c2[s], o_ops.calculate_prototypes_from_labels(x[off[s]:off[s + 1]], lab[off[s]:off[s + 1]], k),
             rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------- tensor-core (tcgen05) E-step
+def _tc_case(nn, d16, loc, k, lens=None, seed=11):
+  rng = np.random.RandomState(seed)
+  dim = d16 + loc
+  x = o_ops.normalize_embedding(rng.randn(nn, dim).astype(np.float32))
+  if loc:
+    x[:, d16:] *= 3.0
+    x = o_ops.normalize_embedding(x)
+  lens = lens or [nn]
+  off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+  c = o_ops.normalize_embedding(rng.randn(len(lens), k, dim).astype(np.float32))
+  c[0, 3] = c[0, 1]                      # exact duplicate
+  c[-1, k - 1] = 0                       # empty cluster
+  c[0, 5] = c[0, 4] * (1 - 1e-4) + 1e-3 * rng.randn(dim).astype(np.float32)   # near duplicate
+  return x, c, off, lens
+
+
+@pytest.mark.parametrize('d16,loc,k,lens', [
+    (256, 2, 256, [20000, 7777, 1, 0, 130]),
+    (256, 0, 256, [33000]),
+    (128, 2, 36, [5000, 4000]),
+    (64, 0, 32, [9000]),
+    (128, 5, 100, [3000, 2000]),
+])
+def test_tc_estep_exact_and_equal_to_simt(d16, loc, k, lens):
+  from hsg_b200 import ops, _lib
+  nn = sum(lens)
+  x, c, off, lens = _tc_case(nn, d16, loc, k, lens)
+  xt, ct, offt = t(x), t(c), t(off)
+  xh, xerr = ops.make_half_copy(xt, d16)
+  tc, nre = ops.kmeans_estep(xt, ct, seg_offsets=offt, max_seg_len=max(lens), xh=xh, xerr=xerr,
+                             flags=_lib.KMEANS_FORCE_TC, return_rechecked=True)
+  simt = ops.kmeans_estep(xt, ct, seg_offsets=offt, max_seg_len=max(lens), flags=_lib.KMEANS_FORCE_SIMT)
+  tc, simt = n(tc), n(simt)
+  for s, l in enumerate(lens):
+    if l == 0:
+      continue
+    best, _, gap = o_ops.argmax_margins(x[off[s]:off[s + 1]], c[s])
+    sel = gap > 1e-12
+    assert np.array_equal(tc[off[s]:off[s + 1]][sel], best[sel]), 'segment %d: not the float64 arg-max' % s
+  assert np.array_equal(tc, simt)
+  assert 0 < int(nre) < nn // 2
+
+
+def test_tc_screening_error_is_inside_the_bound():
+  """the fp16 tcgen05 pass must stay within the bound its re-decision threshold assumes."""
+  from hsg_b200 import ops, _lib
+  d16, loc, k = 256, 2, 256
+  x, c, off, lens = _tc_case(16384, d16, loc, k, [16384], seed=5)
+  xt, ct = t(x), t(c)
+  xh, xerr = ops.make_half_copy(xt, d16)
+  dump = torch.full((x.shape[0], k), float('nan'), device=dev())
+  lib = _lib.load()
+  import ctypes
+  lib.hsg_debug_set_tc_dump(ctypes.c_void_p(dump.data_ptr()))
+  try:
+    ops.kmeans_estep(xt, ct, xh=xh, xerr=xerr, flags=_lib.KMEANS_FORCE_TC)
+    torch.cuda.synchronize()
+  finally:
+    lib.hsg_debug_set_tc_dump(None)
+  sims = n(dump).astype(np.float64)
+  exact = x.astype(np.float64) @ c[0].astype(np.float64).T
+  assert not np.isnan(sims).any()
+  err = np.abs(sims - exact)
+  xe = n(xerr).astype(np.float64).reshape(-1, 1)
+  ce = np.linalg.norm(c[0][:, :d16] - c[0][:, :d16].astype(np.float16).astype(np.float32), axis=1).reshape(1, -1)
+  bound = xe * 1.001 + ce * 1.001 + 3e-5            # without the index-packing term (dump is unpacked)
+  assert np.all(err <= bound), (err.max(), (err / bound).max())
+  # and it is far from sloppy: typical error is an order of magnitude below the bound
+  assert np.median(err / bound) < 0.2
+
+
+def test_segment_by_kmeans_tc_equals_simt(S):
+  """whole operator at D=256: the tensor-core path (taken automatically) and the fp32
+  CUDA-core path must produce identical labels after every iteration count."""
+  from hsg_b200 import ops, _lib
+  rng = np.random.RandomState(3)
+  emb = rng.randn(3, 256, 40, 56).astype(np.float32)
+  e = t(emb)
+  for iters in (1, 4):
+    res = S.segment_by_kmeans(e, None, [4, 4], iterations=iters)
+    # same thing with the fp32 E-step: drive the stages by hand
+    ex = S.segment_by_kmeans_ex(e, None, [4, 4], iterations=0)
+    init = S._grid_init([4, 4], (40, 56), e.device)[0].repeat(3)
+    lab = ops.kmeans(ex['embeddings_with_loc'], init, 16, iters, seg_offsets=ex['seg_offsets'],
+                     max_seg_len=40 * 56, flags=_lib.KMEANS_FORCE_SIMT)
+    ids = ops.relabel(ex['batch_indices'], lab, ex['labels'], 0, 3, 16,
+                      torch.zeros(1, dtype=torch.int64, device=e.device))[0]
+    assert torch.equal(res[3], ids)
+  ref = o_ops.segment_by_kmeans(emb, None, (4, 4), iterations=4)
+  assert np.mean(n(res[3]) == ref[3]) > 0.99
