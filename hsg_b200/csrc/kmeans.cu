@@ -146,29 +146,22 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) estep_fixup_kernel(const EStep
     const float* xr = a.x + pix * a.dim;
     const float* cbase = a.centroids + (int64_t)seg * a.kmax * a.dim;
     const uint16_t* cand = a.fix.cand ? a.fix.cand + (int64_t)e * FIX_MAX_CAND : nullptr;
-    bool all = !cand || cand[0] == 0xFFFF;
+    const bool all = !cand || cand[0] == 0xFFFF;
+    const int n = all ? K : FIX_MAX_CAND;
     double bv = -DBL_MAX;
     int bi = 0x7fffffff;
-    for (int pass = 0; pass < 2; ++pass) {
-      const int n = all ? K : FIX_MAX_CAND;
-      bv = -DBL_MAX;
-      bi = 0x7fffffff;
-      for (int c = 0; c < n; ++c) {
-        int k = c;
-        if (!all) {
-          k = cand[c];
-          if (k == 0xFFFF) break;
-          if (k >= K) continue;
-        }
-        const float* cr = cbase + (int64_t)k * a.dim;
-        double s = 0.0;
-        for (int d = lane; d < a.dim; d += 32) s = fma((double)xr[d], (double)cr[d], s);
-        s = warp_sum(s);
-        if (s > bv || (s == bv && k < bi)) { bv = s; bi = k; }
+    for (int c = 0; c < n; ++c) {
+      int k = c;
+      if (!all) {
+        k = cand[c];
+        if (k == 0xFFFF) break;
+        if (k >= K) continue;
       }
-      // a candidate list is only conclusive when its winner beats everything outside it
-      if (all || !a.fix.bound || bv > (double)a.fix.bound[e]) break;
-      all = true;
+      const float* cr = cbase + (int64_t)k * a.dim;
+      double s = 0.0;
+      for (int d = lane; d < a.dim; d += 32) s = fma((double)xr[d], (double)cr[d], s);
+      s = warp_sum(s);
+      if (s > bv || (s == bv && k < bi)) { bv = s; bi = k; }
     }
     if (lane == 0) a.keys_out[pix] = seg * a.kmax + bi;
   }
@@ -208,7 +201,6 @@ static void km_carve(Carver& c, KmPlan& p, int64_t N, int dim, int S, int kmax, 
   p.fix.capacity = N;
   p.fix.pixels = c.take<int32_t>(N);
   p.fix.cand = c.take<uint16_t>(N * FIX_MAX_CAND);
-  p.fix.bound = c.take<float>(N);
   tc_carve(c, p.tc, S, kmax, d16 > 0 ? d16 : 64);
 }
 

@@ -11,8 +11,6 @@ struct FixList {
   int32_t* pixels;     // [capacity]
   uint16_t* cand;      // [capacity * FIX_MAX_CAND] candidate local ids, 0xFFFF-terminated;
                        // first entry 0xFFFF = "all clusters"; NULL = always all
-  float* bound;        // [capacity] with a candidate list: upper bound on the true similarity of every
-                       // centroid NOT in the list; if the float64 winner does not clear it, all are scanned
   int64_t capacity;
 };
 constexpr int FIX_MAX_CAND = 4;
@@ -39,15 +37,17 @@ int estep_fixup(const EStepArgs& a, cudaStream_t st);
 // tensor-core (tcgen05) E-step -- tc_estep.cu
 struct TcState {
   bool enabled;
-  const __half* xh;          // [N,d16]
+  const __half* xh;          // [N,d16+HSG_XH_TAIL]
   const float* xerr;         // [N]
   int d16;
   int kpad;                  // kmax rounded up to 16
-  __half* ch;                // [S*kpad, d16] fp16 centroids (first d16 dims)
+  __half* ch;                // [S*kpad, d16+HSG_XH_TAIL] fp16 centroids, same row layout as xh
   float* cerr;               // [S*kmax] ||c - fp16(c)|| over the first d16 dims
   float* cerr_max;           // [S]
-  unsigned char tmap_x[128]; // CUtensorMap images (host encoded)
+  unsigned char tmap_x[128]; // CUtensorMap images (host encoded): pixel main slabs / tail slab,
+  unsigned char tmap_xt[128];//   centroid main slabs / tail slab
   unsigned char tmap_c[128];
+  unsigned char tmap_ct[128];
 };
 bool tc_shape_supported(int dim, int d16, int kmax);
 size_t tc_workspace_bytes(int S, int kmax, int d16);

@@ -58,20 +58,44 @@ __global__ void normalize_bwd_kernel(const float* __restrict__ x, const float* _
 }
 
 // ------------------------------------------------------------ half copy
+// fp16 side copy for the tensor-core E-step, HSG_XH_TAIL extra columns per row:
+//   [0,d16)            fp16(x_d)
+//   d16+3l+{0,1,2}     (hi, hi, lo) of the l-th trailing feature (location), hi = fp16(v), lo = fp16(v - hi);
+//                      against the centroid side's (hi, lo, hi) this gives v*c to ~2^-21 relative on the tensor core
+//   d16+15             1.0 (multiplies the centroid side's "row is padding" marker)
+// lanes 0..15 of a warp write the tail of one row.
+__device__ __forceinline__ void write_xh_tail(__half* tail, int lane, int L, float v_l /*feature lane/3*/) {
+  if (lane < HSG_XH_TAIL) {
+    float o = 0.f;
+    const int l = lane / 3, part = lane % 3;
+    if (lane == HSG_XH_TAIL - 1) {
+      o = 1.f;
+    } else if (l < L) {
+      const float hi = __half2float(__float2half_rn(v_l));
+      o = part < 2 ? hi : v_l - hi;
+    }
+    tail[lane] = __float2half_rn(o);
+  }
+}
+
 __global__ void half_copy_kernel(const float* __restrict__ x, int64_t rows, int dim, int d16,
                                  __half* __restrict__ xh, float* __restrict__ xerr) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float* xr = x + row * dim;
+  __half* hr = xh + row * (d16 + HSG_XH_TAIL);
   float e2 = 0.f;
   for (int d = lane; d < d16; d += 32) {
     const float v = xr[d];
     const __half h = __float2half_rn(v);
     const float r = v - __half2float(h);
     e2 = fmaf(r, r, e2);
-    xh[row * d16 + d] = h;
+    hr[d] = h;
   }
+  const int L = dim - d16;
+  const int l = lane / 3;
+  write_xh_tail(hr + d16, lane, L, (lane < HSG_XH_TAIL - 1 && l < L) ? xr[d16 + l] : 0.f);
   e2 = warp_sum(e2);
   if (lane == 0 && xerr) xerr[row] = sqrtf(e2) * 1.0001f + 1e-30f;
 }
@@ -229,10 +253,15 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs 
         const __half h = __float2half_rn(z);
         const float r = z - __half2float(h);
         e2 = fmaf(r, r, e2);
-        a.xh[row * a.D + d] = h;
+        a.xh[row * (a.D + HSG_XH_TAIL) + d] = h;
       }
     }
     if (lane < a.L) xl[a.D + lane] = lv / n2;
+    if (a.xh) {
+      const int l = lane / 3;
+      const float vl = __shfl_sync(FULL, lv / n2, l < a.L ? l : 0);
+      write_xh_tail(a.xh + row * (a.D + HSG_XH_TAIL) + a.D, lane, a.L, vl);
+    }
     if (a.xh && a.xerr) {
       e2 = warp_sum(e2);
       if (lane == 0) a.xerr[row] = sqrtf(e2) * 1.0001f + 1e-30f;
@@ -268,7 +297,8 @@ int hsg_normalize_bwd_f32(const float* x, const float* gy, float* gx, int64_t ro
 
 int hsg_make_half_copy_f32(const float* x, int64_t rows, int dim, int d16, void* xh_out,
                            float* xerr_out, void* stream) {
-  HSG_REQUIRE(rows >= 0 && dim > 0 && d16 > 0 && d16 <= dim, HSG_E_INVALID, "half_copy: bad shape");
+  HSG_REQUIRE(rows >= 0 && dim > 0 && d16 > 0 && d16 <= dim && dim - d16 <= HSG_XH_MAX_TRAILING,
+              HSG_E_INVALID, "half_copy: bad shape (at most %d trailing features)", HSG_XH_MAX_TRAILING);
   if (rows == 0) return HSG_OK;
   HSG_REQUIRE(x && xh_out, HSG_E_INVALID, "half_copy: null pointer");
   const int rpb = 8;
@@ -297,6 +327,8 @@ int hsg_prep_f32(const float* emb_nchw, int B, int D, int H, int W,
   HSG_REQUIRE(emb_nchw && (loc || L == 0) && init_clusters && x_out && xloc_out && labels_out &&
               clusters_out && batch_out && seg_offsets, HSG_E_INVALID, "prep: null pointer");
   HSG_REQUIRE(!use_ignore || labels, HSG_E_INVALID, "prep: ignore_index without labels");
+  HSG_REQUIRE(!xh_out || L <= HSG_XH_MAX_TRAILING, HSG_E_UNSUPPORTED,
+              "prep: the fp16 side copy holds at most %d local-feature channels", HSG_XH_MAX_TRAILING);
   HSG_REQUIRE((int64_t)H * W < (1ll << 31) && B <= 65535, HSG_E_UNSUPPORTED, "prep: image too large");
   const size_t smem = (size_t)D * 33 * sizeof(float);
   HSG_REQUIRE(smem <= 200 * 1024, HSG_E_UNSUPPORTED, "prep: embedding_dim %d too large", D);

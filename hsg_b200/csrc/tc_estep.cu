@@ -7,10 +7,12 @@
 //   TMA        : fp16 pixel tile, one [128 x 64] slab (128B-swizzled) per stage
 //   tcgen05.mma: D[128 x K] (TMEM, fp32) += A[128 x 64] * C[K x 64]^T, the fp16
 //                centroids of the image resident in shared memory (<= 128 KiB)
-//   epilogue   : 8 warps read the accumulator back (tcgen05.ld), add the exact
-//                fp32 contribution of the location features, and keep per pixel
-//                the best and second-best value with the centroid index packed
-//                into the low mantissa bits (one FMNMX pair per value)
+//                plus one K=16 MMA on a 16-column tail slab that carries the
+//                location features as (hi,lo) fp16 pairs (fp32-grade product) and a
+//                marker that pushes padding rows to similarity -4
+//   epilogue   : 8 warps read the accumulator back (tcgen05.ld) and keep per pixel
+//                the top three values with the centroid index packed into the
+//                low mantissa bits (one LOP3 + five FMNMX per value, nothing else)
 //
 // The similarity matrix never leaves the SM.  A pixel whose gap is below twice
 // the rigorous error bound of this pass (fp16 rounding of x and c measured at
@@ -30,9 +32,9 @@ constexpr int TC_BK = 64;               // fp16 per slab row (128 bytes, one swi
 constexpr int TC_STAGE_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_THREADS = 384;         // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
 constexpr int TC_EPI_THREADS = 256;
-constexpr int TC_LMAX = 8;              // location-feature channels handled in the epilogue
+constexpr int TC_TAIL_BYTES = TC_BM * HSG_XH_TAIL * 2;   // 16-column tail slab of a pixel tile
 constexpr int TC_TMEM_COLS = 512;
-constexpr float TC_EPS_CONST = 7e-5f;   // accumulation (3e-5) + index packing (2^-15 * 1.2)
+constexpr float TC_EPS_CONST = 7.1e-5f; // accumulation (3e-5) + index packing (2^-15 * 1.2) + split tail (1e-6)
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,22 +90,20 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+// K-major operand tiles.  128B swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart;
+// 32B swizzle (the 16-column tail slab): rows of 32 bytes, 8-row groups 256 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
   d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset between 8-row groups
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;            // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+  d |= (uint64_t)layout << 61;                      // 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
   return d;
 }
 
 struct TcParams {
-  const float* x;            // [N,dim] fp32 rows (location features live at [d16, dim))
-  int dim, d16, L;
-  const float* centroids;    // [S,kmax,dim]
-  const int32_t* seg_k;
+  int d16;
   int kmax, kpad;
   const float* xerr;
   const float* cerr_max;
@@ -129,44 +129,56 @@ __device__ __forceinline__ bool item_rows(const TcParams& p, long long item, int
   return true;
 }
 
-__device__ __forceinline__ void upd2(float& m, float& s, float v) {
-  s = fmaxf(s, fminf(m, v));
+// running top-3 (values carry the centroid index in their low mantissa bits)
+__device__ __forceinline__ void upd3(float& m, float& s, float& t, float v) {
+  const float a = fminf(m, v);
   m = fmaxf(m, v);
+  const float b = fminf(s, a);
+  s = fmaxf(s, a);
+  t = fmaxf(t, b);
 }
 
-template <int LT>
+template <bool DUMP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_c,
+estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_xt,
+                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_ct,
                 const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve (the dynamic segment is 1024-aligned by the attribute + the launch size)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int nslab = p.d16 / TC_BK;
   const uint32_t slab_b_bytes = (uint32_t)p.kpad * 128u;
-  const uint32_t sB = base;
-  const uint32_t sA = sB + nslab * slab_b_bytes;
+  const uint32_t tail_b_bytes = (uint32_t)p.kpad * 32u;
+  const uint32_t sB = base;                                   // centroids, main slabs
+  const uint32_t sBT = sB + nslab * slab_b_bytes;             // centroids, tail slab
+  const uint32_t sAT = sBT + 256 * 32;                        // pixel tail slab, 2 buffers
+  const uint32_t sA = sAT + 2 * TC_TAIL_BYTES;                // pixel main slabs, nst stages
   const uint32_t sMisc = sA + p.nst * TC_STAGE_BYTES;
   uint8_t* misc = smem_raw + (sMisc - smem_u32(smem_raw));
-  float* cloc = reinterpret_cast<float*>(misc);                         // [kpad][TC_LMAX]
-  float* ex_m = cloc + 256 * TC_LMAX;                                   // [2][128]
-  float* ex_s = ex_m + 2 * TC_BM;                                       // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ex_s + 2 * TC_BM);       // full[nst], empty[nst], bfull, tfull[2], tempty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * 8 + 5);
-  const uint32_t bar_full = smem_u32(bars);
-  const uint32_t bar_empty = bar_full + 8 * 8;
-  const uint32_t bar_bfull = bar_empty + 8 * 8;
-  const uint32_t bar_tfull = bar_bfull + 8;
-  const uint32_t bar_tempty = bar_tfull + 16;
+  float* ex = reinterpret_cast<float*>(misc);                 // [2 parities][3 values][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ex + 2 * 3 * TC_BM);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  const uint32_t bar_full = smem_u32(bars);                   // [8]
+  const uint32_t bar_empty = bar_full + 8 * 8;                // [8]
+  const uint32_t bar_tlfull = bar_empty + 8 * 8;              // [2] tail slab landed
+  const uint32_t bar_tlempty = bar_tlfull + 16;               // [2]
+  const uint32_t bar_bfull = bar_tlempty + 16;                // [1] centroids landed
+  const uint32_t bar_tfull = bar_bfull + 8;                   // [2] accumulator ready
+  const uint32_t bar_tempty = bar_tfull + 16;                 // [2] accumulator drained
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nst; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tlfull + 8 * i, 1); mbar_init(bar_tlempty + 8 * i, 1);
+      mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8);
+    }
     mbar_init(bar_bfull, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_xt) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_c) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_ct) : "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
@@ -184,25 +196,31 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0, cur_seg = -1, last_stage = 0;
-      uint32_t phase = 0, last_phase = 0;
+      int stage = 0, cur_seg = -1, tl = 0, last_tl = 0;
+      uint32_t phase = 0, tl_phase = 0, last_tl_phase = 0;
       for (long long item = i_begin; item < i_end; ++item) {
         int seg, np; int64_t row0;
         if (!item_rows(p, item, count, seg, row0, np)) continue;
         if (seg != cur_seg) {
-          if (cur_seg >= 0) mbar_wait(bar_empty + 8 * last_stage, last_phase);   // every MMA reading the old centroids is done
-          mbar_expect_tx(bar_bfull, nslab * slab_b_bytes);
+          // the tail MMA is the last one of a tile: once it retired, nothing reads the old centroids
+          if (cur_seg >= 0) mbar_wait(bar_tlempty + 8 * last_tl, last_tl_phase);
+          mbar_expect_tx(bar_bfull, nslab * slab_b_bytes + tail_b_bytes);
           for (int j = 0; j < nslab; ++j)
             tma_load_2d(sB + j * slab_b_bytes, &tmap_c, j * TC_BK, seg * p.kpad, bar_bfull);
+          tma_load_2d(sBT, &tmap_ct, p.d16, seg * p.kpad, bar_bfull);
           cur_seg = seg;
         }
         for (int j = 0; j < nslab; ++j) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
           tma_load_2d(sA + stage * TC_STAGE_BYTES, &tmap_x, j * TC_BK, (int)row0, bar_full + 8 * stage);
-          last_stage = stage; last_phase = phase;
           if (++stage == p.nst) { stage = 0; phase ^= 1; }
         }
+        mbar_wait(bar_tlempty + 8 * tl, tl_phase ^ 1);
+        mbar_expect_tx(bar_tlfull + 8 * tl, TC_TAIL_BYTES);
+        tma_load_2d(sAT + tl * TC_TAIL_BYTES, &tmap_xt, p.d16, (int)row0, bar_tlfull + 8 * tl);
+        last_tl = tl; last_tl_phase = tl_phase;
+        if (++tl == 2) { tl = 0; tl_phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -210,8 +228,8 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=f16, both K-major, N=kpad, M=128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.kpad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int stage = 0, cur_seg = -1, acc = 0;
-      uint32_t phase = 0, bcount = 0, acc_phase[2] = {0, 0};
+      int stage = 0, cur_seg = -1, acc = 0, tl = 0;
+      uint32_t phase = 0, bcount = 0, tl_phase = 0, acc_phase0 = 0, acc_phase1 = 0;
       for (long long item = i_begin; item < i_end; ++item) {
         int seg, np; int64_t row0;
         if (!item_rows(p, item, count, seg, row0, np)) continue;
@@ -220,7 +238,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           ++bcount;
           cur_seg = seg;
         }
-        mbar_wait(bar_tempty + 8 * acc, acc_phase[acc] ^ 1);
+        mbar_wait(bar_tempty + 8 * acc, (acc ? acc_phase1 : acc_phase0) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int j = 0; j < nslab; ++j) {
@@ -229,96 +247,84 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           const uint32_t a0 = sA + stage * TC_STAGE_BYTES, b0 = sB + j * slab_b_bytes;
 #pragma unroll
           for (int k4 = 0; k4 < TC_BK / 16; ++k4)
-            tc_mma_f16(d_tmem, umma_desc(a0 + k4 * 32), umma_desc(b0 + k4 * 32), idesc, (j | k4) ? 1u : 0u);
+            tc_mma_f16(d_tmem, umma_desc(a0 + k4 * 32, 1024, 2), umma_desc(b0 + k4 * 32, 1024, 2), idesc,
+                       (j | k4) ? 1u : 0u);
           tc_commit(bar_empty + 8 * stage);
           if (++stage == p.nst) { stage = 0; phase ^= 1; }
         }
+        // tail slab: split location features + padding marker (one K=16 MMA)
+        mbar_wait(bar_tlfull + 8 * tl, tl_phase);
+        tc_fence_after();
+        tc_mma_f16(d_tmem, umma_desc(sAT + tl * TC_TAIL_BYTES, 256, 6), umma_desc(sBT, 256, 6), idesc, 1u);
+        tc_commit(bar_tlempty + 8 * tl);
+        if (++tl == 2) { tl = 0; tl_phase ^= 1; }
         tc_commit(bar_tfull + 8 * acc);
-        acc_phase[acc] ^= 1;
+        if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
         acc ^= 1;
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int et = threadIdx.x - 128;              // 0..255
     const int q = warp & 3;                        // TMEM lane quadrant of this warp
     const int h = (warp - 4) >> 2;                 // column half
     const int r = 32 * q + lane;                   // accumulator row = pixel within the tile
     const int nchunk = p.kpad >> 4;
     const int c_begin = h == 0 ? 0 : (nchunk + 1) / 2;
     const int c_end = h == 0 ? (nchunk + 1) / 2 : nchunk;
-    int cur_seg = -1, acc = 0, K = p.kmax, par = 0;
-    uint32_t acc_phase[2] = {0, 0};
+    int cur_seg = -1, acc = 0, par = 0;
+    uint32_t acc_phase0 = 0, acc_phase1 = 0;
     float cerrmax = 0.f;
     for (long long item = i_begin; item < i_end; ++item) {
       int seg, np; int64_t row0;
       if (!item_rows(p, item, count, seg, row0, np)) continue;
-      if (seg != cur_seg) {
-        // all 256 epilogue threads finished the previous tile (they passed its exchange barrier)
-        for (int idx = et; idx < p.kpad * TC_LMAX; idx += TC_EPI_THREADS) {
-          const int k = idx / TC_LMAX, l = idx % TC_LMAX;
-          cloc[idx] = (k < p.kmax && l < p.L)
-                          ? p.centroids[((int64_t)seg * p.kmax + k) * p.dim + p.d16 + l] : 0.f;
-        }
-        K = p.seg_k ? p.seg_k[seg] : p.kmax;
-        cerrmax = p.cerr_max[seg];
-        cur_seg = seg;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
+      if (seg != cur_seg) { cerrmax = p.cerr_max[seg]; cur_seg = seg; }
       const int64_t pix = row0 + r;
       const bool inb = r < np;
-      float lv[TC_LMAX];
-#pragma unroll
-      for (int l = 0; l < TC_LMAX; ++l)
-        lv[l] = (inb && l < p.L && (LT < 0 || l < LT)) ? p.x[pix * p.dim + p.d16 + l] : 0.f;
+      const float xe = (h == 0 && inb) ? p.xerr[pix] : 0.f;     // issued before the wait, used after the sweep
 
-      mbar_wait(bar_tfull + 8 * acc, acc_phase[acc]);
+      mbar_wait(bar_tfull + 8 * acc, acc ? acc_phase1 : acc_phase0);
       tc_fence_after();
-      float m = -FLT_MAX, s = -FLT_MAX;
+      float m = -FLT_MAX, s = -FLT_MAX, t3 = -FLT_MAX;
+      const uint32_t trow = tmem_base + acc * 256 + ((uint32_t)(32 * q) << 16);
       for (int c = c_begin; c < c_end; ++c) {
         uint32_t v[16];
-        tc_ld16(tmem_base + acc * 256 + c * 16 + ((uint32_t)(32 * q) << 16), v);
+        tc_ld16(trow + c * 16, v);
         tc_ld_wait();
-        if (c * 16 >= K) continue;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int k = c * 16 + j;
-          float val = __uint_as_float(v[j]);
-          if (LT < 0) {
-            for (int l = 0; l < p.L; ++l) val = fmaf(lv[l], cloc[k * TC_LMAX + l], val);
-          } else {
-#pragma unroll
-            for (int l = 0; l < LT; ++l) val = fmaf(lv[l], cloc[k * TC_LMAX + l], val);
-          }
-          if (p.dbg_sims && inb && k < K) p.dbg_sims[pix * p.kmax + k] = val;
-          const float packed = __uint_as_float((__float_as_uint(val) & 0xFFFFFF00u) | (uint32_t)(255 - k));
-          if (k < K) upd2(m, s, packed);
+          if (DUMP) { if (inb && k < p.kmax) p.dbg_sims[pix * p.kmax + k] = __uint_as_float(v[j]); }
+          upd3(m, s, t3, __uint_as_float((v[j] & 0xFFFFFF00u) | (uint32_t)(255 - k)));
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-      acc_phase[acc] ^= 1;
+      if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
       acc ^= 1;
 
-      if (h == 1) { ex_m[par * TC_BM + r] = m; ex_s[par * TC_BM + r] = s; }
+      float* exp_ = ex + par * 3 * TC_BM;
+      if (h == 1) { exp_[r] = m; exp_[TC_BM + r] = s; exp_[2 * TC_BM + r] = t3; }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (h == 0 && inb) {
-        const float m2 = ex_m[par * TC_BM + r], s2 = ex_s[par * TC_BM + r];
-        const float S2 = fmaxf(fmaxf(s, s2), fminf(m, m2));
-        const float M = fmaxf(m, m2);
-        const int kb = 255 - (int)(__float_as_uint(M) & 0xFFu);
+        upd3(m, s, t3, exp_[r]);
+        upd3(m, s, t3, exp_[TC_BM + r]);
+        upd3(m, s, t3, exp_[2 * TC_BM + r]);
+        const int kb = 255 - (int)(__float_as_uint(m) & 0xFFu);
         p.keys_out[pix] = seg * p.kmax + kb;
-        const float eps = p.xerr[pix] * 1.001f + cerrmax * 1.001f + TC_EPS_CONST;
-        if (M - S2 <= 2.f * eps) {
+        const float eps = xe * 1.001f + cerrmax * 1.001f + TC_EPS_CONST;
+        if (m - s <= 2.f * eps) {
           const int slot = atomicAdd(p.fix.count, 1);
           if (slot < p.fix.capacity) {
             p.fix.pixels[slot] = (int32_t)pix;
             uint16_t* cd = p.fix.cand + (int64_t)slot * FIX_MAX_CAND;
-            cd[0] = (uint16_t)kb;
-            cd[1] = S2 > -FLT_MAX ? (uint16_t)(255 - (int)(__float_as_uint(S2) & 0xFFu)) : (uint16_t)0xFFFF;
-            cd[2] = 0xFFFF;
-            p.fix.bound[slot] = S2 + eps;      // no centroid outside {kb, ks} can have a true similarity above this
+            if (m - t3 <= 2.f * eps) {
+              cd[0] = 0xFFFF;                              // three or more inside the bound: scan them all
+            } else {                                       // everything else is provably out of reach
+              cd[0] = (uint16_t)kb;
+              cd[1] = (uint16_t)(255 - (int)(__float_as_uint(s) & 0xFFu));
+              cd[2] = 0xFFFF;
+            }
           }
         }
       }
@@ -335,29 +341,44 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 }
 
 // ---------------------------------------------------------------- centroid conversion
-__global__ void tc_convert_kernel(const float* __restrict__ cent, int S, int kmax, int kpad, int dim, int d16,
-                                  __half* __restrict__ ch, float* __restrict__ cerr, float* __restrict__ cerr_max) {
+__global__ void tc_convert_kernel(const float* __restrict__ cent, const int32_t* __restrict__ seg_k, int S,
+                                  int kmax, int kpad, int dim, int d16, __half* __restrict__ ch,
+                                  float* __restrict__ cerr, float* __restrict__ cerr_max) {
+  // row layout mirrors the pixel side (prep.cu): [0,d16) fp16(c_d); d16+3l+{0,1,2} = (hi, lo, hi) of the
+  // l-th trailing feature; d16+15 = 0 for a real centroid, -4 for a padding row (similarity -4: never wins)
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (int64_t)S * kpad) return;
   const int s = (int)(row / kpad), k = (int)(row % kpad);
-  __half* dst = ch + row * d16;
-  if (k >= kmax) {
-    for (int d = lane; d < d16; d += 32) dst[d] = __float2half_rn(0.f);
-    return;
-  }
-  const float* src = cent + ((int64_t)s * kmax + k) * dim;
+  const int K = seg_k ? seg_k[s] : kmax;
+  const int wx = d16 + HSG_XH_TAIL;
+  __half* dst = ch + row * wx;
+  const bool real = k < K && k < kmax;
+  const float* src = cent + ((int64_t)s * kmax + (real ? k : 0)) * dim;
   float e2 = 0.f;
   for (int d = lane; d < d16; d += 32) {
-    const float v = src[d];
+    const float v = real ? src[d] : 0.f;
     const __half hv = __float2half_rn(v);
     const float rr = v - __half2float(hv);
     e2 = fmaf(rr, rr, e2);
     dst[d] = hv;
   }
+  if (lane < HSG_XH_TAIL) {
+    const int L = dim - d16;
+    const int l = lane / 3, part = lane % 3;
+    float o = 0.f;
+    if (lane == HSG_XH_TAIL - 1) {
+      o = real ? 0.f : -4.f;
+    } else if (real && l < L) {
+      const float v = src[d16 + l];
+      const float hi = __half2float(__float2half_rn(v));
+      o = part == 1 ? v - hi : hi;
+    }
+    dst[d16 + lane] = __float2half_rn(o);
+  }
   e2 = warp_sum(e2);
-  if (lane == 0) {
-    const float e = sqrtf(e2) * 1.0001f + 1e-30f;
+  if (lane == 0 && k < kmax) {
+    const float e = real ? sqrtf(e2) * 1.0001f + 1e-30f : 0.f;
     cerr[(int64_t)s * kmax + k] = e;
     atomicMax(reinterpret_cast<int*>(cerr_max + s), __float_as_int(e));   // non-negative floats order like ints
   }
@@ -366,7 +387,7 @@ __global__ void tc_convert_kernel(const float* __restrict__ cent, int S, int kma
 // ---------------------------------------------------------------- host side
 bool tc_shape_supported(int dim, int d16, int kmax) {
   if (!(d16 == 64 || d16 == 128 || d16 == 256)) return false;
-  if (dim < d16 || dim - d16 > TC_LMAX) return false;
+  if (dim < d16 || dim - d16 > HSG_XH_MAX_TRAILING) return false;
   if (kmax < 1 || kmax > 256) return false;
   const int kpad = (kmax + 15) / 16 * 16;
   return (size_t)kpad * d16 * 2 <= 128 * 1024;
@@ -376,7 +397,7 @@ void tc_carve(Carver& c, TcState& t, int S, int kmax, int d16) {
   t.enabled = false;
   t.kpad = (kmax + 15) / 16 * 16;
   t.d16 = d16;
-  t.ch = c.take<__half>((size_t)S * t.kpad * d16);
+  t.ch = c.take<__half>((size_t)S * t.kpad * (d16 + HSG_XH_TAIL));
   t.cerr = c.take<float>((size_t)S * kmax);
   t.cerr_max = c.take<float>(S);
 }
@@ -404,19 +425,21 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static int encode_2d_f16(void* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2-D fp16 tensor map over a row-major [rows, row_elems] array; box = box_cols x box_rows
+static int encode_2d_f16(void* out, const void* ptr, uint64_t rows, uint64_t row_elems, uint32_t box_cols,
+                         uint32_t box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_fn();
   HSG_REQUIRE(fn, HSG_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {TC_BK, box_rows};
+  cuuint64_t dims[2] = {row_elems, rows};
+  cuuint64_t strides[1] = {row_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  HSG_REQUIRE(r == CUDA_SUCCESS, HSG_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box=%u",
-              (int)r, (unsigned long long)rows, (unsigned long long)cols, box_rows);
+  HSG_REQUIRE(r == CUDA_SUCCESS, HSG_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box=%ux%u",
+              (int)r, (unsigned long long)rows, (unsigned long long)row_elems, box_cols, box_rows);
   static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
   memcpy(out, &m, sizeof(m));
   return HSG_OK;
@@ -424,10 +447,12 @@ static int encode_2d_f16(void* out, const void* ptr, uint64_t rows, uint64_t col
 
 int tc_prepare(TcState& t, int64_t N, int S) {
   HSG_REQUIRE(((uintptr_t)t.xh & 15) == 0, HSG_E_INVALID, "tensor-core E-step: fp16 copy must be 16-byte aligned");
-  int rc = encode_2d_f16(t.tmap_x, t.xh, (uint64_t)N, (uint64_t)t.d16, TC_BM);
-  if (rc) return rc;
-  rc = encode_2d_f16(t.tmap_c, t.ch, (uint64_t)S * t.kpad, (uint64_t)t.d16, (uint32_t)t.kpad);
-  if (rc) return rc;
+  const uint64_t wx = (uint64_t)t.d16 + HSG_XH_TAIL;
+  int rc;
+  if ((rc = encode_2d_f16(t.tmap_x, t.xh, (uint64_t)N, wx, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = encode_2d_f16(t.tmap_xt, t.xh, (uint64_t)N, wx, HSG_XH_TAIL, TC_BM, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = encode_2d_f16(t.tmap_c, t.ch, (uint64_t)S * t.kpad, wx, TC_BK, (uint32_t)t.kpad, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = encode_2d_f16(t.tmap_ct, t.ch, (uint64_t)S * t.kpad, wx, HSG_XH_TAIL, (uint32_t)t.kpad, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   t.enabled = true;
   return HSG_OK;
 }
@@ -435,8 +460,8 @@ int tc_prepare(TcState& t, int64_t N, int S) {
 int tc_convert_centroids(const EStepArgs& a, const TcState& t, cudaStream_t st) {
   HSG_CUDA(cudaMemsetAsync(t.cerr_max, 0, sizeof(float) * a.S, st));
   const int64_t rows = (int64_t)a.S * t.kpad;
-  tc_convert_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(a.centroids, a.S, a.kmax, t.kpad, a.dim, t.d16,
-                                                                  t.ch, t.cerr, t.cerr_max);
+  tc_convert_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(a.centroids, a.seg_k, a.S, a.kmax, t.kpad, a.dim,
+                                                                  t.d16, t.ch, t.cerr, t.cerr_max);
   HSG_LAUNCH_CHECK();
   return HSG_OK;
 }
@@ -446,34 +471,32 @@ float* g_tc_debug_sims = nullptr;   // set by hsg_debug_set_tc_dump (tests only)
 int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
   HSG_REQUIRE(t.enabled, HSG_E_INVALID, "tensor-core E-step used before tc_prepare");
   TcParams p;
-  p.x = a.x; p.dim = a.dim; p.d16 = t.d16; p.L = a.dim - t.d16; p.centroids = a.centroids;
-  p.seg_k = a.seg_k; p.kmax = a.kmax; p.kpad = t.kpad; p.xerr = t.xerr; p.cerr_max = t.cerr_max;
+  p.d16 = t.d16; p.kmax = a.kmax; p.kpad = t.kpad; p.xerr = t.xerr; p.cerr_max = t.cerr_max;
   p.tiles = a.tiles; p.sub = (int)(a.tiles.tile / TC_BM); p.items = (long long)a.tiles.bound * p.sub;
   p.keys_out = a.keys_out; p.fix = a.fix; p.dbg_sims = g_tc_debug_sims;
   const int nslab = t.d16 / TC_BK;
-  const size_t b_bytes = (size_t)nslab * t.kpad * 128;
-  const size_t misc = 256 * TC_LMAX * 4 + 4 * TC_BM * 4 + (2 * 8 + 5) * 8 + 64;
-  const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - b_bytes - misc;
+  const size_t fixed = (size_t)nslab * t.kpad * 128 + 256 * 32 + 2 * TC_TAIL_BYTES   // centroids + tails
+                       + 2 * 3 * TC_BM * 4 + 32 * 8 + 64;                            // exchange, barriers, tmem slot
+  const size_t budget = 227 * 1024 - 1024 /*static*/ - 1024 /*alignment slack*/ - fixed;
   int nst = (int)(budget / TC_STAGE_BYTES);
   if (nst > 8) nst = 8;
   HSG_REQUIRE(nst >= 2, HSG_E_UNSUPPORTED, "tensor-core E-step: shared memory budget (kpad=%d d16=%d)", t.kpad, t.d16);
   p.nst = nst;
-  const size_t smem = 1024 + b_bytes + (size_t)nst * TC_STAGE_BYTES + misc;
-  CUtensorMap mx, mc;
+  const size_t smem = 1024 + fixed + (size_t)nst * TC_STAGE_BYTES;
+  CUtensorMap mx, mxt, mc, mct;
   memcpy(&mx, t.tmap_x, sizeof(mx));
+  memcpy(&mxt, t.tmap_xt, sizeof(mxt));
   memcpy(&mc, t.tmap_c, sizeof(mc));
+  memcpy(&mct, t.tmap_ct, sizeof(mct));
   long long grid = num_sms();
   if (grid > p.items) grid = p.items;
   if (grid < 1) grid = 1;
-  if (p.L == 0) {
-    HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    estep_tc_kernel<0><<<(unsigned)grid, TC_THREADS, smem, st>>>(mx, mc, p);
-  } else if (p.L == 2) {
-    HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    estep_tc_kernel<2><<<(unsigned)grid, TC_THREADS, smem, st>>>(mx, mc, p);
+  if (p.dbg_sims) {
+    HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    estep_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, st>>>(mx, mxt, mc, mct, p);
   } else {
-    HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    estep_tc_kernel<-1><<<(unsigned)grid, TC_THREADS, smem, st>>>(mx, mc, p);
+    HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    estep_tc_kernel<false><<<(unsigned)grid, TC_THREADS, smem, st>>>(mx, mxt, mc, mct, p);
   }
   HSG_LAUNCH_CHECK();
   return HSG_OK;

@@ -12,6 +12,9 @@ from . import _lib
 from ._lib import check
 
 
+XH_TAIL = 16      # HSG_XH_TAIL in include/hsg_b200.h
+
+
 def _ptr(t):
   return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -90,7 +93,7 @@ def prep(embeddings, loc, loc_image_stride, labels, ignore_index, init_clusters,
       'batch': torch.empty((n_max,), dtype=torch.int64, device=dev),
       'pixel': torch.empty((n_max,), dtype=torch.int64, device=dev),
       'seg_offsets': torch.empty((b + 1,), dtype=torch.int64, device=dev),
-      'xh': torch.empty((n_max, d), dtype=torch.float16, device=dev) if want_half else None,
+      'xh': torch.empty((n_max, d + XH_TAIL), dtype=torch.float16, device=dev) if want_half else None,
       'xerr': torch.empty((n_max,), dtype=torch.float32, device=dev) if want_half else None,
   }
   lib = _lib.load()
@@ -110,7 +113,7 @@ def prep(embeddings, loc, loc_image_stride, labels, ignore_index, init_clusters,
 def make_half_copy(x, d16):
   _need_cuda(x)
   x = _f32(x)
-  xh = torch.empty((x.shape[0], d16), dtype=torch.float16, device=x.device)
+  xh = torch.empty((x.shape[0], d16 + XH_TAIL), dtype=torch.float16, device=x.device)
   xerr = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
   with torch.cuda.device(x.device):
     check(_lib.load().hsg_make_half_copy_f32(_ptr(x), x.shape[0], x.shape[1], d16, _ptr(xh),
@@ -129,7 +132,7 @@ def _seg_args(n, seg_offsets, max_seg_len, device):
 def tc_d16(dim, kmax):
   """Width of the fp16 side copy the tensor-core E-step wants for this shape (0 = none)."""
   for d16 in (256, 128, 64):
-    if dim >= d16 and dim - d16 <= 8 and kmax <= 256 and kmax * d16 * 2 <= 128 * 1024:
+    if dim >= d16 and dim - d16 <= 5 and kmax <= 256 and kmax * d16 * 2 <= 128 * 1024:
       return d16
   return 0
 
@@ -148,7 +151,7 @@ def kmeans(x, init_labels, kmax, iterations, seg_offsets=None, max_seg_len=None,
     return (labels, cent) if return_centroids else labels
   lib = _lib.load()
   ws = _workspace(lib.hsg_kmeans_workspace_bytes(n, dim, s, kmax, max_seg_len), x.device)
-  d16 = xh.shape[1] if xh is not None else 0
+  d16 = xh.shape[1] - XH_TAIL if xh is not None else 0
   with torch.cuda.device(x.device):
     check(lib.hsg_kmeans_f32(_ptr(x), n, dim, _ptr(xh), d16, _ptr(xerr), _ptr(seg_offsets), s,
                              max_seg_len, _ptr(seg_k), kmax, _ptr(init_labels), iterations,
@@ -185,7 +188,7 @@ def kmeans_estep(x, centroids, seg_offsets=None, max_seg_len=None, seg_k=None, x
   nre = torch.zeros((1,), dtype=torch.int64, device=x.device)
   lib = _lib.load()
   ws = _workspace(lib.hsg_kmeans_workspace_bytes(n, dim, s, kmax, max_seg_len), x.device)
-  d16 = xh.shape[1] if xh is not None else 0
+  d16 = xh.shape[1] - XH_TAIL if xh is not None else 0
   with torch.cuda.device(x.device):
     check(lib.hsg_kmeans_estep_f32(_ptr(x), n, dim, _ptr(xh), d16, _ptr(xerr), _ptr(seg_offsets), s,
                                    max_seg_len, _ptr(seg_k), kmax, _ptr(centroids), _ptr(labels),

@@ -50,6 +50,12 @@ extern "C" {
 #define HSG_KMEANS_FORCE_SIMT 1  /* fp32 CUDA-core E-step (any shape) */
 #define HSG_KMEANS_FORCE_TC 2    /* fail with HSG_E_UNSUPPORTED instead of falling back */
 
+/* fp16 side copy of the pixel rows used by the tensor-core E-step: each row has
+ * d16 + HSG_XH_TAIL fp16 columns (the tail carries the split trailing features,
+ * see hsg_b200/csrc/prep.cu); at most HSG_XH_MAX_TRAILING trailing features. */
+#define HSG_XH_TAIL 16
+#define HSG_XH_MAX_TRAILING 5
+
 /* modes of hsg_segment_reduce_f32 */
 #define HSG_REDUCE_SUM 0
 #define HSG_REDUCE_NORMALIZE 1 /* sum then L2-normalise: calculate_prototypes_from_labels */
@@ -93,7 +99,7 @@ HSG_API int hsg_normalize_bwd_f32(const float* x, const float* gy, float* gx, in
  * outputs, each with room for B*H*W rows; valid rows are [0, seg_offsets[B]):
  *   x_out [N,D], xloc_out [N,D+L], labels_out [N], clusters_out [N],
  *   batch_out [N] (= b + batch_index_base), seg_offsets [B+1] (device, int64).
- *   xh_out   (optional, may be NULL) [N,D] fp16 copy of xloc_out[:, :D]
+ *   xh_out   (optional, may be NULL) [N,D+HSG_XH_TAIL] fp16 side copy of xloc_out
  *   xerr_out (optional, with xh_out) [N] ||xloc[:, :D] - fp16(xloc[:, :D])||_2
  *   pixel_out (optional) [N] flat source pixel b*H*W + y*W + x of each kept row
  */
@@ -109,7 +115,8 @@ HSG_API int hsg_prep_f32(const float* emb_nchw, int B, int D, int H, int W,
                  void* stream);
 
 /* fp16 side copy used by the tensor-core E-step, for callers that did not go
- * through hsg_prep_f32: xh[r, :d16] = fp16(x[r, :d16]), xerr[r] = rounding norm */
+ * through hsg_prep_f32: xh [rows, d16+HSG_XH_TAIL] fp16, xerr[r] = rounding norm
+ * of the first d16 columns; dim - d16 <= HSG_XH_MAX_TRAILING */
 HSG_API int hsg_make_half_copy_f32(const float* x, int64_t rows, int dim, int d16, void* xh_out,
                            float* xerr_out, void* stream);
 
@@ -124,8 +131,8 @@ HSG_API int hsg_make_half_copy_f32(const float* x, int64_t rows, int dim, int d1
  * init_labels  [N] int64 in [0, k_s)
  * labels_out   [N] int64
  * centroids_out optional [S,kmax,dim]: the centroids the last E-step used
- * xh, xerr     optional fp16 copy (see prep); enables the tcgen05 E-step when
- *              d16 in {64,128,256} and kmax*d16*2 <= 128 KiB
+ * xh, xerr     optional fp16 copy [N,d16+HSG_XH_TAIL] (see prep); enables the
+ *              tcgen05 E-step when d16 in {64,128,256}, dim-d16 <= 5, kmax <= 256
  * Each iteration = M-step (deterministic segmented sum + normalise; empty
  * cluster -> zero row) then E-step (arg-max of <x,c>, ties -> lowest index).
  * The E-step result is the arg-max of the float64 dot products of the fp32
