@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(ES_THREADS) estep_simt_kernel(const EStepArgs 
 }
 
 // ---------------------------------------------------------------- float64 re-decision
-constexpr int FIX_WARPS = 8;
+constexpr int FIX_WARPS = 4;
 
 __device__ __forceinline__ int upper_bound_off(const int64_t* a, int n, int64_t v) {
   int lo = 0, hi = n;
@@ -135,6 +135,27 @@ __device__ __forceinline__ int upper_bound_off(const int64_t* a, int n, int64_t 
   return lo;
 }
 
+// One warp per listed pixel.  The pixel row is read once into registers (all
+// loads in flight together); centroid rows are read four at a time so a scan of
+// every cluster costs K/4 L2 round trips, not K.  Every dot product is the same
+// fixed-order float64 sum (lane-strided partials, xor tree), so the decision
+// does not depend on which pass listed the pixel.
+constexpr int FIX_NV = 20;     // dim <= 640
+
+__device__ __forceinline__ double fix_dot(const float (&xr)[FIX_NV], const float* __restrict__ cr, int dim, int lane) {
+  float cv[FIX_NV];
+#pragma unroll
+  for (int m = 0; m < FIX_NV; ++m) {
+    const int d = lane + 32 * m;
+    cv[m] = d < dim ? cr[d] : 0.f;
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int m = 0; m < FIX_NV; ++m)
+    if (lane + 32 * m < dim) s = fma((double)xr[m], (double)cv[m], s);
+  return s;
+}
+
 __global__ void __launch_bounds__(FIX_WARPS * 32) estep_fixup_kernel(const EStepArgs a) {
   const int lane = threadIdx.x & 31;
   const int total = min((int64_t)*a.fix.count, a.fix.capacity);
@@ -143,25 +164,39 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) estep_fixup_kernel(const EStep
     const int64_t pix = a.fix.pixels[e];
     const int seg = upper_bound_off(a.seg_offsets, a.S + 1, pix) - 1;
     const int K = a.seg_k ? a.seg_k[seg] : a.kmax;
-    const float* xr = a.x + pix * a.dim;
+    const float* xrow = a.x + pix * a.dim;
+    float xr[FIX_NV];
+#pragma unroll
+    for (int m = 0; m < FIX_NV; ++m) {
+      const int d = lane + 32 * m;
+      xr[m] = d < a.dim ? xrow[d] : 0.f;
+    }
     const float* cbase = a.centroids + (int64_t)seg * a.kmax * a.dim;
     const uint16_t* cand = a.fix.cand ? a.fix.cand + (int64_t)e * FIX_MAX_CAND : nullptr;
     const bool all = !cand || cand[0] == 0xFFFF;
-    const int n = all ? K : FIX_MAX_CAND;
     double bv = -DBL_MAX;
     int bi = 0x7fffffff;
-    for (int c = 0; c < n; ++c) {
-      int k = c;
-      if (!all) {
-        k = cand[c];
+    if (all) {
+      for (int k0 = 0; k0 < K; k0 += 4) {
+        double s4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          s4[u] = fix_dot(xr, cbase + (int64_t)min(k0 + u, K - 1) * a.dim, a.dim, lane);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double s = warp_sum(s4[u]);
+          const int k = k0 + u;
+          if (k < K && (s > bv || (s == bv && k < bi))) { bv = s; bi = k; }
+        }
+      }
+    } else {
+      for (int c = 0; c < FIX_MAX_CAND; ++c) {
+        const int k = cand[c];
         if (k == 0xFFFF) break;
         if (k >= K) continue;
+        const double s = warp_sum(fix_dot(xr, cbase + (int64_t)k * a.dim, a.dim, lane));
+        if (s > bv || (s == bv && k < bi)) { bv = s; bi = k; }
       }
-      const float* cr = cbase + (int64_t)k * a.dim;
-      double s = 0.0;
-      for (int d = lane; d < a.dim; d += 32) s = fma((double)xr[d], (double)cr[d], s);
-      s = warp_sum(s);
-      if (s > bv || (s == bv && k < bi)) { bv = s; bi = k; }
     }
     if (lane == 0) a.keys_out[pix] = seg * a.kmax + bi;
   }
@@ -178,7 +213,7 @@ int estep_simt(const EStepArgs& a, cudaStream_t st) {
 }
 
 int estep_fixup(const EStepArgs& a, cudaStream_t st) {
-  estep_fixup_kernel<<<num_sms() * 4, FIX_WARPS * 32, 0, st>>>(a);
+  estep_fixup_kernel<<<num_sms() * 8, FIX_WARPS * 32, 0, st>>>(a);
   HSG_LAUNCH_CHECK();
   return HSG_OK;
 }
@@ -208,6 +243,7 @@ static int check_common(const float* x, int64_t N, int dim, const int64_t* seg_o
                         int64_t max_seg_len, int kmax) {
   HSG_REQUIRE(N >= 0 && N < (1ll << 31), HSG_E_UNSUPPORTED, "kmeans: N=%lld rows (max 2^31-1)", (long long)N);
   HSG_REQUIRE(dim > 0 && S > 0 && kmax > 0, HSG_E_INVALID, "kmeans: bad shape dim=%d S=%d kmax=%d", dim, S, kmax);
+  HSG_REQUIRE(dim <= 32 * 20, HSG_E_UNSUPPORTED, "kmeans: dim %d (max 640)", dim);
   HSG_REQUIRE(max_seg_len >= 0 && max_seg_len <= N, HSG_E_INVALID, "kmeans: max_seg_len %lld outside [0,N]", (long long)max_seg_len);
   HSG_REQUIRE(kmax <= SR_MAX_KEYS, HSG_E_UNSUPPORTED, "kmeans: kmax=%d (max %d)", kmax, SR_MAX_KEYS);
   HSG_REQUIRE((int64_t)S * kmax < (1ll << 31), HSG_E_UNSUPPORTED, "kmeans: S*kmax overflows int32");
