@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(ES_THREADS) estep_simt_kernel(const EStepArgs 
       if (slot < a.fix.capacity) {
         a.fix.pixels[slot] = (int32_t)pix;
         if (a.fix.cand) a.fix.cand[(int64_t)slot * FIX_MAX_CAND] = 0xFFFF;
+        atomicAdd(a.fix.count + 1, 1);
       }
     }
   }
@@ -140,8 +141,7 @@ __device__ __forceinline__ int upper_bound_off(const int64_t* a, int n, int64_t 
 // every cluster costs K/4 L2 round trips, not K.  Every dot product is the same
 // fixed-order float64 sum (lane-strided partials, xor tree), so the decision
 // does not depend on which pass listed the pixel.
-constexpr int FIX_NV = 20;     // dim <= 640
-
+template <int FIX_NV>
 __device__ __forceinline__ double fix_dot(const float (&xr)[FIX_NV], const float* __restrict__ cr, int dim, int lane) {
   float cv[FIX_NV];
 #pragma unroll
@@ -156,6 +156,7 @@ __device__ __forceinline__ double fix_dot(const float (&xr)[FIX_NV], const float
   return s;
 }
 
+template <int FIX_NV>
 __global__ void __launch_bounds__(FIX_WARPS * 32) estep_fixup_kernel(const EStepArgs a) {
   const int lane = threadIdx.x & 31;
   const int total = min((int64_t)*a.fix.count, a.fix.capacity);
@@ -213,12 +214,15 @@ int estep_simt(const EStepArgs& a, cudaStream_t st) {
 }
 
 int estep_fixup(const EStepArgs& a, cudaStream_t st) {
-  estep_fixup_kernel<<<num_sms() * 8, FIX_WARPS * 32, 0, st>>>(a);
+  if (a.dim <= 32 * 9)
+    estep_fixup_kernel<9><<<num_sms() * 16, FIX_WARPS * 32, 0, st>>>(a);
+  else
+    estep_fixup_kernel<20><<<num_sms() * 8, FIX_WARPS * 32, 0, st>>>(a);
   HSG_LAUNCH_CHECK();
   return HSG_OK;
 }
 
-__global__ void copy_count_kernel(const int32_t* c, int64_t* out) { *out = *c; }
+__global__ void copy_count_kernel(const int32_t* c, int64_t* out) { out[0] = c[0]; out[1] = c[1]; }
 
 // ---------------------------------------------------------------- orchestration
 struct KmPlan {
@@ -232,7 +236,7 @@ static void km_carve(Carver& c, KmPlan& p, int64_t N, int dim, int S, int kmax, 
                      int d16) {
   sr_carve(c, p.sr, N, dim, S, kmax, max_seg_len);
   p.centroids = c.take<float>((int64_t)S * kmax * dim);
-  p.fix.count = c.take<int32_t>(1);
+  p.fix.count = c.take<int32_t>(2);    // [0] listed pixels, [1] of those: scans over every cluster
   p.fix.capacity = N;
   p.fix.pixels = c.take<int32_t>(N);
   p.fix.cand = c.take<uint16_t>(N * FIX_MAX_CAND);
@@ -252,7 +256,7 @@ static int check_common(const float* x, int64_t N, int dim, const int64_t* seg_o
 }
 
 static int run_estep(EStepArgs& ea, KmPlan& p, bool use_tc, cudaStream_t st) {
-  HSG_CUDA(cudaMemsetAsync(p.fix.count, 0, sizeof(int32_t), st));
+  HSG_CUDA(cudaMemsetAsync(p.fix.count, 0, 2 * sizeof(int32_t), st));
   if (use_tc) {
     int rc;
     {
@@ -378,7 +382,7 @@ int hsg_kmeans_estep_f32(const float* x, int64_t N, int dim, const void* xh, int
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (N == 0) {
-    if (num_rechecked_out) HSG_CUDA(cudaMemsetAsync(num_rechecked_out, 0, sizeof(int64_t), st));
+    if (num_rechecked_out) HSG_CUDA(cudaMemsetAsync(num_rechecked_out, 0, 2 * sizeof(int64_t), st));
     return HSG_OK;
   }
   HSG_REQUIRE(centroids && labels_out, HSG_E_INVALID, "estep: null pointer");

@@ -13,7 +13,7 @@ struct FixList {
                        // first entry 0xFFFF = "all clusters"; NULL = always all
   int64_t capacity;
 };
-constexpr int FIX_MAX_CAND = 4;
+constexpr int FIX_MAX_CAND = 8;
 
 struct EStepArgs {
   const float* x;            // [N,dim]

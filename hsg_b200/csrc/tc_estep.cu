@@ -34,6 +34,8 @@ constexpr int TC_THREADS = 384;         // warp0 TMA, warp1 MMA, warp2 TMEM allo
 constexpr int TC_EPI_THREADS = 256;
 constexpr int TC_TAIL_BYTES = TC_BM * HSG_XH_TAIL * 2;   // 16-column tail slab of a pixel tile
 constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_MAXC = 8;                                // candidates a row may list per column half
+constexpr int TC_EX_BYTES = 2 * 3 * TC_BM * 4 + 2 * TC_BM * 4 + 2 * TC_BM * 2 * 4 + 16 + 2 * TC_BM * 2 * TC_MAXC;
 constexpr float TC_EPS_CONST = 7.1e-5f; // accumulation (3e-5) + index packing (2^-15 * 1.2) + split tail (1e-6)
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -155,7 +157,11 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const uint32_t sMisc = sA + p.nst * TC_STAGE_BYTES;
   uint8_t* misc = smem_raw + (sMisc - smem_u32(smem_raw));
   float* ex = reinterpret_cast<float*>(misc);                 // [2 parities][3 values][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ex + 2 * 3 * TC_BM);
+  float* ex_thr = ex + 2 * 3 * TC_BM;                         // [2][128]
+  int* ex_cnt = reinterpret_cast<int*>(ex_thr + 2 * TC_BM);   // [2][128][2 halves]
+  int* ex_flag = ex_cnt + 2 * TC_BM * 2;                      // [2] (+2 pad)
+  uint8_t* ex_list = reinterpret_cast<uint8_t*>(ex_flag + 4); // [2][128][2 halves][TC_MAXC]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ex_list + 2 * TC_BM * 2 * TC_MAXC);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
   const uint32_t bar_full = smem_u32(bars);                   // [8]
   const uint32_t bar_empty = bar_full + 8 * 8;                // [8]
@@ -281,6 +287,10 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const int64_t pix = row0 + r;
       const bool inb = r < np;
       const float xe = (h == 0 && inb) ? p.xerr[pix] : 0.f;     // issued before the wait, used after the sweep
+      float* exv = ex + par * 3 * TC_BM;           // (m, s, t3) of the upper column half
+      float* thr_row = ex_thr + par * TC_BM;       // per row: collect every value >= this (or +inf)
+      int* many_flag = ex_flag + par;
+      if (threadIdx.x == 128) *many_flag = 0;      // ordered before this tile's writers by barrier 1
 
       mbar_wait(bar_tfull + 8 * acc, acc ? acc_phase1 : acc_phase0);
       tc_fence_after();
@@ -297,33 +307,67 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           upd3(m, s, t3, __uint_as_float((v[j] & 0xFFFFFF00u) | (uint32_t)(255 - k)));
         }
       }
+      if (h == 1) { exv[r] = m; exv[TC_BM + r] = s; exv[2 * TC_BM + r] = t3; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");                                   // barrier 1
+      bool amb = false, many = false;
+      int kb = 0, ks = 0;
+      if (h == 0) {
+        upd3(m, s, t3, exv[r]);
+        upd3(m, s, t3, exv[TC_BM + r]);
+        upd3(m, s, t3, exv[2 * TC_BM + r]);
+        kb = 255 - (int)(__float_as_uint(m) & 0xFFu);
+        ks = 255 - (int)(__float_as_uint(s) & 0xFFu);
+        const float thr = 2.f * (xe * 1.001f + cerrmax * 1.001f + TC_EPS_CONST);
+        amb = inb && (m - s <= thr);
+        many = amb && (m - t3 <= thr);             // three or more inside the bound
+        thr_row[r] = many ? m - thr : FLT_MAX;
+        if (many) *many_flag = 1;
+        if (inb) p.keys_out[pix] = seg * p.kmax + kb;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");                                   // barrier 2
+      const bool tile_many = *many_flag != 0;
+      if (tile_many) {
+        // second sweep (rare after the first iterations): rows flagged `many` list every candidate
+        const float thr_v = thr_row[r];
+        uint8_t* lst = ex_list + (par * TC_BM + r) * 2 * TC_MAXC + h * TC_MAXC;
+        int cnt = 0;
+        for (int c = c_begin; c < c_end; ++c) {
+          uint32_t v[16];
+          tc_ld16(trow + c * 16, v);
+          tc_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = c * 16 + j;
+            const float pv = __uint_as_float((v[j] & 0xFFFFFF00u) | (uint32_t)(255 - k));
+            if (pv >= thr_v) { if (cnt < TC_MAXC) lst[cnt] = (uint8_t)k; ++cnt; }
+          }
+        }
+        ex_cnt[(par * TC_BM + r) * 2 + h] = cnt;
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
       acc ^= 1;
-
-      float* exp_ = ex + par * 3 * TC_BM;
-      if (h == 1) { exp_[r] = m; exp_[TC_BM + r] = s; exp_[2 * TC_BM + r] = t3; }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (h == 0 && inb) {
-        upd3(m, s, t3, exp_[r]);
-        upd3(m, s, t3, exp_[TC_BM + r]);
-        upd3(m, s, t3, exp_[2 * TC_BM + r]);
-        const int kb = 255 - (int)(__float_as_uint(m) & 0xFFu);
-        p.keys_out[pix] = seg * p.kmax + kb;
-        const float eps = xe * 1.001f + cerrmax * 1.001f + TC_EPS_CONST;
-        if (m - s <= 2.f * eps) {
-          const int slot = atomicAdd(p.fix.count, 1);
-          if (slot < p.fix.capacity) {
-            p.fix.pixels[slot] = (int32_t)pix;
-            uint16_t* cd = p.fix.cand + (int64_t)slot * FIX_MAX_CAND;
-            if (m - t3 <= 2.f * eps) {
-              cd[0] = 0xFFFF;                              // three or more inside the bound: scan them all
-            } else {                                       // everything else is provably out of reach
-              cd[0] = (uint16_t)kb;
-              cd[1] = (uint16_t)(255 - (int)(__float_as_uint(s) & 0xFFu));
-              cd[2] = 0xFFFF;
+      if (tile_many) asm volatile("bar.sync 1, 256;" ::: "memory");                    // barrier 3
+      if (amb) {
+        const int slot = atomicAdd(p.fix.count, 1);
+        if (slot < p.fix.capacity) {
+          p.fix.pixels[slot] = (int32_t)pix;
+          uint16_t* cd = p.fix.cand + (int64_t)slot * FIX_MAX_CAND;
+          if (!many) {                               // everything but the top two is provably out of reach
+            cd[0] = (uint16_t)kb; cd[1] = (uint16_t)ks; cd[2] = 0xFFFF;
+          } else {
+            const int c0 = ex_cnt[(par * TC_BM + r) * 2], c1 = ex_cnt[(par * TC_BM + r) * 2 + 1];
+            if (c0 > TC_MAXC || c1 > TC_MAXC || c0 + c1 > FIX_MAX_CAND) {
+              cd[0] = 0xFFFF;                        // too many to list: scan every cluster
+              atomicAdd(p.fix.count + 1, 1);
+            } else {
+              const uint8_t* l0 = ex_list + (par * TC_BM + r) * 2 * TC_MAXC;
+              int w = 0;
+              for (int i = 0; i < c0; ++i) cd[w++] = l0[i];
+              for (int i = 0; i < c1; ++i) cd[w++] = l0[TC_MAXC + i];
+              if (w < FIX_MAX_CAND) cd[w] = 0xFFFF;
             }
           }
         }
@@ -476,7 +520,7 @@ int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
   p.keys_out = a.keys_out; p.fix = a.fix; p.dbg_sims = g_tc_debug_sims;
   const int nslab = t.d16 / TC_BK;
   const size_t fixed = (size_t)nslab * t.kpad * 128 + 256 * 32 + 2 * TC_TAIL_BYTES   // centroids + tails
-                       + 2 * 3 * TC_BM * 4 + 32 * 8 + 64;                            // exchange, barriers, tmem slot
+                       + TC_EX_BYTES + 32 * 8 + 64;                                  // exchange, barriers, tmem slot
   const size_t budget = 227 * 1024 - 1024 /*static*/ - 1024 /*alignment slack*/ - fixed;
   int nst = (int)(budget / TC_STAGE_BYTES);
   if (nst > 8) nst = 8;

@@ -185,7 +185,7 @@ def kmeans_estep(x, centroids, seg_offsets=None, max_seg_len=None, seg_k=None, x
   kmax = centroids.shape[-2]
   assert centroids.numel() == s * kmax * dim
   labels = torch.empty((n,), dtype=torch.int64, device=x.device)
-  nre = torch.zeros((1,), dtype=torch.int64, device=x.device)
+  nre = torch.zeros((2,), dtype=torch.int64, device=x.device)
   lib = _lib.load()
   ws = _workspace(lib.hsg_kmeans_workspace_bytes(n, dim, s, kmax, max_seg_len), x.device)
   d16 = xh.shape[1] - XH_TAIL if xh is not None else 0

@@ -160,7 +160,7 @@ HSG_API int hsg_kmeans_estep_f32(const float* x, int64_t N, int dim,
                          const void* xh, int d16, const float* xerr,
                          const int64_t* seg_offsets, int S, int64_t max_seg_len,
                          const int32_t* seg_k, int kmax, const float* centroids,
-                         int64_t* labels_out, int64_t* num_rechecked_out, int flags,
+                         int64_t* labels_out, int64_t* num_rechecked_out /* [2]: re-decided, full scans */, int flags,
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K3: segmented reduction by label

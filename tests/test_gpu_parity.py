@@ -223,7 +223,7 @@ def test_estep_random_is_exact_float64_argmax(S):
   assert not np.any(lab == 5)
   sel = gap > 1e-12
   assert np.array_equal(lab[sel], best[sel])
-  assert 0 < int(nre) < nn // 10
+  assert 0 < int(nre[0]) < nn // 10
 
 
 def test_nce_forward_backward(golden):
@@ -348,7 +348,7 @@ def test_tc_estep_exact_and_equal_to_simt(d16, loc, k, lens):
     sel = gap > 1e-12
     assert np.array_equal(tc[off[s]:off[s + 1]][sel], best[sel]), 'segment %d: not the float64 arg-max' % s
   assert np.array_equal(tc, simt)
-  assert 0 < int(nre) < nn // 2
+  assert 0 < int(nre[0]) < nn // 2 and int(nre[1]) <= int(nre[0])
 
 
 def test_tc_screening_error_is_inside_the_bound():
