@@ -131,6 +131,16 @@ __device__ __forceinline__ bool item_rows(const TcParams& p, long long item, int
   return true;
 }
 
+// value with its low 8 mantissa bits replaced by `idx`.  Written as mul.hi / mad.lo so it
+// issues on the FMA pipe (IMAD): the epilogue is bound by the ALU pipe, which the five
+// FMNMX of upd3 already fill.
+__device__ __forceinline__ float pack_idx(uint32_t bits, int idx) {
+  uint32_t hi, out;
+  asm("mul.hi.u32 %0, %1, 16777216;" : "=r"(hi) : "r"(bits));          // bits >> 8
+  asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(out) : "r"(hi), "r"((uint32_t)idx));
+  return __uint_as_float(out);
+}
+
 // running top-3 (values carry the centroid index in their low mantissa bits)
 __device__ __forceinline__ void upd3(float& m, float& s, float& t, float v) {
   const float a = fminf(m, v);
@@ -296,15 +306,27 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       tc_fence_after();
       float m = -FLT_MAX, s = -FLT_MAX, t3 = -FLT_MAX;
       const uint32_t trow = tmem_base + acc * 256 + ((uint32_t)(32 * q) << 16);
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t v[16];
-        tc_ld16(trow + c * 16, v);
+      // software pipelined: the TMEM load of chunk c+1 is in flight while chunk c is reduced
+      uint32_t va[16], vb[16];
+      if (c_begin < c_end) tc_ld16(trow + c_begin * 16, va);
+      for (int c = c_begin; c < c_end; c += 2) {
         tc_ld_wait();
+        if (c + 1 < c_end) tc_ld16(trow + (c + 1) * 16, vb);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int k = c * 16 + j;
-          if (DUMP) { if (inb && k < p.kmax) p.dbg_sims[pix * p.kmax + k] = __uint_as_float(v[j]); }
-          upd3(m, s, t3, __uint_as_float((v[j] & 0xFFFFFF00u) | (uint32_t)(255 - k)));
+          if (DUMP) { if (inb && k < p.kmax) p.dbg_sims[pix * p.kmax + k] = __uint_as_float(va[j]); }
+          upd3(m, s, t3, pack_idx(va[j], 255 - k));
+        }
+        if (c + 1 < c_end) {
+          tc_ld_wait();
+          if (c + 2 < c_end) tc_ld16(trow + (c + 2) * 16, va);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = (c + 1) * 16 + j;
+            if (DUMP) { if (inb && k < p.kmax) p.dbg_sims[pix * p.kmax + k] = __uint_as_float(vb[j]); }
+            upd3(m, s, t3, pack_idx(vb[j], 255 - k));
+          }
         }
       }
       if (h == 1) { exv[r] = m; exv[TC_BM + r] = s; exv[2 * TC_BM + r] = t3; }
@@ -338,7 +360,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int k = c * 16 + j;
-            const float pv = __uint_as_float((v[j] & 0xFFFFFF00u) | (uint32_t)(255 - k));
+            const float pv = pack_idx(v[j], 255 - k);
             if (pv >= thr_v) { if (cnt < TC_MAXC) lst[cnt] = (uint8_t)k; ++cnt; }
           }
         }
