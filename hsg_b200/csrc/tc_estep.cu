@@ -35,7 +35,7 @@ constexpr int TC_EPI_THREADS = 256;
 constexpr int TC_TAIL_BYTES = TC_BM * HSG_XH_TAIL * 2;   // 16-column tail slab of a pixel tile
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_MAXC = 8;                                // candidates a row may list per column half
-constexpr int TC_EX_BYTES = 2 * 3 * TC_BM * 4 + 2 * TC_BM * 4 + 2 * TC_BM * 2 * 4 + 16 + 2 * TC_BM * 2 * TC_MAXC;
+constexpr int TC_EX_BYTES = 2 * 3 * TC_BM * 4 + 2 * TC_BM * 4 + 2 * TC_BM * 2 * 4 + 32 + 2 * TC_BM * 2 * TC_MAXC;
 constexpr float TC_EPS_CONST = 7.1e-5f; // accumulation (3e-5) + index packing (2^-15 * 1.2) + split tail (1e-6)
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -131,14 +131,10 @@ __device__ __forceinline__ bool item_rows(const TcParams& p, long long item, int
   return true;
 }
 
-// value with its low 8 mantissa bits replaced by `idx`.  Written as mul.hi / mad.lo so it
-// issues on the FMA pipe (IMAD): the epilogue is bound by the ALU pipe, which the five
-// FMNMX of upd3 already fill.
+// value with its low 8 mantissa bits replaced by `idx` (an IMAD.HI/IMAD version that moves
+// this off the ALU pipe measured slower)
 __device__ __forceinline__ float pack_idx(uint32_t bits, int idx) {
-  uint32_t hi, out;
-  asm("mul.hi.u32 %0, %1, 16777216;" : "=r"(hi) : "r"(bits));          // bits >> 8
-  asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(out) : "r"(hi), "r"((uint32_t)idx));
-  return __uint_as_float(out);
+  return __uint_as_float((bits & 0xFFFFFF00u) | (uint32_t)idx);         // one LOP3
 }
 
 // running top-3 (values carry the centroid index in their low mantissa bits)
@@ -169,8 +165,8 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   float* ex = reinterpret_cast<float*>(misc);                 // [2 parities][3 values][128 rows]
   float* ex_thr = ex + 2 * 3 * TC_BM;                         // [2][128]
   int* ex_cnt = reinterpret_cast<int*>(ex_thr + 2 * TC_BM);   // [2][128][2 halves]
-  int* ex_flag = ex_cnt + 2 * TC_BM * 2;                      // [2] (+2 pad)
-  uint8_t* ex_list = reinterpret_cast<uint8_t*>(ex_flag + 4); // [2][128][2 halves][TC_MAXC]
+  int* ex_flag = ex_cnt + 2 * TC_BM * 2;                      // [2][4 quadrants]
+  uint8_t* ex_list = reinterpret_cast<uint8_t*>(ex_flag + 8); // [2][128][2 halves][TC_MAXC]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ex_list + 2 * TC_BM * 2 * TC_MAXC);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
   const uint32_t bar_full = smem_u32(bars);                   // [8]
@@ -299,8 +295,8 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const float xe = (h == 0 && inb) ? p.xerr[pix] : 0.f;     // issued before the wait, used after the sweep
       float* exv = ex + par * 3 * TC_BM;           // (m, s, t3) of the upper column half
       float* thr_row = ex_thr + par * TC_BM;       // per row: collect every value >= this (or +inf)
-      int* many_flag = ex_flag + par;
-      if (threadIdx.x == 128) *many_flag = 0;      // ordered before this tile's writers by barrier 1
+      int* many_flag = ex_flag + par * 4 + q;       // one flag per 32-row quadrant
+      if (h == 0 && lane == 0) *many_flag = 0;     // ordered before this tile's writers by barrier 1
 
       mbar_wait(bar_tfull + 8 * acc, acc ? acc_phase1 : acc_phase0);
       tc_fence_after();
@@ -330,7 +326,8 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         }
       }
       if (h == 1) { exv[r] = m; exv[TC_BM + r] = s; exv[2 * TC_BM + r] = t3; }
-      asm volatile("bar.sync 1, 256;" ::: "memory");                                   // barrier 1
+      // the two warps that share these 32 rows (column halves) synchronise among themselves only
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");                        // barrier 1
       bool amb = false, many = false;
       int kb = 0, ks = 0;
       if (h == 0) {
@@ -346,7 +343,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         if (many) *many_flag = 1;
         if (inb) p.keys_out[pix] = seg * p.kmax + kb;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");                                   // barrier 2
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");                        // barrier 2
       const bool tile_many = *many_flag != 0;
       if (tile_many) {
         // second sweep (rare after the first iterations): rows flagged `many` list every candidate
@@ -371,7 +368,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
       acc ^= 1;
-      if (tile_many) asm volatile("bar.sync 1, 256;" ::: "memory");                    // barrier 3
+      if (tile_many) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");         // barrier 3
       if (amb) {
         const int slot = atomicAdd(p.fix.count, 1);
         if (slot < p.fix.capacity) {
