@@ -268,6 +268,14 @@ __global__ void __launch_bounds__(NC_THREADS) sgemm_kernel(const float* __restri
   }
 }
 
+// tensor-core forward (nce_tc.cu)
+bool nce_tc_supported(int64_t N, int64_t P, int dim, int n_sets);
+size_t nce_tc_workspace_bytes(int64_t N, int64_t P, int dim, int n_sets);
+int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, int dim, const int64_t* inst,
+               const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus, float conc,
+               float* per_pixel, float* stats, void* workspace, cudaStream_t st);
+int g_debug_flags = 0;   // bit 0: keep the NCE forward on the fp32 CUDA-core kernel (tests)
+
 static int64_t nce_chunk_pixels(int64_t N, int64_t P) {
   // keep the G chunk near 256 MB
   int64_t c = (int64_t)(64ll << 20) / (P > 0 ? P : 1);
@@ -296,15 +304,23 @@ using namespace hsg;
 extern "C" {
 
 size_t hsg_nce_workspace_bytes(int64_t N, int64_t P, int dim, int n_sets) {
-  (void)dim; (void)n_sets;
-  return (size_t)nce_chunk_pixels(N, P) * P * sizeof(float) + 1024;
+  size_t need = (size_t)nce_chunk_pixels(N, P) * P * sizeof(float) + 1024;       // backward: one G chunk
+  if (nce_tc_supported(N, P, dim, n_sets)) {
+    const size_t tc = nce_tc_workspace_bytes(N, P, dim, n_sets);                 // forward: fp16 (hi,lo) copies
+    if (tc > need) need = tc;
+  }
+  return need;
+}
+
+int hsg_debug_set_flags(int flags) {
+  g_debug_flags = flags;
+  return HSG_OK;
 }
 
 int hsg_nce_fwd_f32(const float* e, const float* prototypes, int64_t N, int64_t P, int dim,
                     const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets,
                     const int32_t* group_plus_host, float concentration, float* per_pixel_out,
                     float* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   NceArgs a;
   int rc = fill_args(a, e, prototypes, N, P, dim, inst, sem, psem, n_sets, group_plus_host, concentration);
   if (rc) return rc;
@@ -313,6 +329,10 @@ int hsg_nce_fwd_f32(const float* e, const float* prototypes, int64_t N, int64_t 
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)ceil_div64(N, NC_T);
   ProfRange prof(PROF_NCE_FWD, st);
+  if (!(g_debug_flags & 1) && nce_tc_supported(N, P, dim, n_sets) && workspace &&
+      workspace_bytes >= nce_tc_workspace_bytes(N, P, dim, n_sets))
+    return nce_fwd_tc(e, prototypes, N, P, dim, inst, sem, psem, n_sets, group_plus_host, concentration,
+                      per_pixel_out, stats_out, workspace, st);
   switch (n_sets) {
     case 1: nce_fwd_kernel<1><<<grid, NC_THREADS, 0, st>>>(a, per_pixel_out, stats_out); break;
     case 2: nce_fwd_kernel<2><<<grid, NC_THREADS, 0, st>>>(a, per_pixel_out, stats_out); break;

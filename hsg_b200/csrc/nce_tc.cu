@@ -1,0 +1,355 @@
+// K4 on tensor cores: forward of the pixel-to-prototype NCE loss
+// (_calculate_log_likelihood, hsg/utils/segsort/loss.py:15-82) as a flash-style
+// tcgen05 kernel: S = exp(c E P^T) is produced tile by tile in TMEM and reduced
+// per pixel and per label set in the epilogue; nothing of size [N,P] exists.
+//
+// Precision.  The loss needs fp32-grade similarities (1e-5 relative on the loss
+// => ~1e-6 absolute on <e,p> at concentration 16), which a single fp16/bf16 pass
+// cannot give.  Both operands are split into fp16 (hi, lo) pairs, pre-scaled by
+// 16 so the lo parts stay normal numbers:
+//     <e,p> ~ eh.ph + el.ph + eh.pl      (el.pl ~ 2^-22 is dropped)
+// i.e. three K=D passes accumulated into the same TMEM tile; error ~3*2^-22.
+// Rows are stored as [hi | lo] (2D fp16 per row) so a pixel tile [128 x 2D] stays
+// resident in shared memory for a whole sweep over the prototypes, which stream
+// through a ring of [128 x 64] slabs; each ph slab is used twice (eh and el).
+//
+// Per pixel and label set the epilogue accumulates  pos = sum_{same class} S
+// (own prototype included) and neg = sum_{other class} S, and captures own =
+// S[i, inst_i]; the finish is literally the reference's: num = pos - own if that
+// is > 0 else own, den = neg + num, l = -log(num/den).
+#include "tc_common.cuh"
+
+#include <float.h>
+#include <limits.h>
+
+namespace hsg {
+
+constexpr int NT_BM = 128;                 // pixels per tile
+constexpr int NT_BN = 128;                 // prototypes per accumulator tile
+constexpr int NT_BK = 64;
+constexpr int NT_SLAB = NT_BM * NT_BK * 2; // 16 KiB
+constexpr int NT_THREADS = 384;
+constexpr int NT_ACC = 4;                  // TMEM accumulator buffers (4 x 128 columns)
+constexpr int NT_MAX_SETS = 4;
+
+struct NceTcParams {
+  int64_t N, P;
+  int D;                    // 64, 128 or 256
+  int n_sets;
+  int plus[NT_MAX_SETS];
+  const int32_t* inst;      // [N]
+  const int32_t* sem;       // [n_sets,N]
+  const int32_t* psem;      // [n_sets,Ppad]  (Ppad = P rounded up to 128; padding never read as valid)
+  int64_t Ppad;
+  float scale;              // concentration * log2(e) / 256
+  float* per_pixel;         // [n_sets,N]
+  float* stats;             // [n_sets,N,4] or NULL
+  int nstb;                 // stages of the prototype ring
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2, relative error <= 2^-22
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void nce_split_kernel(const float* __restrict__ x, int64_t rows, int D, __half* __restrict__ out) {
+  // out[r, d] = fp16(16 x), out[r, D + d] = fp16(16 x - hi)
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * D) return;
+  const int64_t r = i / D;
+  const int d = (int)(i % D);
+  const float v = 16.f * x[i];
+  const __half hi = __float2half_rn(v);
+  out[r * 2 * D + d] = hi;
+  out[r * 2 * D + D + d] = __float2half_rn(v - __half2float(hi));
+}
+
+__global__ void nce_labels32_kernel(const int64_t* __restrict__ src, int64_t n_src, int64_t n_dst, int rows,
+                                    int32_t* __restrict__ dst, int32_t pad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_dst * rows) return;
+  const int64_t r = i / n_dst, c = i % n_dst;
+  dst[i] = c < n_src ? (int32_t)src[r * n_src + c] : pad;
+}
+
+__global__ void __launch_bounds__(NT_THREADS, 1)
+nce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const NceTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nslab = p.D / NT_BK;                       // slabs per half (hi or lo)
+  const uint32_t sA = base;                            // [2*nslab] slabs: eh_0.., el_0..
+  const uint32_t sB = sA + 2 * nslab * NT_SLAB;        // ring of nstb slabs
+  const uint32_t sMisc = sB + p.nstb * NT_SLAB;
+  uint8_t* misc = smem_raw + (sMisc - smem_u32(smem_raw));
+  int32_t* psem_s = reinterpret_cast<int32_t*>(misc);                      // [2][NT_MAX_SETS][NT_BN]
+  float* ex = reinterpret_cast<float*>(psem_s + 2 * NT_MAX_SETS * NT_BN);   // [NT_BM][2*NT_MAX_SETS+1]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ex + NT_BM * (2 * NT_MAX_SETS + 1) + 1);
+  bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~uintptr_t(7));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  const uint32_t bar_bfull = smem_u32(bars);            // [8]
+  const uint32_t bar_bempty = bar_bfull + 64;           // [8]
+  const uint32_t bar_afull = bar_bempty + 64;           // [1]
+  const uint32_t bar_aempty = bar_afull + 8;            // [1]
+  const uint32_t bar_tfull = bar_aempty + 8;            // [4]
+  const uint32_t bar_tempty = bar_tfull + 32;           // [4]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.nstb; ++i) { mbar_init(bar_bfull + 8 * i, 1); mbar_init(bar_bempty + 8 * i, 1); }
+    mbar_init(bar_afull, 1);
+    mbar_init(bar_aempty, 1);
+    for (int i = 0; i < NT_ACC; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t n_ptiles = (p.N + NT_BM - 1) / NT_BM;
+  const int n_ntiles = (int)(p.Ppad / NT_BN);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, a_round = 0;
+      for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++a_round) {
+        mbar_wait(bar_aempty, (a_round & 1) ^ 1);               // previous pixel tile fully consumed
+        mbar_expect_tx(bar_afull, 2 * nslab * NT_SLAB);
+        for (int j = 0; j < 2 * nslab; ++j)
+          tma_load_2d(sA + j * NT_SLAB, &tmap_a, j * NT_BK, (int)(pt * NT_BM), bar_afull);
+        for (int nt = 0; nt < n_ntiles; ++nt) {
+          for (int j = 0; j < 2 * nslab; ++j) {                  // ph_0.., then pl_0..
+            mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
+            mbar_expect_tx(bar_bfull + 8 * stage, NT_SLAB);
+            tma_load_2d(sB + stage * NT_SLAB, &tmap_b, j * NT_BK, nt * NT_BN, bar_bfull + 8 * stage);
+            if (++stage == p.nstb) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(NT_BN >> 3) << 17) | ((uint32_t)(NT_BM >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, a_round = 0, acc_round = 0;
+      for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++a_round) {
+        mbar_wait(bar_afull, a_round & 1);
+        tc_fence_after();
+        for (int nt = 0; nt < n_ntiles; ++nt) {
+          mbar_wait(bar_tempty + 8 * acc, ((acc_round >> 0) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * NT_BN;
+          uint32_t first = 1;
+          for (int j = 0; j < 2 * nslab; ++j) {
+            mbar_wait(bar_bfull + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t b0 = sB + stage * NT_SLAB;
+            const int js = j < nslab ? j : j - nslab;             // matching slab of eh
+            const int passes = j < nslab ? 2 : 1;                 // ph: eh.ph and el.ph ; pl: eh.pl
+            for (int ps = 0; ps < passes; ++ps) {
+              const uint32_t a0 = sA + (ps * nslab + js) * NT_SLAB;
+#pragma unroll
+              for (int k4 = 0; k4 < NT_BK / 16; ++k4) {
+                tc_mma_f16(d_tmem, umma_desc(a0 + k4 * 32, 1024, 2), umma_desc(b0 + k4 * 32, 1024, 2), idesc,
+                           first ? 0u : 1u);
+                first = 0;
+              }
+            }
+            tc_commit(bar_bempty + 8 * stage);
+            if (++stage == p.nstb) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(bar_tfull + 8 * acc);
+          if (++acc == NT_ACC) { acc = 0; ++acc_round; }
+        }
+        tc_commit(bar_aempty);                                     // arrives when every MMA of this pixel tile retired
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int et = threadIdx.x - 128;
+    const int q = warp & 3, h = (warp - 4) >> 2;
+    const int r = 32 * q + lane;
+    int acc = 0, par = 0;
+    uint32_t acc_round = 0;
+    for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x) {
+      const int64_t pix = pt * NT_BM + r;
+      const bool inb = pix < p.N;
+      int my_sem[NT_MAX_SETS];
+#pragma unroll
+      for (int s = 0; s < NT_MAX_SETS; ++s) my_sem[s] = (inb && s < p.n_sets) ? p.sem[(int64_t)s * p.N + pix] : INT_MIN;
+      const int my_inst = inb ? p.inst[pix] : -1;
+      float pos[NT_MAX_SETS], neg[NT_MAX_SETS], own = 0.f;
+#pragma unroll
+      for (int s = 0; s < NT_MAX_SETS; ++s) { pos[s] = 0.f; neg[s] = 0.f; }
+
+      for (int nt = 0; nt < n_ntiles; ++nt) {
+        // stage this tile's prototype labels (double buffered; one barrier per tile among the epilogue warps)
+        int32_t* ps_ = psem_s + par * NT_MAX_SETS * NT_BN;
+        for (int idx = et; idx < p.n_sets * NT_BN; idx += 256) {
+          const int s = idx / NT_BN, c = idx % NT_BN;
+          ps_[s * NT_BN + c] = p.psem[(int64_t)s * p.Ppad + (int64_t)nt * NT_BN + c];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int n_valid = (int)min((int64_t)NT_BN, p.P - (int64_t)nt * NT_BN);
+        const int own_rel = my_inst - nt * NT_BN - h * (NT_BN / 2);       // column of the own prototype in my half
+
+        mbar_wait(bar_tfull + 8 * acc, acc_round & 1);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + acc * NT_BN + h * (NT_BN / 2) + ((uint32_t)(32 * q) << 16);
+#pragma unroll 1
+        for (int c = 0; c < NT_BN / 2 / 16; ++c) {
+          uint32_t v[16];
+          tc_ld16(trow + c * 16, v);
+          tc_ld_wait();
+          const int col0 = h * (NT_BN / 2) + c * 16;
+          if (col0 >= n_valid) continue;
+          float sv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sv[j] = ex2_approx(__uint_as_float(v[j]) * p.scale);
+          if (col0 + 16 > n_valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (col0 + j >= n_valid) sv[j] = 0.f;
+          }
+          const int rel = own_rel - c * 16;
+          if ((unsigned)rel < 16u) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (j == rel) own = sv[j];
+          }
+#pragma unroll
+          for (int s = 0; s < NT_MAX_SETS; ++s) {
+            if (s < p.n_sets) {
+              const int32_t* lab = ps_ + s * NT_BN + col0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (lab[j] == my_sem[s]) pos[s] += sv[j]; else neg[s] += sv[j];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        if (++acc == NT_ACC) { acc = 0; ++acc_round; }
+        par ^= 1;
+      }
+
+      // combine the two column halves and finish like the reference
+      float* row = ex + r * (2 * NT_MAX_SETS + 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (h == 1) {
+#pragma unroll
+        for (int s = 0; s < NT_MAX_SETS; ++s) { row[2 * s] = pos[s]; row[2 * s + 1] = neg[s]; }
+        row[2 * NT_MAX_SETS] = own;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (h == 0 && inb) {
+        own += row[2 * NT_MAX_SETS];
+#pragma unroll
+        for (int s = 0; s < NT_MAX_SETS; ++s) {
+          if (s < p.n_sets) {
+            const float pp = pos[s] + row[2 * s], nn = neg[s] + row[2 * s + 1];
+            const bool own_same = my_inst >= 0 && my_inst < p.P && p.psem[(int64_t)s * p.Ppad + my_inst] == my_sem[s];
+            float num = own, flags = own_same ? 2.f : 0.f;
+            if (p.plus[s]) {
+              const float ps2 = __fsub_rn(pp, own);            // loss.py:64-66: sum over the class, then subtract own
+              if (ps2 > 0.f) { num = ps2; flags += 1.f; }
+            }
+            const float den = nn + num;
+            p.per_pixel[(int64_t)s * p.N + pix] = -logf(num / den);
+            if (p.stats) {
+              float* st = p.stats + ((int64_t)s * p.N + pix) * 4;
+              st[0] = num; st[1] = den; st[2] = own; st[3] = flags;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---------------------------------------------------------------- host side
+bool nce_tc_supported(int64_t N, int64_t P, int dim, int n_sets) {
+  return (dim == 64 || dim == 128 || dim == 256) && N >= 1 && P >= 1 && P < (1ll << 31) - 256 && N < (1ll << 31) &&
+         n_sets >= 1 && n_sets <= NT_MAX_SETS;
+}
+
+static int64_t nce_ppad(int64_t P) { return (P + NT_BN - 1) / NT_BN * NT_BN; }
+
+size_t nce_tc_workspace_bytes(int64_t N, int64_t P, int dim, int n_sets) {
+  Carver c(nullptr);
+  c.take<__half>((size_t)N * 2 * dim);
+  c.take<__half>((size_t)nce_ppad(P) * 2 * dim);
+  c.take<int32_t>(N);
+  c.take<int32_t>((size_t)n_sets * N);
+  c.take<int32_t>((size_t)n_sets * nce_ppad(P));
+  return c.used() + 256;
+}
+
+int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, int dim, const int64_t* inst,
+               const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus, float conc,
+               float* per_pixel, float* stats, void* workspace, cudaStream_t st) {
+  const int64_t Ppad = nce_ppad(P);
+  Carver c(workspace);
+  __half* ah = c.take<__half>((size_t)N * 2 * dim);
+  __half* bh = c.take<__half>((size_t)Ppad * 2 * dim);
+  int32_t* inst32 = c.take<int32_t>(N);
+  int32_t* sem32 = c.take<int32_t>((size_t)n_sets * N);
+  int32_t* psem32 = c.take<int32_t>((size_t)n_sets * Ppad);
+
+  HSG_CUDA(cudaMemsetAsync(bh, 0, sizeof(__half) * Ppad * 2 * dim, st));
+  nce_split_kernel<<<(unsigned)ceil_div64(N * dim, 256), 256, 0, st>>>(e, N, dim, ah);
+  HSG_LAUNCH_CHECK();
+  nce_split_kernel<<<(unsigned)ceil_div64(P * dim, 256), 256, 0, st>>>(prototypes, P, dim, bh);
+  HSG_LAUNCH_CHECK();
+  nce_labels32_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(inst, N, N, 1, inst32, -1);
+  HSG_LAUNCH_CHECK();
+  nce_labels32_kernel<<<(unsigned)ceil_div64(N * n_sets, 256), 256, 0, st>>>(sem, N, N, n_sets, sem32, 0);
+  HSG_LAUNCH_CHECK();
+  nce_labels32_kernel<<<(unsigned)ceil_div64(Ppad * n_sets, 256), 256, 0, st>>>(psem, P, Ppad, n_sets, psem32, INT_MIN + 1);
+  HSG_LAUNCH_CHECK();
+
+  NceTcParams p;
+  p.N = N; p.P = P; p.D = dim; p.n_sets = n_sets; p.inst = inst32; p.sem = sem32; p.psem = psem32;
+  p.Ppad = Ppad; p.scale = conc * 1.4426950408889634f / 256.f; p.per_pixel = per_pixel; p.stats = stats;
+  for (int s = 0; s < NT_MAX_SETS; ++s) p.plus[s] = s < n_sets ? plus[s] : 0;
+  const int nslab = dim / NT_BK;
+  const size_t fixed = (size_t)2 * nslab * NT_SLAB + 2 * NT_MAX_SETS * NT_BN * 4 +
+                       (size_t)NT_BM * (2 * NT_MAX_SETS + 1) * 4 + 16 + 34 * 8 + 64;
+  const size_t budget = 227 * 1024 - 1024 - 1024 - fixed;
+  int nstb = (int)(budget / NT_SLAB);
+  if (nstb > 8) nstb = 8;
+  HSG_REQUIRE(nstb >= 2, HSG_E_UNSUPPORTED, "nce: shared memory budget");
+  p.nstb = nstb;
+  const size_t smem = 1024 + fixed + (size_t)nstb * NT_SLAB;
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = encode_2d_f16(&ma, ah, (uint64_t)N, (uint64_t)2 * dim, NT_BK, NT_BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = encode_2d_f16(&mb, bh, (uint64_t)Ppad, (uint64_t)2 * dim, NT_BK, NT_BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  HSG_CUDA(cudaFuncSetAttribute(nce_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t grid = num_sms();
+  const int64_t n_ptiles = ceil_div64(N, NT_BM);
+  if (grid > n_ptiles) grid = n_ptiles;
+  nce_fwd_tc_kernel<<<(unsigned)grid, NT_THREADS, smem, st>>>(ma, mb, p);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+}  // namespace hsg

@@ -265,10 +265,12 @@ class _Nce(torch.autograd.Function):
     out = torch.empty((n_sets, n), dtype=torch.float32, device=dev)
     stats = torch.empty((n_sets, n, 4), dtype=torch.float32, device=dev)
     plus_arr = (ctypes.c_int32 * n_sets)(*[int(v) for v in plus])
+    lib = _lib.load()
+    ws = _workspace(lib.hsg_nce_workspace_bytes(n, p, dim, n_sets), dev)
     with torch.cuda.device(dev):
-      check(_lib.load().hsg_nce_fwd_f32(_ptr(e2), _ptr(p2), n, p, dim, _ptr(inst), _ptr(sem), _ptr(psem),
-                                        n_sets, plus_arr, float(conc), _ptr(out), _ptr(stats), None, 0,
-                                        _stream()), 'nce_fwd')
+      check(lib.hsg_nce_fwd_f32(_ptr(e2), _ptr(p2), n, p, dim, _ptr(inst), _ptr(sem), _ptr(psem),
+                                n_sets, plus_arr, float(conc), _ptr(out), _ptr(stats), _ptr(ws), ws.numel(),
+                                _stream()), 'nce_fwd')
     ctx.save_for_backward(e2, p2, inst, sem, psem, stats)
     ctx.plus = [int(v) for v in plus]
     ctx.conc = float(conc)

@@ -78,6 +78,8 @@ HSG_API int hsg_profile_collect(double* total_ms_host, long long* counts_host, i
 /* test hook: the next tensor-core E-steps also write their screening
  * similarities to sims [N,kmax] (device); NULL switches the dump off. */
 HSG_API int hsg_debug_set_tc_dump(float* sims);
+/* test hook: bit 0 keeps the NCE forward on the fp32 CUDA-core kernel */
+HSG_API int hsg_debug_set_flags(int flags);
 
 /* ---- a1: normalize_embedding  (hsg/utils/general/common.py:101-120) -------
  * y[r,:] = x[r,:] / max(||x[r,:]||_2, 1e-12).  x may alias y. */
@@ -194,6 +196,9 @@ HSG_API int hsg_segment_reduce_bwd_f32(const float* grad_out, const float* out, 
  * sets evaluated in ONE pass over e x prototypes (Hsg.losses calls the loss 3x
  * on the same (e, prototypes), hsg/models/predictions/hsg.py:105,130,149):
  *   sem  [n_sets,N]  psem [n_sets,P]   group_plus[n_sets] (1 = 'segsort+')
+ * The forward runs on tensor cores (fp16 hi/lo split, fp32-grade products) when
+ * dim is 64, 128 or 256 and the workspace of hsg_nce_workspace_bytes() is given;
+ * otherwise on the exact fp32 CUDA-core kernel.
  * per_pixel_out [n_sets,N] = -log(num/den);  stats_out [n_sets,N,4] =
  * (num, den, own, flags) saved for the backward pass (may be NULL).
  * Backward for L = sum_s sum_i w[s,i] * l[s,i]:

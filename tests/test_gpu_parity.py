@@ -398,3 +398,34 @@ def test_segment_by_kmeans_tc_equals_simt(S):
     assert torch.equal(res[3], ids)
   ref = o_ops.segment_by_kmeans(emb, None, (4, 4), iterations=4)
   assert np.mean(n(res[3]) == ref[3]) > 0.99
+
+
+# ---------------------------------------------------------------- tensor-core NCE forward
+@pytest.mark.parametrize('nn,pp,d,conc', [(3000, 300, 64, 16.0), (1500, 1100, 256, 16.0), (700, 37, 128, 10.0)])
+def test_nce_tensor_core_forward(nn, pp, d, conc):
+  """fp16 hi/lo split tcgen05 forward vs the float64 oracle: per-pixel loss within 1e-5
+  relative (plus the reference's own cancellation term), and vs the fp32 CUDA-core kernel."""
+  from hsg_b200 import ops, _lib
+  rng = np.random.RandomState(17)
+  e = o_ops.normalize_embedding(rng.randn(nn, d).astype(np.float32))
+  inst = rng.randint(0, pp, nn).astype(np.int64)
+  protos = o_ops.calculate_prototypes_from_labels(e, inst, pp)
+  psem_a = rng.randint(0, 9, pp).astype(np.int64)
+  psem_b = np.arange(pp).astype(np.int64)              # every prototype its own class -> fallback branch
+  sem_a, sem_b = psem_a[inst], psem_b[inst]
+  sem = torch.stack([t(sem_a), t(sem_b)], 0)
+  psem = torch.stack([t(psem_a), t(psem_b)], 0)
+  tc = n(ops.nce_log_likelihood(t(e), t(inst), sem, t(protos), psem, conc, ['segsort+', 'segsort+']))
+  lib = _lib.load()
+  lib.hsg_debug_set_flags(1)
+  try:
+    simt = n(ops.nce_log_likelihood(t(e), t(inst), sem, t(protos), psem, conc, ['segsort+', 'segsort+']))
+  finally:
+    lib.hsg_debug_set_flags(0)
+  for s, (sm, ps) in enumerate(((sem_a, psem_a), (sem_b, psem_b))):
+    want = o_loss.calculate_log_likelihood(e, sm, inst, protos, ps, conc, dtype=np.float64).reshape(-1)
+    kappa = o_loss.nce_condition(e, sm, inst, protos, ps, conc)
+    tol = 1e-5 * np.abs(want) + 1e-6 * kappa + 1e-6
+    assert np.all(np.abs(tc[s] - want) <= tol), np.abs(tc[s] - want).max()
+    assert np.all(np.abs(simt[s] - want) <= tol)
+    assert abs(tc[s].mean() - want.mean()) <= 1e-5 * abs(want.mean())          # the scalar loss, 1e-5 relative
