@@ -428,4 +428,5 @@ def test_nce_tensor_core_forward(nn, pp, d, conc):
     tol = 1e-5 * np.abs(want) + 1e-6 * kappa + 1e-6
     assert np.all(np.abs(tc[s] - want) <= tol), np.abs(tc[s] - want).max()
     assert np.all(np.abs(simt[s] - want) <= tol)
-    assert abs(tc[s].mean() - want.mean()) <= 1e-5 * abs(want.mean())          # the scalar loss, 1e-5 relative
+    # the scalar loss: 1e-5 relative, plus the mean of the reference's own fp32 cancellation allowance
+    assert abs(tc[s].mean() - want.mean()) <= 1e-5 * abs(want.mean()) + np.mean(1e-6 * kappa)
