@@ -71,3 +71,36 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
   monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
   with pytest.raises(hsg_b200.HsgError):
     _lib.load()
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/hsg'), reason='reference tree only exists in the build container')
+def test_patch_rebinds_the_reference_operators(lib):
+  import sys
+  sys.path.insert(0, '/root/reference')
+  try:
+    import hsg.utils.segsort.common as ref_common
+    import hsg.utils.segsort.loss as ref_loss
+    import hsg.utils.general.common as ref_general
+    import hsg.models.utils as ref_mutils
+    orig = ref_common.segment_by_kmeans
+    hsg_b200.patch()
+    try:
+      import inspect
+      from hsg_b200.utils.segsort import common as ours
+      assert ref_common.segment_by_kmeans is ours.segment_by_kmeans
+      assert ref_loss.SegSortLoss.__module__.startswith('hsg_b200')
+      assert ref_general.normalize_embedding.__module__.startswith('hsg_b200')
+      assert ref_mutils.gather_clustering_and_update_prototypes.__module__.startswith('hsg_b200')
+      # same signatures as the reference operators they replace
+      for name in ('segment_by_kmeans', 'kmeans_with_initial_labels', 'calculate_prototypes_from_labels',
+                   'find_nearest_prototypes', 'prepare_prototype_labels'):
+        ref_sig = inspect.signature(hsg_b200._PATCHED[('hsg.utils.segsort.common', name)])
+        our_sig = inspect.signature(getattr(ours, name))
+        assert list(ref_sig.parameters) == list(our_sig.parameters), name
+        for k, v in ref_sig.parameters.items():
+          assert v.default == our_sig.parameters[k].default or v.default is inspect._empty, (name, k)
+    finally:
+      hsg_b200.unpatch()
+    assert ref_common.segment_by_kmeans is orig
+  finally:
+    sys.path.remove('/root/reference')
