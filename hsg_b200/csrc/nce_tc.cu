@@ -157,12 +157,13 @@ nce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint32_t b0 = sB + stage * NT_SLAB;
             const int js = j < nslab ? j : j - nslab;             // matching slab of eh
             const int passes = j < nslab ? 2 : 1;                 // ph: eh.ph and el.ph ; pl: eh.pl
+            // descriptors differ only in the 14-bit start-address field: build once, then add
+            const uint64_t bd = umma_desc(b0, 1024, 2);
             for (int ps = 0; ps < passes; ++ps) {
-              const uint32_t a0 = sA + (ps * nslab + js) * NT_SLAB;
+              const uint64_t ad = umma_desc(sA + (ps * nslab + js) * NT_SLAB, 1024, 2);
 #pragma unroll
               for (int k4 = 0; k4 < NT_BK / 16; ++k4) {
-                tc_mma_f16(d_tmem, umma_desc(a0 + k4 * 32, 1024, 2), umma_desc(b0 + k4 * 32, 1024, 2), idesc,
-                           first ? 0u : 1u);
+                tc_mma_f16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, first ? 0u : 1u);   // +32 bytes per K=16 step
                 first = 0;
               }
             }

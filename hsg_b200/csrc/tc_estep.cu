@@ -190,11 +190,11 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         for (int j = 0; j < nslab; ++j) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t a0 = sA + stage * TC_STAGE_BYTES, b0 = sB + j * slab_b_bytes;
+          const uint64_t ad = umma_desc(sA + stage * TC_STAGE_BYTES, 1024, 2);
+          const uint64_t bd = umma_desc(sB + j * slab_b_bytes, 1024, 2);
 #pragma unroll
-          for (int k4 = 0; k4 < TC_BK / 16; ++k4)
-            tc_mma_f16(d_tmem, umma_desc(a0 + k4 * 32, 1024, 2), umma_desc(b0 + k4 * 32, 1024, 2), idesc,
-                       (j | k4) ? 1u : 0u);
+          for (int k4 = 0; k4 < TC_BK / 16; ++k4)                       // +32 bytes per K=16 step
+            tc_mma_f16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (j | k4) ? 1u : 0u);
           tc_commit(bar_empty + 8 * stage);
           if (++stage == p.nst) { stage = 0; phase ^= 1; }
         }
