@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Summarise ncu outputs into profiles/ (tracked).  Usage:
+   python tools/ncu_summary.py launches gpurun_out/launches_r1.csv profiles/r1_launches.txt
+   python tools/ncu_summary.py kernel   gpurun_out/prof_x.ncu-rep   profiles/r1_x.txt
+"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    'gpu__time_duration.sum', 'sm__cycles_elapsed.max', 'launch__grid_size', 'launch__block_size',
+    'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic',
+    'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__bytes_read.sum.per_second',
+    'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+    'lts__t_bytes.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_sector_hit_rate.pct',
+    'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+    'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+    'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active',
+    'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+    'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+    'smsp__issue_active.avg.pct_of_peak_sustained_active',
+    'sm__warps_active.avg.pct_of_peak_sustained_active',
+    'smsp__inst_executed.sum',
+]
+
+
+def launches(src, dst):
+  lines = [l for l in open(src) if l.startswith('"')]
+  agg = collections.OrderedDict()
+  for row in csv.DictReader(lines):
+    v = float(row['Metric Value'].replace(',', ''))
+    u = row['Metric Unit']
+    v = v / 1e6 if u in ('nsecond', 'ns') else v / 1e3 if u in ('usecond', 'us') else v
+    agg.setdefault(row['Kernel Name'].split('(')[0][-70:], []).append(v)
+  tot = sum(sum(v) for v in agg.values())
+  with open(dst, 'w') as f:
+    f.write('# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare shares)\n')
+    f.write('# source: %s ; one bench step (python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e)\n' % src)
+    f.write('%-72s %5s %12s %10s %7s\n' % ('kernel', 'n', 'total_ms', 'avg_ms', 'share'))
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+      f.write('%-72s %5d %12.3f %10.4f %7.4f\n' % (k, len(v), sum(v), sum(v) / len(v), sum(v) / tot))
+    f.write('%-72s %5d %12.3f\n' % ('TOTAL', sum(len(v) for v in agg.values()), tot))
+
+
+def kernel(src, dst):
+  out = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], stdout=subprocess.PIPE, text=True).stdout
+  rows = list(csv.reader(io.StringIO(out)))
+  hdr, units = rows[0], rows[1]
+  with open(dst, 'w') as f:
+    f.write('# ncu --set full --clock-control none --import-source on ; source: %s\n' % src)
+    for vals in rows[2:]:
+      name = vals[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else '?'
+      f.write('\n## %s\n' % name)
+      for k in KEYS:
+        if k in hdr:
+          i = hdr.index(k)
+          f.write('%-82s %18s %s\n' % (k, vals[i], units[i]))
+      scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+      tot = 0.0
+      for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+        if k in hdr:
+          tot += float(vals[hdr.index(k)]) * scale.get(units[hdr.index(k)], 1.0)
+      f.write('%-82s %18.4f %s\n' % ('traffic = dram read + write', tot / 1e9, 'Gbyte'))
+
+
+if __name__ == '__main__':
+  {'launches': launches, 'kernel': kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
