@@ -216,6 +216,27 @@ HSG_API int hsg_nce_bwd_f32(const float* e, const float* prototypes, int64_t N, 
                     const float* stats, const float* w, float* grad_e, float* grad_p,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K5: fused attention core of the clustering transformer
+ *      (nn.MultiheadAttention slow path used by hsg/models/heads/transformer.py:235,300,304:
+ *       q/sqrt(hd), baddbmm with the -inf key-padding mask, softmax, dropout, bmm with v)
+ * q [B*heads, L, hd], k/v [B*heads, S, hd] (head index fastest, as torch lays them out),
+ * key_padding_mask [B,S] bytes (1 = ignore) or NULL; scale = 1/sqrt(hd).
+ * out [B*heads, L, hd]; lse [B*heads, L] saved for the backward pass.  dropout_p > 0
+ * drops probabilities with a counter-based generator keyed by `seed` (train-mode
+ * parity with the reference is defined at p = 0).  A row whose keys are all
+ * masked yields NaN, as in the reference. */
+HSG_API size_t hsg_mha_workspace_bytes(int B, int heads, int L, int S);
+HSG_API int hsg_mha_fwd_f32(const float* q, const float* k, const float* v,
+                            const unsigned char* key_padding_mask, int B, int heads, int L, int S,
+                            int hd, float scale, float dropout_p, unsigned long long seed,
+                            float* out, float* lse, void* stream);
+HSG_API int hsg_mha_bwd_f32(const float* q, const float* k, const float* v,
+                            const unsigned char* key_padding_mask, int B, int heads, int L, int S,
+                            int hd, float scale, float dropout_p, unsigned long long seed,
+                            const float* out, const float* lse, const float* dout,
+                            float* dq, float* dk, float* dv,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K2: dense relabel  (segment_by_kmeans tail, common.py:397-405;
  *      prepare_prototype_labels :192-218)
  * ids_out[i] = rank of the triple (batch[i], cluster[i], label[i]) among the

@@ -286,5 +286,48 @@ def main():
        mapping=_np(mapping[0]), **arrays)
 
 
+def transformer_fixture():
+  """a10/a11: TransformerClustering of the reference, small shapes, with its weights,
+  outputs in eval mode and in train mode with dropout 0, and gradients (train mode)."""
+  from hsg.models.embeddings.transformer_clusters import TransformerClustering
+  torch.manual_seed(235)
+  b, c, s, q, k = 3, 32, 24, 6, 4
+  net = TransformerClustering(num_clusters=k, d_model=c, nhead=4, num_encoder_layers=2,
+                              num_decoder_layers=2, dim_feedforward=2 * c, dropout=0.0)
+  # make the BN layers non-trivial
+  for m in net.modules():
+    if isinstance(m, torch.nn.BatchNorm1d):
+      m.running_mean.normal_(0, 0.2)
+      m.running_var.uniform_(0.5, 1.5)
+      m.weight.data.uniform_(0.5, 1.5)
+      m.bias.data.normal_(0, 0.2)
+  src = torch.randn(b, c, s)
+  pos = torch.randn(b, c, s)
+  query = torch.randn(q, c)
+  mask = torch.zeros(b, s, dtype=torch.bool)
+  mask[0, 20:] = True
+  mask[1, 9:] = True
+  arrays = {'w__' + n.replace('.', '__'): _np(p) for n, p in net.state_dict().items()}
+  net.eval()
+  with torch.no_grad():
+    ev = net(src, mask, query, pos)
+  net.train()
+  src_g = src.clone().requires_grad_(True)
+  tr = net(src_g, mask, query, pos)
+  w = [torch.randn_like(t) for t in tr]
+  sum((t * wi).sum() for t, wi in zip(tr, w)).backward()
+  grads = {'g__' + n.replace('.', '__'): _np(p.grad) for n, p in net.named_parameters() if p.grad is not None}
+  save('transformer_clustering', src=_np(src), pos=_np(pos), query=_np(query), mask=_np(mask),
+       cfg=np.asarray([b, c, s, q, k]),
+       **{'eval%d' % i: _np(t) for i, t in enumerate(ev)},
+       **{'train%d' % i: _np(t) for i, t in enumerate(tr)},
+       **{'w%d' % i: _np(t) for i, t in enumerate(w)},
+       dsrc=_np(src_g.grad), **arrays, **grads)
+
+
 if __name__ == '__main__':
-  main()
+  if len(sys.argv) > 1 and sys.argv[1] == 'transformer':
+    transformer_fixture()
+  else:
+    main()
+    transformer_fixture()

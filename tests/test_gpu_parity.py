@@ -430,3 +430,65 @@ def test_nce_tensor_core_forward(nn, pp, d, conc):
     assert np.all(np.abs(simt[s] - want) <= tol)
     # the scalar loss: 1e-5 relative, plus the mean of the reference's own fp32 cancellation allowance
     assert abs(tc[s].mean() - want.mean()) <= 1e-5 * abs(want.mean()) + np.mean(1e-6 * kappa)
+
+
+# ---------------------------------------------------------------- clustering transformer (fused attention)
+def _load_transformer(g):
+  from hsg_b200.models.embeddings.transformer_clusters import TransformerClustering
+  b, c, s, q, k = [int(v) for v in g['cfg']]
+  net = TransformerClustering(num_clusters=k, d_model=c, nhead=4, num_encoder_layers=2,
+                              num_decoder_layers=2, dim_feedforward=2 * c, dropout=0.0)
+  state = {key[3:].replace('__', '.'): torch.from_numpy(val) for key, val in g.items() if key.startswith('w__')}
+  missing = net.load_state_dict(state, strict=True)      # same parameter names as the reference
+  return net.to(dev())
+
+
+def test_transformer_clustering_matches_reference(golden):
+  g = golden('transformer_clustering')
+  net = _load_transformer(g)
+  args = (t(g['src']), t(g['mask']), t(g['query']), t(g['pos']))
+  net.eval()
+  with torch.no_grad():
+    ev = net(*args)
+  for i, out in enumerate(ev):
+    close(n(out), g['eval%d' % i], rtol=1e-4, atol=2e-5)
+  net.train()                                             # dropout 0: train-mode parity is defined
+  src = t(g['src']).requires_grad_(True)
+  tr = net(src, *args[1:])
+  for i, out in enumerate(tr):
+    close(n(out), g['train%d' % i], rtol=1e-4, atol=2e-5)
+  sum((o * t(g['w%d' % i])).sum() for i, o in enumerate(tr)).backward()
+  close(n(src.grad), g['dsrc'], rtol=2e-3, atol=2e-5)
+  for name, p in net.named_parameters():
+    key = 'g__' + name.replace('.', '__')
+    if key in g:
+      ref = g[key]
+      assert np.abs(n(p.grad) - ref).max() <= 2e-3 * np.abs(ref).max() + 2e-5, name
+
+
+def test_fused_attention_core_vs_float64():
+  from hsg_b200.models.heads.transformer import attention_core
+  rng = np.random.RandomState(4)
+  b, h, l, s, hd = 3, 4, 37, 70, 32
+  q = rng.randn(b * h, l, hd).astype(np.float32)
+  k = rng.randn(b * h, s, hd).astype(np.float32)
+  v = rng.randn(b * h, s, hd).astype(np.float32)
+  mask = np.zeros((b, s), bool)
+  mask[1, 50:] = True
+  mask[2, :3] = True
+  w = rng.randn(b * h, l, hd).astype(np.float32)
+  qt, kt, vt = [t(a).requires_grad_(True) for a in (q, k, v)]
+  out = attention_core(qt, kt, vt, t(mask), b, h)
+  (out * t(w)).sum().backward()
+  q64, k64, v64 = [torch.from_numpy(a).double().requires_grad_(True) for a in (q, k, v)]
+  sc = torch.einsum('zld,zsd->zls', q64 / hd ** 0.5, k64)
+  sc = sc.masked_fill(torch.from_numpy(np.repeat(mask, h, axis=0)).unsqueeze(1), float('-inf'))
+  ref = torch.einsum('zls,zsd->zld', torch.softmax(sc, -1), v64)
+  (ref * torch.from_numpy(w).double()).sum().backward()
+  close(n(out), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+  for a, r in ((qt, q64), (kt, k64), (vt, v64)):
+    close(n(a.grad), r.grad.numpy(), rtol=1e-4, atol=1e-5)
+  # dropout: same seed in forward and backward, expectation preserved
+  torch.manual_seed(0)
+  od = attention_core(t(q), t(k), t(v), t(mask), b, h, dropout_p=0.5)
+  assert abs(float(od.mean()) - float(out.mean())) < 0.05 and not torch.equal(od, out)
