@@ -307,7 +307,7 @@ def transformer_fixture():
   mask = torch.zeros(b, s, dtype=torch.bool)
   mask[0, 20:] = True
   mask[1, 9:] = True
-  arrays = {'w__' + n.replace('.', '__'): _np(p) for n, p in net.state_dict().items()}
+  arrays = {'w__' + n.replace('.', '__'): _np(p).copy() for n, p in net.state_dict().items()}   # copy: BN buffers change below
   net.eval()
   with torch.no_grad():
     ev = net(src, mask, query, pos)
