@@ -29,6 +29,17 @@ _TARGETS = {
     'hsg.models.utils': ('hsg_b200.models.utils', [
         'gather_clustering_and_update_prototypes', 'gather_and_update_cluster_mappings',
         'gather_and_reorder_image_indices', 'gather_and_update_datas']),
+    # clustering transformer: same classes / parameter names, fused attention core
+    'hsg.models.heads.transformer': ('hsg_b200.models.heads.transformer', [
+        'Transformer', 'TransformerEncoder', 'TransformerDecoder', 'TransformerEncoderLayer',
+        'TransformerDecoderLayer']),
+    'hsg.models.embeddings.transformer_clusters': ('hsg_b200.models.embeddings.transformer_clusters', [
+        'TransformerClustering', 'Transformer']),
+    # modules that did `from ... import TransformerClustering` hold their own reference to the class
+    'hsg.models.embeddings.resnet_fcn_hsg': ('hsg_b200.models.embeddings.transformer_clusters', [
+        'TransformerClustering']),
+    'hsg.models.embeddings.resnet_fcn_hsg_cs': ('hsg_b200.models.embeddings.transformer_clusters', [
+        'TransformerClustering']),
 }
 
 
@@ -39,7 +50,10 @@ def patch():
   import importlib
   load_library()                       # fail loudly before touching anything
   for ref_name, (our_name, names) in _TARGETS.items():
-    ref = importlib.import_module(ref_name)
+    try:
+      ref = importlib.import_module(ref_name)
+    except ImportError:            # optional reference modules (e.g. the cityscapes model needs extra deps)
+      continue
     ours = importlib.import_module(our_name)
     for n in names:
       if (ref_name, n) not in _PATCHED:

@@ -450,13 +450,15 @@ def test_transformer_clustering_matches_reference(golden):
   net.eval()
   with torch.no_grad():
     ev = net(*args)
+  # a 4-layer fp32 chain on the GPU (cuBLAS GEMMs + our attention) against the reference on the CPU:
+  # agreement to ~1e-4 of the O(1) activations
   for i, out in enumerate(ev):
-    close(n(out), g['eval%d' % i], rtol=1e-4, atol=2e-5)
+    close(n(out), g['eval%d' % i], rtol=5e-4, atol=1e-4)
   net.train()                                             # dropout 0: train-mode parity is defined
   src = t(g['src']).requires_grad_(True)
   tr = net(src, *args[1:])
   for i, out in enumerate(tr):
-    close(n(out), g['train%d' % i], rtol=1e-4, atol=2e-5)
+    close(n(out), g['train%d' % i], rtol=5e-4, atol=1e-4)
   sum((o * t(g['w%d' % i])).sum() for i, o in enumerate(tr)).backward()
   close(n(src.grad), g['dsrc'], rtol=2e-3, atol=2e-5)
   for name, p in net.named_parameters():
@@ -491,4 +493,4 @@ def test_fused_attention_core_vs_float64():
   # dropout: same seed in forward and backward, expectation preserved
   torch.manual_seed(0)
   od = attention_core(t(q), t(k), t(v), t(mask), b, h, dropout_p=0.5)
-  assert abs(float(od.mean()) - float(out.mean())) < 0.05 and not torch.equal(od, out)
+  assert abs(float(od.mean()) - float(out.detach().mean())) < 0.05 and not torch.equal(od, out.detach())
