@@ -117,7 +117,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     for (int i = 0; i < p.nst; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tlfull + 8 * i, 1); mbar_init(bar_tlempty + 8 * i, 1);
-      mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8);
+      mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4);
     }
     mbar_init(bar_bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -211,46 +211,44 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // Two groups of four warps; group g owns TMEM accumulator g, i.e. every second tile of this
+    // CTA.  A thread owns one pixel row and sweeps all its columns, so nothing is exchanged
+    // between warps: no shared memory, no named barriers.
     const int q = warp & 3;                        // TMEM lane quadrant of this warp
-    const int h = (warp - 4) >> 2;                 // column half
+    const int g = (warp - 4) >> 2;                 // accumulator / tile parity of this group
     const int r = 32 * q + lane;                   // accumulator row = pixel within the tile
     const int nchunk = p.kpad >> 4;
-    const int c_begin = h == 0 ? 0 : (nchunk + 1) / 2;
-    const int c_end = h == 0 ? (nchunk + 1) / 2 : nchunk;
-    int cur_seg = -1, acc = 0, par = 0;
-    uint32_t acc_phase0 = 0, acc_phase1 = 0;
+    int cur_seg = -1, seq = 0;
+    uint32_t acc_phase = 0;
     float cerrmax = 0.f;
     for (long long item = i_begin; item < i_end; ++item) {
       int seg, np; int64_t row0;
       if (!item_rows(p, item, count, seg, row0, np)) continue;
+      if (((seq++) & 1) != g) continue;
       if (seg != cur_seg) { cerrmax = p.cerr_max[seg]; cur_seg = seg; }
       const int64_t pix = row0 + r;
       const bool inb = r < np;
-      const float xe = (h == 0 && inb) ? p.xerr[pix] : 0.f;     // issued before the wait, used after the sweep
-      float* exv = ex + par * 3 * TC_BM;           // (m, s, t3) of the upper column half
-      float* thr_row = ex_thr + par * TC_BM;       // per row: collect every value >= this (or +inf)
-      int* many_flag = ex_flag + par * 4 + q;       // one flag per 32-row quadrant
-      if (h == 0 && lane == 0) *many_flag = 0;     // ordered before this tile's writers by barrier 1
+      const float xe = inb ? p.xerr[pix] : 0.f;    // issued before the wait, used after the sweep
 
-      mbar_wait(bar_tfull + 8 * acc, acc ? acc_phase1 : acc_phase0);
+      mbar_wait(bar_tfull + 8 * g, acc_phase);
       tc_fence_after();
       float m = -FLT_MAX, s = -FLT_MAX, t3 = -FLT_MAX;
-      const uint32_t trow = tmem_base + acc * 256 + ((uint32_t)(32 * q) << 16);
+      const uint32_t trow = tmem_base + g * 256 + ((uint32_t)(32 * q) << 16);
       // software pipelined: the TMEM load of chunk c+1 is in flight while chunk c is reduced
       uint32_t va[16], vb[16];
-      if (c_begin < c_end) tc_ld16(trow + c_begin * 16, va);
-      for (int c = c_begin; c < c_end; c += 2) {
+      tc_ld16(trow, va);
+      for (int c = 0; c < nchunk; c += 2) {
         tc_ld_wait();
-        if (c + 1 < c_end) tc_ld16(trow + (c + 1) * 16, vb);
+        if (c + 1 < nchunk) tc_ld16(trow + (c + 1) * 16, vb);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int k = c * 16 + j;
           if (DUMP) { if (inb && k < p.kmax) p.dbg_sims[pix * p.kmax + k] = __uint_as_float(va[j]); }
           upd3(m, s, t3, pack_idx(va[j], 255 - k));
         }
-        if (c + 1 < c_end) {
+        if (c + 1 < nchunk) {
           tc_ld_wait();
-          if (c + 2 < c_end) tc_ld16(trow + (c + 2) * 16, va);
+          if (c + 2 < nchunk) tc_ld16(trow + (c + 2) * 16, va);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int k = (c + 1) * 16 + j;
@@ -259,50 +257,37 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           }
         }
       }
-      if (h == 1) { exv[r] = m; exv[TC_BM + r] = s; exv[2 * TC_BM + r] = t3; }
-      // the two warps that share these 32 rows (column halves) synchronise among themselves only
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");                        // barrier 1
-      bool amb = false, many = false;
-      int kb = 0, ks = 0;
-      if (h == 0) {
-        upd3(m, s, t3, exv[r]);
-        upd3(m, s, t3, exv[TC_BM + r]);
-        upd3(m, s, t3, exv[2 * TC_BM + r]);
-        kb = 255 - (int)(__float_as_uint(m) & 0xFFu);
-        ks = 255 - (int)(__float_as_uint(s) & 0xFFu);
-        const float thr = 2.f * (xe * 1.001f + cerrmax * 1.001f + TC_EPS_CONST);
-        amb = inb && (m - s <= thr);
-        many = amb && (m - t3 <= thr);             // three or more inside the bound
-        thr_row[r] = many ? m - thr : FLT_MAX;
-        if (many) *many_flag = 1;
-        if (inb) p.keys_out[pix] = seg * p.kmax + kb;
-      }
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");                        // barrier 2
-      const bool tile_many = *many_flag != 0;
-      if (tile_many) {
+      const int kb = 255 - (int)(__float_as_uint(m) & 0xFFu);
+      const int ks = 255 - (int)(__float_as_uint(s) & 0xFFu);
+      const float thr = 2.f * (xe * 1.001f + cerrmax * 1.001f + TC_EPS_CONST);
+      const bool amb = inb && (m - s <= thr);
+      const bool many = amb && (m - t3 <= thr);    // three or more inside the bound
+      uint32_t cl0 = 0, cl1 = 0;                   // up to 8 candidate ids, one byte each
+      int cnt = 0;
+      if (__any_sync(FULL, many)) {
         // second sweep (rare after the first iterations): rows flagged `many` list every candidate
-        const float thr_v = thr_row[r];
-        uint8_t* lst = ex_list + (par * TC_BM + r) * 2 * TC_MAXC + h * TC_MAXC;
-        int cnt = 0;
-        for (int c = c_begin; c < c_end; ++c) {
+        const float thr_v = many ? m - thr : FLT_MAX;
+        for (int c = 0; c < nchunk; ++c) {
           uint32_t v[16];
           tc_ld16(trow + c * 16, v);
           tc_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int k = c * 16 + j;
-            const float pv = pack_idx(v[j], 255 - k);
-            if (pv >= thr_v) { if (cnt < TC_MAXC) lst[cnt] = (uint8_t)k; ++cnt; }
+            if (pack_idx(v[j], 255 - k) >= thr_v) {
+              if (cnt < 4) cl0 |= (uint32_t)k << (8 * cnt);
+              else if (cnt < 8) cl1 |= (uint32_t)k << (8 * (cnt - 4));
+              ++cnt;
+            }
           }
         }
-        ex_cnt[(par * TC_BM + r) * 2 + h] = cnt;
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-      if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
-      acc ^= 1;
-      if (tile_many) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");         // barrier 3
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * g);
+      acc_phase ^= 1;
+
+      if (inb) p.keys_out[pix] = seg * p.kmax + kb;
       if (amb) {
         const int slot = atomicAdd(p.fix.count, 1);
         if (slot < p.fix.capacity) {
@@ -310,22 +295,15 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           uint16_t* cd = p.fix.cand + (int64_t)slot * FIX_MAX_CAND;
           if (!many) {                               // everything but the top two is provably out of reach
             cd[0] = (uint16_t)kb; cd[1] = (uint16_t)ks; cd[2] = 0xFFFF;
+          } else if (cnt > FIX_MAX_CAND) {
+            cd[0] = 0xFFFF;                          // too many to list: scan every cluster
+            atomicAdd(p.fix.count + 1, 1);
           } else {
-            const int c0 = ex_cnt[(par * TC_BM + r) * 2], c1 = ex_cnt[(par * TC_BM + r) * 2 + 1];
-            if (c0 > TC_MAXC || c1 > TC_MAXC || c0 + c1 > FIX_MAX_CAND) {
-              cd[0] = 0xFFFF;                        // too many to list: scan every cluster
-              atomicAdd(p.fix.count + 1, 1);
-            } else {
-              const uint8_t* l0 = ex_list + (par * TC_BM + r) * 2 * TC_MAXC;
-              int w = 0;
-              for (int i = 0; i < c0; ++i) cd[w++] = l0[i];
-              for (int i = 0; i < c1; ++i) cd[w++] = l0[TC_MAXC + i];
-              if (w < FIX_MAX_CAND) cd[w] = 0xFFFF;
-            }
+            for (int i = 0; i < cnt; ++i) cd[i] = (uint16_t)(((i < 4 ? cl0 : cl1) >> (8 * (i & 3))) & 0xFFu);
+            if (cnt < FIX_MAX_CAND) cd[cnt] = 0xFFFF;
           }
         }
       }
-      par ^= 1;
     }
   }
 
