@@ -5,9 +5,10 @@
 //
 // Precision.  The loss needs fp32-grade similarities (1e-5 relative on the loss
 // => ~1e-6 absolute on <e,p> at concentration 16), which a single fp16/bf16 pass
-// cannot give.  Both operands are split into fp16 (hi, lo) pairs, pre-scaled by
-// 16 so the lo parts stay normal numbers:
-//     <e,p> ~ eh.ph + el.ph + eh.pl      (el.pl ~ 2^-22 is dropped)
+// cannot give.  Both operands are split into fp16 (hi, lo) pairs after scaling
+// each by t = sqrt(c log2 e) -- the accumulator is then directly the base-2
+// exponent, and the lo parts stay (mostly) normal numbers:
+//     t^2 <e,p> ~ eh.ph + el.ph + eh.pl      (el.pl ~ 2^-22 is dropped)
 // i.e. three K=D passes accumulated into the same TMEM tile; error ~3*2^-22.
 // Rows are stored as [hi | lo] (2D fp16 per row) so a pixel tile [128 x 2D] stays
 // resident in shared memory for a whole sweep over the prototypes, which stream
@@ -25,11 +26,10 @@
 namespace hsg {
 
 constexpr int NT_BM = 128;                 // pixels per tile
-constexpr int NT_BN = 128;                 // prototypes per accumulator tile
+constexpr int NT_BN = 128;                 // prototype rows per slab (one CTA's half of a tile)
 constexpr int NT_BK = 64;
 constexpr int NT_SLAB = NT_BM * NT_BK * 2; // 16 KiB
 constexpr int NT_THREADS = 384;
-constexpr int NT_ACC = 4;                  // TMEM accumulator buffers (4 x 128 columns)
 constexpr int NT_MAX_SETS = 4;
 
 struct NceTcParams {
@@ -41,7 +41,6 @@ struct NceTcParams {
   const int32_t* sem;       // [n_sets,N]
   const int32_t* psem;      // [n_sets,Ppad]  (Ppad = P rounded up to 128; padding never read as valid)
   int64_t Ppad;
-  float scale;              // concentration * log2(e) / 256
   float* per_pixel;         // [n_sets,N]
   float* stats;             // [n_sets,N,4] or NULL
   int nstb;                 // stages of the prototype ring
@@ -53,16 +52,24 @@ __device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2, relative e
   return y;
 }
 
-__global__ void nce_split_kernel(const float* __restrict__ x, int64_t rows, int D, __half* __restrict__ out) {
-  // out[r, d] = fp16(16 x), out[r, D + d] = fp16(16 x - hi)
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) nce_split_kernel(const float* __restrict__ x, int64_t rows, int D, float mul,
+                                                        __half* __restrict__ out) {
+  // out[r, d] = fp16(mul x), out[r, D + d] = fp16(mul x - hi); eight elements per thread (D % 8 == 0)
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= rows * D) return;
   const int64_t r = i / D;
-  const int d = (int)(i % D);
-  const float v = 16.f * x[i];
-  const __half hi = __float2half_rn(v);
-  out[r * 2 * D + d] = hi;
-  out[r * 2 * D + D + d] = __float2half_rn(v - __half2float(hi));
+  const int d = (int)(i - r * D);
+  const float4 a = ld_stream4(x + i), b = ld_stream4(x + i + 4);
+  const float v[8] = {a.x * mul, a.y * mul, a.z * mul, a.w * mul, b.x * mul, b.y * mul, b.z * mul, b.w * mul};
+  __align__(16) __half hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    hi[j] = __float2half_rn(v[j]);
+    lo[j] = __float2half_rn(v[j] - __half2float(hi[j]));
+  }
+  __half* o = out + r * 2 * D + d;
+  *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(o + D) = *reinterpret_cast<const uint4*>(lo);
 }
 
 __global__ void nce_labels32_kernel(const int64_t* __restrict__ src, int64_t n_src, int64_t n_dst, int rows,
@@ -73,9 +80,75 @@ __global__ void nce_labels32_kernel(const int64_t* __restrict__ src, int64_t n_s
   dst[i] = c < n_src ? (int32_t)src[r * n_src + c] : pad;
 }
 
-__global__ void __launch_bounds__(NT_THREADS, 1)
-nce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const NceTcParams p) {
+// One accumulator tile [128 lanes x ncols] of this thread's TMEM row: exp2, label masks, sums.
+// TMEM loads (and, for up to two label sets, the label loads) of chunk c+1 are in flight while
+// chunk c is reduced.
+template <int NS>
+struct EpiChunk {
+  static constexpr int NL = NS <= 2 ? NS : 1;     // labels ride with the chunk only for <= 2 sets (registers)
+  uint32_t v[16];
+  int4 lab[NL][4];
+};
+
+template <int NS>
+__device__ __forceinline__ void epi_labels(int4 (&lab)[4], const int32_t* lab_ptr, int64_t Ppad, int s) {
+  const int4* lp = reinterpret_cast<const int4*>(lab_ptr + (int64_t)s * Ppad);
+#pragma unroll
+  for (int w = 0; w < 4; ++w) lab[w] = __ldg(lp + w);
+}
+
+template <int NS>
+__device__ __forceinline__ void epi_issue(EpiChunk<NS>& ch, uint32_t taddr, const int32_t* lab, int64_t Ppad) {
+  tc_ld16(taddr, ch.v);
+  if constexpr (NS <= 2) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) epi_labels<NS>(ch.lab[s], lab, Ppad, s);
+  }
+}
+
+template <int NS>
+__device__ __forceinline__ void epi_reduce(EpiChunk<NS>& ch, const int32_t* lab_ptr, int64_t Ppad, int col0,
+                                           int n_valid, int own_rel, const int (&my_sem)[NS], float (&pos)[NS], float (&neg)[NS], float& own) {
+  float sv[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) sv[j] = ex2_approx(__uint_as_float(ch.v[j]));
+  if (col0 + 16 > n_valid) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (col0 + j >= n_valid) sv[j] = 0.f;
+  }
+  const int rel = own_rel - col0;
+  if ((unsigned)rel < 16u) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (j == rel) own = sv[j];
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    if constexpr (NS > 2) epi_labels<NS>(ch.lab[0], lab_ptr, Ppad, s);
+    const int4 (&lab)[4] = ch.lab[NS <= 2 ? s : 0];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      if (lab[w].x == my_sem[s]) pos[s] += sv[4 * w + 0]; else neg[s] += sv[4 * w + 0];
+      if (lab[w].y == my_sem[s]) pos[s] += sv[4 * w + 1]; else neg[s] += sv[4 * w + 1];
+      if (lab[w].z == my_sem[s]) pos[s] += sv[4 * w + 2]; else neg[s] += sv[4 * w + 2];
+      if (lab[w].w == my_sem[s]) pos[s] += sv[4 * w + 3]; else neg[s] += sv[4 * w + 3];
+    }
+  }
+}
+
+// Two CTAs of a cluster form one tcgen05 cta_group::2 tile of 256 pixels x 256 prototypes:
+// each CTA keeps its own 128 pixel rows [128 x 2D] resident and streams only ITS half (128
+// rows) of every prototype tile; the tensor cores read the other half from the peer's shared
+// memory, so L2->SM traffic per flop is half that of a 128x128 single-CTA tile (which sat at
+// the chip's ~6300 B/clk L2 budget).  The leader (cluster rank 0) issues every MMA; both CTAs
+// run a TMA producer (crediting the leader's "full" barriers) and an epilogue over their own
+// 128 TMEM lanes.
+constexpr int N2_BN = 256;                  // prototypes per accumulator tile (128 per CTA of the pair)
+constexpr int N2_ACC = 2;                   // TMEM accumulator buffers (2 x 256 columns)
+
+template <int NS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_THREADS, 1)
+nce_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const NceTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int nslab = p.D / NT_BK;                       // slabs per half (hi or lo)
@@ -83,73 +156,81 @@ nce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t sB = sA + 2 * nslab * NT_SLAB;        // ring of nstb slabs
   const uint32_t sMisc = sB + p.nstb * NT_SLAB;
   uint8_t* misc = smem_raw + (sMisc - smem_u32(smem_raw));
-  int32_t* psem_s = reinterpret_cast<int32_t*>(misc);                      // [2][NT_MAX_SETS][NT_BN]
-  float* ex = reinterpret_cast<float*>(psem_s + 2 * NT_MAX_SETS * NT_BN);   // [NT_BM][2*NT_MAX_SETS+1]
+  float* ex = reinterpret_cast<float*>(misc);                               // [NT_BM][2*NT_MAX_SETS+1]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ex + NT_BM * (2 * NT_MAX_SETS + 1) + 1);
   bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~uintptr_t(7));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
-  const uint32_t bar_bfull = smem_u32(bars);            // [8]
+  const uint32_t bar_bfull = smem_u32(bars);            // [8]  (waited on in the leader only)
   const uint32_t bar_bempty = bar_bfull + 64;           // [8]
-  const uint32_t bar_afull = bar_bempty + 64;           // [1]
+  const uint32_t bar_afull = bar_bempty + 64;           // [1]  (leader only)
   const uint32_t bar_aempty = bar_afull + 8;            // [1]
-  const uint32_t bar_tfull = bar_aempty + 8;            // [4]
-  const uint32_t bar_tempty = bar_tfull + 32;           // [4]
+  const uint32_t bar_tfull = bar_aempty + 8;            // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;           // [2]  (leader only; 8 arrivals: 4 warps x 2 CTAs)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nstb; ++i) { mbar_init(bar_bfull + 8 * i, 1); mbar_init(bar_bempty + 8 * i, 1); }
     mbar_init(bar_afull, 1);
     mbar_init(bar_aempty, 1);
-    for (int i = 0; i < NT_ACC; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    for (int i = 0; i < N2_ACC; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                                   // the peer's barriers exist before anything remote touches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int64_t n_ptiles = (p.N + NT_BM - 1) / NT_BM;
-  const int n_ntiles = (int)(p.Ppad / NT_BN);
+  const int64_t n_ptiles = (p.N + 2 * NT_BM - 1) / (2 * NT_BM);     // pair tiles of 256 pixels
+  const int n_ntiles = (int)(p.Ppad / N2_BN);
+  const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
+      const uint32_t l_afull = mapa_cluster(bar_afull, 0);
+      const uint32_t l_bfull = mapa_cluster(bar_bfull, 0);
       int stage = 0;
       uint32_t phase = 0, a_round = 0;
-      for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++a_round) {
+      for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs, ++a_round) {
         mbar_wait(bar_aempty, (a_round & 1) ^ 1);               // previous pixel tile fully consumed
-        mbar_expect_tx(bar_afull, 2 * nslab * NT_SLAB);
+        if (leader) mbar_expect_tx(bar_afull, 2 * 2 * nslab * NT_SLAB);     // both CTAs' rows
+        const int row0 = (int)(pt * 2 * NT_BM + rank * NT_BM);
         for (int j = 0; j < 2 * nslab; ++j)
-          tma_load_2d(sA + j * NT_SLAB, &tmap_a, j * NT_BK, (int)(pt * NT_BM), bar_afull);
+          tma_load_2d_pair(sA + j * NT_SLAB, &tmap_a, j * NT_BK, row0, l_afull);
         for (int nt = 0; nt < n_ntiles; ++nt) {
+          const int prow0 = nt * N2_BN + (int)rank * NT_BN;
           for (int j = 0; j < 2 * nslab; ++j) {                  // ph_0.., then pl_0..
             mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
-            mbar_expect_tx(bar_bfull + 8 * stage, NT_SLAB);
-            tma_load_2d(sB + stage * NT_SLAB, &tmap_b, j * NT_BK, nt * NT_BN, bar_bfull + 8 * stage);
+            if (leader) mbar_expect_tx(bar_bfull + 8 * stage, 2 * NT_SLAB);
+            tma_load_2d_pair(sB + stage * NT_SLAB, &tmap_b, j * NT_BK, prow0, l_bfull + 8 * stage);
             if (++stage == p.nstb) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(NT_BN >> 3) << 17) | ((uint32_t)(NT_BM >> 4) << 24);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, a_round = 0, acc_round = 0;
-      for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x, ++a_round) {
+    // ===================== MMA issuer (leader only) =====================
+    if (lane == 0 && leader) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(N2_BN >> 3) << 17) | ((uint32_t)((2 * NT_BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, a_round = 0, seq = 0;
+      for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs, ++a_round) {
         mbar_wait(bar_afull, a_round & 1);
         tc_fence_after();
-        for (int nt = 0; nt < n_ntiles; ++nt) {
-          mbar_wait(bar_tempty + 8 * acc, ((acc_round >> 0) & 1) ^ 1);
+        for (int nt = 0; nt < n_ntiles; ++nt, ++seq) {
+          const uint32_t acc = seq & 1;
+          mbar_wait(bar_tempty + 8 * acc, ((seq >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * NT_BN;
+          const uint32_t d_tmem = tmem_base + acc * N2_BN;
           uint32_t first = 1;
           for (int j = 0; j < 2 * nslab; ++j) {
             mbar_wait(bar_bfull + 8 * stage, phase);
@@ -163,95 +244,64 @@ nce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               const uint64_t ad = umma_desc(sA + (ps * nslab + js) * NT_SLAB, 1024, 2);
 #pragma unroll
               for (int k4 = 0; k4 < NT_BK / 16; ++k4) {
-                tc_mma_f16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, first ? 0u : 1u);   // +32 bytes per K=16 step
+                tc_mma_f16_pair(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, first ? 0u : 1u);   // +32 bytes per K=16 step
                 first = 0;
               }
             }
-            tc_commit(bar_bempty + 8 * stage);
+            tc_commit_pair(bar_bempty + 8 * stage);
             if (++stage == p.nstb) { stage = 0; phase ^= 1; }
           }
-          tc_commit(bar_tfull + 8 * acc);
-          if (++acc == NT_ACC) { acc = 0; ++acc_round; }
+          tc_commit_pair(bar_tfull + 8 * acc);
         }
-        tc_commit(bar_aempty);                                     // arrives when every MMA of this pixel tile retired
+        tc_commit_pair(bar_aempty);                                // arrives when every MMA of this pixel tile retired
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    // Two groups of four warps; group g takes every second prototype tile (TMEM buffers g and
-    // g+2).  A thread owns one pixel row and all 128 columns of its tiles; the prototype labels are
-    // read straight from global memory (warp-uniform addresses, L1 resident), so there is no
-    // staging and no barrier inside the sweep over the prototypes.
+    // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
+    // Two groups of four warps; group g owns accumulator buffer g, i.e. every second prototype
+    // tile.  A thread owns one pixel row and all 256 columns of its tiles; prototype labels are
+    // read straight from global memory (warp-uniform addresses, L1 resident).
     const int q = warp & 3, g = (warp - 4) >> 2;
     const int r = 32 * q + lane;
-    uint32_t phase_bits = 0;                           // phase of each of this group's two buffers
-    int seq = 0;                                       // running tile count of this CTA
-    for (int64_t pt = blockIdx.x; pt < n_ptiles; pt += gridDim.x) {
-      const int64_t pix = pt * NT_BM + r;
+    const uint32_t l_tempty = mapa_cluster(bar_tempty, 0);
+    uint32_t seq = 0;
+    for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs) {
+      const int64_t pix = pt * 2 * NT_BM + rank * NT_BM + r;
       const bool inb = pix < p.N;
-      int my_sem[NT_MAX_SETS];
+      int my_sem[NS];
 #pragma unroll
-      for (int s = 0; s < NT_MAX_SETS; ++s) my_sem[s] = (inb && s < p.n_sets) ? p.sem[(int64_t)s * p.N + pix] : INT_MIN;
+      for (int s = 0; s < NS; ++s) my_sem[s] = inb ? p.sem[(int64_t)s * p.N + pix] : INT_MIN;
       const int my_inst = inb ? p.inst[pix] : -1;
-      float pos[NT_MAX_SETS], neg[NT_MAX_SETS], own = 0.f;
+      float pos[NS], neg[NS], own = 0.f;
 #pragma unroll
-      for (int s = 0; s < NT_MAX_SETS; ++s) { pos[s] = 0.f; neg[s] = 0.f; }
+      for (int s = 0; s < NS; ++s) { pos[s] = 0.f; neg[s] = 0.f; }
 
       for (int nt = 0; nt < n_ntiles; ++nt, ++seq) {
-        if ((seq & 1) != g) continue;
-        const int acc = seq & (NT_ACC - 1);
-        const int n_valid = (int)min((int64_t)NT_BN, p.P - (int64_t)nt * NT_BN);
-        const int own_rel = my_inst - nt * NT_BN;                        // column of the own prototype in this tile
-        const int32_t* lab_tile = p.psem + (int64_t)nt * NT_BN;
+        if ((int)(seq & 1) != g) continue;
+        const int n_valid = (int)min((int64_t)N2_BN, p.P - (int64_t)nt * N2_BN);
+        const int nchunk = (n_valid + 15) >> 4;
+        const int own_rel = my_inst - nt * N2_BN;                        // column of the own prototype in this tile
+        const int32_t* lab_tile = p.psem + (int64_t)nt * N2_BN;
 
-        mbar_wait(bar_tfull + 8 * acc, (phase_bits >> (acc >> 1)) & 1);
+        mbar_wait(bar_tfull + 8 * g, (seq >> 1) & 1);
         tc_fence_after();
-        const uint32_t trow = tmem_base + acc * NT_BN + ((uint32_t)(32 * q) << 16);
+        const uint32_t trow = tmem_base + g * N2_BN + ((uint32_t)(32 * q) << 16);
+        EpiChunk<NS> ca, cb;
+        epi_issue<NS>(ca, trow, lab_tile, p.Ppad);
 #pragma unroll 1
-        for (int c = 0; c < NT_BN / 16; ++c) {
-          const int col0 = c * 16;
-          if (col0 >= n_valid) break;
-          uint32_t v[16];
-          tc_ld16(trow + col0, v);
-          int4 lab[NT_MAX_SETS][4];
-#pragma unroll
-          for (int s = 0; s < NT_MAX_SETS; ++s) {
-            if (s < p.n_sets) {
-              const int4* lp = reinterpret_cast<const int4*>(lab_tile + (int64_t)s * p.Ppad + col0);
-#pragma unroll
-              for (int w = 0; w < 4; ++w) lab[s][w] = __ldg(lp + w);
-            }
-          }
+        for (int c = 0; c < nchunk; c += 2) {
           tc_ld_wait();
-          float sv[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) sv[j] = ex2_approx(__uint_as_float(v[j]) * p.scale);
-          if (col0 + 16 > n_valid) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (col0 + j >= n_valid) sv[j] = 0.f;
-          }
-          const int rel = own_rel - col0;
-          if ((unsigned)rel < 16u) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (j == rel) own = sv[j];
-          }
-#pragma unroll
-          for (int s = 0; s < NT_MAX_SETS; ++s) {
-            if (s < p.n_sets) {
-#pragma unroll
-              for (int w = 0; w < 4; ++w) {
-                if (lab[s][w].x == my_sem[s]) pos[s] += sv[4 * w + 0]; else neg[s] += sv[4 * w + 0];
-                if (lab[s][w].y == my_sem[s]) pos[s] += sv[4 * w + 1]; else neg[s] += sv[4 * w + 1];
-                if (lab[s][w].z == my_sem[s]) pos[s] += sv[4 * w + 2]; else neg[s] += sv[4 * w + 2];
-                if (lab[s][w].w == my_sem[s]) pos[s] += sv[4 * w + 3]; else neg[s] += sv[4 * w + 3];
-              }
-            }
+          if (c + 1 < nchunk) epi_issue<NS>(cb, trow + (c + 1) * 16, lab_tile + (c + 1) * 16, p.Ppad);
+          epi_reduce<NS>(ca, lab_tile + c * 16, p.Ppad, c * 16, n_valid, own_rel, my_sem, pos, neg, own);
+          if (c + 1 < nchunk) {
+            tc_ld_wait();
+            if (c + 2 < nchunk) epi_issue<NS>(ca, trow + (c + 2) * 16, lab_tile + (c + 2) * 16, p.Ppad);
+            epi_reduce<NS>(cb, lab_tile + (c + 1) * 16, p.Ppad, (c + 1) * 16, n_valid, own_rel, my_sem, pos, neg, own);
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-        phase_bits ^= 1u << (acc >> 1);
+        if (lane == 0) mbar_arrive_cluster(l_tempty + 8 * g);
       }
 
       // combine the two groups' partial sums and finish like the reference
@@ -259,28 +309,26 @@ nce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (g == 1) {
 #pragma unroll
-        for (int s = 0; s < NT_MAX_SETS; ++s) { row[2 * s] = pos[s]; row[2 * s + 1] = neg[s]; }
+        for (int s = 0; s < NS; ++s) { row[2 * s] = pos[s]; row[2 * s + 1] = neg[s]; }
         row[2 * NT_MAX_SETS] = own;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (g == 0 && inb) {
         own += row[2 * NT_MAX_SETS];
 #pragma unroll
-        for (int s = 0; s < NT_MAX_SETS; ++s) {
-          if (s < p.n_sets) {
-            const float pp = pos[s] + row[2 * s], nn = neg[s] + row[2 * s + 1];
-            const bool own_same = my_inst >= 0 && my_inst < p.P && p.psem[(int64_t)s * p.Ppad + my_inst] == my_sem[s];
-            float num = own, flags = own_same ? 2.f : 0.f;
-            if (p.plus[s]) {
-              const float ps2 = __fsub_rn(pp, own);            // loss.py:64-66: sum over the class, then subtract own
-              if (ps2 > 0.f) { num = ps2; flags += 1.f; }
-            }
-            const float den = nn + num;
-            p.per_pixel[(int64_t)s * p.N + pix] = -logf(num / den);
-            if (p.stats) {
-              float* st = p.stats + ((int64_t)s * p.N + pix) * 4;
-              st[0] = num; st[1] = den; st[2] = own; st[3] = flags;
-            }
+        for (int s = 0; s < NS; ++s) {
+          const float pp = pos[s] + row[2 * s], nn = neg[s] + row[2 * s + 1];
+          const bool own_same = my_inst >= 0 && my_inst < p.P && p.psem[(int64_t)s * p.Ppad + my_inst] == my_sem[s];
+          float num = own, flags = own_same ? 2.f : 0.f;
+          if (p.plus[s]) {
+            const float ps2 = __fsub_rn(pp, own);            // loss.py:64-66: sum over the class, then subtract own
+            if (ps2 > 0.f) { num = ps2; flags += 1.f; }
+          }
+          const float den = nn + num;
+          p.per_pixel[(int64_t)s * p.N + pix] = -logf(num / den);
+          if (p.stats) {
+            float* st = p.stats + ((int64_t)s * p.N + pix) * 4;
+            st[0] = num; st[1] = den; st[2] = own; st[3] = flags;
           }
         }
       }
@@ -289,9 +337,10 @@ nce_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                      // neither CTA leaves (or frees TMEM) while the pair still works
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -301,7 +350,7 @@ bool nce_tc_supported(int64_t N, int64_t P, int dim, int n_sets) {
          n_sets >= 1 && n_sets <= NT_MAX_SETS;
 }
 
-static int64_t nce_ppad(int64_t P) { return (P + NT_BN - 1) / NT_BN * NT_BN; }
+static int64_t nce_ppad(int64_t P) { return (P + N2_BN - 1) / N2_BN * N2_BN; }
 
 size_t nce_tc_workspace_bytes(int64_t N, int64_t P, int dim, int n_sets) {
   Carver c(nullptr);
@@ -325,9 +374,10 @@ int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, in
   int32_t* psem32 = c.take<int32_t>((size_t)n_sets * Ppad);
 
   HSG_CUDA(cudaMemsetAsync(bh, 0, sizeof(__half) * Ppad * 2 * dim, st));
-  nce_split_kernel<<<(unsigned)ceil_div64(N * dim, 256), 256, 0, st>>>(e, N, dim, ah);
+  const float t = sqrtf(fabsf(conc) * 1.4426950408889634f);      // both operands scaled by t: accumulator = c log2(e) <e,p>
+  nce_split_kernel<<<(unsigned)ceil_div64(N * dim, 2048), 256, 0, st>>>(e, N, dim, t, ah);
   HSG_LAUNCH_CHECK();
-  nce_split_kernel<<<(unsigned)ceil_div64(P * dim, 256), 256, 0, st>>>(prototypes, P, dim, bh);
+  nce_split_kernel<<<(unsigned)ceil_div64(P * dim, 2048), 256, 0, st>>>(prototypes, P, dim, conc < 0.f ? -t : t, bh);
   HSG_LAUNCH_CHECK();
   nce_labels32_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(inst, N, N, 1, inst32, -1);
   HSG_LAUNCH_CHECK();
@@ -338,10 +388,10 @@ int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, in
 
   NceTcParams p;
   p.N = N; p.P = P; p.D = dim; p.n_sets = n_sets; p.inst = inst32; p.sem = sem32; p.psem = psem32;
-  p.Ppad = Ppad; p.scale = conc * 1.4426950408889634f / 256.f; p.per_pixel = per_pixel; p.stats = stats;
+  p.Ppad = Ppad; p.per_pixel = per_pixel; p.stats = stats;
   for (int s = 0; s < NT_MAX_SETS; ++s) p.plus[s] = s < n_sets ? plus[s] : 0;
   const int nslab = dim / NT_BK;
-  const size_t fixed = (size_t)2 * nslab * NT_SLAB + 2 * NT_MAX_SETS * NT_BN * 4 +
+  const size_t fixed = (size_t)2 * nslab * NT_SLAB +
                        (size_t)NT_BM * (2 * NT_MAX_SETS + 1) * 4 + 16 + 34 * 8 + 64;
   const size_t budget = 227 * 1024 - 1024 - 1024 - fixed;
   int nstb = (int)(budget / NT_SLAB);
@@ -353,11 +403,21 @@ int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, in
   int rc;
   if ((rc = encode_2d_f16(&ma, ah, (uint64_t)N, (uint64_t)2 * dim, NT_BK, NT_BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = encode_2d_f16(&mb, bh, (uint64_t)Ppad, (uint64_t)2 * dim, NT_BK, NT_BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  HSG_CUDA(cudaFuncSetAttribute(nce_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int64_t grid = num_sms();
-  const int64_t n_ptiles = ceil_div64(N, NT_BM);
-  if (grid > n_ptiles) grid = n_ptiles;
-  nce_fwd_tc_kernel<<<(unsigned)grid, NT_THREADS, smem, st>>>(ma, mb, p);
+  int64_t grid = num_sms() & ~1;                  // CTA pairs
+  const int64_t n_pairs = ceil_div64(N, 2 * NT_BM);
+  if (grid > 2 * n_pairs) grid = 2 * n_pairs;
+#define HSG_NCE_LAUNCH(NS)                                                                                   \
+  do {                                                                                                       \
+    HSG_CUDA(cudaFuncSetAttribute(nce_fwd_tc2_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    nce_fwd_tc2_kernel<NS><<<(unsigned)grid, NT_THREADS, smem, st>>>(ma, mb, p);                             \
+  } while (0)
+  switch (n_sets) {
+    case 1: HSG_NCE_LAUNCH(1); break;
+    case 2: HSG_NCE_LAUNCH(2); break;
+    case 3: HSG_NCE_LAUNCH(3); break;
+    default: HSG_NCE_LAUNCH(4); break;
+  }
+#undef HSG_NCE_LAUNCH
   HSG_LAUNCH_CHECK();
   return HSG_OK;
 }
