@@ -24,6 +24,7 @@ HSG_E_COMM = -5
 KMEANS_AUTO = 0
 KMEANS_FORCE_SIMT = 1
 KMEANS_FORCE_TC = 2
+KMEANS_FULL_MSTEP = 4
 
 REDUCE_SUM = 0
 REDUCE_NORMALIZE = 1

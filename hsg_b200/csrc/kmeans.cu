@@ -225,12 +225,36 @@ int estep_fixup(const EStepArgs& a, cudaStream_t st) {
 __global__ void copy_count_kernel(const int32_t* c, int64_t* out) { out[0] = c[0]; out[1] = c[1]; }
 
 // ---------------------------------------------------------------- orchestration
+// Incremental M-step.  After the first iterations only a few per cent of the labels change per
+// iteration (measured on the benchmark's iid data: 78 %, 34 %, 14 %, 9 %, 7 %, ... 2.4 %), so the
+// cluster sums are kept as running float64 sums and updated from the rows that moved
+// (sum[old] -= x, sum[new] += x) instead of re-reading every row.  The moved rows become a list
+// of signed entries that goes through the same deterministic sort + run-sum machinery as a full
+// pass (float64 partials), so results do not depend on scheduling.  Whether an iteration takes the
+// delta or the full pass is decided on the device (entries <= capacity); both are enqueued and
+// the other one returns at once (Gate).
+struct DeltaPlan {
+  SegReducePlan sr;        // entries as the sorted objects; shares perm/hist/bin arrays with the full plan
+  int32_t* flag;           // [2]
+  int32_t* keys_prev;      // [N]
+  int32_t* tile_entries;   // [full tiles bound]
+  int64_t* eoff;           // [S+1]
+  uint32_t* erow;          // [cap]
+  int32_t* ekey;           // [cap]
+  int64_t cap;
+  double* sums;            // [S*kmax*dim] running sums
+  int32_t* members;        // [S*kmax]
+};
+
 struct KmPlan {
   SegReducePlan sr;
   float* centroids;      // [S*kmax*dim]
   FixList fix;
   TcState tc;
+  DeltaPlan d;
 };
+
+constexpr double KM_DELTA_MAX_FRACTION = 0.4;   // of the rows may have moved (2 entries each) for a delta pass
 
 static void km_carve(Carver& c, KmPlan& p, int64_t N, int dim, int S, int kmax, int64_t max_seg_len,
                      int d16) {
@@ -241,6 +265,54 @@ static void km_carve(Carver& c, KmPlan& p, int64_t N, int dim, int S, int kmax, 
   p.fix.pixels = c.take<int32_t>(N);
   p.fix.cand = c.take<uint16_t>(N * FIX_MAX_CAND);
   tc_carve(c, p.tc, S, kmax, d16 > 0 ? d16 : 64);
+  // delta plan: own tiles / keys / float64 pieces, everything else aliases the full plan (only
+  // one of the two passes runs in an iteration)
+  DeltaPlan& d = p.d;
+  d.cap = (int64_t)(2.0 * KM_DELTA_MAX_FRACTION * (double)N);
+  d.sr = p.sr;
+  d.sr.N = d.cap;
+  const int64_t dseg = max_seg_len * 2 < d.cap ? max_seg_len * 2 : d.cap;
+  d.sr.tiles.tile = sr_tile_size(dseg > 0 ? dseg : 1);
+  d.sr.tiles.bound = sr_tiles_bound(d.cap, S, d.sr.tiles.tile);
+  if (d.sr.tiles.bound > p.sr.tiles.bound) d.sr.tiles.bound = p.sr.tiles.bound;   // tile_hist is shared
+  d.sr.tiles.seg = c.take<int32_t>(d.sr.tiles.bound);
+  d.sr.tiles.begin = c.take<int64_t>(d.sr.tiles.bound);
+  d.sr.tiles.end = c.take<int64_t>(d.sr.tiles.bound);
+  d.sr.tiles.seg_first = c.take<int32_t>(S + 1);
+  d.sr.tiles.count = c.take<int32_t>(1);
+  d.flag = c.take<int32_t>(2);
+  d.keys_prev = c.take<int32_t>(N);
+  d.tile_entries = c.take<int32_t>(p.sr.tiles.bound);
+  d.eoff = c.take<int64_t>(S + 1);
+  d.erow = c.take<uint32_t>(d.cap + 2);
+  d.ekey = c.take<int32_t>(d.cap + 2);
+  d.sr.keys = d.ekey;
+  d.sr.pieces = reinterpret_cast<float*>(c.take<double>((ceil_div64(d.cap, SR_RUN) + p.sr.bins + 2) * dim));
+  d.sums = c.take<double>(p.sr.bins * dim);
+  d.members = c.take<int32_t>(p.sr.bins);
+}
+
+// one M-step of the k-means loop: full pass on the first iteration, afterwards delta or full
+// as decided on the device
+static int km_mstep(KmPlan& p, const float* x, const int64_t* seg_offsets, int it, bool incremental,
+                    cudaStream_t st) {
+  int rc;
+  if (it == 0 || !incremental) {
+    if ((rc = sr_sort_and_sum(p.sr, x, seg_offsets, st))) return rc;
+    if ((rc = sr_combine64(p.sr, p.sr.pieces, nullptr, nullptr, p.d.sums, p.d.members, p.centroids, st))) return rc;
+    if (incremental)
+      HSG_CUDA(cudaMemcpyAsync(p.d.keys_prev, p.sr.keys, sizeof(int32_t) * p.sr.N, cudaMemcpyDeviceToDevice, st));
+    return HSG_OK;
+  }
+  DeltaPlan& d = p.d;
+  if ((rc = sr_delta_build(p.sr, seg_offsets, d.keys_prev, d.tile_entries, d.eoff, d.flag, d.cap, d.erow,
+                           d.ekey, st))) return rc;
+  if ((rc = sr_build_tiles(d.sr, d.eoff, st))) return rc;
+  if ((rc = sr_sort_and_sum_gated(p.sr, x, seg_offsets, Gate{d.flag, 0}, nullptr, nullptr, st))) return rc;
+  if ((rc = sr_sort_and_sum_gated(d.sr, x, seg_offsets, Gate{d.flag, 1}, d.eoff, d.erow, st))) return rc;
+  // the two plans share bin_start / bin_count; pieces differ (float vs float64)
+  return sr_combine64(p.sr, p.sr.pieces, reinterpret_cast<const double*>(d.sr.pieces), d.flag, d.sums, d.members,
+                      p.centroids, st);
 }
 
 static int check_common(const float* x, int64_t N, int dim, const int64_t* seg_offsets, int S,
@@ -278,12 +350,12 @@ static int run_estep(EStepArgs& ea, KmPlan& p, bool use_tc, cudaStream_t st) {
 
 static int decide_tc(int flags, int dim, const void* xh, int d16, const float* xerr, int kmax, bool* use_tc) {
   const bool possible = xh && xerr && tc_shape_supported(dim, d16, kmax);
-  if (flags == HSG_KMEANS_FORCE_TC) {
+  if ((flags & 3) == HSG_KMEANS_FORCE_TC) {
     HSG_REQUIRE(possible, HSG_E_UNSUPPORTED,
                 "kmeans: tensor-core E-step needs the fp16 copy, d16 in {64,128,256}, kmax*d16*2 <= 128 KiB "
                 "(got dim=%d d16=%d kmax=%d, xh=%p)", dim, d16, kmax, xh);
     *use_tc = true;
-  } else if (flags == HSG_KMEANS_FORCE_SIMT) {
+  } else if ((flags & 3) == HSG_KMEANS_FORCE_SIMT) {
     *use_tc = false;
   } else {
     *use_tc = possible;
@@ -338,8 +410,7 @@ int hsg_kmeans_f32(const float* x, int64_t N, int dim, const void* xh, int d16, 
   ea.fix = p.fix;
 
   for (int it = 0; it < iterations; ++it) {
-    if ((rc = sr_sort_and_sum(p.sr, x, seg_offsets, st))) return rc;
-    if ((rc = sr_combine(p.sr, p.sr.bins, nullptr, HSG_REDUCE_NORMALIZE, p.centroids, nullptr, nullptr, st))) return rc;
+    if ((rc = km_mstep(p, x, seg_offsets, it, !(flags & HSG_KMEANS_FULL_MSTEP), st))) return rc;
     if ((rc = run_estep(ea, p, use_tc, st))) return rc;
   }
   if ((rc = sr_keys_to_labels(p.sr, p.sr.keys, labels_out, st))) return rc;

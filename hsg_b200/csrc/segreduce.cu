@@ -1,6 +1,8 @@
 // Deterministic segmented row sums (see segreduce.cuh for the scheme).
 #include "segreduce.cuh"
 
+#include <type_traits>
+
 namespace hsg {
 
 // ---------------------------------------------------------------- helpers
@@ -111,10 +113,10 @@ __global__ void keys_to_labels_kernel(Tiles t, const int32_t* __restrict__ keys,
 
 // ---------------------------------------------------------------- hist / scan / scatter
 __global__ void __launch_bounds__(512) hist_kernel(Tiles t, const int32_t* __restrict__ keys, int kmax,
-                                                   uint32_t* __restrict__ tile_hist) {
+                                                   uint32_t* __restrict__ tile_hist, Gate gate) {
   extern __shared__ uint32_t hist[];
   const int ti = blockIdx.x;
-  if (ti >= *t.count) return;
+  if (gate.closed() || ti >= *t.count) return;
   for (int k = threadIdx.x; k < kmax; k += blockDim.x) hist[k] = 0;
   __syncthreads();
   const int seg = t.seg[ti];
@@ -128,9 +130,10 @@ __global__ void __launch_bounds__(512) hist_kernel(Tiles t, const int32_t* __res
 __global__ void __launch_bounds__(1024) scan_kernel(Tiles t, const int64_t* __restrict__ off, int kmax,
                                                     uint32_t* __restrict__ tile_hist,
                                                     int64_t* __restrict__ bin_start,
-                                                    int32_t* __restrict__ bin_count) {
+                                                    int32_t* __restrict__ bin_count, Gate gate) {
   __shared__ int64_t warp_tot[32];
   __shared__ int64_t carry_s;
+  if (gate.closed()) return;
   const int s = blockIdx.x;
   const int t0 = t.seg_first[s], t1 = t.seg_first[s + 1];
   if (threadIdx.x == 0) carry_s = 0;
@@ -162,11 +165,11 @@ template <int SCATTER_WARPS>
 __global__ void __launch_bounds__(SCATTER_WARPS * 32) scatter_kernel(
     Tiles t, const int64_t* __restrict__ off, const int32_t* __restrict__ keys, int kmax,
     const uint32_t* __restrict__ tile_hist, const int64_t* __restrict__ bin_start,
-    uint32_t* __restrict__ perm) {
+    uint32_t* __restrict__ perm, Gate gate) {
   extern __shared__ uint32_t cursors[];          // [SCATTER_WARPS][kmax]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ti = blockIdx.x * SCATTER_WARPS + warp;
-  if (ti >= *t.count) return;                    // only __syncwarp below
+  if (gate.closed() || ti >= *t.count) return;   // only __syncwarp below
   uint32_t* cur = cursors + (size_t)warp * kmax;
   const int seg = t.seg[ti];
   const int64_t so = off[seg];
@@ -195,38 +198,54 @@ __global__ void __launch_bounds__(SCATTER_WARPS * 32) scatter_kernel(
 // ---------------------------------------------------------------- gather-sum
 constexpr int GATHER_WARPS = 8;
 
-template <int NV>
+// DELTA = false: entry j of the key-sorted permutation is row off[s] + perm[j] (key keys[row]).
+// DELTA = true : the sorted objects are the signed entries of a DeltaList (kmeans.cuh): entry
+//                e = eoff[s] + perm[j] adds (+) or removes (-) row off[s] + (erow[e] & 0x7fffffff)
+//                to / from key keys[e]; sums are accumulated and emitted in float64.
+template <int NV, bool DELTA>
 __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_sum_kernel(
     const float* __restrict__ x, int dim, int64_t N, const int64_t* __restrict__ off, int S,
     const int32_t* __restrict__ keys, const uint32_t* __restrict__ perm,
-    float* __restrict__ pieces, int32_t* __restrict__ piece_cnt) {
+    float* __restrict__ pieces, int32_t* __restrict__ piece_cnt, Gate gate,
+    const int64_t* __restrict__ eoff, const uint32_t* __restrict__ erow) {
+  typedef typename std::conditional<DELTA, double, float>::type acc_t;
+  if (gate.closed()) return;
   const int lane = threadIdx.x & 31;
   const int64_t run = (int64_t)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
   const int64_t j0 = run * SR_RUN;
+  if (DELTA) N = eoff[S];
   if (j0 >= N) return;
   const int n = (int)min((int64_t)SR_RUN, N - j0);
 
-  int64_t pix[2];
+  int64_t pix[2];          // DELTA: bit 62 = "remove"
   int key[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int64_t j = j0 + h * 32 + lane;
     pix[h] = 0; key[h] = -1;
     if (j < j0 + n) {
-      const int s = upper_bound_i64(off, S + 1, j) - 1;
-      pix[h] = off[s] + perm[j];
-      key[h] = keys[pix[h]];
+      if (DELTA) {
+        const int s = upper_bound_i64(eoff, S + 1, j) - 1;
+        const int64_t e = eoff[s] + perm[j];
+        const uint32_t r = erow[e];
+        pix[h] = (off[s] + (int64_t)(r & 0x7fffffffu)) | ((int64_t)(r >> 31) << 62);
+        key[h] = keys[e];
+      } else {
+        const int s = upper_bound_i64(off, S + 1, j) - 1;
+        pix[h] = off[s] + perm[j];
+        key[h] = keys[pix[h]];
+      }
     }
   }
 
-  float acc[NV];
+  acc_t acc[NV];
 #pragma unroll
-  for (int m = 0; m < NV; ++m) acc[m] = 0.f;
+  for (int m = 0; m < NV; ++m) acc[m] = 0;
   int cur = -1, cnt = 0;
 
   auto flush = [&]() {
     const int64_t id = run + cur;
-    float* dst = pieces + id * dim;
+    acc_t* dst = reinterpret_cast<acc_t*>(pieces) + id * dim;
 #pragma unroll
     for (int m = 0; m < NV; ++m) {
       const int d = lane + 32 * m;
@@ -239,12 +258,15 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_sum_kernel(
   for (int e0 = 0; e0 < n; e0 += U) {
     float v[U][NV];
     int kk[U];
+    bool neg[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int e = e0 + u;
       const int src = e & 31;
-      const int64_t p = __shfl_sync(FULL, e < 32 ? pix[0] : pix[1], src);
+      int64_t p = __shfl_sync(FULL, e < 32 ? pix[0] : pix[1], src);
       kk[u] = __shfl_sync(FULL, e < 32 ? key[0] : key[1], src);
+      neg[u] = DELTA && ((p >> 62) & 1);
+      p &= ~(1ll << 62);
       if (e < n) {
         const float* row = x + p * dim;
 #pragma unroll
@@ -262,11 +284,17 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_sum_kernel(
           cur = kk[u];
           cnt = 0;
 #pragma unroll
-          for (int m = 0; m < NV; ++m) acc[m] = 0.f;
+          for (int m = 0; m < NV; ++m) acc[m] = 0;
         }
+        if (DELTA) {
 #pragma unroll
-        for (int m = 0; m < NV; ++m) acc[m] += v[u][m];
-        ++cnt;
+          for (int m = 0; m < NV; ++m) acc[m] += (acc_t)(neg[u] ? -v[u][m] : v[u][m]);
+          cnt += neg[u] ? -1 : 1;
+        } else {
+#pragma unroll
+          for (int m = 0; m < NV; ++m) acc[m] += v[u][m];
+          ++cnt;
+        }
       }
     }
   }
@@ -312,6 +340,167 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_kernel(
     const float c = cnt > 0 ? (float)cnt : 1.f;
     for (int d = lane; d < dim; d += 32) o[d] = o[d] / c;
   }
+}
+
+// k-means centroids from running float64 sums (kmeans.cu keeps them across iterations):
+// a full pass SETS sums = sum of the float pieces, a delta pass ADDS the float64 pieces of the
+// signed entries.  Member counts are carried exactly, so a cluster that lost every member is
+// reset to an exact zero sum (the reference's empty cluster: zero centroid).
+__global__ void __launch_bounds__(COMBINE_WARPS * 32) combine64_kernel(
+    int64_t bins, int dim, const int64_t* __restrict__ bin_start, const int32_t* __restrict__ bin_count,
+    const float* __restrict__ pieces, const double* __restrict__ p64, const int32_t* __restrict__ piece_cnt,
+    const int32_t* __restrict__ delta_flag, double* __restrict__ sums, int32_t* __restrict__ members,
+    float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t key = (int64_t)blockIdx.x * COMBINE_WARPS + (threadIdx.x >> 5);
+  if (key >= bins) return;
+  const bool delta = delta_flag && *delta_flag == 1;
+  const int cnt = bin_count[key];
+  const int64_t start = bin_start[key];
+  const int64_t r0 = start / SR_RUN, r1 = cnt > 0 ? (start + cnt - 1) / SR_RUN : r0 - 1;
+  int mem = cnt;
+  if (delta) {
+    mem = members[key];
+    for (int64_t r = r0; r <= r1; ++r) mem += piece_cnt[r + key];
+  }
+  if (lane == 0) members[key] = mem;
+  double* sk = sums + key * dim;
+  float* o = out + key * dim;
+  float ss = 0.f;
+  for (int d = lane; d < dim; d += 32) {
+    double a = delta ? sk[d] : 0.0;
+    if (delta) {
+      for (int64_t r = r0; r <= r1; ++r) a += p64[(r + key) * dim + d];
+    } else {
+      for (int64_t r = r0; r <= r1; ++r) a += (double)pieces[(r + key) * dim + d];
+    }
+    if (mem == 0) a = 0.0;
+    sk[d] = a;
+    const float f = (float)a;
+    o[d] = f;
+    ss = fmaf(f, f, ss);
+  }
+  const float n = safe_norm(warp_sum(ss));
+  for (int d = lane; d < dim; d += 32) o[d] = o[d] / n;
+}
+
+// ---------------------------------------------------------------- delta list (incremental k-means M-step)
+// Rows whose key changed since the previous M-step, as signed entries in row order:
+// (row, old key, remove) then (row, new key, add).  Built without host synchronisation;
+// flag[0] says whether the list fits the capacity (delta pass) or the full pass has to run.
+__global__ void __launch_bounds__(256) delta_count_kernel(Tiles t, const int32_t* __restrict__ keys,
+                                                          const int32_t* __restrict__ prev,
+                                                          int32_t* __restrict__ tile_entries) {
+  __shared__ int wsum[8];
+  const int ti = blockIdx.x;
+  if (ti >= *t.count) return;
+  const int64_t b = t.begin[ti], e = t.end[ti];
+  int c = 0;
+  for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) c += keys[i] != prev[i];
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) tot += wsum[w];
+    tile_entries[ti] = 2 * tot;
+  }
+}
+
+__global__ void __launch_bounds__(1024) delta_scan_kernel(Tiles t, int S, int32_t* __restrict__ tile_entries,
+                                                          int64_t* __restrict__ eoff, int32_t* __restrict__ flag,
+                                                          int64_t cap) {
+  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t carry_s;
+  const int nt = *t.count;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nt; base += 1024) {
+    const int ti = base + threadIdx.x;
+    const int64_t v = ti < nt ? tile_entries[ti] : 0;
+    int64_t total;
+    const int64_t before = carry_s + block_scan_excl_1024(v, warp_tot, &total);
+    if (ti < nt) tile_entries[ti] = (int32_t)min(before, (int64_t)0x7fffffff);
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s += total;
+    __syncthreads();
+  }
+  const int64_t M = carry_s;
+  for (int s = threadIdx.x; s <= S; s += blockDim.x) {
+    const int first = t.seg_first[s];
+    eoff[s] = (s == S || first >= nt) ? M : (int64_t)tile_entries[first];
+  }
+  if (threadIdx.x == 0) {
+    flag[0] = M <= cap ? 1 : 0;
+    flag[1] = (int32_t)min(M / 2, (int64_t)0x7fffffff);
+  }
+}
+
+__global__ void __launch_bounds__(256) delta_compact_kernel(Tiles t, const int64_t* __restrict__ off,
+                                                            const int32_t* __restrict__ keys,
+                                                            int32_t* __restrict__ prev,
+                                                            const int32_t* __restrict__ tile_entries,
+                                                            const int32_t* __restrict__ flag,
+                                                            uint32_t* __restrict__ erow, int32_t* __restrict__ ekey) {
+  __shared__ int wsum[8];
+  __shared__ int carry_s;
+  const int ti = blockIdx.x;
+  if (ti >= *t.count) return;
+  const bool emit = flag[0] == 1;
+  const int64_t b = t.begin[ti], e = t.end[ti];
+  const int64_t so = off[t.seg[ti]];
+  const int64_t base = tile_entries[ti];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t c0 = b; c0 < e; c0 += 256 * 8) {
+    const int64_t i0 = c0 + (int64_t)threadIdx.x * 8;
+    int kn[8], ko[8];
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t i = i0 + k;
+      kn[k] = ko[k] = 0;
+      if (i < e) { kn[k] = keys[i]; ko[k] = prev[i]; }
+      c += kn[k] != ko[k];
+    }
+    const int incl = warp_scan_incl(c, lane);
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int before = carry_s + incl - c;
+    for (int w = 0; w < warp; ++w) before += wsum[w];
+    int64_t pos = base + 2 * (int64_t)before;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (kn[k] != ko[k]) {
+        const int64_t i = i0 + k;
+        if (emit) {
+          const uint32_t r = (uint32_t)(i - so);
+          erow[pos] = r | 0x80000000u; ekey[pos] = ko[k];
+          erow[pos + 1] = r;           ekey[pos + 1] = kn[k];
+          pos += 2;
+        }
+        prev[i] = kn[k];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) carry_s = before + c;
+    __syncthreads();
+  }
+}
+
+int sr_delta_build(const SegReducePlan& p, const int64_t* seg_offsets, int32_t* keys_prev,
+                   int32_t* tile_entries, int64_t* eoff, int32_t* flag, int64_t cap, uint32_t* erow,
+                   int32_t* ekey, cudaStream_t st) {
+  ProfRange prof(PROF_MSTEP_SORT, st);
+  delta_count_kernel<<<(unsigned)p.tiles.bound, 256, 0, st>>>(p.tiles, p.keys, keys_prev, tile_entries);
+  HSG_LAUNCH_CHECK();
+  delta_scan_kernel<<<1, 1024, 0, st>>>(p.tiles, p.S, tile_entries, eoff, flag, cap);
+  HSG_LAUNCH_CHECK();
+  delta_compact_kernel<<<(unsigned)p.tiles.bound, 256, 0, st>>>(p.tiles, seg_offsets, p.keys, keys_prev,
+                                                                tile_entries, flag, erow, ekey);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
 }
 
 // ---------------------------------------------------------------- host side
@@ -375,53 +564,74 @@ int sr_keys_to_labels(const SegReducePlan& p, const int32_t* keys, int64_t* labe
   return HSG_OK;
 }
 
-template <int NV>
-static int launch_gather(const SegReducePlan& p, const float* x, const int64_t* off, cudaStream_t st) {
+template <int NV, bool DELTA>
+static int launch_gather(const SegReducePlan& p, const float* x, const int64_t* off, Gate gate,
+                         const int64_t* eoff, const uint32_t* erow, cudaStream_t st) {
   const int64_t runs = ceil_div64(p.N, SR_RUN);
-  gather_sum_kernel<NV><<<(unsigned)ceil_div64(runs, GATHER_WARPS), GATHER_WARPS * 32, 0, st>>>(
-      x, p.dim, p.N, off, p.S, p.keys, p.perm, p.pieces, p.piece_cnt);
+  gather_sum_kernel<NV, DELTA><<<(unsigned)ceil_div64(runs, GATHER_WARPS), GATHER_WARPS * 32, 0, st>>>(
+      x, p.dim, p.N, off, p.S, p.keys, p.perm, p.pieces, p.piece_cnt, gate, eoff, erow);
   HSG_LAUNCH_CHECK();
   return HSG_OK;
 }
 
-int sr_sort_and_sum(const SegReducePlan& p, const float* x, const int64_t* off, cudaStream_t st) {
+template <bool DELTA>
+static int gather_dispatch(const SegReducePlan& p, const float* x, const int64_t* off, Gate gate,
+                           const int64_t* eoff, const uint32_t* erow, cudaStream_t st) {
+  const int nv = (p.dim + 31) / 32;
+  if (nv <= 1) return launch_gather<1, DELTA>(p, x, off, gate, eoff, erow, st);
+  if (nv <= 2) return launch_gather<2, DELTA>(p, x, off, gate, eoff, erow, st);
+  if (nv <= 3) return launch_gather<3, DELTA>(p, x, off, gate, eoff, erow, st);
+  if (nv <= 5) return launch_gather<5, DELTA>(p, x, off, gate, eoff, erow, st);
+  if (nv <= 9) return launch_gather<9, DELTA>(p, x, off, gate, eoff, erow, st);
+  if (nv <= 12) return launch_gather<12, DELTA>(p, x, off, gate, eoff, erow, st);
+  if (nv <= 17) return launch_gather<17, DELTA>(p, x, off, gate, eoff, erow, st);
+  return launch_gather<20, DELTA>(p, x, off, gate, eoff, erow, st);
+}
+
+int sr_sort_and_sum_gated(const SegReducePlan& p, const float* x, const int64_t* off, Gate gate,
+                          const int64_t* eoff, const uint32_t* erow, cudaStream_t st) {
   HSG_REQUIRE(p.kmax <= SR_MAX_KEYS, HSG_E_UNSUPPORTED, "segment reduce: %d keys per segment (max %d)", p.kmax, SR_MAX_KEYS);
   HSG_REQUIRE(p.dim <= 32 * 20, HSG_E_UNSUPPORTED, "segment reduce: dim %d (max 640)", p.dim);
-  int rc;
+  const int64_t* sort_off = eoff ? eoff : off;       // the objects being sorted: delta entries or rows
   {
   ProfRange prof(PROF_MSTEP_SORT, st);
   const size_t hist_smem = (size_t)p.kmax * sizeof(uint32_t);
   if (hist_smem > 48 * 1024)
     HSG_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-  hist_kernel<<<(unsigned)p.tiles.bound, 512, hist_smem, st>>>(p.tiles, p.keys, p.kmax, p.tile_hist);
+  hist_kernel<<<(unsigned)p.tiles.bound, 512, hist_smem, st>>>(p.tiles, p.keys, p.kmax, p.tile_hist, gate);
   HSG_LAUNCH_CHECK();
-  scan_kernel<<<p.S, 1024, 0, st>>>(p.tiles, off, p.kmax, p.tile_hist, p.bin_start, p.bin_count);
+  scan_kernel<<<p.S, 1024, 0, st>>>(p.tiles, sort_off, p.kmax, p.tile_hist, p.bin_start, p.bin_count, gate);
   HSG_LAUNCH_CHECK();
   if (p.kmax <= 8192) {
     const size_t sc_smem = (size_t)4 * p.kmax * sizeof(uint32_t);
     if (sc_smem > 48 * 1024)
       HSG_CUDA(cudaFuncSetAttribute(scatter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
     scatter_kernel<4><<<(unsigned)ceil_div64(p.tiles.bound, 4), 128, sc_smem, st>>>(
-        p.tiles, off, p.keys, p.kmax, p.tile_hist, p.bin_start, p.perm);
+        p.tiles, sort_off, p.keys, p.kmax, p.tile_hist, p.bin_start, p.perm, gate);
   } else {
     const size_t sc_smem = (size_t)p.kmax * sizeof(uint32_t);
     HSG_CUDA(cudaFuncSetAttribute(scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
     scatter_kernel<1><<<(unsigned)p.tiles.bound, 32, sc_smem, st>>>(
-        p.tiles, off, p.keys, p.kmax, p.tile_hist, p.bin_start, p.perm);
+        p.tiles, sort_off, p.keys, p.kmax, p.tile_hist, p.bin_start, p.perm, gate);
   }
   HSG_LAUNCH_CHECK();
   }
   ProfRange prof(PROF_MSTEP_GATHER, st);
-  const int nv = (p.dim + 31) / 32;
-  if (nv <= 1) rc = launch_gather<1>(p, x, off, st);
-  else if (nv <= 2) rc = launch_gather<2>(p, x, off, st);
-  else if (nv <= 3) rc = launch_gather<3>(p, x, off, st);
-  else if (nv <= 5) rc = launch_gather<5>(p, x, off, st);
-  else if (nv <= 9) rc = launch_gather<9>(p, x, off, st);
-  else if (nv <= 12) rc = launch_gather<12>(p, x, off, st);
-  else if (nv <= 17) rc = launch_gather<17>(p, x, off, st);
-  else rc = launch_gather<20>(p, x, off, st);
-  return rc;
+  return eoff ? gather_dispatch<true>(p, x, off, gate, eoff, erow, st)
+              : gather_dispatch<false>(p, x, off, gate, nullptr, nullptr, st);
+}
+
+int sr_sort_and_sum(const SegReducePlan& p, const float* x, const int64_t* off, cudaStream_t st) {
+  return sr_sort_and_sum_gated(p, x, off, Gate{nullptr, 0}, nullptr, nullptr, st);
+}
+
+int sr_combine64(const SegReducePlan& p, const float* pieces_full, const double* pieces_delta,
+                 const int32_t* delta_flag, double* sums, int32_t* members, float* out, cudaStream_t st) {
+  ProfRange prof(PROF_MSTEP_COMBINE, st);
+  combine64_kernel<<<(unsigned)ceil_div64(p.bins, COMBINE_WARPS), COMBINE_WARPS * 32, 0, st>>>(
+      p.bins, p.dim, p.bin_start, p.bin_count, pieces_full, pieces_delta, p.piece_cnt, delta_flag, sums, members, out);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
 }
 
 int sr_combine(const SegReducePlan& p, int64_t P, const int64_t* seg_base, int mode, float* out,

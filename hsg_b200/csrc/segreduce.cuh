@@ -56,6 +56,17 @@ struct SegReducePlan {
   int32_t* piece_cnt;    // [N/SR_RUN + bins + 2]
 };
 
+// Device-side switch: a gated kernel returns at once unless *flag == want (flag NULL = open).
+// Lets a stream carry both variants of a step and pick one from a value computed on the
+// device, with no host synchronisation.
+struct Gate {
+  const int32_t* flag;
+  int want;
+#ifdef __CUDACC__
+  __device__ __forceinline__ bool closed() const { return flag && *flag != want; }
+#endif
+};
+
 int64_t sr_tile_size(int64_t max_seg_len);
 int64_t sr_tiles_bound(int64_t N, int S, int64_t tile);
 size_t sr_workspace_bytes(int64_t N, int dim, int S, int kmax, int64_t max_seg_len);
@@ -71,6 +82,21 @@ int sr_keys_to_labels(const SegReducePlan& p, const int32_t* keys, int64_t* labe
 // hist + scan + scatter + gather: after this, pieces/bin_start/bin_count describe the sums
 int sr_sort_and_sum(const SegReducePlan& p, const float* x, const int64_t* seg_offsets,
                     cudaStream_t st);
+// the same behind a gate; with eoff/erow (kmeans.cuh: DeltaList) the sorted objects are signed
+// delta entries (p.keys = entry keys, p.N = entry capacity, p.tiles built from eoff) and the
+// pieces are float64
+int sr_sort_and_sum_gated(const SegReducePlan& p, const float* x, const int64_t* seg_offsets, Gate gate,
+                          const int64_t* eoff, const uint32_t* erow, cudaStream_t st);
+// k-means finish on running float64 sums: *delta_flag == 1 adds the (float64) pieces of a delta
+// pass, otherwise the sums are set from the float pieces of a full pass; out = normalised rows
+int sr_combine64(const SegReducePlan& p, const float* pieces_full, const double* pieces_delta,
+                 const int32_t* delta_flag, double* sums, int32_t* members, float* out, cudaStream_t st);
+// rows of p whose key differs from keys_prev -> signed entries (erow/ekey, per-segment offsets
+// eoff[S+1]); flag[0] = 1 when they fit `cap` entries (else 0: take the full pass), flag[1] =
+// changed rows; keys_prev is brought up to date either way
+int sr_delta_build(const SegReducePlan& p, const int64_t* seg_offsets, int32_t* keys_prev,
+                   int32_t* tile_entries, int64_t* eoff, int32_t* flag, int64_t cap, uint32_t* erow,
+                   int32_t* ekey, cudaStream_t st);
 // out[r,:] for r in [0,P): row r = key (seg_base == NULL) or the label whose
 // key it is; mode as in hsg_b200.h.  sums_out / counts_out optional.
 int sr_combine(const SegReducePlan& p, int64_t P, const int64_t* seg_base, int mode, float* out,

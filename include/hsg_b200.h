@@ -49,6 +49,7 @@ extern "C" {
 #define HSG_KMEANS_AUTO 0        /* tensor-core E-step when the shape allows it */
 #define HSG_KMEANS_FORCE_SIMT 1  /* fp32 CUDA-core E-step (any shape) */
 #define HSG_KMEANS_FORCE_TC 2    /* fail with HSG_E_UNSUPPORTED instead of falling back */
+#define HSG_KMEANS_FULL_MSTEP 4  /* OR-able: re-sum every row in every M-step (no incremental update) */
 
 /* fp16 side copy of the pixel rows used by the tensor-core E-step: each row has
  * d16 + HSG_XH_TAIL fp16 columns (the tail carries the split trailing features,

@@ -307,6 +307,47 @@ def test_kmeans_moderate_segments_property(S):
             rtol=1e-5, atol=1e-6)
 
 
+def test_kmeans_incremental_mstep_matches_full_resum(S):
+  """From the second iteration on the M-step updates running float64 sums from the rows
+  that changed cluster (delta pass, chosen on the device) instead of re-summing every
+  row.  Same labels as the full re-sum except on float64 near-ties, centroids equal to
+  the oracle's mean direction of the final members, an emptied cluster goes back to an
+  exact zero centroid, and the result is bit-reproducible."""
+  from hsg_b200 import ops, _lib
+  rng = np.random.RandomState(5)
+  lens = [30000, 1, 0, 21111, 4097]
+  d, k = 66, 24
+  centres = o_ops.normalize_embedding(rng.randn(6, d).astype(np.float32))
+  x = centres[rng.randint(0, 6, sum(lens))] + 0.35 * rng.randn(sum(lens), d).astype(np.float32)
+  x = o_ops.normalize_embedding(x)
+  off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+  init = np.concatenate([rng.randint(0, k, l) for l in lens]).astype(np.int64)
+  kw = dict(seg_offsets=t(off), max_seg_len=max(lens), return_centroids=True)
+  for iters in (2, 9):
+    lab_i, cen_i = ops.kmeans(t(x), t(init), k, iters, **kw)
+    lab_j, cen_j = ops.kmeans(t(x), t(init), k, iters, **kw)
+    assert torch.equal(lab_i, lab_j) and torch.equal(cen_i, cen_j)          # reproducible
+    lab_f, cen_f = ops.kmeans(t(x), t(init), k, iters, flags=_lib.KMEANS_FULL_MSTEP, **kw)
+    assert np.mean(n(lab_i) == n(lab_f)) > 0.9995
+    close(n(cen_i), n(cen_f), rtol=2e-5, atol=2e-6)
+  # centroids of the last M-step = mean direction of the labels that entered it; replay it:
+  lab8 = ops.kmeans(t(x), t(init), k, 8, seg_offsets=t(off), max_seg_len=max(lens))
+  want = n(ops.kmeans_mstep(t(x), lab8, k, seg_offsets=t(off), max_seg_len=max(lens)))
+  lab8b, cen9 = ops.kmeans(t(x), lab8, k, 1, **kw)
+  close(n(cen9), want, rtol=1e-6, atol=1e-7)
+  lab9, cen_i = ops.kmeans(t(x), t(init), k, 9, **kw)
+  for s, l in enumerate(lens):
+    if l:
+      sl = slice(off[s], off[s + 1])
+      ref = o_ops.calculate_prototypes_from_labels(x[sl], n(lab8)[sl], k)
+      close(n(cen_i)[s], ref, rtol=1e-5, atol=1e-6)
+      empty = np.bincount(n(lab8)[sl], minlength=k) == 0
+      assert np.all(n(cen_i)[s][empty] == 0)
+      best, _, gap = o_ops.argmax_margins(x[sl], n(cen_i)[s])
+      sel = gap > 1e-12
+      assert np.array_equal(n(lab9)[sl][sel], best[sel])
+
+
 # ---------------------------------------------------------------- tensor-core (tcgen05) E-step
 def _tc_case(nn, d16, loc, k, lens=None, seed=11):
   rng = np.random.RandomState(seed)
