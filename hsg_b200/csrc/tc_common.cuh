@@ -28,12 +28,23 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug must trap (launch failure), never hang the GPU
+// Failed probes suspend the thread in hardware (up to the hint, in ns) instead of spinning through
+// the issue slots the epilogue warps need.  Bounded: a protocol bug must trap (launch failure),
+// never hang the GPU.
+__device__ __forceinline__ bool mbar_try_suspend(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+  uint32_t spins = 0;
+  while (!mbar_try_suspend(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {

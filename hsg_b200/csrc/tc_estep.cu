@@ -30,12 +30,11 @@ namespace hsg {
 constexpr int TC_BM = 128;              // pixels per tile (UMMA M)
 constexpr int TC_BK = 64;               // fp16 per slab row (128 bytes, one swizzle atom)
 constexpr int TC_STAGE_BYTES = TC_BM * TC_BK * 2;
-constexpr int TC_THREADS = 384;         // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
-constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_THREADS = 640;         // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-19 epilogue
 constexpr int TC_TAIL_BYTES = TC_BM * HSG_XH_TAIL * 2;   // 16-column tail slab of a pixel tile
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_MAXC = 8;                                // candidates a row may list per column half
-constexpr int TC_EX_BYTES = 2 * 3 * TC_BM * 4 + 2 * TC_BM * 4 + 2 * TC_BM * 2 * 4 + 32 + 2 * TC_BM * 2 * TC_MAXC;
+constexpr int TC_EX_BYTES = 2 * 3 * TC_BM * 4 + 2 * TC_BM * 4 + 2 * TC_BM * 2 * 4 + 64 + 2 * TC_BM * 2 * TC_MAXC;
 constexpr float TC_EPS_CONST = 7.1e-5f; // accumulation (3e-5) + index packing (2^-15 * 1.2) + split tail (1e-6)
 
 struct TcParams {
@@ -96,11 +95,11 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const uint32_t sA = sAT + 2 * TC_TAIL_BYTES;                // pixel main slabs, nst stages
   const uint32_t sMisc = sA + p.nst * TC_STAGE_BYTES;
   uint8_t* misc = smem_raw + (sMisc - smem_u32(smem_raw));
-  float* ex = reinterpret_cast<float*>(misc);                 // [2 parities][3 values][128 rows]
+  float* ex = reinterpret_cast<float*>(misc);                 // [2 accumulators][3 values][128 rows]
   float* ex_thr = ex + 2 * 3 * TC_BM;                         // [2][128]
   int* ex_cnt = reinterpret_cast<int*>(ex_thr + 2 * TC_BM);   // [2][128][2 halves]
-  int* ex_flag = ex_cnt + 2 * TC_BM * 2;                      // [2][4 quadrants]
-  uint8_t* ex_list = reinterpret_cast<uint8_t*>(ex_flag + 8); // [2][128][2 halves][TC_MAXC]
+  int* ex_flag = ex_cnt + 2 * TC_BM * 2;                      // [2 accumulators][2 parities][4 quadrants]
+  uint8_t* ex_list = reinterpret_cast<uint8_t*>(ex_flag + 16); // [2][128][2 halves][TC_MAXC]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ex_list + 2 * TC_BM * 2 * TC_MAXC);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
   const uint32_t bar_full = smem_u32(bars);                   // [8]
@@ -117,7 +116,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     for (int i = 0; i < p.nst; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tlfull + 8 * i, 1); mbar_init(bar_tlempty + 8 * i, 1);
-      mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4);
+      mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8);
     }
     mbar_init(bar_bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -211,14 +210,25 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    // Two groups of four warps; group g owns TMEM accumulator g, i.e. every second tile of this
-    // CTA.  A thread owns one pixel row and sweeps all its columns, so nothing is exchanged
-    // between warps: no shared memory, no named barriers.
+    // 16 warps.  Accumulator g (every second tile of this CTA) belongs to warps with e>>3 == g;
+    // inside it a pixel row (TMEM lane) is shared by two threads, one per column half h, in the
+    // two warps of the same lane quadrant q.  They merge their top-3 through shared memory and
+    // synchronise among themselves only (a 64-thread named barrier per warp pair).  Four warps
+    // per scheduler keep the ALU pipe busy while the other accumulator is being refilled.
+    const int e = warp - 4;
     const int q = warp & 3;                        // TMEM lane quadrant of this warp
-    const int g = (warp - 4) >> 2;                 // accumulator / tile parity of this group
+    const int h = (e >> 2) & 1;                    // column half
+    const int g = e >> 3;                          // accumulator / tile parity
     const int r = 32 * q + lane;                   // accumulator row = pixel within the tile
     const int nchunk = p.kpad >> 4;
-    int cur_seg = -1, seq = 0;
+    const int c_mid = (nchunk + 1) >> 1;
+    const int c_begin = h ? c_mid : 0, c_end = h ? nchunk : c_mid;
+    const int bar_id = 1 + q + 4 * g;
+    float* exv = ex + g * 3 * TC_BM;               // (m, s, t3) of the upper column half
+    float* thr_row = ex_thr + g * TC_BM;           // per row: collect every value >= this (or +inf)
+    int* cnt_row = ex_cnt + (g * TC_BM + r) * 2;
+    uint8_t* lst_row = ex_list + (g * TC_BM + r) * 2 * TC_MAXC;
+    int cur_seg = -1, seq = 0, par = 0;
     uint32_t acc_phase = 0;
     float cerrmax = 0.f;
     for (long long item = i_begin; item < i_end; ++item) {
@@ -228,7 +238,9 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (seg != cur_seg) { cerrmax = p.cerr_max[seg]; cur_seg = seg; }
       const int64_t pix = row0 + r;
       const bool inb = r < np;
-      const float xe = inb ? p.xerr[pix] : 0.f;    // issued before the wait, used after the sweep
+      const float xe = (h == 0 && inb) ? p.xerr[pix] : 0.f;    // issued before the wait, used after the sweep
+      int* many_flag = ex_flag + (g * 2 + par) * 4 + q;          // one flag per 32-row quadrant, double buffered
+      if (h == 0 && lane == 0) *many_flag = 0;                   // ordered before this tile's writers by barrier 1
 
       mbar_wait(bar_tfull + 8 * g, acc_phase);
       tc_fence_after();
@@ -236,19 +248,19 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const uint32_t trow = tmem_base + g * 256 + ((uint32_t)(32 * q) << 16);
       // software pipelined: the TMEM load of chunk c+1 is in flight while chunk c is reduced
       uint32_t va[16], vb[16];
-      tc_ld16(trow, va);
-      for (int c = 0; c < nchunk; c += 2) {
+      if (c_begin < c_end) tc_ld16(trow + c_begin * 16, va);
+      for (int c = c_begin; c < c_end; c += 2) {
         tc_ld_wait();
-        if (c + 1 < nchunk) tc_ld16(trow + (c + 1) * 16, vb);
+        if (c + 1 < c_end) tc_ld16(trow + (c + 1) * 16, vb);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int k = c * 16 + j;
           if (DUMP) { if (inb && k < p.kmax) p.dbg_sims[pix * p.kmax + k] = __uint_as_float(va[j]); }
           upd3(m, s, t3, pack_idx(va[j], 255 - k));
         }
-        if (c + 1 < nchunk) {
+        if (c + 1 < c_end) {
           tc_ld_wait();
-          if (c + 2 < nchunk) tc_ld16(trow + (c + 2) * 16, va);
+          if (c + 2 < c_end) tc_ld16(trow + (c + 2) * 16, va);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int k = (c + 1) * 16 + j;
@@ -257,37 +269,49 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           }
         }
       }
-      const int kb = 255 - (int)(__float_as_uint(m) & 0xFFu);
-      const int ks = 255 - (int)(__float_as_uint(s) & 0xFFu);
-      const float thr = 2.f * (xe * 1.001f + cerrmax * 1.001f + TC_EPS_CONST);
-      const bool amb = inb && (m - s <= thr);
-      const bool many = amb && (m - t3 <= thr);    // three or more inside the bound
-      uint32_t cl0 = 0, cl1 = 0;                   // up to 8 candidate ids, one byte each
-      int cnt = 0;
-      if (__any_sync(FULL, many)) {
+      if (h == 1) { exv[r] = m; exv[TC_BM + r] = s; exv[2 * TC_BM + r] = t3; }
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");                       // barrier 1
+      bool amb = false, many = false;
+      int kb = 0, ks = 0;
+      if (h == 0) {
+        upd3(m, s, t3, exv[r]);
+        upd3(m, s, t3, exv[TC_BM + r]);
+        upd3(m, s, t3, exv[2 * TC_BM + r]);
+        kb = 255 - (int)(__float_as_uint(m) & 0xFFu);
+        ks = 255 - (int)(__float_as_uint(s) & 0xFFu);
+        const float thr = 2.f * (xe * 1.001f + cerrmax * 1.001f + TC_EPS_CONST);
+        amb = inb && (m - s <= thr);
+        many = amb && (m - t3 <= thr);             // three or more inside the bound
+        thr_row[r] = many ? m - thr : FLT_MAX;
+        if (many) *many_flag = 1;
+        if (inb) p.keys_out[pix] = seg * p.kmax + kb;
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");                       // barrier 2
+      const bool tile_many = *many_flag != 0;
+      if (tile_many) {
         // second sweep (rare after the first iterations): rows flagged `many` list every candidate
-        const float thr_v = many ? m - thr : FLT_MAX;
-        for (int c = 0; c < nchunk; ++c) {
+        const float thr_v = thr_row[r];
+        uint8_t* lst = lst_row + h * TC_MAXC;
+        int cnt = 0;
+        for (int c = c_begin; c < c_end; ++c) {
           uint32_t v[16];
           tc_ld16(trow + c * 16, v);
           tc_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int k = c * 16 + j;
-            if (pack_idx(v[j], 255 - k) >= thr_v) {
-              if (cnt < 4) cl0 |= (uint32_t)k << (8 * cnt);
-              else if (cnt < 8) cl1 |= (uint32_t)k << (8 * (cnt - 4));
-              ++cnt;
-            }
+            const float pv = pack_idx(v[j], 255 - k);
+            if (pv >= thr_v) { if (cnt < TC_MAXC) lst[cnt] = (uint8_t)k; ++cnt; }
           }
         }
+        cnt_row[h] = cnt;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * g);
       acc_phase ^= 1;
-
-      if (inb) p.keys_out[pix] = seg * p.kmax + kb;
+      par ^= 1;
+      if (tile_many) asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");        // barrier 3
       if (amb) {
         const int slot = atomicAdd(p.fix.count, 1);
         if (slot < p.fix.capacity) {
@@ -295,12 +319,17 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           uint16_t* cd = p.fix.cand + (int64_t)slot * FIX_MAX_CAND;
           if (!many) {                               // everything but the top two is provably out of reach
             cd[0] = (uint16_t)kb; cd[1] = (uint16_t)ks; cd[2] = 0xFFFF;
-          } else if (cnt > FIX_MAX_CAND) {
-            cd[0] = 0xFFFF;                          // too many to list: scan every cluster
-            atomicAdd(p.fix.count + 1, 1);
           } else {
-            for (int i = 0; i < cnt; ++i) cd[i] = (uint16_t)(((i < 4 ? cl0 : cl1) >> (8 * (i & 3))) & 0xFFu);
-            if (cnt < FIX_MAX_CAND) cd[cnt] = 0xFFFF;
+            const int c0 = cnt_row[0], c1 = cnt_row[1];
+            if (c0 > TC_MAXC || c1 > TC_MAXC || c0 + c1 > FIX_MAX_CAND) {
+              cd[0] = 0xFFFF;                        // too many to list: scan every cluster
+              atomicAdd(p.fix.count + 1, 1);
+            } else {
+              int w = 0;
+              for (int i = 0; i < c0; ++i) cd[w++] = lst_row[i];
+              for (int i = 0; i < c1; ++i) cd[w++] = lst_row[TC_MAXC + i];
+              if (w < FIX_MAX_CAND) cd[w] = 0xFFFF;
+            }
           }
         }
       }
