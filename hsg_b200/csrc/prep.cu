@@ -10,8 +10,9 @@
 
 namespace hsg {
 
-constexpr int PREP_TPX = 32;       // pixels per CTA tile
-constexpr int PREP_THREADS = 256;  // 8 warps
+constexpr int PREP_TPX = 64;       // pixels per CTA tile (256 contiguous bytes of every channel row)
+constexpr int PREP_THREADS = 512;  // 16 warps
+constexpr int PREP_LD = PREP_TPX + 1;   // shared-memory row stride (conflict-free column reads)
 
 // ------------------------------------------------------------ normalize (a1)
 __global__ void normalize_kernel(const float* __restrict__ x, float* __restrict__ y,
@@ -104,17 +105,21 @@ __global__ void half_copy_kernel(const float* __restrict__ x, int64_t rows, int 
 __global__ void prep_count_kernel(const int64_t* __restrict__ labels, int64_t ignore_index,
                                   int HW, int tiles_per_image, int64_t n_tiles,
                                   int32_t* __restrict__ tile_count) {
-  // one warp per tile of 32 pixels
+  // one warp per tile of PREP_TPX pixels
   const int lane = threadIdx.x & 31;
   const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tile >= n_tiles) return;
   const int64_t b = tile / tiles_per_image;
   const int t = (int)(tile % tiles_per_image);
-  const int p = t * PREP_TPX + lane;
-  bool valid = false;
-  if (p < HW) valid = labels[b * HW + p] != ignore_index;
-  const unsigned m = __ballot_sync(FULL, valid);
-  if (lane == 0) tile_count[tile] = __popc(m);
+  int cnt = 0;
+#pragma unroll
+  for (int u = 0; u < PREP_TPX / 32; ++u) {
+    const int p = t * PREP_TPX + 32 * u + lane;
+    bool valid = false;
+    if (p < HW) valid = labels[b * HW + p] != ignore_index;
+    cnt += __popc(__ballot_sync(FULL, valid));
+  }
+  if (lane == 0) tile_count[tile] = cnt;
 }
 
 // exclusive scan of tile counts (single CTA, 1024 threads, chunked)
@@ -160,6 +165,15 @@ __global__ void fill_dense_offsets_kernel(int64_t* seg_offsets, int B, int64_t H
   if (i <= B) seg_offsets[i] = (int64_t)i * HW;
 }
 
+// a / b rounded to nearest, given rb = RN(1/b): one FMA correction step of the product a*rb
+// is correctly rounded (Markstein) -- three FMA-pipe operations instead of the ~10-instruction
+// IEEE division sequence, which made this pass instruction-bound
+__device__ __forceinline__ float div_rn_by(float a, float b, float rb) {
+  const float q = a * rb;
+  const float e = fmaf(-q, b, a);
+  return fmaf(e, rb, q);
+}
+
 // ------------------------------------------------------------ main pass
 struct PrepArgs {
   const float* emb;
@@ -186,29 +200,44 @@ struct PrepArgs {
 };
 
 __global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs a) {
-  extern __shared__ float tile[];                 // [D][33]
+  extern __shared__ float tile[];                 // [D][PREP_LD]
   __shared__ int64_t rows[PREP_TPX];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int t = blockIdx.x;
   const int p0 = t * PREP_TPX;
-  const int p = p0 + lane;
-  const bool inb = p < a.HW;
 
-  // NCHW read: one channel row of 32 pixels per warp-iteration (coalesced)
+  // NCHW read: one channel row of 64 pixels per warp-iteration (two coalesced 128-byte requests)
   const float* src = a.emb + (int64_t)b * a.D * a.HW;
-  for (int d = warp; d < a.D; d += PREP_THREADS / 32)
-    tile[d * 33 + lane] = inb ? ld_stream(src + (int64_t)d * a.HW + p) : 0.f;
+  for (int d = warp; d < a.D; d += PREP_THREADS / 32) {
+    const float* cr = src + (int64_t)d * a.HW + p0;
+#pragma unroll
+    for (int u = 0; u < PREP_TPX / 32; ++u) {
+      const int px = 32 * u + lane;
+      tile[d * PREP_LD + px] = p0 + px < a.HW ? ld_stream(cr + px) : 0.f;
+    }
+  }
 
-  if (warp == 0) {
+  if (warp < PREP_TPX / 32) {
+    // rows of the output: pixels kept in order, ignore pixels dropped (ranks inside the tile)
+    const int px = 32 * warp + lane;
+    const int p = p0 + px;
+    const bool inb = p < a.HW;
     int64_t lab = 0;
     if (inb && a.labels) lab = a.labels[(int64_t)b * a.HW + p];
     const bool valid = inb && !(a.use_ignore && lab == a.ignore_index);
     const unsigned m = __ballot_sync(FULL, valid);
+    int before = 0;                                // valid pixels in the lower 32-pixel groups of this tile
+    for (int w = 0; w < warp; ++w) {
+      const int pw = p0 + 32 * w + lane;
+      bool v = pw < a.HW;
+      if (v && a.use_ignore) v = a.labels[(int64_t)b * a.HW + pw] != a.ignore_index;
+      before += __popc(__ballot_sync(FULL, v));
+    }
     const int64_t base = a.tile_base ? a.tile_base[(int64_t)b * a.tiles_per_image + t]
                                      : (int64_t)b * a.HW + p0;
-    const int64_t row = valid ? base + __popc(m & ((1u << lane) - 1u)) : -1;
-    rows[lane] = row;
+    const int64_t row = valid ? base + before + __popc(m & ((1u << lane) - 1u)) : -1;
+    rows[px] = row;
     if (valid) {
       a.labels_out[row] = lab;
       a.clusters_out[row] = a.init[(int64_t)b * a.init_image_stride + p];
@@ -225,14 +254,17 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs 
     if (row < 0) continue;                          // warp-uniform
     float ss = 0.f;
     for (int d = lane; d < a.D; d += 32) {
-      const float v = tile[d * 33 + px];
+      const float v = tile[d * PREP_LD + px];
       ss = fmaf(v, v, ss);
     }
     const float n1 = safe_norm(warp_sum(ss));
-    // second normalisation over cat(normalised embedding, local features)
+    const float r1 = __frcp_rn(n1);
+    // second normalisation over cat(normalised embedding, local features); the normalised value
+    // replaces the raw one in the tile so the last pass divides only once
     float ss2 = 0.f;
     for (int d = lane; d < a.D; d += 32) {
-      const float y = tile[d * 33 + px] / n1;
+      const float y = div_rn_by(tile[d * PREP_LD + px], n1, r1);
+      tile[d * PREP_LD + px] = y;
       ss2 = fmaf(y, y, ss2);
     }
     float lv = 0.f;
@@ -241,12 +273,13 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs 
       ss2 = fmaf(lv, lv, ss2);
     }
     const float n2 = safe_norm(warp_sum(ss2));
+    const float r2 = __frcp_rn(n2);
     float* xr = a.x + row * a.D;
     float* xl = a.xloc + row * Dp;
     float e2 = 0.f;
     for (int d = lane; d < a.D; d += 32) {
-      const float y = tile[d * 33 + px] / n1;
-      const float z = y / n2;
+      const float y = tile[d * PREP_LD + px];
+      const float z = div_rn_by(y, n2, r2);
       xr[d] = y;
       xl[d] = z;
       if (a.xh) {
@@ -330,7 +363,7 @@ int hsg_prep_f32(const float* emb_nchw, int B, int D, int H, int W,
   HSG_REQUIRE(!xh_out || L <= HSG_XH_MAX_TRAILING, HSG_E_UNSUPPORTED,
               "prep: the fp16 side copy holds at most %d local-feature channels", HSG_XH_MAX_TRAILING);
   HSG_REQUIRE((int64_t)H * W < (1ll << 31) && B <= 65535, HSG_E_UNSUPPORTED, "prep: image too large");
-  const size_t smem = (size_t)D * 33 * sizeof(float);
+  const size_t smem = (size_t)D * PREP_LD * sizeof(float);
   HSG_REQUIRE(smem <= 200 * 1024, HSG_E_UNSUPPORTED, "prep: embedding_dim %d too large", D);
   cudaStream_t st = (cudaStream_t)stream;
   const int HW = H * W;
