@@ -207,16 +207,21 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs 
   const int t = blockIdx.x;
   const int p0 = t * PREP_TPX;
 
-  // NCHW read: one channel row of 64 pixels per warp-iteration (two coalesced 128-byte requests)
+  // NCHW read: one channel row of 64 pixels per warp-iteration (two coalesced 128-byte requests),
+  // as asynchronous global->shared copies so every request of the CTA is in flight at once
   const float* src = a.emb + (int64_t)b * a.D * a.HW;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
   for (int d = warp; d < a.D; d += PREP_THREADS / 32) {
     const float* cr = src + (int64_t)d * a.HW + p0;
 #pragma unroll
     for (int u = 0; u < PREP_TPX / 32; ++u) {
       const int px = 32 * u + lane;
-      tile[d * PREP_LD + px] = p0 + px < a.HW ? ld_stream(cr + px) : 0.f;
+      const bool in = p0 + px < a.HW;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(tile_s + 4u * (uint32_t)(d * PREP_LD + px)),
+                   "l"(in ? cr + px : src), "r"(in ? 4 : 0) : "memory");
     }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 
   if (warp < PREP_TPX / 32) {
     // rows of the output: pixels kept in order, ignore pixels dropped (ranks inside the tile)
@@ -245,6 +250,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs 
       if (a.pixel_out) a.pixel_out[row] = (int64_t)b * a.HW + p;
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   const int Dp = a.D + a.L;
