@@ -43,6 +43,28 @@ _TARGETS = {
 }
 
 
+# reference module -> class -> methods rebound (per-image prototype bookkeeping, batched)
+_METHOD_MODULES = ['hsg.models.embeddings.resnet_fcn_hsg', 'hsg.models.embeddings.resnet_fcn_hsg_cs']
+
+
+def _patch_methods(importlib):
+  from .models.embeddings import hierarchy
+  for ref_name in _METHOD_MODULES:
+    try:
+      ref = importlib.import_module(ref_name)
+    except ImportError:
+      continue
+    for cls_name, methods in hierarchy.METHODS.items():
+      cls = getattr(ref, cls_name, None)
+      if cls is None:
+        continue
+      for n, fn in methods.items():
+        key = (ref_name, cls_name + '.' + n)
+        if key not in _PATCHED:
+          _PATCHED[key] = cls.__dict__.get(n)
+        setattr(cls, n, fn)
+
+
 def patch():
   """Rebind the reference's hot-path operators to this package.  The reference
   resolves them late through module attributes (e.g. segsort_common.segment_by_kmeans
@@ -59,10 +81,19 @@ def patch():
       if (ref_name, n) not in _PATCHED:
         _PATCHED[(ref_name, n)] = getattr(ref, n)
       setattr(ref, n, getattr(ours, n))
+  _patch_methods(importlib)
 
 
 def unpatch():
   import importlib
   for (ref_name, n), orig in list(_PATCHED.items()):
-    setattr(importlib.import_module(ref_name), n, orig)
+    target = importlib.import_module(ref_name)
+    attr = n
+    if '.' in n:                       # Class.method
+      cls_name, attr = n.split('.')
+      target = getattr(target, cls_name)
+    if orig is None:
+      delattr(target, attr)
+    else:
+      setattr(target, attr, orig)
     del _PATCHED[(ref_name, n)]

@@ -255,6 +255,25 @@ def main():
        **{'mv%d' % i: _np(t) for i, t in enumerate(mv)},
        **{'sv%d' % i: _np(t) for i, t in enumerate(sv)})
 
+  # ---------------------------------------------------------------- a12 hierarchy helpers
+  torch.manual_seed(235)
+  protos = torch.randn(3, 16, 20)
+  glab = torch.randint(0, 5, (3, 20))
+  pmask = torch.zeros(3, 20, dtype=torch.bool)
+  pmask[0, 15:] = True
+  pmask[2, 3:] = True
+  coarse_n = ResnetFcn._collect_nd_coarser_prototype(fake_self, protos, glab, pmask, num_groups=6, normalized=True)
+  coarse_m = ResnetFcn._collect_nd_coarser_prototype(fake_self, protos, glab, None, num_groups=None, normalized=False)
+  pg = protos.clone().requires_grad_(True)
+  gout = torch.randn(3, 16, 6)
+  (ResnetFcn._collect_nd_coarser_prototype(fake_self, pg, glab, pmask, num_groups=6, normalized=True) * gout).sum().backward()
+  pix_batch = torch.tensor([4, 4, 4, 7, 7, 9, 9, 9, 9, 4, 7])          # not sorted: the reference regroups
+  pix_cidx = torch.randint(0, 20, (11,))
+  pix_fine = ResnetFcn._collect_pixel_hierarchical_clustering_indices(fake_self, pix_cidx, pix_batch, glab)
+  save('hierarchy', protos=_np(protos), glab=_np(glab), pmask=_np(pmask), coarse_norm=_np(coarse_n),
+       coarse_mean=_np(coarse_m), gout=_np(gout), dprotos=_np(pg.grad), pix_batch=_np(pix_batch),
+       pix_cidx=_np(pix_cidx), pix_fine=_np(pix_fine))
+
   # ---------------------------------------------------------------- a13 cross-GPU gather (2 "GPUs")
   m_utils.scatter_gather.gather = lambda xs, dev, dim=0: torch.cat(list(xs), dim)
   torch.manual_seed(235)

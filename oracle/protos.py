@@ -117,3 +117,43 @@ def gather_and_reorder_image_indices(image_indices):
   np.minimum.at(first, inv, np.arange(len(inv)))
   _, out = np.unique(first[inv], return_inverse=True)
   return out.reshape(-1).astype(np.int64)
+
+
+# --------------------------------------------------------------------------
+# a12  hierarchy helpers            resnet_fcn_hsg.py:683-780
+# --------------------------------------------------------------------------
+def collect_nd_coarser_prototype(prototypes, grouping_labels, padding_masks=None,
+                                 num_groups=None, normalized=True):
+  """resnet_fcn_hsg.py:683-748: per batch entry, mean of the node columns of each
+  coarser group (padded nodes go to a dummy group that is dropped), optional L2
+  normalisation.  [B,C,N] -> [B,C,G]."""
+  p = np.asarray(prototypes, np.float32)
+  lab = np.asarray(grouping_labels, np.int64).copy()
+  b, c, nodes = p.shape
+  if num_groups is None:
+    num_groups = int(lab.max()) + 1                                   # :707-708
+  if padding_masks is not None:
+    lab[np.asarray(padding_masks, bool)] = num_groups                 # :716-719
+  out = np.zeros((b, num_groups + 1, c), np.float32)
+  cnt = np.zeros((b, num_groups + 1, c), np.float32)
+  for i in range(b):
+    np.add.at(out[i], lab[i], p[i].T)                                 # :733-737
+    np.add.at(cnt[i], lab[i], np.ones((nodes, c), np.float32))
+  out = out / np.maximum(cnt, np.float32(1e-12))                      # :738-739
+  out = out[:, :-1, :]
+  if normalized:
+    out = ops.normalize_embedding(out)                                # :743-744
+  return np.transpose(out, (0, 2, 1))
+
+
+def collect_pixel_hierarchical_clustering_indices(cluster_indices_by_batch,
+                                                  cluster_batch_indices, grouping_labels):
+  """resnet_fcn_hsg.py:751-780: row i of `grouping_labels` belongs to the i-th
+  distinct batch index; pixels are emitted batch index by batch index."""
+  cidx = np.asarray(cluster_indices_by_batch, np.int64)
+  bidx = np.asarray(cluster_batch_indices, np.int64)
+  lab = np.asarray(grouping_labels, np.int64)
+  out = []
+  for i, b in enumerate(np.unique(bidx)):
+    out.append(lab[i][cidx[bidx == b]])
+  return np.concatenate(out, 0)

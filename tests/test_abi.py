@@ -99,8 +99,19 @@ def test_patch_rebinds_the_reference_operators(lib):
         assert list(ref_sig.parameters) == list(our_sig.parameters), name
         for k, v in ref_sig.parameters.items():
           assert v.default == our_sig.parameters[k].default or v.default is inspect._empty, (name, k)
+      # per-image prototype bookkeeping: methods of the reference's model classes, same parameters
+      import hsg.models.embeddings.resnet_fcn_hsg as ref_model
+      for cls, name in (('ResnetFcn', '_calculate_kmeans_prototypes'), ('MultiviewResnetFcn', '_calculate_kmeans_prototypes'),
+                        ('ResnetFcn', '_collect_nd_coarser_prototype'),
+                        ('ResnetFcn', '_collect_pixel_hierarchical_clustering_indices')):
+        now = getattr(ref_model, cls).__dict__[name]
+        assert now.__module__.startswith('hsg_b200'), (cls, name)
+        was = hsg_b200._PATCHED[('hsg.models.embeddings.resnet_fcn_hsg', cls + '.' + name)]
+        assert list(inspect.signature(was).parameters) == list(inspect.signature(now).parameters), (cls, name)
+      method_orig = hsg_b200._PATCHED[('hsg.models.embeddings.resnet_fcn_hsg', 'ResnetFcn._calculate_kmeans_prototypes')]
     finally:
       hsg_b200.unpatch()
     assert ref_common.segment_by_kmeans is orig
+    assert ref_model.ResnetFcn.__dict__['_calculate_kmeans_prototypes'] is method_orig
   finally:
     sys.path.remove('/root/reference')

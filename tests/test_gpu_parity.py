@@ -280,6 +280,51 @@ def test_gather_prototypes_single_process_lists(golden):
   assert np.array_equal(n(re[1]), g['r1_img_reordered'])
 
 
+def test_kmeans_prototypes_per_image_batched(golden):
+  """a9: `_calculate_kmeans_prototypes` (one view and image pairs) for all images at once."""
+  from hsg_b200.models.embeddings import hierarchy as H
+  g = golden('kmeans_prototypes')
+  for prefix, img in (('mv', t(g['image_indices'])), ('sv', None)):
+    emb = t(g['emb']).requires_grad_(True)
+    out = H.calculate_kmeans_prototypes(emb, t(g['cluster']), t(g['batch']), t(g['pos']), t(g['labels']),
+                                        img, 2048, 256)
+    assert tuple(out[0].shape) == g[prefix + '0'].shape
+    close(n(out[0]), g[prefix + '0'], rtol=1e-5, atol=1e-7)
+    close(n(out[1]), g[prefix + '1'], rtol=1e-5, atol=1e-6)
+    assert out[2].dtype == torch.bool and np.array_equal(n(out[2]), g[prefix + '2'])
+    for i in (3, 4, 5):
+      assert out[i].dtype == torch.int64 and np.array_equal(n(out[i]), g[prefix + str(i)])
+    out[0].sum().backward()                      # prototypes stay differentiable (SURVEY 3.1 notes)
+    assert emb.grad is not None and torch.isfinite(emb.grad).all()
+  # views interleaved (image ids 0,1,0,1): the reference regroups the pixels image by image
+  img = torch.tensor([0, 1, 0, 1])
+  mine = H.calculate_kmeans_prototypes(t(g['emb']), t(g['cluster']), t(g['batch']), t(g['pos']), t(g['labels']),
+                                       t(img), 2048, 256)
+  ref = o_protos.calculate_kmeans_prototypes(g['emb'], g['cluster'], g['batch'], g['pos'], g['labels'],
+                                             img.numpy(), 2048, 256)
+  close(n(mine[0]), ref[0], rtol=1e-5, atol=1e-7)
+  close(n(mine[1]), ref[1], rtol=1e-5, atol=1e-6)
+  for i in (2, 3, 4, 5):
+    assert np.array_equal(n(mine[i]), ref[i])
+  with pytest.raises(Exception):                 # more prototypes than slots: loud, not out of bounds
+    H.calculate_kmeans_prototypes(t(g['emb']), t(g['cluster']), t(g['batch']), None, t(g['labels']), None, 2048, 4)
+
+
+def test_hierarchy_helpers(golden):
+  """a12: coarser-prototype pooling (fwd + bwd) and per-pixel hierarchy ids."""
+  from hsg_b200.models.embeddings import hierarchy as H
+  g = golden('hierarchy')
+  p = t(g['protos']).requires_grad_(True)
+  out = H.collect_nd_coarser_prototype(p, t(g['glab']), t(g['pmask']), num_groups=6, normalized=True)
+  close(n(out), g['coarse_norm'], rtol=1e-5, atol=1e-6)
+  (out * t(g['gout'])).sum().backward()
+  close(n(p.grad), g['dprotos'], rtol=1e-4, atol=1e-6)
+  out = H.collect_nd_coarser_prototype(t(g['protos']), t(g['glab']), None, None, normalized=False)
+  close(n(out), g['coarse_mean'], rtol=1e-5, atol=1e-6)
+  fine = H.collect_pixel_hierarchical_clustering_indices(t(g['pix_cidx']), t(g['pix_batch']), t(g['glab']))
+  assert fine.dtype == torch.int64 and np.array_equal(n(fine), g['pix_fine'])
+
+
 def test_kmeans_moderate_segments_property(S):
   """ragged segments, K not a multiple of anything, per-iteration objective
   non-decreasing and labels equal to an oracle E-step on the kernel's own centroids."""

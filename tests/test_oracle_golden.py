@@ -201,6 +201,16 @@ def test_kmeans_prototypes_per_image(golden):
     assert np.array_equal(out[5], g[prefix + '5'])
 
 
+def test_hierarchy_helpers(golden):
+  g = golden('hierarchy')
+  close(protos.collect_nd_coarser_prototype(g['protos'], g['glab'], g['pmask'], 6, True), g['coarse_norm'],
+        rtol=1e-6, atol=1e-7)
+  close(protos.collect_nd_coarser_prototype(g['protos'], g['glab'], None, None, False), g['coarse_mean'],
+        rtol=1e-6, atol=1e-7)
+  assert np.array_equal(protos.collect_pixel_hierarchical_clustering_indices(g['pix_cidx'], g['pix_batch'], g['glab']),
+                        g['pix_fine'])
+
+
 def test_cross_gpu_gather(golden):
   g = golden('gather_prototypes')
   ranks = [[g['r%d_%s' % (r, nm)] for nm in ('emb', 'emb_loc', 'cluster', 'batch', 'sem', 'inst')]
