@@ -26,6 +26,7 @@ _TARGETS = {
         'normalize_embedding', 'segment_mean']),
     'hsg.utils.segsort.loss': ('hsg_b200.utils.segsort.loss', [
         '_calculate_log_likelihood', 'SegSortLoss']),
+    'hsg.utils.segsort.eval': ('hsg_b200.utils.segsort.eval', ['top_k_ranking']),
     'hsg.models.utils': ('hsg_b200.models.utils', [
         'gather_clustering_and_update_prototypes', 'gather_and_update_cluster_mappings',
         'gather_and_reorder_image_indices', 'gather_and_update_datas']),
@@ -47,14 +48,20 @@ _TARGETS = {
 _METHOD_MODULES = ['hsg.models.embeddings.resnet_fcn_hsg', 'hsg.models.embeddings.resnet_fcn_hsg_cs']
 
 
+_LOSS_MODULES = ['hsg.models.predictions.hsg', 'hsg.models.predictions.hsg_cs']
+
+
 def _patch_methods(importlib):
   from .models.embeddings import hierarchy
-  for ref_name in _METHOD_MODULES:
+  from .models.predictions import hsg as loss_head
+  tables = [(m, hierarchy.METHODS) for m in _METHOD_MODULES]
+  tables += [(m, {'Hsg': {'losses': loss_head.losses}}) for m in _LOSS_MODULES]
+  for ref_name, table in tables:
     try:
       ref = importlib.import_module(ref_name)
     except ImportError:
       continue
-    for cls_name, methods in hierarchy.METHODS.items():
+    for cls_name, methods in table.items():
       cls = getattr(ref, cls_name, None)
       if cls is None:
         continue
@@ -62,6 +69,8 @@ def _patch_methods(importlib):
         key = (ref_name, cls_name + '.' + n)
         if key not in _PATCHED:
           _PATCHED[key] = cls.__dict__.get(n)
+        if n == 'losses':                        # the drop-in delegates DMoN / centroid terms to the original
+          loss_head.ORIGINALS[(cls.__module__, cls.__name__)] = _PATCHED[key]
         setattr(cls, n, fn)
 
 

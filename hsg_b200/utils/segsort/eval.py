@@ -1,0 +1,19 @@
+"""Drop-in for hsg/utils/segsort/eval.py: top-k retrieval accuracy.
+
+The reference sorts every row of the [N,P] affinity matrix (`argsort`, :32-34) to read
+k columns; it runs every training step on the prototypes themselves
+(hsg/models/predictions/hsg.py:113-118).  Same result from a top-k selection.
+"""
+
+import torch
+
+
+def top_k_ranking(embeddings, labels, prototypes, prototype_labels, top_k=3):
+  """(accuracy, retrieved labels [N,top_k]); reference :9-52."""
+  embeddings = embeddings.reshape(-1, embeddings.shape[-1])
+  prototypes = prototypes.reshape(-1, prototypes.shape[-1])
+  affinity = torch.mm(embeddings, prototypes.t())
+  top = torch.topk(affinity, top_k, dim=1, largest=True, sorted=True).indices
+  retrieved = prototype_labels.reshape(-1)[top.reshape(-1)].view(-1, top_k)
+  accuracy = torch.mean((retrieved == labels.reshape(-1, 1)).float())
+  return accuracy, retrieved

@@ -274,6 +274,47 @@ def main():
        coarse_mean=_np(coarse_m), gout=_np(gout), dprotos=_np(pg.grad), pix_batch=_np(pix_batch),
        pix_cidx=_np(pix_cidx), pix_fine=_np(pix_fine))
 
+  # ---------------------------------------------------------------- a15 Hsg.losses (three NCE terms + accuracy)
+  from hsg.models.predictions.hsg import Hsg
+  ns = types.SimpleNamespace
+  cfg = ns(train=ns(img_sim_loss_types='segsort', img_sim_concentration=16, img_sim_loss_weight=1.0,
+                    fine_hrchy_loss_types='segsort', fine_hrchy_concentration=16, fine_hrchy_loss_weight=0.1,
+                    coarse_hrchy_loss_types='segsort', coarse_hrchy_concentration=16, coarse_hrchy_loss_weight=0.1,
+                    dmon_loss_types='none', dmon_knn=2, dmon_loss_weight=1.0,
+                    centroid_cont_loss_types='segsort', centroid_cont_concentration=16,
+                    centroid_cont_loss_weight=1.0),
+           dataset=ns(semantic_ignore_index=255, num_classes=21), network=ns(label_divisor=2048))
+  head = Hsg(cfg)
+  torch.manual_seed(235)
+  n_pix, n_proto, dim, n_img = 1500, 90, 32, 6              # 6 batch entries = 3 images x 2 views
+  image_index = torch.tensor([0, 0, 1, 1, 2, 2])
+  proto_batch = torch.sort(torch.randint(0, n_img, (n_proto,))).values
+  proto_inst = torch.randint(0, 4, (n_proto,))
+  cidx = torch.randint(0, n_proto, (n_pix,))
+  emb = g_common.normalize_embedding(torch.randn(n_pix, dim)).requires_grad_(True)
+  protos = g_common.normalize_embedding(torch.randn(n_proto, dim)).requires_grad_(True)
+  fine_map = torch.randint(0, 24, (n_proto,))
+  coarse_map = fine_map // 3
+  cent_t = {k: torch.randn(3, dim, q) for k, q in (('fine', 8), ('coarse', 4))}
+  cent_d = {k: torch.randn(3, dim, q).requires_grad_(True) for k, q in (('fine', 8), ('coarse', 4))}
+  datas = {'cluster_index': cidx, 'cluster_embedding': emb, 'cluster_batch_index': proto_batch[cidx],
+           'cluster_instance_label': proto_inst[cidx],
+           'finehrchy_nd_prototype_grouping_centroid': cent_d['fine'],
+           'coarsehrchy_nd_prototype_grouping_centroid': cent_d['coarse']}
+  targets = {'image_index': image_index, 'prototype': protos, 'prototype_batch_index': proto_batch,
+             'prototype_instance_label': proto_inst, 'finehrchy_mapping_index': fine_map,
+             'coarsehrchy_mapping_index': coarse_map,
+             'finehrchy_nd_prototype_grouping_centroid': cent_t['fine'],
+             'coarsehrchy_nd_prototype_grouping_centroid': cent_t['coarse']}
+  l_img, l_hr, l_cl, acc = head.losses(datas, targets)
+  (l_img + l_hr + l_cl).backward()
+  save('hsg_losses', image_index=_np(image_index), proto_batch=_np(proto_batch), proto_inst=_np(proto_inst),
+       cidx=_np(cidx), emb=_np(emb), protos=_np(protos), fine_map=_np(fine_map), coarse_map=_np(coarse_map),
+       cent_t_fine=_np(cent_t['fine']), cent_t_coarse=_np(cent_t['coarse']),
+       cent_d_fine=_np(cent_d['fine']), cent_d_coarse=_np(cent_d['coarse']),
+       img_sim_loss=_np(l_img), hrchy_group_loss=_np(l_hr), clustering_loss=_np(l_cl), accuracy=_np(acc),
+       demb=_np(emb.grad), dprotos=_np(protos.grad), dcent_fine=_np(cent_d['fine'].grad))
+
   # ---------------------------------------------------------------- a13 cross-GPU gather (2 "GPUs")
   m_utils.scatter_gather.gather = lambda xs, dev, dim=0: torch.cat(list(xs), dim)
   torch.manual_seed(235)

@@ -166,3 +166,28 @@ def normalize_backward(x, grad_out, dtype=np.float64, eps=EPS):
   big = nrm >= eps
   xh = x / np.where(big, nrm, eps)
   return np.where(big, (g - xh * (xh * g).sum(-1, keepdims=True)) / np.where(big, nrm, 1.0), g / eps)
+
+
+# --------------------------------------------------------------------------
+# a15  Hsg.losses (NCE terms + accuracy)   hsg/models/predictions/hsg.py:78-160
+# --------------------------------------------------------------------------
+def top_k_accuracy(embeddings, labels, prototypes, prototype_labels, top_k):
+  """hsg/utils/segsort/eval.py:9-52 (accuracy only)."""
+  aff = np.asarray(embeddings, np.float32) @ np.asarray(prototypes, np.float32).T
+  top = np.argsort(-aff, axis=1, kind='stable')[:, :top_k]
+  hit = np.asarray(prototype_labels)[top] == np.asarray(labels).reshape(-1, 1)
+  return np.float32(hit.astype(np.float32).mean())
+
+
+def hsg_nce_losses(emb, cidx, batch_index, instance_label, image_index, protos, proto_batch, proto_inst,
+                   fine_map, coarse_map, concentration, weights, label_divisor=2048):
+  """The three pixel-to-prototype terms of Hsg.losses and the retrieval accuracy:
+  (img_sim_loss, hrchy_group_loss, img_sim_acc).  predictions/hsg.py:88-160."""
+  image_index = np.asarray(image_index, np.int64)
+  inst = np.asarray(instance_label, np.int64) * label_divisor + image_index[batch_index]      # :91-96
+  p_inst = np.asarray(proto_inst, np.int64) * label_divisor + image_index[proto_batch]       # :98-104
+  img = segsort_loss(emb, inst, cidx, protos, p_inst, concentration) * weights[0]             # :105-111
+  acc = top_k_accuracy(protos, p_inst, protos, p_inst, 5)                                     # :113-118
+  fine = segsort_loss(emb, np.asarray(fine_map)[cidx], cidx, protos, fine_map, concentration) * weights[1]
+  coarse = segsort_loss(emb, np.asarray(coarse_map)[cidx], cidx, protos, coarse_map, concentration) * weights[2]
+  return img, fine + coarse, acc

@@ -15,6 +15,7 @@ import numpy as np
 import pytest
 import torch
 
+import hsg_b200
 from oracle import ops as o_ops, loss as o_loss, protos as o_protos
 
 pytestmark = pytest.mark.gpu
@@ -323,6 +324,44 @@ def test_hierarchy_helpers(golden):
   close(n(out), g['coarse_mean'], rtol=1e-5, atol=1e-6)
   fine = H.collect_pixel_hierarchical_clustering_indices(t(g['pix_cidx']), t(g['pix_batch']), t(g['glab']))
   assert fine.dtype == torch.int64 and np.array_equal(n(fine), g['pix_fine'])
+
+
+def test_hsg_losses_one_pass(golden):
+  """a15: the drop-in `Hsg.losses` -- three NCE terms in one pass over E x P^T, accuracy, and the
+  gradients w.r.t. embeddings and prototypes -- against the reference's method run on CPU."""
+  import types
+  from hsg_b200.models.predictions import hsg as head
+  from hsg_b200.utils.segsort import loss as L
+  from hsg_b200 import ops
+  g = golden('hsg_losses')
+  me = types.SimpleNamespace(
+      img_sim_loss=L.SegSortLoss(16), img_sim_loss_weight=1.0, fine_hrchy_loss=L.SegSortLoss(16),
+      fine_hrchy_loss_weight=0.1, coarse_hrchy_loss=L.SegSortLoss(16), coarse_hrchy_loss_weight=0.1,
+      dmon_loss=None, centroid_cont_loss=None, label_divisor=2048)
+  emb = t(g['emb']).requires_grad_(True)
+  protos = t(g['protos']).requires_grad_(True)
+  cidx = t(g['cidx'])
+  datas = {'cluster_index': cidx, 'cluster_embedding': emb, 'cluster_batch_index': t(g['proto_batch'])[cidx],
+           'cluster_instance_label': t(g['proto_inst'])[cidx]}
+  targets = {'image_index': t(g['image_index']), 'prototype': protos, 'prototype_batch_index': t(g['proto_batch']),
+             'prototype_instance_label': t(g['proto_inst']), 'finehrchy_mapping_index': t(g['fine_map']),
+             'coarsehrchy_mapping_index': t(g['coarse_map'])}
+  launches = hsg_b200.load_library().hsg_launch_count()
+  img, hr, cl, acc = head.losses(me, datas, targets)
+  assert cl is None
+  close(n(img), g['img_sim_loss'], rtol=2e-5)
+  close(n(hr), g['hrchy_group_loss'], rtol=2e-5)
+  assert abs(float(acc) - float(g['accuracy'])) < 1e-6
+  (img + hr).backward()
+  close(n(emb.grad), g['demb'], rtol=2e-4, atol=1e-7)
+  close(n(protos.grad), g['dprotos'], rtol=2e-4, atol=1e-7)
+  # only one of the terms switched on, and a term with its own concentration (separate pass)
+  me.fine_hrchy_loss = None
+  me.coarse_hrchy_loss = L.SegSortLoss(10)
+  img2, hr2, _, _ = head.losses(me, datas, targets)
+  close(n(img2), g['img_sim_loss'], rtol=2e-5)
+  want = o_loss.segsort_loss(g['emb'], g['coarse_map'][g['cidx']], g['cidx'], g['protos'], g['coarse_map'], 10) * 0.1
+  close(n(hr2), want, rtol=2e-5)
 
 
 def test_kmeans_moderate_segments_property(S):

@@ -211,6 +211,16 @@ def test_hierarchy_helpers(golden):
                         g['pix_fine'])
 
 
+def test_hsg_losses_nce_terms(golden):
+  g = golden('hsg_losses')
+  img, hr, acc = loss.hsg_nce_losses(g['emb'], g['cidx'], g['proto_batch'][g['cidx']], g['proto_inst'][g['cidx']],
+                                     g['image_index'], g['protos'], g['proto_batch'], g['proto_inst'],
+                                     g['fine_map'], g['coarse_map'], 16, (1.0, 0.1, 0.1))
+  assert abs(img - g['img_sim_loss']) <= 2e-5 * abs(g['img_sim_loss'])
+  assert abs(hr - g['hrchy_group_loss']) <= 2e-5 * abs(g['hrchy_group_loss'])
+  assert abs(acc - g['accuracy']) < 1e-6
+
+
 def test_cross_gpu_gather(golden):
   g = golden('gather_prototypes')
   ranks = [[g['r%d_%s' % (r, nm)] for nm in ('emb', 'emb_loc', 'cluster', 'batch', 'sem', 'inst')]
