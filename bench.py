@@ -244,7 +244,7 @@ def run_ours(args):
     e2e_step(0, True)
     barrier()
     t0 = time.perf_counter()
-    e_steps = max(2, min(args.steps, 3))
+    e_steps = max(2, args.steps)
     upload(0)
     for i in range(e_steps):
       e2e_step(i, i == e_steps - 1)
@@ -267,15 +267,20 @@ def run_ours(args):
   kmeans_ms = (phase_ms['mstep_sort'] + phase_ms['mstep_gather'] + phase_ms['mstep_combine'] +
                phase_ms['estep'] + phase_ms['estep_fixup'] + phase_ms['convert']) / iters
   alg_bytes = n_pix * (4.0 * dp + 8.0)
-  # DRAM bytes of one k-means iteration from the committed ncu captures (only for the default workload)
-  default_cfg = (args.images, args.size, args.dim, args.grid) == (48, 448, 256, 16)
-  traffic = 5.3503e9 + 10.9888e9 if default_cfg else None
+  # DRAM bytes of one k-means iteration from the committed ncu pass (only for the default workload)
+  default_cfg = (args.images, args.size, args.dim, args.grid, args.iters, args.dist) == (48, 448, 256, 16, 10, 'iid')
+  traffic, traffic_src = None, None
+  tpath = os.path.join(ROOT, 'profiles', 'r1_kmeans_traffic.json')
+  if default_cfg and os.path.exists(tpath):
+    with open(tpath) as f:
+      traffic = json.load(f)['kmeans_dram_bytes_per_step'] / args.iters
+    traffic_src = ('profiles/r1_kmeans_traffic.json: ncu dram read+write of every kernel of the k-means loop over one '
+                   'step, divided by the %d iterations (the incremental M-step re-reads only the rows that moved)' % args.iters)
   achieved = alg_bytes / (kmeans_ms * 1e-3) / 1e9 if kmeans_ms > 0 else 0.0
   roofline = {'kernel': 'spherical k-means iteration (E-step + M-step kernels)', 'bound': 'hbm',
               'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / pk['hbm_gbs'],
               'peak_source': pk_src + ' (burst copy bandwidth)', 'traffic': traffic,
-              'traffic_source': 'profiles/r1_estep_tc.txt + profiles/r1_mstep_gather.txt (ncu --set full, dram read+write '
-                                'of the two dominant kernels of one iteration)' if traffic else None,
+              'traffic_source': traffic_src,
               'algorithmic_bytes_per_launch': alg_bytes, 'ms_per_launch': kmeans_ms}
   per_phase = {k: {'ms_per_step': phase_ms[k] / args.steps, 'ranges': phase_n[k]} for k in PHASES if phase_n[k]}
 
@@ -292,7 +297,13 @@ def run_ours(args):
                                 args.grid ** 2, args.iters, args.images * args.grid ** 2, args.dist,
                                 n_pix * args.dim * 4 / 1e9),
                  'images_per_gpu': args.images, 'embedding_grid': [args.size, args.size], 'dim': args.dim,
-                 'k': args.grid ** 2, 'iterations': args.iters, 'parallelism': 'images sharded over %d GPU(s)' % world},
+                 'k': args.grid ** 2, 'iterations': args.iters, 'parallelism': 'images sharded over %d GPU(s)' % world,
+                 'nce_prototypes_global': world * args.images * args.grid ** 2,
+                 'scaling_note': 'images (and their k-means) are sharded with no collective; the NCE contrasts every '
+                                 'pixel with the prototypes of the WHOLE global batch (all-gather), so NCE work per GPU '
+                                 'grows with the GPU count: see nce_pairs_per_s_per_gpu for the work-normalised rate'},
+      'nce_pairs_per_s_per_gpu': (n_pix * float(world * args.images * args.grid ** 2) /
+                                  (phase_ms['nce_fwd'] / args.steps * 1e-3)) if phase_ms['nce_fwd'] > 0 else None,
       'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
       'roofline': roofline, 'phases': per_phase, 'cpu_baseline': cpu, 'loss': float(loss),
   }

@@ -2,6 +2,8 @@
 """Summarise ncu outputs into profiles/ (tracked).  Usage:
    python tools/ncu_summary.py launches gpurun_out/launches_r1.csv profiles/r1_launches.txt
    python tools/ncu_summary.py kernel   gpurun_out/prof_x.ncu-rep   profiles/r1_x.txt
+   python tools/ncu_summary.py traffic  gpurun_out/traffic.csv      profiles/r1_kmeans_traffic.json
+       (traffic.csv: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --csv over ONE bench step)
 """
 import collections
 import csv
@@ -69,5 +71,34 @@ def kernel(src, dst):
       f.write('%-82s %18.4f %s\n' % ('traffic = dram read + write', tot / 1e9, 'Gbyte'))
 
 
+KMEANS_KERNELS = ('estep_tc_kernel', 'estep_simt_kernel', 'estep_fixup_kernel', 'gather_sum_kernel', 'combine64_kernel',
+                  'hist_kernel', 'scan_kernel', 'scatter_kernel', 'delta_count_kernel', 'delta_scan_kernel',
+                  'delta_compact_kernel', 'tc_convert_kernel', 'build_tiles_kernel')
+
+
+def traffic(src, dst):
+  """DRAM bytes (read + write) of every kernel of the k-means loop over one bench step, from a
+  metrics-only ncu pass; bench.py divides by the iteration count for roofline.traffic."""
+  import json
+  lines = [l for l in open(src) if l.startswith('"')]
+  scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+  per = collections.OrderedDict()
+  for row in csv.DictReader(lines):
+    name = row['Kernel Name'].split('(')[0].split('::')[-1].split('<')[0]
+    if name not in KMEANS_KERNELS:
+      continue
+    v = float(row['Metric Value'].replace(',', '')) * scale.get(row['Metric Unit'], 1.0)
+    d = per.setdefault(name, {'launches': 0, 'bytes': 0.0})
+    d['bytes'] += v
+    if row['Metric Name'] == 'dram__bytes_read.sum':
+      d['launches'] += 1
+  total = sum(d['bytes'] for d in per.values())
+  with open(dst, 'w') as f:
+    json.dump({'source': src, 'what': 'dram__bytes_read.sum + dram__bytes_write.sum of the k-means loop kernels over '
+               'one bench step (ncu --metrics ..., --clock-control none)', 'kmeans_dram_bytes_per_step': total,
+               'per_kernel': per}, f, indent=1)
+  print('k-means loop DRAM bytes per step: %.3f GB' % (total / 1e9))
+
+
 if __name__ == '__main__':
-  {'launches': launches, 'kernel': kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+  {'launches': launches, 'kernel': kernel, 'traffic': traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
