@@ -620,3 +620,101 @@ def test_fused_attention_core_vs_float64():
   torch.manual_seed(0)
   od = attention_core(t(q), t(k), t(v), t(mask), b, h, dropout_p=0.5)
   assert abs(float(od.mean()) - float(out.detach().mean())) < 0.05 and not torch.equal(od, out.detach())
+
+
+# ---------------------------------------------------------------- BASELINE.json configs 3-5 (shapes of the other configs)
+def _block_labels(rng, b, h, w, blk, divisor=2048):
+  """block oversegmentation (~(h/blk)*(w/blk) regions per image) packed as sem*divisor + inst"""
+  yy, xx = np.meshgrid(np.arange(h) // blk, np.arange(w) // blk, indexing='ij')
+  region = yy * ((w + blk - 1) // blk) + xx
+  sem = rng.randint(0, 5, (b, int(region.max()) + 1))
+  return np.stack([sem[i][region] * divisor + region for i in range(b)]).astype(np.int64)
+
+
+def _prototypes_and_loss_follow_my_ids(res, conc=16.0):
+  """prototypes and NCE loss (prototype-level positives) recomputed by the oracle from the
+  kernel's own pixel->prototype ids: fp32 within 1e-5"""
+  from hsg_b200.utils.segsort import common as S, loss as L
+  x, ids = res[0], res[3]
+  protos = S.calculate_prototypes_from_labels(x, ids)
+  want = o_ops.calculate_prototypes_from_labels(n(x), n(ids))
+  close(n(protos), want, rtol=1e-5, atol=1e-6)
+  psem = torch.arange(protos.shape[0], device=x.device) // 3
+  sem = psem[ids]
+  mine = L.SegSortLoss(conc)(x, sem, ids, protos, psem)
+  args = (n(x), n(sem), n(ids), n(protos), n(psem), conc)
+  ref = o_loss.calculate_log_likelihood(*args, dtype=np.float64).mean()
+  # 1e-5 relative plus the reference's own fp32 cancellation allowance (DESIGN.md section 2)
+  tol = 1e-5 * abs(ref) + np.mean(1e-6 * o_loss.nce_condition(*args))
+  assert abs(float(mine) - float(ref)) <= tol, (float(mine), float(ref), tol)
+
+
+def test_config3_coco_stage1_shapes(S):
+  """configs[2]: 32 images x 14x14, D=128 per GPU; recipe grid 1x1 / 1 iteration and 4x4 / 15 iterations."""
+  rng = np.random.RandomState(31)
+  emb = rng.randn(32, 128, 14, 14).astype(np.float32)
+  labels = _block_labels(rng, 32, 14, 14, 3)
+  res = S.segment_by_kmeans(t(emb), t(labels), [1, 1], iterations=1)
+  ref = o_ops.segment_by_kmeans(emb, labels, (1, 1), iterations=1)
+  for a, b in zip(res[2:], ref[2:]):
+    assert np.array_equal(n(a), b)                       # one cluster per image: ids are exact
+  close(n(res[1]), ref[1], rtol=1e-5, atol=1e-6)
+  _prototypes_and_loss_follow_my_ids(res)
+  res = S.segment_by_kmeans(t(emb), t(labels), [4, 4], iterations=15)
+  ref = o_ops.segment_by_kmeans(emb, labels, (4, 4), iterations=15)
+  assert np.array_equal(n(res[2]), ref[2]) and np.array_equal(n(res[4]), ref[4])
+  assert np.mean(n(res[3]) == ref[3]) > 0.97            # 15 iterations on noise amplify fp32 near-ties
+  _prototypes_and_loss_follow_my_ids(res)
+
+
+def test_config4_cityscapes_shapes(S):
+  """configs[3]: 16 images x 48x48 grid, D=256 (tensor-core E-step), grid 4x4 / 15 iterations, then the
+  per-image-pair prototypes and the attention core at the hierarchy's shapes (S=256 -> Q=64 -> Q=16)."""
+  from hsg_b200.models.embeddings import hierarchy as H
+  from hsg_b200.models.heads.transformer import attention_core
+  rng = np.random.RandomState(41)
+  emb = rng.randn(16, 256, 48, 48).astype(np.float32)
+  labels = _block_labels(rng, 16, 48, 48, 12)
+  res = S.segment_by_kmeans(t(emb), t(labels), [4, 4], iterations=15)
+  ref = o_ops.segment_by_kmeans(emb, labels, (4, 4), iterations=15)
+  assert np.array_equal(n(res[2]), ref[2]) and np.array_equal(n(res[4]), ref[4])
+  assert np.mean(n(res[3]) == ref[3]) > 0.97
+  _prototypes_and_loss_follow_my_ids(res)
+  img = np.repeat(np.arange(8), 2)
+  pos = rng.randn(res[0].shape[0], 256).astype(np.float32)
+  mine = H.calculate_kmeans_prototypes(res[0], res[3], res[4], t(pos), res[2], t(img), 2048, 256)
+  want = o_protos.calculate_kmeans_prototypes(n(res[0]), n(res[3]), n(res[4]), pos, n(res[2]), img, 2048, 256)
+  close(n(mine[0]), want[0], rtol=1e-5, atol=1e-6)
+  close(n(mine[1]), want[1], rtol=1e-5, atol=1e-6)
+  for i in (2, 3, 4, 5):
+    assert np.array_equal(n(mine[i]), want[i])
+  for (l, s_) in ((256, 256), (64, 256), (64, 64), (16, 64)):
+    b, h, hd = 8, 4, 64
+    q, k, v = [rng.randn(b * h, m, hd).astype(np.float32) for m in (l, s_, s_)]
+    mask = np.zeros((b, s_), bool)
+    mask[:, int(0.8 * s_):] = True
+    out = attention_core(t(q), t(k), t(v), t(mask), b, h)
+    sc = torch.einsum('zld,zsd->zls', torch.from_numpy(q).double() / hd ** 0.5, torch.from_numpy(k).double())
+    sc = sc.masked_fill(torch.from_numpy(np.repeat(mask, h, axis=0)).unsqueeze(1), float('-inf'))
+    want_o = torch.einsum('zls,zsd->zld', torch.softmax(sc, -1), torch.from_numpy(v).double()).numpy()
+    close(n(out), want_o, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('nn,d,k', [(100000, 64, 32), (100000, 256, 256), (20000, 512, 2048), (65536, 128, 200)])
+def test_config5_flat_kmeans_sweep_points(S, nn, d, k):
+  """configs[4]: flat spherical k-means, T=20, random initial labels (seed 235).  Teacher-forced last step:
+  centroids = the oracle's mean directions of the previous labels, labels = float64 arg-max over them."""
+  from hsg_b200 import ops
+  rng = np.random.RandomState(235)
+  x = o_ops.normalize_embedding(rng.randn(nn, d).astype(np.float32))
+  init = rng.randint(0, k, nn).astype(np.int64)
+  lab19 = S.kmeans_with_initial_labels(t(x), t(init), k, 19)
+  lab20, cent = ops.kmeans(t(x), lab19, k, 1, return_centroids=True)
+  assert torch.equal(lab20, S.kmeans_with_initial_labels(t(x), t(init), k, 20)) or \
+      np.mean(n(lab20) == n(S.kmeans_with_initial_labels(t(x), t(init), k, 20))) > 0.999
+  close(n(cent)[0], o_ops.calculate_prototypes_from_labels(x, n(lab19), k), rtol=1e-5, atol=1e-6)
+  best, _, gap = o_ops.argmax_margins(x, n(cent)[0])
+  sel = gap > 1e-12
+  assert np.array_equal(n(lab20)[sel], best[sel])
+  ref = o_ops.kmeans_with_initial_labels(x, init, k, 20)
+  assert np.mean(n(lab20) == ref) > (0.9 if k >= 200 else 0.97)       # 20 iterations on iid noise: flips cascade
