@@ -264,7 +264,7 @@ static void km_carve(Carver& c, KmPlan& p, int64_t N, int dim, int S, int kmax, 
   p.fix.capacity = N;
   p.fix.pixels = c.take<int32_t>(N);
   p.fix.cand = c.take<uint16_t>(N * FIX_MAX_CAND);
-  tc_carve(c, p.tc, S, kmax, d16 > 0 ? d16 : 64);
+  tc_carve(c, p.tc, S, kmax, d16 > 0 ? d16 : 64, N);
   // delta plan: own tiles / keys / float64 pieces, everything else aliases the full plan (only
   // one of the two passes runs in an iteration)
   DeltaPlan& d = p.d;
@@ -352,7 +352,7 @@ static int decide_tc(int flags, int dim, const void* xh, int d16, const float* x
   const bool possible = xh && xerr && tc_shape_supported(dim, d16, kmax);
   if ((flags & 3) == HSG_KMEANS_FORCE_TC) {
     HSG_REQUIRE(possible, HSG_E_UNSUPPORTED,
-                "kmeans: tensor-core E-step needs the fp16 copy, d16 in {64,128,256}, kmax*d16*2 <= 128 KiB "
+                "kmeans: tensor-core E-step needs the fp16 copy, d16 in {64,128,256,512}, at most 5 trailing features "
                 "(got dim=%d d16=%d kmax=%d, xh=%p)", dim, d16, kmax, xh);
     *use_tc = true;
   } else if ((flags & 3) == HSG_KMEANS_FORCE_SIMT) {
@@ -370,10 +370,14 @@ using namespace hsg;
 extern "C" {
 
 size_t hsg_kmeans_workspace_bytes(int64_t N, int dim, int S, int kmax, int64_t max_seg_len) {
-  Carver c(nullptr);
-  KmPlan p;
-  km_carve(c, p, N, dim, S, kmax, max_seg_len, 256);
-  return c.used() + 1024;
+  size_t need = 0;
+  for (int d16 = 64; d16 <= 512; d16 *= 2) {     // whichever fp16 side copy the caller brings
+    Carver c(nullptr);
+    KmPlan p;
+    km_carve(c, p, N, dim, S, kmax, max_seg_len, d16);
+    if (c.used() > need) need = c.used();
+  }
+  return need + 1024;
 }
 
 int hsg_kmeans_f32(const float* x, int64_t N, int dim, const void* xh, int d16, const float* xerr,

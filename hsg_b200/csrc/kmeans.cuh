@@ -40,7 +40,10 @@ struct TcState {
   const __half* xh;          // [N,d16+HSG_XH_TAIL]
   const float* xerr;         // [N]
   int d16;
-  int kpad;                  // kmax rounded up to 16
+  int kpad;                  // centroids per pass: kmax rounded up to 16, or the tile size when K needs several passes
+  int kpad_total, n_pass;    // rows per segment in `ch` = n_pass * kpad
+  float* st_val;             // [N,3] / [N,4]: running top-3 between passes (n_pass > 1)
+  uint8_t* st_tile;
   __half* ch;                // [S*kpad, d16+HSG_XH_TAIL] fp16 centroids, same row layout as xh
   float* cerr;               // [S*kmax] ||c - fp16(c)|| over the first d16 dims
   float* cerr_max;           // [S]
@@ -50,8 +53,7 @@ struct TcState {
   unsigned char tmap_ct[128];
 };
 bool tc_shape_supported(int dim, int d16, int kmax);
-size_t tc_workspace_bytes(int S, int kmax, int d16);
-void tc_carve(Carver& c, TcState& t, int S, int kmax, int d16);
+void tc_carve(Carver& c, TcState& t, int S, int kmax, int d16, int64_t N);
 int tc_prepare(TcState& t, int64_t N, int S);                 // encode tensor maps
 int tc_convert_centroids(const EStepArgs& a, const TcState& t, cudaStream_t st);
 int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st);

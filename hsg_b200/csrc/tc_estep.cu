@@ -39,7 +39,11 @@ constexpr float TC_EPS_CONST = 7.1e-5f; // accumulation (3e-5) + index packing (
 
 struct TcParams {
   int d16;
-  int kmax, kpad;
+  int kmax, kpad;            // kpad = centroids per pass (MMA N), a multiple of 16
+  int kpad_total;            // centroid rows per segment in the fp16 copy (n_pass * kpad)
+  int pass, n_pass;          // K > kpad: the centroids go by in n_pass tiles, one launch each
+  float* st_val;             // [N,3] running top-3 (index-packed values) carried between passes
+  uint8_t* st_tile;          // [N,4] centroid tile of each of the three
   const float* xerr;
   const float* cerr_max;
   Tiles tiles;
@@ -151,8 +155,8 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           if (cur_seg >= 0) mbar_wait(bar_tlempty + 8 * last_tl, last_tl_phase);
           mbar_expect_tx(bar_bfull, nslab * slab_b_bytes + tail_b_bytes);
           for (int j = 0; j < nslab; ++j)
-            tma_load_2d(sB + j * slab_b_bytes, &tmap_c, j * TC_BK, seg * p.kpad, bar_bfull);
-          tma_load_2d(sBT, &tmap_ct, p.d16, seg * p.kpad, bar_bfull);
+            tma_load_2d(sB + j * slab_b_bytes, &tmap_c, j * TC_BK, seg * p.kpad_total + p.pass * p.kpad, bar_bfull);
+          tma_load_2d(sBT, &tmap_ct, p.d16, seg * p.kpad_total + p.pass * p.kpad, bar_bfull);
           cur_seg = seg;
         }
         for (int j = 0; j < nslab; ++j) {
@@ -242,9 +246,19 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       int* many_flag = ex_flag + (g * 2 + par) * 4 + q;          // one flag per 32-row quadrant, double buffered
       if (h == 0 && lane == 0) *many_flag = 0;                   // ordered before this tile's writers by barrier 1
 
+      // earlier centroid tiles of this pixel (K > kpad): the running top-3 and the tile each came from
+      float m = -FLT_MAX, s = -FLT_MAX, t3 = -FLT_MAX;
+      float om = -FLT_MAX, os = -FLT_MAX, ot = -FLT_MAX;
+      uint32_t otile = 0;
+      if (p.pass > 0 && h == 0 && inb) {
+        om = p.st_val[pix * 3]; os = p.st_val[pix * 3 + 1]; ot = p.st_val[pix * 3 + 2];
+        otile = *reinterpret_cast<const uint32_t*>(p.st_tile + pix * 4);
+        m = om; s = os; t3 = ot;
+      }
+      const int kofs = p.pass * p.kpad;             // global index of this tile's first centroid
+
       mbar_wait(bar_tfull + 8 * g, acc_phase);
       tc_fence_after();
-      float m = -FLT_MAX, s = -FLT_MAX, t3 = -FLT_MAX;
       const uint32_t trow = tmem_base + g * 256 + ((uint32_t)(32 * q) << 16);
       // software pipelined: the TMEM load of chunk c+1 is in flight while chunk c is reduced
       uint32_t va[16], vb[16];
@@ -255,7 +269,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int k = c * 16 + j;
-          if (DUMP) { if (inb && k < p.kmax) p.dbg_sims[pix * p.kmax + k] = __uint_as_float(va[j]); }
+          if (DUMP) { if (inb && kofs + k < p.kmax) p.dbg_sims[pix * p.kmax + kofs + k] = __uint_as_float(va[j]); }
           upd3(m, s, t3, pack_idx(va[j], 255 - k));
         }
         if (c + 1 < c_end) {
@@ -264,7 +278,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int k = (c + 1) * 16 + j;
-            if (DUMP) { if (inb && k < p.kmax) p.dbg_sims[pix * p.kmax + k] = __uint_as_float(vb[j]); }
+            if (DUMP) { if (inb && kofs + k < p.kmax) p.dbg_sims[pix * p.kmax + kofs + k] = __uint_as_float(vb[j]); }
             upd3(m, s, t3, pack_idx(vb[j], 255 - k));
           }
         }
@@ -273,18 +287,35 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");                       // barrier 1
       bool amb = false, many = false;
       int kb = 0, ks = 0;
+      const bool last_pass = p.pass == p.n_pass - 1;
       if (h == 0) {
         upd3(m, s, t3, exv[r]);
         upd3(m, s, t3, exv[TC_BM + r]);
         upd3(m, s, t3, exv[2 * TC_BM + r]);
-        kb = 255 - (int)(__float_as_uint(m) & 0xFFu);
-        ks = 255 - (int)(__float_as_uint(s) & 0xFFu);
-        const float thr = 2.f * (xe * 1.001f + cerrmax * 1.001f + TC_EPS_CONST);
-        amb = inb && (m - s <= thr);
-        many = amb && (m - t3 <= thr);             // three or more inside the bound
-        thr_row[r] = many ? m - thr : FLT_MAX;
-        if (many) *many_flag = 1;
-        if (inb) p.keys_out[pix] = seg * p.kmax + kb;
+        // which centroid tile each survivor came from: a value equal to a carried one IS the carried one
+        // (bit-equal packed values from two tiles are an exact tie; both stay candidates below)
+        const uint32_t cur = (uint32_t)p.pass;
+        auto tile_of = [&](float v) -> uint32_t {
+          return v == om ? (otile & 0xFFu) : v == os ? ((otile >> 8) & 0xFFu) : v == ot ? ((otile >> 16) & 0xFFu) : cur;
+        };
+        const uint32_t tm = p.n_pass > 1 ? tile_of(m) : 0u, ts = p.n_pass > 1 ? tile_of(s) : 0u,
+                       tt = p.n_pass > 1 ? tile_of(t3) : 0u;
+        if (!last_pass) {
+          if (inb) {
+            p.st_val[pix * 3] = m; p.st_val[pix * 3 + 1] = s; p.st_val[pix * 3 + 2] = t3;
+            *reinterpret_cast<uint32_t*>(p.st_tile + pix * 4) = tm | (ts << 8) | (tt << 16);
+          }
+          thr_row[r] = FLT_MAX;
+        } else {
+          kb = (int)tm * p.kpad + 255 - (int)(__float_as_uint(m) & 0xFFu);
+          ks = (int)ts * p.kpad + 255 - (int)(__float_as_uint(s) & 0xFFu);
+          const float thr = 2.f * (xe * 1.001f + cerrmax * 1.001f + TC_EPS_CONST);
+          amb = inb && (m - s <= thr);
+          many = amb && (m - t3 <= thr);             // three or more inside the bound
+          thr_row[r] = (many && p.n_pass == 1) ? m - thr : FLT_MAX;
+          if (many && p.n_pass == 1) *many_flag = 1;
+          if (inb) p.keys_out[pix] = seg * p.kmax + kb;
+        }
       }
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");                       // barrier 2
       const bool tile_many = *many_flag != 0;
@@ -319,6 +350,9 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           uint16_t* cd = p.fix.cand + (int64_t)slot * FIX_MAX_CAND;
           if (!many) {                               // everything but the top two is provably out of reach
             cd[0] = (uint16_t)kb; cd[1] = (uint16_t)ks; cd[2] = 0xFFFF;
+          } else if (p.n_pass > 1) {                 // candidates of earlier tiles are gone: scan every cluster
+            cd[0] = 0xFFFF;
+            atomicAdd(p.fix.count + 1, 1);
           } else {
             const int c0 = cnt_row[0], c1 = cnt_row[1];
             if (c0 > TC_MAXC || c1 > TC_MAXC || c0 + c1 > FIX_MAX_CAND) {
@@ -389,28 +423,29 @@ __global__ void tc_convert_kernel(const float* __restrict__ cent, const int32_t*
 }
 
 // ---------------------------------------------------------------- host side
+// centroids per pass: the fp16 tile [ktile x (d16+16)] has to fit next to the pixel ring (<= 136 KiB)
+static int tc_ktile(int d16) { return d16 <= 256 ? 256 : 128; }
+
 bool tc_shape_supported(int dim, int d16, int kmax) {
-  if (!(d16 == 64 || d16 == 128 || d16 == 256)) return false;
+  if (!(d16 == 64 || d16 == 128 || d16 == 256 || d16 == 512)) return false;
   if (dim < d16 || dim - d16 > HSG_XH_MAX_TRAILING) return false;
-  if (kmax < 1 || kmax > 256) return false;
+  if (kmax < 1) return false;
   const int kpad = (kmax + 15) / 16 * 16;
-  return (size_t)kpad * d16 * 2 <= 128 * 1024;
+  return kpad <= 255 * tc_ktile(d16);              // tile ids are carried as bytes
 }
 
-void tc_carve(Carver& c, TcState& t, int S, int kmax, int d16) {
+void tc_carve(Carver& c, TcState& t, int S, int kmax, int d16, int64_t N) {
   t.enabled = false;
-  t.kpad = (kmax + 15) / 16 * 16;
   t.d16 = d16;
-  t.ch = c.take<__half>((size_t)S * t.kpad * (d16 + HSG_XH_TAIL));
+  const int kpad = (kmax + 15) / 16 * 16, ktile = tc_ktile(d16);
+  t.n_pass = (kpad + ktile - 1) / ktile;
+  t.kpad = t.n_pass == 1 ? kpad : ktile;
+  t.kpad_total = t.n_pass * t.kpad;
+  t.ch = c.take<__half>((size_t)S * t.kpad_total * (d16 + HSG_XH_TAIL));
   t.cerr = c.take<float>((size_t)S * kmax);
   t.cerr_max = c.take<float>(S);
-}
-
-size_t tc_workspace_bytes(int S, int kmax, int d16) {
-  Carver c(nullptr);
-  TcState t;
-  tc_carve(c, t, S, kmax, d16);
-  return c.used();
+  t.st_val = t.n_pass > 1 ? c.take<float>((size_t)N * 3) : nullptr;
+  t.st_tile = t.n_pass > 1 ? c.take<uint8_t>((size_t)N * 4) : nullptr;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -455,16 +490,16 @@ int tc_prepare(TcState& t, int64_t N, int S) {
   int rc;
   if ((rc = encode_2d_f16(t.tmap_x, t.xh, (uint64_t)N, wx, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = encode_2d_f16(t.tmap_xt, t.xh, (uint64_t)N, wx, HSG_XH_TAIL, TC_BM, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
-  if ((rc = encode_2d_f16(t.tmap_c, t.ch, (uint64_t)S * t.kpad, wx, TC_BK, (uint32_t)t.kpad, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = encode_2d_f16(t.tmap_ct, t.ch, (uint64_t)S * t.kpad, wx, HSG_XH_TAIL, (uint32_t)t.kpad, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = encode_2d_f16(t.tmap_c, t.ch, (uint64_t)S * t.kpad_total, wx, TC_BK, (uint32_t)t.kpad, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = encode_2d_f16(t.tmap_ct, t.ch, (uint64_t)S * t.kpad_total, wx, HSG_XH_TAIL, (uint32_t)t.kpad, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   t.enabled = true;
   return HSG_OK;
 }
 
 int tc_convert_centroids(const EStepArgs& a, const TcState& t, cudaStream_t st) {
   HSG_CUDA(cudaMemsetAsync(t.cerr_max, 0, sizeof(float) * a.S, st));
-  const int64_t rows = (int64_t)a.S * t.kpad;
-  tc_convert_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(a.centroids, a.seg_k, a.S, a.kmax, t.kpad, a.dim,
+  const int64_t rows = (int64_t)a.S * t.kpad_total;
+  tc_convert_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(a.centroids, a.seg_k, a.S, a.kmax, t.kpad_total, a.dim,
                                                                   t.d16, t.ch, t.cerr, t.cerr_max);
   HSG_LAUNCH_CHECK();
   return HSG_OK;
@@ -475,7 +510,8 @@ float* g_tc_debug_sims = nullptr;   // set by hsg_debug_set_tc_dump (tests only)
 int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
   HSG_REQUIRE(t.enabled, HSG_E_INVALID, "tensor-core E-step used before tc_prepare");
   TcParams p;
-  p.d16 = t.d16; p.kmax = a.kmax; p.kpad = t.kpad; p.xerr = t.xerr; p.cerr_max = t.cerr_max;
+  p.d16 = t.d16; p.kmax = a.kmax; p.kpad = t.kpad; p.kpad_total = t.kpad_total; p.n_pass = t.n_pass; p.pass = 0;
+  p.st_val = t.st_val; p.st_tile = t.st_tile; p.xerr = t.xerr; p.cerr_max = t.cerr_max;
   p.tiles = a.tiles; p.sub = (int)(a.tiles.tile / TC_BM); p.items = (long long)a.tiles.bound * p.sub;
   p.keys_out = a.keys_out; p.fix = a.fix; p.dbg_sims = g_tc_debug_sims;
   const int nslab = t.d16 / TC_BK;
@@ -495,14 +531,16 @@ int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
   long long grid = num_sms();
   if (grid > p.items) grid = p.items;
   if (grid < 1) grid = 1;
-  if (p.dbg_sims) {
-    HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    estep_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, st>>>(mx, mxt, mc, mct, p);
-  } else {
-    HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    estep_tc_kernel<false><<<(unsigned)grid, TC_THREADS, smem, st>>>(mx, mxt, mc, mct, p);
+  for (p.pass = 0; p.pass < p.n_pass; ++p.pass) {
+    if (p.dbg_sims) {
+      HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      estep_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, st>>>(mx, mxt, mc, mct, p);
+    } else {
+      HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      estep_tc_kernel<false><<<(unsigned)grid, TC_THREADS, smem, st>>>(mx, mxt, mc, mct, p);
+    }
+    HSG_LAUNCH_CHECK();
   }
-  HSG_LAUNCH_CHECK();
   return HSG_OK;
 }
 

@@ -131,8 +131,8 @@ def _seg_args(n, seg_offsets, max_seg_len, device):
 
 def tc_d16(dim, kmax):
   """Width of the fp16 side copy the tensor-core E-step wants for this shape (0 = none)."""
-  for d16 in (256, 128, 64):
-    if dim >= d16 and dim - d16 <= 5 and kmax <= 256 and kmax * d16 * 2 <= 128 * 1024:
+  for d16 in (512, 256, 128, 64):
+    if dim >= d16 and dim - d16 <= 5 and kmax <= 255 * (256 if d16 <= 256 else 128):
       return d16
   return 0
 

@@ -455,6 +455,10 @@ def _tc_case(nn, d16, loc, k, lens=None, seed=11):
     (128, 2, 36, [5000, 4000]),
     (64, 0, 32, [9000]),
     (128, 5, 100, [3000, 2000]),
+    (256, 2, 288, [9000, 5000]),          # K > 256: two centroid tiles (Cityscapes inference grid 12x24)
+    (64, 0, 2048, [6000]),                # eight centroid tiles
+    (512, 2, 40, [4000, 3000]),           # D = 512: eight slabs per pixel tile, 128-centroid tiles
+    (512, 0, 300, [5000]),                # both
 ])
 def test_tc_estep_exact_and_equal_to_simt(d16, loc, k, lens):
   from hsg_b200 import ops, _lib
