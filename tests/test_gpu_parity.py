@@ -722,3 +722,70 @@ def test_config5_flat_kmeans_sweep_points(S, nn, d, k):
   assert np.array_equal(n(lab20)[sel], best[sel])
   ref = o_ops.kmeans_with_initial_labels(x, init, k, 20)
   assert np.mean(n(lab20) == ref) > (0.9 if k >= 200 else 0.97)       # 20 iterations on iid noise: flips cascade
+
+
+# ---------------------------------------------------------------- BASELINE.json configs[1] at FULL size: properties
+def test_config2_full_size_properties(S):
+  """48 images x 448x448, D=256, grid 16x16 (K=256), 10 iterations, P=12288: the oracle cannot run
+  this size, so the check is through size-independent properties on the full result --
+  (1) run-to-run identical ids, (2) the dense ids are exactly the ranks of the (image, cluster)
+  pairs, (3) on sampled images the last E-step is the float64 arg-max over the oracle's centroids
+  of the previous labels and the k-means objective did not decrease, (4) sampled prototypes are the
+  oracle's mean directions of their members, (5) sampled per-pixel NCE losses equal the float64
+  oracle against all 12288 prototypes."""
+  from hsg_b200 import ops
+  from hsg_b200.utils.segsort import loss as L
+  b, d, hw, grid, iters = 48, 256, 448, 16, 10
+  free, _ = torch.cuda.mem_get_info()
+  if free < 90 * (1 << 30):
+    pytest.skip('needs ~90 GB of free HBM')
+  g = torch.Generator(device=dev())
+  g.manual_seed(235)
+  emb = torch.randn((b, d, hw, hw), generator=g, device=dev(), dtype=torch.float32)
+  ex = S.segment_by_kmeans_ex(emb, None, [grid, grid], iterations=iters, count_prototypes=True)
+  ex2 = S.segment_by_kmeans_ex(emb, None, [grid, grid], iterations=iters, count_prototypes=True)
+  assert torch.equal(ex['cluster_indices'], ex2['cluster_indices'])                               # (1)
+  del ex2
+  ids, bat, km = ex['cluster_indices'], ex['batch_indices'], ex['kmeans_labels']
+  uniq, inv = torch.unique(bat * grid * grid + km, return_inverse=True)
+  assert torch.equal(inv, ids) and int(uniq.numel()) == ex['num_prototypes']                      # (2)
+  n_img = hw * hw
+  xloc = ex['embeddings_with_loc']
+  init = S._grid_init([grid, grid], (hw, hw), emb.device)[0].repeat(b)
+  xh, xerr = ops.make_half_copy(xloc, d)
+  prev = ops.kmeans(xloc, init, grid * grid, iters - 1, seg_offsets=ex['seg_offsets'], max_seg_len=n_img,
+                    xh=xh, xerr=xerr)
+  del xh, xerr
+  rng = np.random.RandomState(1)
+  for img in (0, 17, 47):                                                                          # (3)
+    sl = slice(img * n_img, (img + 1) * n_img)
+    xs = n(xloc[sl])
+    cent = o_ops.calculate_prototypes_from_labels(xs, n(prev[sl]), grid * grid)
+    pick = rng.choice(n_img, 20000, replace=False)
+    best, _, gap = o_ops.argmax_margins(xs[pick], cent)
+    mine = n(km[sl])[pick]
+    sel = gap > 1e-9
+    assert np.mean(sel) > 0.99 and np.array_equal(mine[sel], best[sel])
+    obj_new = o_ops.kmeans_objective(xs[pick], cent, n(km[sl])[pick])
+    obj_old = o_ops.kmeans_objective(xs[pick], cent, n(prev[sl])[pick])
+    assert obj_new >= obj_old - 1e-3
+  protos = S.pool_prototypes(ex)
+  x = ex['embeddings']
+  ids_h = n(ids[:3 * n_img])
+  for pid in rng.choice(3 * grid * grid, 40, replace=False):                                       # (4)
+    members = np.nonzero(ids_h == pid)[0]
+    want = o_ops.calculate_prototypes_from_labels(n(x[torch.from_numpy(members).to(x.device)]),
+                                                  np.zeros(members.size, np.int64), 1)[0]
+    close(n(protos[pid]), want, rtol=1e-5, atol=1e-6)
+  pb = ex['proto_batch']
+  pid_all = torch.arange(protos.shape[0], device=emb.device)
+  sets = torch.stack([bat, ids], 0)
+  psets = torch.stack([pb, pid_all], 0)
+  ll = ops.nce_log_likelihood(x, ids, sets, protos, psets, 16.0, ['segsort+', 'segsort+'])
+  pick = torch.from_numpy(rng.choice(b * n_img, 1024, replace=False)).to(emb.device)
+  xe, xi = n(x[pick]), n(ids[pick])
+  for s in range(2):                                                                               # (5)
+    args = (xe, n(sets[s][pick]), xi, n(protos), n(psets[s]), 16.0)
+    want = o_loss.calculate_log_likelihood(*args, dtype=np.float64).reshape(-1)
+    tol = 1e-5 * np.abs(want) + 1e-6 * o_loss.nce_condition(*args) + 1e-6
+    assert np.all(np.abs(n(ll[s][pick]) - want) <= tol), np.abs(n(ll[s][pick]) - want).max()
