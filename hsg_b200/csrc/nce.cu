@@ -274,7 +274,53 @@ size_t nce_tc_workspace_bytes(int64_t N, int64_t P, int dim, int n_sets);
 int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, int dim, const int64_t* inst,
                const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus, float conc,
                float* per_pixel, float* stats, void* workspace, cudaStream_t st);
-int g_debug_flags = 0;   // bit 0: keep the NCE forward on the fp32 CUDA-core kernel (tests)
+int g_debug_flags = 0;   // bit 0: keep the NCE forward on the fp32 CUDA-core kernel, bit 2: the backward GEMMs (tests)
+
+// fp32-grade tensor-core GEMM on pre-split fp16 (hi|lo) operands (gemm_tc.cu)
+bool gemm_tc_supported(int N, int K);
+int gemm_tc_split(const __half* a2, const __half* b2, int64_t M, int N, int K, float* C, int64_t ldc,
+                  const float* inv_scale, float alpha, bool accumulate, cudaStream_t st);
+int split_rows(const float* src, int64_t R, int C, int Kp, float mul, const float* dev_mul, __half* dst, cudaStream_t st);
+int split_transpose(const float* src, int64_t R, int C, int64_t Rp, float mul, const float* dev_mul, __half* dst,
+                    cudaStream_t st);
+int absmax(const float* x, int64_t n, float* out, cudaStream_t st);
+
+// operand scales of the backward GEMMs: G is multiplied by sc[0] = 2^10 / (conc * n_sets * max|w|) before the
+// fp16 split (|G_ij| <= conc * sum_s |w_si|), E and P by 16; sc[1] = 1 / (16 sc[0]) undoes both
+__global__ void nce_bwd_scales_kernel(const float* __restrict__ wmax, float conc, int n_sets, float* __restrict__ sc) {
+  const float bound = fabsf(conc) * n_sets * wmax[0];
+  const float sa = bound > 0.f ? 1024.f / bound : 1.f;
+  sc[0] = sa;
+  sc[1] = 1.f / (16.f * sa);
+}
+
+struct BwdTcPlan {
+  bool on;
+  int64_t Pp, chunkp;
+  float* G;
+  __half* G2;
+  __half* Gt2;
+  __half* Pt2;
+  __half* Et2;
+  float* scal;     // [0] max|w|, [1] G scale, [2] output scale
+};
+
+static void bwd_carve(Carver& c, BwdTcPlan& b, int64_t N, int64_t P, int dim, int64_t chunk, bool tc) {
+  b.on = tc;
+  b.Pp = (P + 63) / 64 * 64;
+  b.chunkp = (chunk + 63) / 64 * 64;
+  b.G = c.take<float>((size_t)chunk * P);
+  if (!tc) return;
+  b.G2 = c.take<__half>((size_t)chunk * 2 * b.Pp);
+  b.Gt2 = c.take<__half>((size_t)P * 2 * b.chunkp);
+  b.Pt2 = c.take<__half>((size_t)dim * 2 * b.Pp);
+  b.Et2 = c.take<__half>((size_t)dim * 2 * b.chunkp);
+  b.scal = c.take<float>(4);
+}
+
+static bool bwd_tc_shape(int64_t P, int dim) {
+  return dim >= 16 && dim <= 256 && dim % 16 == 0 && P >= 1;
+}
 
 static int64_t nce_chunk_pixels(int64_t N, int64_t P) {
   // keep the G chunk near 256 MB
@@ -304,7 +350,10 @@ using namespace hsg;
 extern "C" {
 
 size_t hsg_nce_workspace_bytes(int64_t N, int64_t P, int dim, int n_sets) {
-  size_t need = (size_t)nce_chunk_pixels(N, P) * P * sizeof(float) + 1024;       // backward: one G chunk
+  Carver cb(nullptr);
+  BwdTcPlan bp;
+  bwd_carve(cb, bp, N, P, dim, nce_chunk_pixels(N, P), bwd_tc_shape(P, dim));
+  size_t need = cb.used() + 1024;                                                // backward: one G chunk (+ its fp16 splits)
   if (nce_tc_supported(N, P, dim, n_sets)) {
     const size_t tc = nce_tc_workspace_bytes(N, P, dim, n_sets);                 // forward: fp16 (hi,lo) copies
     if (tc > need) need = tc;
@@ -357,9 +406,19 @@ int hsg_nce_bwd_f32(const float* e, const float* prototypes, int64_t N, int64_t 
   if (N == 0) return HSG_OK;
   HSG_REQUIRE(workspace && workspace_bytes >= hsg_nce_workspace_bytes(N, P, dim, n_sets), HSG_E_WORKSPACE,
               "nce_bwd: workspace too small");
-  float* G = (float*)workspace;
   ProfRange prof(PROF_NCE_BWD, st);
   const int64_t chunk = nce_chunk_pixels(N, P);
+  Carver cw(workspace);
+  BwdTcPlan b;
+  bwd_carve(cw, b, N, P, dim, chunk, bwd_tc_shape(P, dim) && !(g_debug_flags & 4));
+  float* G = b.G;
+  if (b.on) {
+    // dE = G P and dP = G^T E on the tensor cores (three fp16 passes each, gemm_tc.cu)
+    if ((rc = absmax(w, (int64_t)n_sets * N, b.scal, st))) return rc;
+    nce_bwd_scales_kernel<<<1, 1, 0, st>>>(b.scal, concentration, n_sets, b.scal + 1);
+    HSG_LAUNCH_CHECK();
+    if ((rc = split_transpose(prototypes, P, dim, b.Pp, 16.f, nullptr, b.Pt2, st))) return rc;
+  }
   for (int64_t i0 = 0; i0 < N; i0 += chunk) {
     const int64_t i1 = i0 + chunk < N ? i0 + chunk : N;
     const int64_t m = i1 - i0;
@@ -371,6 +430,17 @@ int hsg_nce_bwd_f32(const float* e, const float* prototypes, int64_t N, int64_t 
       default: nce_grad_kernel<4><<<gg, NC_THREADS, 0, st>>>(a, stats, w, i0, i1, G); break;
     }
     HSG_LAUNCH_CHECK();
+    if (b.on) {
+      const int64_t mp = (m + 63) / 64 * 64;
+      // dE[i0:i1] = G P          ([m,P] x [P,dim])
+      if ((rc = split_rows(G, m, (int)P, (int)b.Pp, 1.f, b.scal + 1, b.G2, st))) return rc;
+      if ((rc = gemm_tc_split(b.G2, b.Pt2, m, dim, (int)b.Pp, grad_e + i0 * dim, dim, b.scal + 2, 1.f, false, st))) return rc;
+      // dP += G^T E[i0:i1]       ([P,m] x [m,dim])
+      if ((rc = split_transpose(G, m, (int)P, mp, 1.f, b.scal + 1, b.Gt2, st))) return rc;
+      if ((rc = split_transpose(e + i0 * dim, m, dim, mp, 16.f, nullptr, b.Et2, st))) return rc;
+      if ((rc = gemm_tc_split(b.Gt2, b.Et2, P, dim, (int)mp, grad_p, dim, b.scal + 2, 1.f, true, st))) return rc;
+      continue;
+    }
     // dE[i0:i1] = G P          ([m,P] x [P,dim])
     dim3 g1((unsigned)ceil_div64(dim, NC_T), (unsigned)ceil_div64(m, NC_T));
     sgemm_kernel<false><<<g1, NC_THREADS, 0, st>>>(G, prototypes, grad_e + i0 * dim, m, dim, P, 0);

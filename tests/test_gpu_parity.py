@@ -561,6 +561,40 @@ def test_nce_tensor_core_forward(nn, pp, d, conc):
     assert abs(tc[s].mean() - want.mean()) <= 1e-5 * abs(want.mean()) + np.mean(1e-6 * kappa)
 
 
+def test_nce_backward_tensor_core_gemms_vs_float64():
+  """dE = G P and dP = G^T E on tcgen05 (three fp16 passes, gemm_tc.cu) against the float64 closed
+  form, next to the fp32 CUDA-core GEMMs they replace; ragged sizes (P, N not multiples
+  of the tile sizes), per-pixel weights, two label sets in one pass."""
+  from hsg_b200 import ops, _lib
+  rng = np.random.RandomState(23)
+  nn, pp, d, conc = 4133, 333, 256, 4.0       # well-conditioned numerators: the error measured is the GEMMs'
+  e = o_ops.normalize_embedding(rng.randn(nn, d).astype(np.float32))
+  inst = rng.randint(0, pp, nn).astype(np.int64)
+  protos = o_ops.calculate_prototypes_from_labels(e, inst, pp)
+  psem = np.stack([rng.randint(0, 12, pp), rng.randint(0, 40, pp)]).astype(np.int64)
+  sem = np.stack([psem[0][inst], psem[1][inst]])
+  w = (rng.rand(2, nn).astype(np.float32) + 0.1) / nn
+  want_e, want_p = np.zeros((nn, d)), np.zeros((pp, d))
+  for s in range(2):
+    de, dp = o_loss.segsort_loss_backward(e, sem[s], inst, protos, psem[s], conc, w[s])
+    want_e += de
+    want_p += dp
+  lib = _lib.load()
+  errs = {}
+  for flags in (0, 4):
+    lib.hsg_debug_set_flags(flags)
+    try:
+      et, pt = t(e).requires_grad_(True), t(protos).requires_grad_(True)
+      ll = ops.nce_log_likelihood(et, t(inst), t(sem), pt, t(psem), conc, ['segsort+', 'segsort+'])
+      (ll * t(w)).sum().backward()
+    finally:
+      lib.hsg_debug_set_flags(0)
+    errs[flags] = (np.linalg.norm(n(et.grad) - want_e) / np.linalg.norm(want_e),
+                   np.linalg.norm(n(pt.grad) - want_p) / np.linalg.norm(want_p))
+  assert max(errs[0]) < 1e-5, errs          # tensor cores: fp32-grade
+  assert max(errs[4]) < 1e-4, errs
+
+
 # ---------------------------------------------------------------- clustering transformer (fused attention)
 def _load_transformer(g):
   from hsg_b200.models.embeddings.transformer_clusters import TransformerClustering

@@ -36,3 +36,31 @@ lib.hsg_debug_set_flags(0)
 rel = ((ll[:, :n_s] - ref).abs() / ref.abs().clamp_min(1e-3)).max().item()
 print('max relative difference to the fp32 kernel on %d pixels: %.3g' % (n_s, rel))
 assert rel < 2e-5
+
+# backward (dE, dP): recomputed G chunk + two fp32-grade tensor-core GEMMs
+nb = min(N, 1 << 20)
+eb = e[:nb].clone().requires_grad_(True)
+pb = pr.clone().requires_grad_(True)
+semb = sem[:, :nb].contiguous()
+for flags, name in ((0, 'tensor-core GEMMs'), (4, 'CUDA-core GEMMs')):
+  lib.hsg_debug_set_flags(flags)
+  grads = []
+  for rep in range(2):
+    eb.grad = None; pb.grad = None
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ll = ops.nce_log_likelihood(eb, inst[:nb], semb, pb, psem, 16.0, sets)
+    loss = ll.mean()
+    t0.record()
+    loss.backward()
+    t1.record(); torch.cuda.synchronize()
+  print('backward on %d pixels, %s: %.1f ms' % (nb, name, t0.elapsed_time(t1)))
+  grads.append((eb.grad.clone(), pb.grad.clone()))
+  if flags == 0:
+    ref_g = grads[-1]
+  else:
+    for a_, b_ in zip(ref_g, grads[-1]):
+      rel = ((a_ - b_).norm() / b_.norm()).item()
+      print('  relative difference to the tensor-core gradients: %.3g' % rel)
+      assert rel < 1e-5
+lib.hsg_debug_set_flags(0)
