@@ -171,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 // ---------------------------------------------------------------- operand preparation
 // dst[r, c] = fp16(s x), dst[r, Kp + c] = fp16(s x - hi) for c < C, zero for C <= c < Kp;  s = mul * (*dev_mul)
-__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ src, int64_t R, int C, int Kp,
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ src, int64_t ld, int64_t R, int C, int Kp,
                                                          float mul, const float* __restrict__ dev_mul,
                                                          __half* __restrict__ dst) {
   const float s = mul * (dev_mul ? *dev_mul : 1.f);
@@ -179,14 +179,14 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
   if (i >= R * Kp) return;
   const int64_t r = i / Kp;
   const int c = (int)(i - r * Kp);
-  const float v = c < C ? src[r * C + c] * s : 0.f;
+  const float v = c < C ? src[r * ld + c] * s : 0.f;
   const __half hi = __float2half_rn(v);
   dst[r * 2 * Kp + c] = hi;
   dst[r * 2 * Kp + Kp + c] = __float2half_rn(v - __half2float(hi));
 }
 
 // transpose + split: dst[c, r] = hi(s x[r, c]), dst[c, Rp + r] = lo, for src [R, C]; rows r >= R are zero
-__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ src, int64_t R, int C, int64_t Rp,
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ src, int64_t ld, int64_t R, int C, int64_t Rp,
                                                               float mul, const float* __restrict__ dev_mul,
                                                               __half* __restrict__ dst) {
   __shared__ float tile[32][33];
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
   for (int k = ty; k < 32; k += 8) {
     const int64_t r = r0 + k;
     const int c = c0 + tx;
-    tile[k][tx] = (r < R && c < C) ? src[r * C + c] * s : 0.f;
+    tile[k][tx] = (r < R && c < C) ? src[r * ld + c] * s : 0.f;
   }
   __syncthreads();
   for (int k = ty; k < 32; k += 8) {
@@ -249,16 +249,17 @@ int gemm_tc_split(const __half* a2, const __half* b2, int64_t M, int N, int K, f
   return HSG_OK;
 }
 
-int split_rows(const float* src, int64_t R, int C, int Kp, float mul, const float* dev_mul, __half* dst, cudaStream_t st) {
-  split_rows_kernel<<<(unsigned)ceil_div64(R * Kp, 256), 256, 0, st>>>(src, R, C, Kp, mul, dev_mul, dst);
+int split_rows(const float* src, int64_t ld, int64_t R, int C, int Kp, float mul, const float* dev_mul, __half* dst,
+               cudaStream_t st) {
+  split_rows_kernel<<<(unsigned)ceil_div64(R * Kp, 256), 256, 0, st>>>(src, ld, R, C, Kp, mul, dev_mul, dst);
   HSG_LAUNCH_CHECK();
   return HSG_OK;
 }
 
-int split_transpose(const float* src, int64_t R, int C, int64_t Rp, float mul, const float* dev_mul, __half* dst,
-                    cudaStream_t st) {
+int split_transpose(const float* src, int64_t ld, int64_t R, int C, int64_t Rp, float mul, const float* dev_mul,
+                    __half* dst, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div64(Rp, 32), (unsigned)ceil_div64(C, 32));
-  split_transpose_kernel<<<grid, 256, 0, st>>>(src, R, C, Rp, mul, dev_mul, dst);
+  split_transpose_kernel<<<grid, 256, 0, st>>>(src, ld, R, C, Rp, mul, dev_mul, dst);
   HSG_LAUNCH_CHECK();
   return HSG_OK;
 }

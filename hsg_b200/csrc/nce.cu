@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(NC_THREADS) nce_fwd_kernel(const NceArgs a, fl
 template <int NS>
 __global__ void __launch_bounds__(NC_THREADS) nce_grad_kernel(const NceArgs a, const float* __restrict__ stats,
                                                               const float* __restrict__ w, int64_t i_begin,
-                                                              int64_t i_end, float* __restrict__ G) {
+                                                              int64_t i_end, float* __restrict__ G, int64_t ldg) {
   __shared__ float As[NC_T][NC_DC + 1];
   __shared__ float Bs[NC_T][NC_DC + 1];
   const int tid = threadIdx.x;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(NC_THREADS) nce_grad_kernel(const NceArgs a, c
         const float dl = (same ? 0.f : 1.f / den) + wij * (1.f / den - 1.f / num);
         coef = fmaf(w[(int64_t)s * a.N + pix], dl, coef);
       }
-      G[(pix - i_begin) * a.P + pj] = a.conc * coef * sv;
+      G[(pix - i_begin) * ldg + pj] = a.conc * coef * sv;
     }
   }
 }
@@ -274,15 +274,24 @@ size_t nce_tc_workspace_bytes(int64_t N, int64_t P, int dim, int n_sets);
 int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, int dim, const int64_t* inst,
                const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus, float conc,
                float* per_pixel, float* stats, void* workspace, cudaStream_t st);
-int g_debug_flags = 0;   // bit 0: keep the NCE forward on the fp32 CUDA-core kernel, bit 2: the backward GEMMs (tests)
+int g_debug_flags = 0;   // tests: bit 0 keeps the NCE forward on the fp32 CUDA-core kernel, bit 2 the backward GEMMs,
+                         // bit 3 the backward's G chunk
 
 // fp32-grade tensor-core GEMM on pre-split fp16 (hi|lo) operands (gemm_tc.cu)
 bool gemm_tc_supported(int N, int K);
 int gemm_tc_split(const __half* a2, const __half* b2, int64_t M, int N, int K, float* C, int64_t ldc,
                   const float* inv_scale, float alpha, bool accumulate, cudaStream_t st);
-int split_rows(const float* src, int64_t R, int C, int Kp, float mul, const float* dev_mul, __half* dst, cudaStream_t st);
-int split_transpose(const float* src, int64_t R, int C, int64_t Rp, float mul, const float* dev_mul, __half* dst,
-                    cudaStream_t st);
+int split_rows(const float* src, int64_t ld, int64_t R, int C, int Kp, float mul, const float* dev_mul, __half* dst,
+               cudaStream_t st);
+int split_transpose(const float* src, int64_t ld, int64_t R, int C, int64_t Rp, float mul, const float* dev_mul,
+                    __half* dst, cudaStream_t st);
+// tensor-core G chunk (nce_tc.cu): one prepare per backward call, one launch per pixel chunk
+size_t nce_grad_tc_host_state_bytes();
+int nce_grad_tc_prepare(void* host_state, const float* e, const float* prototypes, int64_t N, int64_t P, int dim,
+                        const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus,
+                        float conc, void* workspace, cudaStream_t st);
+int nce_grad_tc(void* host_state, const float* stats, const float* w, float conc, int64_t i_begin, int64_t i_end,
+                float* G, int64_t ldg, cudaStream_t st);
 int absmax(const float* x, int64_t n, float* out, cudaStream_t st);
 
 // operand scales of the backward GEMMs: G is multiplied by sc[0] = 2^10 / (conc * n_sets * max|w|) before the
@@ -295,7 +304,10 @@ __global__ void nce_bwd_scales_kernel(const float* __restrict__ wmax, float conc
 }
 
 struct BwdTcPlan {
-  bool on;
+  bool on;                 // GEMMs on tensor cores
+  bool g_on;               // G chunk on tensor cores as well
+  int64_t ldg;             // row stride of the G chunk
+  void* fwd_ws;            // fp16 operand copies / int32 labels of the pair kernels
   int64_t Pp, chunkp;
   float* G;
   __half* G2;
@@ -305,11 +317,14 @@ struct BwdTcPlan {
   float* scal;     // [0] max|w|, [1] G scale, [2] output scale
 };
 
-static void bwd_carve(Carver& c, BwdTcPlan& b, int64_t N, int64_t P, int dim, int64_t chunk, bool tc) {
+static void bwd_carve(Carver& c, BwdTcPlan& b, int64_t N, int64_t P, int dim, int n_sets, int64_t chunk, bool tc) {
   b.on = tc;
   b.Pp = (P + 63) / 64 * 64;
   b.chunkp = (chunk + 63) / 64 * 64;
-  b.G = c.take<float>((size_t)chunk * P);
+  b.ldg = tc ? b.Pp : P;
+  b.g_on = tc && nce_tc_supported(N, P, dim, n_sets);
+  b.G = c.take<float>((size_t)chunk * b.ldg);
+  b.fwd_ws = b.g_on ? c.take<char>(nce_tc_workspace_bytes(N, P, dim, n_sets)) : nullptr;
   if (!tc) return;
   b.G2 = c.take<__half>((size_t)chunk * 2 * b.Pp);
   b.Gt2 = c.take<__half>((size_t)P * 2 * b.chunkp);
@@ -352,7 +367,7 @@ extern "C" {
 size_t hsg_nce_workspace_bytes(int64_t N, int64_t P, int dim, int n_sets) {
   Carver cb(nullptr);
   BwdTcPlan bp;
-  bwd_carve(cb, bp, N, P, dim, nce_chunk_pixels(N, P), bwd_tc_shape(P, dim));
+  bwd_carve(cb, bp, N, P, dim, n_sets, nce_chunk_pixels(N, P), bwd_tc_shape(P, dim));
   size_t need = cb.used() + 1024;                                                // backward: one G chunk (+ its fp16 splits)
   if (nce_tc_supported(N, P, dim, n_sets)) {
     const size_t tc = nce_tc_workspace_bytes(N, P, dim, n_sets);                 // forward: fp16 (hi,lo) copies
@@ -410,34 +425,44 @@ int hsg_nce_bwd_f32(const float* e, const float* prototypes, int64_t N, int64_t 
   const int64_t chunk = nce_chunk_pixels(N, P);
   Carver cw(workspace);
   BwdTcPlan b;
-  bwd_carve(cw, b, N, P, dim, chunk, bwd_tc_shape(P, dim) && !(g_debug_flags & 4));
+  bwd_carve(cw, b, N, P, dim, n_sets, chunk, bwd_tc_shape(P, dim) && !(g_debug_flags & 4));
+  if (g_debug_flags & 8) b.g_on = false;
+  alignas(64) unsigned char tc_state[1024];
+  HSG_REQUIRE(nce_grad_tc_host_state_bytes() <= sizeof(tc_state), HSG_E_UNSUPPORTED, "nce_bwd: host state");
   float* G = b.G;
   if (b.on) {
     // dE = G P and dP = G^T E on the tensor cores (three fp16 passes each, gemm_tc.cu)
     if ((rc = absmax(w, (int64_t)n_sets * N, b.scal, st))) return rc;
     nce_bwd_scales_kernel<<<1, 1, 0, st>>>(b.scal, concentration, n_sets, b.scal + 1);
     HSG_LAUNCH_CHECK();
-    if ((rc = split_transpose(prototypes, P, dim, b.Pp, 16.f, nullptr, b.Pt2, st))) return rc;
+    if ((rc = split_transpose(prototypes, dim, P, dim, b.Pp, 16.f, nullptr, b.Pt2, st))) return rc;
+    if (b.g_on && (rc = nce_grad_tc_prepare(tc_state, e, prototypes, N, P, dim, inst, sem, psem, n_sets, group_plus_host,
+                                            concentration, b.fwd_ws, st))) return rc;
   }
   for (int64_t i0 = 0; i0 < N; i0 += chunk) {
     const int64_t i1 = i0 + chunk < N ? i0 + chunk : N;
     const int64_t m = i1 - i0;
-    dim3 gg((unsigned)ceil_div64(m, NC_T), (unsigned)ceil_div64(P, NC_T));
-    switch (n_sets) {
-      case 1: nce_grad_kernel<1><<<gg, NC_THREADS, 0, st>>>(a, stats, w, i0, i1, G); break;
-      case 2: nce_grad_kernel<2><<<gg, NC_THREADS, 0, st>>>(a, stats, w, i0, i1, G); break;
-      case 3: nce_grad_kernel<3><<<gg, NC_THREADS, 0, st>>>(a, stats, w, i0, i1, G); break;
-      default: nce_grad_kernel<4><<<gg, NC_THREADS, 0, st>>>(a, stats, w, i0, i1, G); break;
+    if (b.g_on) {
+      if ((rc = nce_grad_tc(tc_state, stats, w, concentration, i0, i1, G, b.ldg, st))) return rc;
+    } else {
+      if (b.on && b.ldg != P) HSG_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * m * b.ldg, st));   // zero pad columns
+      dim3 gg((unsigned)ceil_div64(m, NC_T), (unsigned)ceil_div64(P, NC_T));
+      switch (n_sets) {
+        case 1: nce_grad_kernel<1><<<gg, NC_THREADS, 0, st>>>(a, stats, w, i0, i1, G, b.ldg); break;
+        case 2: nce_grad_kernel<2><<<gg, NC_THREADS, 0, st>>>(a, stats, w, i0, i1, G, b.ldg); break;
+        case 3: nce_grad_kernel<3><<<gg, NC_THREADS, 0, st>>>(a, stats, w, i0, i1, G, b.ldg); break;
+        default: nce_grad_kernel<4><<<gg, NC_THREADS, 0, st>>>(a, stats, w, i0, i1, G, b.ldg); break;
+      }
+      HSG_LAUNCH_CHECK();
     }
-    HSG_LAUNCH_CHECK();
     if (b.on) {
       const int64_t mp = (m + 63) / 64 * 64;
       // dE[i0:i1] = G P          ([m,P] x [P,dim])
-      if ((rc = split_rows(G, m, (int)P, (int)b.Pp, 1.f, b.scal + 1, b.G2, st))) return rc;
+      if ((rc = split_rows(G, b.ldg, m, (int)P, (int)b.Pp, 1.f, b.scal + 1, b.G2, st))) return rc;
       if ((rc = gemm_tc_split(b.G2, b.Pt2, m, dim, (int)b.Pp, grad_e + i0 * dim, dim, b.scal + 2, 1.f, false, st))) return rc;
       // dP += G^T E[i0:i1]       ([P,m] x [m,dim])
-      if ((rc = split_transpose(G, m, (int)P, mp, 1.f, b.scal + 1, b.Gt2, st))) return rc;
-      if ((rc = split_transpose(e + i0 * dim, m, dim, mp, 16.f, nullptr, b.Et2, st))) return rc;
+      if ((rc = split_transpose(G, b.ldg, m, (int)P, mp, 1.f, b.scal + 1, b.Gt2, st))) return rc;
+      if ((rc = split_transpose(e + i0 * dim, dim, m, dim, mp, 16.f, nullptr, b.Et2, st))) return rc;
       if ((rc = gemm_tc_split(b.Gt2, b.Et2, P, dim, (int)mp, grad_p, dim, b.scal + 2, 1.f, true, st))) return rc;
       continue;
     }

@@ -344,6 +344,245 @@ nce_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------- backward: G chunk on tensor cores
+// G[i, j] = c * S_ij * sum_s w_si * dl_si/dS_ij for the pixels [i_begin, i_end) (the
+// fp32 CUDA-core version is nce_grad_kernel in nce.cu).  Same CTA-pair tiles and three fp16 passes as
+// the forward; the work items are (pixel pair-tile, prototype tile) pairs so that a chunk of a few
+// thousand pixels still fills the machine, and the epilogue writes the tile instead of reducing it.
+struct NceGradTcParams {
+  NceTcParams f;
+  int64_t i_begin, i_end;
+  const float* stats;        // [n_sets,N,4] num, den, own, flags (forward)
+  const float* w;            // [n_sets,N] upstream gradient per pixel
+  float conc;
+  float* G;                  // [i_end - i_begin, ldg]
+  int64_t ldg;               // multiple of 64, >= P; columns >= P are written as zeros
+};
+
+template <int NS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_THREADS, 1)
+nce_grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const NceGradTcParams g) {
+  const NceTcParams& p = g.f;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nslab = p.D / NT_BK;
+  const uint32_t sA = base;
+  const uint32_t sB = sA + 2 * nslab * NT_SLAB;
+  const uint32_t sMisc = sB + p.nstb * NT_SLAB;
+  uint8_t* misc = smem_raw + (sMisc - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  const uint32_t bar_bfull = smem_u32(bars);            // [8]  (waited on in the leader only)
+  const uint32_t bar_bempty = bar_bfull + 64;           // [8]
+  const uint32_t bar_afull = bar_bempty + 64;           // [1]  (leader only)
+  const uint32_t bar_aempty = bar_afull + 8;            // [1]
+  const uint32_t bar_tfull = bar_aempty + 8;            // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;           // [2]  (leader only; 8 arrivals)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.nstb; ++i) { mbar_init(bar_bfull + 8 * i, 1); mbar_init(bar_bempty + 8 * i, 1); }
+    mbar_init(bar_afull, 1);
+    mbar_init(bar_aempty, 1);
+    for (int i = 0; i < N2_ACC; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t rows = g.i_end - g.i_begin;
+  const int64_t n_ptiles = (rows + 2 * NT_BM - 1) / (2 * NT_BM);
+  const int n_ntiles = (int)(p.Ppad / N2_BN);
+  const int64_t items = n_ptiles * n_ntiles;
+  const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int64_t per = (items + n_pairs - 1) / n_pairs;
+  const int64_t it0 = min(items, pair * per), it1 = min(items, it0 + per);
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      const uint32_t l_afull = mapa_cluster(bar_afull, 0);
+      const uint32_t l_bfull = mapa_cluster(bar_bfull, 0);
+      int stage = 0;
+      uint32_t phase = 0, a_round = 0;
+      int64_t cur_pt = -1;
+      for (int64_t it = it0; it < it1; ++it) {
+        const int64_t pt = it / n_ntiles;
+        const int nt = (int)(it - pt * n_ntiles);
+        if (pt != cur_pt) {
+          mbar_wait(bar_aempty, (a_round & 1) ^ 1);
+          if (leader) mbar_expect_tx(bar_afull, 2 * 2 * nslab * NT_SLAB);
+          const int row0 = (int)(g.i_begin + pt * 2 * NT_BM + rank * NT_BM);
+          for (int j = 0; j < 2 * nslab; ++j)
+            tma_load_2d_pair(sA + j * NT_SLAB, &tmap_a, j * NT_BK, row0, l_afull);
+          cur_pt = pt;
+          ++a_round;
+        }
+        const int prow0 = nt * N2_BN + (int)rank * NT_BN;
+        for (int j = 0; j < 2 * nslab; ++j) {
+          mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
+          if (leader) mbar_expect_tx(bar_bfull + 8 * stage, 2 * NT_SLAB);
+          tma_load_2d_pair(sB + stage * NT_SLAB, &tmap_b, j * NT_BK, prow0, l_bfull + 8 * stage);
+          if (++stage == p.nstb) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (lane == 0 && leader) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(N2_BN >> 3) << 17) | ((uint32_t)((2 * NT_BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, a_round = 0, seq = 0;
+      int64_t cur_pt = -1;
+      for (int64_t it = it0; it < it1; ++it, ++seq) {
+        const int64_t pt = it / n_ntiles;
+        if (pt != cur_pt) {
+          mbar_wait(bar_afull, a_round & 1);
+          tc_fence_after();
+          cur_pt = pt;
+          ++a_round;
+        }
+        const uint32_t acc = seq & 1;
+        mbar_wait(bar_tempty + 8 * acc, ((seq >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * N2_BN;
+        uint32_t first = 1;
+        for (int j = 0; j < 2 * nslab; ++j) {
+          mbar_wait(bar_bfull + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t b0 = sB + stage * NT_SLAB;
+          const int js = j < nslab ? j : j - nslab;
+          const int passes = j < nslab ? 2 : 1;
+          const uint64_t bd = umma_desc(b0, 1024, 2);
+          for (int ps = 0; ps < passes; ++ps) {
+            const uint64_t ad = umma_desc(sA + (ps * nslab + js) * NT_SLAB, 1024, 2);
+#pragma unroll
+            for (int k4 = 0; k4 < NT_BK / 16; ++k4) {
+              tc_mma_f16_pair(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, first ? 0u : 1u);
+              first = 0;
+            }
+          }
+          tc_commit_pair(bar_bempty + 8 * stage);
+          if (++stage == p.nstb) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(bar_tfull + 8 * acc);
+        // last item of this pixel tile (in this pair's slice): its rows may be replaced once these MMAs retire
+        if (it + 1 == it1 || (it + 1) / n_ntiles != pt) tc_commit_pair(bar_aempty);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
+    const int q = warp & 3, grp = (warp - 4) >> 2;
+    const int r = 32 * q + lane;
+    const uint32_t l_tempty = mapa_cluster(bar_tempty, 0);
+    uint32_t seq = 0;
+    int64_t cur_pt = -1;
+    int my_sem[NS];
+    float ca[NS], cb[NS];        // coefficient of a negative / of another positive, per label set (c * w folded in)
+    float c_own = 0.f;           // coefficient of the pixel's own prototype (all sets)
+    int my_inst = -1;
+    int64_t pix = 0;
+    bool inb = false;
+    for (int64_t it = it0; it < it1; ++it, ++seq) {
+      const int64_t pt = it / n_ntiles;
+      const int nt = (int)(it - pt * n_ntiles);
+      if (pt != cur_pt) {
+        cur_pt = pt;
+        pix = g.i_begin + pt * 2 * NT_BM + rank * NT_BM + r;
+        inb = pix < g.i_end;
+        my_inst = inb ? p.inst[pix] : -1;
+        c_own = 0.f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          my_sem[s] = inb ? p.sem[(int64_t)s * p.N + pix] : INT_MIN;
+          ca[s] = 0.f; cb[s] = 0.f;
+          if (inb) {
+            const float* st = g.stats + ((int64_t)s * p.N + pix) * 4;
+            const float num = st[0], den = st[1];
+            const int fl = (int)st[3];
+            const bool use = fl & 1, own_same = fl & 2;
+            const float ws = g.conc * g.w[(int64_t)s * p.N + pix];
+            const float inv_den = 1.f / den, dlt = inv_den - 1.f / num;
+            ca[s] = ws * inv_den;
+            cb[s] = use ? ws * dlt : 0.f;
+            const float w_own = use ? (own_same ? 0.f : -1.f) : 1.f;
+            c_own += ws * ((own_same ? 0.f : inv_den) + w_own * dlt);
+          }
+        }
+      }
+      if ((int)(seq & 1) != grp) continue;
+      const int n_valid = (int)min((int64_t)N2_BN, p.P - (int64_t)nt * N2_BN);
+      const int n_store = (int)min((int64_t)N2_BN, g.ldg - (int64_t)nt * N2_BN);      // columns of G that exist
+      const int nchunk = (max(n_store, 0) + 15) >> 4;
+      const int own_rel = my_inst - nt * N2_BN;
+      const int32_t* lab_tile = p.psem + (int64_t)nt * N2_BN;
+      float* grow = g.G + (pix - g.i_begin) * g.ldg + (int64_t)nt * N2_BN;
+
+      mbar_wait(bar_tfull + 8 * grp, (seq >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + grp * N2_BN + ((uint32_t)(32 * q) << 16);
+#pragma unroll 1
+      for (int c = 0; c < nchunk; ++c) {
+        const int col0 = c * 16;
+        uint32_t v[16];
+        tc_ld16(trow + col0, v);
+        int4 lab[NS][4];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) epi_labels<NS>(lab[s], lab_tile + col0, p.Ppad, s);
+        tc_ld_wait();
+        float gv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gv[j] = 0.f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) {
+            gv[4 * w4 + 0] += lab[s][w4].x == my_sem[s] ? cb[s] : ca[s];
+            gv[4 * w4 + 1] += lab[s][w4].y == my_sem[s] ? cb[s] : ca[s];
+            gv[4 * w4 + 2] += lab[s][w4].z == my_sem[s] ? cb[s] : ca[s];
+            gv[4 * w4 + 3] += lab[s][w4].w == my_sem[s] ? cb[s] : ca[s];
+          }
+        }
+        const int rel = own_rel - col0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j == rel) gv[j] = c_own;
+          const float sv = col0 + j < n_valid ? ex2_approx(__uint_as_float(v[j])) : 0.f;
+          gv[j] *= sv;
+        }
+        if (inb) {
+          float4* dst = reinterpret_cast<float4*>(grow + col0);
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) dst[w4] = make_float4(gv[4 * w4], gv[4 * w4 + 1], gv[4 * w4 + 2], gv[4 * w4 + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(l_tempty + 8 * grp);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // ---------------------------------------------------------------- host side
 bool nce_tc_supported(int64_t N, int64_t P, int dim, int n_sets) {
   return (dim == 64 || dim == 128 || dim == 256) && N >= 1 && P >= 1 && P < (1ll << 31) - 256 && N < (1ll << 31) &&
@@ -362,9 +601,16 @@ size_t nce_tc_workspace_bytes(int64_t N, int64_t P, int dim, int n_sets) {
   return c.used() + 256;
 }
 
-int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, int dim, const int64_t* inst,
-               const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus, float conc,
-               float* per_pixel, float* stats, void* workspace, cudaStream_t st) {
+struct NceTcSetup {
+  NceTcParams p;
+  CUtensorMap ma, mb;
+  size_t smem;
+};
+
+// fp16 (hi|lo) copies of both operands, int32 labels, tensor maps: everything the pair kernels read
+static int nce_tc_setup(NceTcSetup& u, const float* e, const float* prototypes, int64_t N, int64_t P, int dim,
+                        const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus,
+                        float conc, void* workspace, cudaStream_t st) {
   const int64_t Ppad = nce_ppad(P);
   Carver c(workspace);
   __half* ah = c.take<__half>((size_t)N * 2 * dim);
@@ -386,9 +632,9 @@ int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, in
   nce_labels32_kernel<<<(unsigned)ceil_div64(Ppad * n_sets, 256), 256, 0, st>>>(psem, P, Ppad, n_sets, psem32, INT_MIN + 1);
   HSG_LAUNCH_CHECK();
 
-  NceTcParams p;
+  NceTcParams& p = u.p;
   p.N = N; p.P = P; p.D = dim; p.n_sets = n_sets; p.inst = inst32; p.sem = sem32; p.psem = psem32;
-  p.Ppad = Ppad; p.per_pixel = per_pixel; p.stats = stats;
+  p.Ppad = Ppad; p.per_pixel = nullptr; p.stats = nullptr;
   for (int s = 0; s < NT_MAX_SETS; ++s) p.plus[s] = s < n_sets ? plus[s] : 0;
   const int nslab = dim / NT_BK;
   const size_t fixed = (size_t)2 * nslab * NT_SLAB +
@@ -398,11 +644,24 @@ int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, in
   if (nstb > 8) nstb = 8;
   HSG_REQUIRE(nstb >= 2, HSG_E_UNSUPPORTED, "nce: shared memory budget");
   p.nstb = nstb;
-  const size_t smem = 1024 + fixed + (size_t)nstb * NT_SLAB;
-  CUtensorMap ma, mb;
+  u.smem = 1024 + fixed + (size_t)nstb * NT_SLAB;
   int rc;
-  if ((rc = encode_2d_f16(&ma, ah, (uint64_t)N, (uint64_t)2 * dim, NT_BK, NT_BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = encode_2d_f16(&mb, bh, (uint64_t)Ppad, (uint64_t)2 * dim, NT_BK, NT_BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = encode_2d_f16(&u.ma, ah, (uint64_t)N, (uint64_t)2 * dim, NT_BK, NT_BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = encode_2d_f16(&u.mb, bh, (uint64_t)Ppad, (uint64_t)2 * dim, NT_BK, NT_BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  return HSG_OK;
+}
+
+int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, int dim, const int64_t* inst,
+               const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus, float conc,
+               float* per_pixel, float* stats, void* workspace, cudaStream_t st) {
+  NceTcSetup u;
+  int rc = nce_tc_setup(u, e, prototypes, N, P, dim, inst, sem, psem, n_sets, plus, conc, workspace, st);
+  if (rc) return rc;
+  NceTcParams& p = u.p;
+  p.per_pixel = per_pixel; p.stats = stats;
+  const size_t smem = u.smem;
+  const CUtensorMap& ma = u.ma;
+  const CUtensorMap& mb = u.mb;
   int64_t grid = num_sms() & ~1;                  // CTA pairs
   const int64_t n_pairs = ceil_div64(N, 2 * NT_BM);
   if (grid > 2 * n_pairs) grid = 2 * n_pairs;
@@ -412,6 +671,42 @@ int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, in
     nce_fwd_tc2_kernel<NS><<<(unsigned)grid, NT_THREADS, smem, st>>>(ma, mb, p);                             \
   } while (0)
   switch (n_sets) {
+    case 1: HSG_NCE_LAUNCH(1); break;
+    case 2: HSG_NCE_LAUNCH(2); break;
+    case 3: HSG_NCE_LAUNCH(3); break;
+    default: HSG_NCE_LAUNCH(4); break;
+  }
+#undef HSG_NCE_LAUNCH
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+// backward: one setup per call (state lives in the caller's workspace), then one launch per pixel chunk
+static NceTcSetup* setup_slot(void* host_state) { return reinterpret_cast<NceTcSetup*>(host_state); }
+size_t nce_grad_tc_host_state_bytes() { return sizeof(NceTcSetup); }
+
+int nce_grad_tc_prepare(void* host_state, const float* e, const float* prototypes, int64_t N, int64_t P, int dim,
+                        const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus,
+                        float conc, void* workspace, cudaStream_t st) {
+  return nce_tc_setup(*setup_slot(host_state), e, prototypes, N, P, dim, inst, sem, psem, n_sets, plus, conc, workspace, st);
+}
+
+int nce_grad_tc(void* host_state, const float* stats, const float* w, float conc, int64_t i_begin, int64_t i_end,
+                float* G, int64_t ldg, cudaStream_t st) {
+  NceTcSetup& u = *setup_slot(host_state);
+  HSG_REQUIRE(ldg % 64 == 0 && ldg >= u.p.P, HSG_E_INVALID, "nce_grad_tc: ldg=%lld", (long long)ldg);
+  NceGradTcParams g;
+  g.f = u.p; g.i_begin = i_begin; g.i_end = i_end; g.stats = stats; g.w = w; g.conc = conc; g.G = G; g.ldg = ldg;
+  const int64_t items = ceil_div64(i_end - i_begin, 2 * NT_BM) * (u.p.Ppad / N2_BN);
+  int64_t grid = num_sms() & ~1;
+  if (grid > 2 * items) grid = 2 * items;
+  const size_t smem = u.smem;
+#define HSG_NCE_LAUNCH(NS)                                                                                   \
+  do {                                                                                                       \
+    HSG_CUDA(cudaFuncSetAttribute(nce_grad_tc2_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    nce_grad_tc2_kernel<NS><<<(unsigned)grid, NT_THREADS, smem, st>>>(u.ma, u.mb, g);                        \
+  } while (0)
+  switch (u.p.n_sets) {
     case 1: HSG_NCE_LAUNCH(1); break;
     case 2: HSG_NCE_LAUNCH(2); break;
     case 3: HSG_NCE_LAUNCH(3); break;

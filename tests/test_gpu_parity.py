@@ -581,7 +581,7 @@ def test_nce_backward_tensor_core_gemms_vs_float64():
     want_p += dp
   lib = _lib.load()
   errs = {}
-  for flags in (0, 4):
+  for flags in (0, 8, 4):          # everything on tensor cores / G chunk on CUDA cores / GEMMs on CUDA cores too
     lib.hsg_debug_set_flags(flags)
     try:
       et, pt = t(e).requires_grad_(True), t(protos).requires_grad_(True)
@@ -592,6 +592,7 @@ def test_nce_backward_tensor_core_gemms_vs_float64():
     errs[flags] = (np.linalg.norm(n(et.grad) - want_e) / np.linalg.norm(want_e),
                    np.linalg.norm(n(pt.grad) - want_p) / np.linalg.norm(want_p))
   assert max(errs[0]) < 1e-5, errs          # tensor cores: fp32-grade
+  assert max(errs[8]) < 1e-5, errs
   assert max(errs[4]) < 1e-4, errs
 
 

@@ -37,12 +37,13 @@ rel = ((ll[:, :n_s] - ref).abs() / ref.abs().clamp_min(1e-3)).max().item()
 print('max relative difference to the fp32 kernel on %d pixels: %.3g' % (n_s, rel))
 assert rel < 2e-5
 
-# backward (dE, dP): recomputed G chunk + two fp32-grade tensor-core GEMMs
+# backward (dE, dP): recomputed G chunk + two fp32-grade GEMMs
 nb = min(N, 1 << 20)
 eb = e[:nb].clone().requires_grad_(True)
 pb = pr.clone().requires_grad_(True)
 semb = sem[:, :nb].contiguous()
-for flags, name in ((0, 'tensor-core GEMMs'), (4, 'CUDA-core GEMMs')):
+for flags, name in ((0, 'G chunk and GEMMs on tensor cores'), (8, 'G chunk on CUDA cores, GEMMs on tensor cores'),
+                    (4, 'all on CUDA cores')):
   lib.hsg_debug_set_flags(flags)
   grads = []
   for rep in range(2):
