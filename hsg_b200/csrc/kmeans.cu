@@ -163,18 +163,18 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) estep_fixup_kernel(const EStep
   const int warps = gridDim.x * FIX_WARPS;
   for (int e = blockIdx.x * FIX_WARPS + (threadIdx.x >> 5); e < total; e += warps) {
     const int64_t pix = a.fix.pixels[e];
-    const int seg = upper_bound_off(a.seg_offsets, a.S + 1, pix) - 1;
-    const int K = a.seg_k ? a.seg_k[seg] : a.kmax;
     const float* xrow = a.x + pix * a.dim;
-    float xr[FIX_NV];
+    float xr[FIX_NV];                               // issued first: the segment search below overlaps their latency
 #pragma unroll
     for (int m = 0; m < FIX_NV; ++m) {
       const int d = lane + 32 * m;
-      xr[m] = d < a.dim ? xrow[d] : 0.f;
+      xr[m] = d < a.dim ? ld_stream(xrow + d) : 0.f;
     }
-    const float* cbase = a.centroids + (int64_t)seg * a.kmax * a.dim;
     const uint16_t* cand = a.fix.cand ? a.fix.cand + (int64_t)e * FIX_MAX_CAND : nullptr;
     const bool all = !cand || cand[0] == 0xFFFF;
+    const int seg = upper_bound_off(a.seg_offsets, a.S + 1, pix) - 1;
+    const int K = a.seg_k ? a.seg_k[seg] : a.kmax;
+    const float* cbase = a.centroids + (int64_t)seg * a.kmax * a.dim;
     double bv = -DBL_MAX;
     int bi = 0x7fffffff;
     if (all) {
@@ -191,12 +191,18 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) estep_fixup_kernel(const EStep
         }
       }
     } else {
-      for (int c = 0; c < FIX_MAX_CAND; ++c) {
-        const int k = cand[c];
-        if (k == 0xFFFF) break;
-        if (k >= K) continue;
-        const double s = warp_sum(fix_dot(xr, cbase + (int64_t)k * a.dim, a.dim, lane));
-        if (s > bv || (s == bv && k < bi)) { bv = s; bi = k; }
+      // candidates two at a time (the usual entry lists exactly two): both centroid rows in flight together
+      for (int c = 0; c < FIX_MAX_CAND; c += 2) {
+        const int k0 = cand[c];
+        if (k0 == 0xFFFF) break;
+        const int k1 = cand[c + 1];
+        const bool two = k1 != 0xFFFF;
+        const double p0 = fix_dot(xr, cbase + (int64_t)min(k0, K - 1) * a.dim, a.dim, lane);
+        const double p1 = fix_dot(xr, cbase + (int64_t)min(two ? k1 : k0, K - 1) * a.dim, a.dim, lane);
+        const double s0 = warp_sum(p0), s1 = warp_sum(p1);
+        if (k0 < K && (s0 > bv || (s0 == bv && k0 < bi))) { bv = s0; bi = k0; }
+        if (two && k1 < K && (s1 > bv || (s1 == bv && k1 < bi))) { bv = s1; bi = k1; }
+        if (!two) break;
       }
     }
     if (lane == 0) a.keys_out[pix] = seg * a.kmax + bi;

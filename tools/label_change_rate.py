@@ -1,3 +1,5 @@
+"""Fraction of the k-means labels that change in each iteration at the benchmark shape (the numbers
+behind the incremental M-step):  python tools/label_change_rate.py"""
 import sys, torch
 sys.path.insert(0, '.')
 from hsg_b200 import ops
