@@ -14,8 +14,10 @@ value   : pixel-embeddings/s with the input embeddings already resident in HBM.
 e2e     : the same metric through the reference-facing Python operators with HOST
           (pinned) input, the host->device copy and the loss read-back inside the
           timed region.
-roofline: the spherical k-means iteration (its E-step + M-step kernels), CUDA-event
-          timed inside the timed region through the library's phase profiler;
+roofline: the dominant kernel of the step, the NCE forward (tensor-bound; algorithmic
+          flops 2*N*P*D against the sustained cuBLAS bf16 figure), CUDA-event timed inside
+          the timed region through the library's phase profiler.
+roofline_kmeans: the spherical k-means iteration (north_star's HBM-bound kernel):
           algorithmic bytes N*(4*(D+2)+8) per iteration.
 """
 
@@ -277,11 +279,31 @@ def run_ours(args):
     traffic_src = ('profiles/r1_kmeans_traffic.json: ncu dram read+write of every kernel of the k-means loop over one '
                    'step, divided by the %d iterations (the incremental M-step re-reads only the rows that moved)' % args.iters)
   achieved = alg_bytes / (kmeans_ms * 1e-3) / 1e9 if kmeans_ms > 0 else 0.0
-  roofline = {'kernel': 'spherical k-means iteration (E-step + M-step kernels)', 'bound': 'hbm',
-              'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / pk['hbm_gbs'],
-              'peak_source': pk_src + ' (burst copy bandwidth)', 'traffic': traffic,
-              'traffic_source': traffic_src,
-              'algorithmic_bytes_per_launch': alg_bytes, 'ms_per_launch': kmeans_ms}
+  roofline_kmeans = {'kernel': 'spherical k-means iteration (all kernels of the loop: delta list, sort, gather, combine, '
+                               'E-step, float64 re-decision)', 'bound': 'hbm',
+                     'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / pk['hbm_gbs'],
+                     'peak_source': pk_src + ' (burst copy bandwidth)', 'traffic': traffic,
+                     'traffic_source': traffic_src,
+                     'algorithmic_bytes_per_launch': alg_bytes, 'ms_per_launch': kmeans_ms,
+                     'share_of_step': kmeans_ms * args.iters / (ms / args.steps)}
+  # the dominant kernel of the step by time: the NCE forward (tcgen05, CTA pairs).  Algorithmic flops
+  # 2*N*P*D; the kernel executes three fp16 passes of them to reach fp32-grade similarities.
+  p_glob = world * args.images * args.grid ** 2
+  nce_ms = phase_ms['nce_fwd'] / args.steps
+  nce_flops = 2.0 * n_pix * p_glob * args.dim
+  nce_tf = nce_flops / (nce_ms * 1e-3) / 1e12 if nce_ms > 0 else 0.0
+  peak_tf = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
+  nce_traffic = None
+  if default_cfg and world == 1:
+    nce_traffic = 10.415e9          # profiles/r1_nce_fwd_tc.txt: dram read + write of the kernel (ncu --set full)
+  roofline = {'kernel': 'NCE forward (nce_fwd_tc2_kernel + its fp16 operand split; %.0f %% of the step)'
+                        % (100.0 * nce_ms / (ms / args.steps)),
+              'bound': 'tensor', 'achieved': nce_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': nce_tf / peak_tf,
+              'peak_source': pk_src + ' (cuBLAS bf16, sustained under the power cap: the kernel is timed inside a long step)',
+              'traffic': nce_traffic, 'algorithmic_flops_per_launch': nce_flops, 'ms_per_launch': nce_ms,
+              'executed_tflops': 3.0 * nce_tf,
+              'note': 'algorithmic flops 2*N*P*D; three fp16 tcgen05 passes (hi/lo split) are executed per algorithmic '
+                      'flop because the loss needs fp32-grade similarities, so executed/peak = %.2f' % (3.0 * nce_tf / peak_tf)}
   per_phase = {k: {'ms_per_step': phase_ms[k] / args.steps, 'ranges': phase_n[k]} for k in PHASES if phase_n[k]}
 
   cpu = None if args.no_cpu else cpu_baseline(args)
@@ -305,7 +327,7 @@ def run_ours(args):
       'nce_pairs_per_s_per_gpu': (n_pix * float(world * args.images * args.grid ** 2) /
                                   (phase_ms['nce_fwd'] / args.steps * 1e-3)) if phase_ms['nce_fwd'] > 0 else None,
       'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
-      'roofline': roofline, 'phases': per_phase, 'cpu_baseline': cpu, 'loss': float(loss),
+      'roofline': roofline, 'roofline_kmeans': roofline_kmeans, 'phases': per_phase, 'cpu_baseline': cpu, 'loss': float(loss),
   }
   print(json.dumps(out))
   if world > 1:
