@@ -169,6 +169,8 @@ def run_ours(args):
   device = torch.device('cuda', local_rank)
   group = None
   if world > 1:
+    # NCCL writes its version / debug lines to stdout by default; stdout is reserved for the one JSON line
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     torch.distributed.init_process_group('nccl', device_id=device)
   import hsg_b200
   from hsg_b200 import _lib
