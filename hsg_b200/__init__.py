@@ -27,6 +27,8 @@ _TARGETS = {
     'hsg.utils.segsort.loss': ('hsg_b200.utils.segsort.loss', [
         '_calculate_log_likelihood', 'SegSortLoss']),
     'hsg.utils.segsort.eval': ('hsg_b200.utils.segsort.eval', ['top_k_ranking']),
+    'hsg.utils.graph.common': ('hsg_b200.utils.graph.common', ['affinity_matrix_as_attention']),
+    'hsg.utils.graph.loss': ('hsg_b200.utils.graph.loss', ['dmon_pool_loss', 'DMonLoss']),
     'hsg.models.utils': ('hsg_b200.models.utils', [
         'gather_clustering_and_update_prototypes', 'gather_and_update_cluster_mappings',
         'gather_and_reorder_image_indices', 'gather_and_update_datas']),

@@ -238,6 +238,18 @@ HSG_API int hsg_mha_bwd_f32(const float* q, const float* k, const float* v,
                             float* dq, float* dk, float* dv,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- k-NN affinity graph of the DMoN regulariser
+ * Replaces the masking / per-segment top-k / binarise part of affinity_matrix_as_attention
+ * (hsg/utils/graph/common.py:76-125) on a given kernel matrix A [B,n,n]: padded nodes
+ * (padding_mask [B,n] != 0, may be NULL) and, when remove_self_loop and the graph has more
+ * than one valid node, the diagonal are zeroed; with knn > 0 entry (i,j) survives iff fewer
+ * than min(#valid nodes of j's segment, knn) valid columns of j's segment (segment_labels
+ * [B,n], NULL = one segment) are strictly larger in row i; binarize maps positives to 1.
+ * out [B,n,n].  No host synchronisation (the reference takes two per segment). */
+HSG_API int hsg_knn_adjacency_f32(const float* A, const unsigned char* padding_mask,
+                                  const int64_t* segment_labels, int B, int n, int knn,
+                                  int remove_self_loop, int binarize, float* out, void* stream);
+
 /* ---- K2: dense relabel  (segment_by_kmeans tail, common.py:397-405;
  *      prepare_prototype_labels :192-218)
  * ids_out[i] = rank of the triple (batch[i], cluster[i], label[i]) among the

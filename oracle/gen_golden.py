@@ -315,6 +315,24 @@ def main():
        img_sim_loss=_np(l_img), hrchy_group_loss=_np(l_hr), clustering_loss=_np(l_cl), accuracy=_np(acc),
        demb=_np(emb.grad), dprotos=_np(protos.grad), dcent_fine=_np(cent_d['fine'].grad))
 
+  # ---------------------------------------------------------------- 8f DMoN: k-NN affinity graph + loss
+  import hsg.utils.graph.common as g_graph
+  import hsg.utils.graph.loss as g_gloss
+  torch.manual_seed(235)
+  gx = g_common.normalize_embedding(torch.randn(3, 40, 24)).transpose(1, 2).contiguous()   # [B,C,n]: 40 nodes, 24 channels
+  gpad = torch.zeros(3, 40, dtype=torch.bool)
+  gpad[0, 33:] = True
+  gpad[1, 1:] = True                      # a graph with a single valid node keeps its self loop
+  gseg = torch.randint(0, 2, (3, 40)) * 7 + 3
+  adj2 = g_graph.affinity_matrix_as_attention(gx, gpad, gseg, 2, True, True, lambda t_: g_graph.exp_inner_product_kernel(t_, 5))
+  adj4 = g_graph.affinity_matrix_as_attention(gx, gpad, gseg, 4, True, False, lambda t_: g_graph.exp_inner_product_kernel(t_, 5))
+  adj0 = g_graph.affinity_matrix_as_attention(gx, None, None, None, True, True)
+  glog = torch.softmax(torch.randn(3, 6, 40), 1).requires_grad_(True)
+  dl, cl = g_gloss.DMonLoss(adj_knn=2)(glog, gx, gpad, gseg)
+  (dl + cl).backward()
+  save('dmon', x=_np(gx), pad=_np(gpad), seg=_np(gseg), adj_knn2=_np(adj2), adj_knn4_values=_np(adj4), adj_noknn=_np(adj0),
+       logits=_np(glog), dmon_loss=_np(dl), collapse_loss=_np(cl), dlogits=_np(glog.grad))
+
   # ---------------------------------------------------------------- a13 cross-GPU gather (2 "GPUs")
   m_utils.scatter_gather.gather = lambda xs, dev, dim=0: torch.cat(list(xs), dim)
   torch.manual_seed(235)

@@ -99,6 +99,14 @@ def test_patch_rebinds_the_reference_operators(lib):
         assert list(ref_sig.parameters) == list(our_sig.parameters), name
         for k, v in ref_sig.parameters.items():
           assert v.default == our_sig.parameters[k].default or v.default is inspect._empty, (name, k)
+      import hsg.utils.graph.common as ref_graph
+      import hsg.utils.graph.loss as ref_gloss
+      assert ref_graph.affinity_matrix_as_attention.__module__.startswith('hsg_b200')
+      assert ref_gloss.DMonLoss.__module__.startswith('hsg_b200')
+      for mod, name in (('hsg.utils.graph.common', 'affinity_matrix_as_attention'), ('hsg.utils.graph.loss', 'dmon_pool_loss')):
+        was = inspect.signature(hsg_b200._PATCHED[(mod, name)])
+        now = inspect.signature(getattr(sys.modules[mod], name))
+        assert list(was.parameters) == list(now.parameters), name
       # per-image prototype bookkeeping: methods of the reference's model classes, same parameters
       import hsg.models.embeddings.resnet_fcn_hsg as ref_model
       for cls, name in (('ResnetFcn', '_calculate_kmeans_prototypes'), ('MultiviewResnetFcn', '_calculate_kmeans_prototypes'),

@@ -364,6 +364,27 @@ def test_hsg_losses_one_pass(golden):
   close(n(hr2), want, rtol=2e-5)
 
 
+def test_dmon_knn_graph_and_loss(golden):
+  """the k-NN affinity graph (one launch instead of the reference's Python double loop)
+  and the DMoN / collapse losses with their gradient w.r.t. the assignment logits."""
+  from hsg_b200.utils.graph import common as GC, loss as GL
+  g = golden('dmon')
+  x, pad, seg = t(g['x']), t(g['pad']), t(g['seg'])
+  kern = lambda v: GC.exp_inner_product_kernel(v, 5)
+  adj = GC.affinity_matrix_as_attention(x, pad, seg, 2, True, True, kern)
+  assert adj.dtype == torch.float32 and np.array_equal(n(adj), g['adj_knn2'])
+  vals = GC.affinity_matrix_as_attention(x, pad, seg, 4, True, False, kern)
+  close(n(vals), g['adj_knn4_values'], rtol=1e-5, atol=0)
+  assert np.array_equal(n(vals) > 0, g['adj_knn4_values'] > 0)
+  assert np.array_equal(n(GC.affinity_matrix_as_attention(x)), g['adj_noknn'])
+  logits = t(g['logits']).requires_grad_(True)
+  dl, cl = GL.DMonLoss(adj_knn=2)(logits, x, pad, seg)
+  close(n(dl), g['dmon_loss'], rtol=1e-5)
+  close(n(cl), g['collapse_loss'], rtol=1e-5)
+  (dl + cl).backward()
+  close(n(logits.grad), g['dlogits'], rtol=1e-4, atol=1e-7)
+
+
 def test_kmeans_moderate_segments_property(S):
   """ragged segments, K not a multiple of anything, per-iteration objective
   non-decreasing and labels equal to an oracle E-step on the kernel's own centroids."""

@@ -221,6 +221,18 @@ def test_hsg_losses_nce_terms(golden):
   assert abs(acc - g['accuracy']) < 1e-6
 
 
+def test_dmon_graph_and_loss(golden):
+  from oracle import graph as o_graph
+  g = golden('dmon')
+  a = o_graph.exp_inner_product_kernel(g['x'], 5)
+  assert np.array_equal(o_graph.knn_adjacency(a, g['pad'], g['seg'], 2, True, True), g['adj_knn2'])
+  close(o_graph.knn_adjacency(a, g['pad'], g['seg'], 4, True, False), g['adj_knn4_values'], rtol=1e-6, atol=0)
+  assert np.array_equal(o_graph.knn_adjacency(o_graph.exp_inner_product_kernel(g['x'], 5), None, None, None, True, True),
+                        g['adj_noknn'])
+  dl, cl = o_graph.dmon_pool_loss(g['adj_knn2'], np.transpose(g['logits'], (0, 2, 1)), ~g['pad'])
+  assert abs(dl - g['dmon_loss']) < 1e-5 and abs(cl - g['collapse_loss']) < 1e-6
+
+
 def test_cross_gpu_gather(golden):
   g = golden('gather_prototypes')
   ranks = [[g['r%d_%s' % (r, nm)] for nm in ('emb', 'emb_loc', 'cluster', 'batch', 'sem', 'inst')]
