@@ -57,7 +57,8 @@ def _patch_methods(importlib):
   from .models.embeddings import hierarchy
   from .models.predictions import hsg as loss_head
   tables = [(m, hierarchy.METHODS) for m in _METHOD_MODULES]
-  tables += [(m, {'Hsg': {'losses': loss_head.losses}}) for m in _LOSS_MODULES]
+  tables += [(m, {'Hsg': {'losses': loss_head.losses_cs if m.endswith('_cs') else loss_head.losses}})
+             for m in _LOSS_MODULES]
   for ref_name, table in tables:
     try:
       ref = importlib.import_module(ref_name)

@@ -4,17 +4,18 @@ pixel-to-prototype NCE terms evaluated in ONE pass over E x P^T.
 The reference calls SegSortLoss three times on the same (embeddings, prototypes) with three
 label sets -- image-level positives (:88-110), fine grouping (:120-136), coarse grouping
 (:138-158) -- i.e. three [N,P] similarity matrices.  `nce_losses` hands the three label sets to
-the fused kernel (`segsort_loss_multi`, K4) together; `losses` is the drop-in method: it keeps
-the reference's return tuple and delegates the remaining regularisers (DMoN, centroid
-contrast: SURVEY 8f "next") to the reference's own code.
+the fused kernel (`segsort_loss_multi`, K4) together; `losses` is the drop-in method with the
+reference's return tuple: NCE terms, top-5 accuracy, the DMoN regulariser on the k-NN graph kernel
+(:161-183) and the across-image centroid contrast (:185-225).
 """
 
 import torch
 
+from ...utils.general import common as common_utils
 from ...utils.segsort import eval as segsort_eval
 from ...utils.segsort import loss as segsort_loss
 
-ORIGINALS = {}      # (module, class) -> the reference's `losses`, filled by hsg_b200.patch()
+ORIGINALS = {}      # (module, class) -> the reference's `losses` (kept for unpatch / inspection)
 
 
 def nce_losses(self, datas, targets):
@@ -55,20 +56,41 @@ def nce_losses(self, datas, targets):
   return tuple(out)
 
 
-class _WithoutNce(object):
-  """`self` as the reference's `losses` sees it, with the three NCE terms switched off."""
+def clustering_losses(self, datas, targets):
+  """DMoN + collapse regularisation of both grouping levels and the centroid contrast across images,
+  weighted and summed like the reference (:161-225); None when both are switched off."""
+  total = None
+  if self.dmon_loss is not None:                         # :161-183
+    protos = datas['nd_prototype']
+    mask = datas['nd_prototype_padding_mask']
+    dmon_terms, collapse_terms = [], []
+    for logits in (datas['coarsehrchy_nd_prototype_grouping_logit'], datas['finehrchy_nd_prototype_grouping_logit']):
+      if 'nd_prototype_batch_index' in datas:
+        d, c = self.dmon_loss(logits, protos, mask, datas['nd_prototype_batch_index'])
+      else:                                              # the Cityscapes head passes no segment labels (hsg_cs.py:174-175)
+        d, c = self.dmon_loss(logits, protos, mask)
+      dmon_terms.append(d)
+      collapse_terms.append(c)
+    total = (sum(dmon_terms) + sum(collapse_terms)) * self.dmon_loss_weight
+  if self.centroid_cont_loss is not None:                # :185-225
+    img = targets['image_index'][datas['cluster_batch_index']]
+    lo, hi = img.min().detach(), (img.max() + 1).detach()
+    terms = []
+    for prefix in ('coarse', 'fine'):
+      tgt = targets[prefix + 'hrchy_nd_prototype_grouping_centroid']                 # [B', C, Q] of the whole batch
+      b_all, _, q = tgt.shape
+      tgt_rows = common_utils.normalize_embedding(tgt.permute(0, 2, 1).contiguous().flatten(0, 1))
+      tgt_labels = torch.arange(tgt_rows.shape[0], dtype=torch.long, device=tgt_rows.device)
+      mine = datas[prefix + 'hrchy_nd_prototype_grouping_centroid']
+      mine_rows = common_utils.normalize_embedding(mine.permute(0, 2, 1).contiguous().flatten(0, 1))
+      mine_labels = tgt_labels.view(b_all, q)[lo:hi].reshape(-1)                     # this GPU's images inside the batch
+      terms.append(self.centroid_cont_loss(mine_rows, mine_labels, mine_labels, tgt_rows, tgt_labels))
+    cont = sum(terms) * self.centroid_cont_loss_weight
+    total = cont if total is None else total + cont
+  return total
 
-  def __init__(self, module):
-    object.__setattr__(self, '_m', module)
 
-  def __getattr__(self, name):
-    if name in ('img_sim_loss', 'fine_hrchy_loss', 'coarse_hrchy_loss'):
-      return None
-    return getattr(object.__getattribute__(self, '_m'), name)
-
-
-def losses(self, datas, targets={}):
-  """Drop-in for `Hsg.losses`: (img_sim_loss, hrchy_group_loss, clustering_loss, img_sim_acc)."""
+def _losses(self, datas, targets, split_graph_by_view):
   img_sim_loss, fine, coarse = nce_losses(self, datas, targets)
   hrchy_group_loss = fine
   if coarse is not None:
@@ -78,16 +100,18 @@ def losses(self, datas, targets={}):
     p_img = targets['image_index'][targets['prototype_batch_index']]
     p_lab = targets['prototype_instance_label'] * self.label_divisor + p_img
     img_sim_acc, _ = segsort_eval.top_k_ranking(targets['prototype'], p_lab, targets['prototype'], p_lab, 5)
-  clustering_loss = None
-  if self.dmon_loss is not None or self.centroid_cont_loss is not None:
-    cls = type(self)
-    original = None
-    for c in cls.__mro__:
-      original = ORIGINALS.get((c.__module__, c.__name__))
-      if original is not None:
-        break
-    if original is None:
-      raise RuntimeError('hsg_b200: the DMoN / centroid-contrast regularisers run through the reference\'s '
-                         'Hsg.losses; call hsg_b200.patch() with the reference importable')
-    clustering_loss = original(_WithoutNce(self), datas, targets)[2]
-  return img_sim_loss, hrchy_group_loss, clustering_loss, img_sim_acc
+  if not split_graph_by_view:
+    datas = {k: v for k, v in datas.items() if k != 'nd_prototype_batch_index'}
+  return img_sim_loss, hrchy_group_loss, clustering_losses(self, datas, targets), img_sim_acc
+
+
+def losses(self, datas, targets={}):
+  """Drop-in for `Hsg.losses` (predictions/hsg.py:78-227):
+  (img_sim_loss, hrchy_group_loss, clustering_loss, img_sim_acc)."""
+  return _losses(self, datas, targets, True)
+
+
+def losses_cs(self, datas, targets={}):
+  """The Cityscapes head (predictions/hsg_cs.py): identical except that the DMoN graph is not split by view
+  (:173-175 pass no segment labels)."""
+  return _losses(self, datas, targets, False)

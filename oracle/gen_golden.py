@@ -280,7 +280,7 @@ def main():
   cfg = ns(train=ns(img_sim_loss_types='segsort', img_sim_concentration=16, img_sim_loss_weight=1.0,
                     fine_hrchy_loss_types='segsort', fine_hrchy_concentration=16, fine_hrchy_loss_weight=0.1,
                     coarse_hrchy_loss_types='segsort', coarse_hrchy_concentration=16, coarse_hrchy_loss_weight=0.1,
-                    dmon_loss_types='none', dmon_knn=2, dmon_loss_weight=1.0,
+                    dmon_loss_types='dmon', dmon_knn=2, dmon_loss_weight=0.5,
                     centroid_cont_loss_types='segsort', centroid_cont_concentration=16,
                     centroid_cont_loss_weight=1.0),
            dataset=ns(semantic_ignore_index=255, num_classes=21), network=ns(label_divisor=2048))
@@ -297,8 +297,18 @@ def main():
   coarse_map = fine_map // 3
   cent_t = {k: torch.randn(3, dim, q) for k, q in (('fine', 8), ('coarse', 4))}
   cent_d = {k: torch.randn(3, dim, q).requires_grad_(True) for k, q in (('fine', 8), ('coarse', 4))}
+  m_nodes = 20
+  nd_proto = g_common.normalize_embedding(torch.randn(3, m_nodes, dim)).transpose(1, 2).contiguous()
+  nd_mask = torch.zeros(3, m_nodes, dtype=torch.bool)
+  nd_mask[0, 17:] = True
+  nd_mask[2, 12:] = True
+  nd_batch = torch.randint(0, 2, (3, m_nodes)) + 2 * torch.arange(3).view(3, 1)
+  nd_fine = torch.softmax(torch.randn(3, 8, m_nodes), 1).requires_grad_(True)
+  nd_coarse = torch.softmax(torch.randn(3, 4, m_nodes), 1).requires_grad_(True)
   datas = {'cluster_index': cidx, 'cluster_embedding': emb, 'cluster_batch_index': proto_batch[cidx],
            'cluster_instance_label': proto_inst[cidx],
+           'finehrchy_nd_prototype_grouping_logit': nd_fine, 'coarsehrchy_nd_prototype_grouping_logit': nd_coarse,
+           'nd_prototype': nd_proto, 'nd_prototype_batch_index': nd_batch, 'nd_prototype_padding_mask': nd_mask,
            'finehrchy_nd_prototype_grouping_centroid': cent_d['fine'],
            'coarsehrchy_nd_prototype_grouping_centroid': cent_d['coarse']}
   targets = {'image_index': image_index, 'prototype': protos, 'prototype_batch_index': proto_batch,
@@ -313,7 +323,9 @@ def main():
        cent_t_fine=_np(cent_t['fine']), cent_t_coarse=_np(cent_t['coarse']),
        cent_d_fine=_np(cent_d['fine']), cent_d_coarse=_np(cent_d['coarse']),
        img_sim_loss=_np(l_img), hrchy_group_loss=_np(l_hr), clustering_loss=_np(l_cl), accuracy=_np(acc),
-       demb=_np(emb.grad), dprotos=_np(protos.grad), dcent_fine=_np(cent_d['fine'].grad))
+       demb=_np(emb.grad), dprotos=_np(protos.grad), dcent_fine=_np(cent_d['fine'].grad),
+       dcent_coarse=_np(cent_d['coarse'].grad), nd_proto=_np(nd_proto), nd_mask=_np(nd_mask), nd_batch=_np(nd_batch),
+       nd_fine=_np(nd_fine), nd_coarse=_np(nd_coarse), dnd_fine=_np(nd_fine.grad), dnd_coarse=_np(nd_coarse.grad))
 
   # ---------------------------------------------------------------- 8f DMoN: k-NN affinity graph + loss
   import hsg.utils.graph.common as g_graph

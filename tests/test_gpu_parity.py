@@ -327,38 +327,51 @@ def test_hierarchy_helpers(golden):
 
 
 def test_hsg_losses_one_pass(golden):
-  """a15: the drop-in `Hsg.losses` -- three NCE terms in one pass over E x P^T, accuracy, and the
-  gradients w.r.t. embeddings and prototypes -- against the reference's method run on CPU."""
+  """a15: the drop-in `Hsg.losses` -- three NCE terms in one pass over E x P^T, accuracy, DMoN on the k-NN
+  graph, centroid contrast, and every gradient -- against the reference's method run on CPU."""
   import types
   from hsg_b200.models.predictions import hsg as head
   from hsg_b200.utils.segsort import loss as L
-  from hsg_b200 import ops
+  from hsg_b200.utils.graph import loss as GL
   g = golden('hsg_losses')
   me = types.SimpleNamespace(
       img_sim_loss=L.SegSortLoss(16), img_sim_loss_weight=1.0, fine_hrchy_loss=L.SegSortLoss(16),
       fine_hrchy_loss_weight=0.1, coarse_hrchy_loss=L.SegSortLoss(16), coarse_hrchy_loss_weight=0.1,
-      dmon_loss=None, centroid_cont_loss=None, label_divisor=2048)
-  emb = t(g['emb']).requires_grad_(True)
-  protos = t(g['protos']).requires_grad_(True)
+      dmon_loss=GL.DMonLoss(adj_knn=2), dmon_loss_weight=0.5, centroid_cont_loss=L.SegSortLoss(16),
+      centroid_cont_loss_weight=1.0, label_divisor=2048)
+  leaf = lambda k: t(g[k]).requires_grad_(True)
+  emb, protos = leaf('emb'), leaf('protos')
+  cent_f, cent_c, nd_f, nd_c = leaf('cent_d_fine'), leaf('cent_d_coarse'), leaf('nd_fine'), leaf('nd_coarse')
   cidx = t(g['cidx'])
   datas = {'cluster_index': cidx, 'cluster_embedding': emb, 'cluster_batch_index': t(g['proto_batch'])[cidx],
-           'cluster_instance_label': t(g['proto_inst'])[cidx]}
+           'cluster_instance_label': t(g['proto_inst'])[cidx],
+           'finehrchy_nd_prototype_grouping_logit': nd_f, 'coarsehrchy_nd_prototype_grouping_logit': nd_c,
+           'nd_prototype': t(g['nd_proto']), 'nd_prototype_batch_index': t(g['nd_batch']),
+           'nd_prototype_padding_mask': t(g['nd_mask']),
+           'finehrchy_nd_prototype_grouping_centroid': cent_f, 'coarsehrchy_nd_prototype_grouping_centroid': cent_c}
   targets = {'image_index': t(g['image_index']), 'prototype': protos, 'prototype_batch_index': t(g['proto_batch']),
              'prototype_instance_label': t(g['proto_inst']), 'finehrchy_mapping_index': t(g['fine_map']),
-             'coarsehrchy_mapping_index': t(g['coarse_map'])}
-  launches = hsg_b200.load_library().hsg_launch_count()
+             'coarsehrchy_mapping_index': t(g['coarse_map']),
+             'finehrchy_nd_prototype_grouping_centroid': t(g['cent_t_fine']),
+             'coarsehrchy_nd_prototype_grouping_centroid': t(g['cent_t_coarse'])}
   img, hr, cl, acc = head.losses(me, datas, targets)
-  assert cl is None
   close(n(img), g['img_sim_loss'], rtol=2e-5)
   close(n(hr), g['hrchy_group_loss'], rtol=2e-5)
+  close(n(cl), g['clustering_loss'], rtol=2e-5)
   assert abs(float(acc) - float(g['accuracy'])) < 1e-6
-  (img + hr).backward()
+  (img + hr + cl).backward()
   close(n(emb.grad), g['demb'], rtol=2e-4, atol=1e-7)
   close(n(protos.grad), g['dprotos'], rtol=2e-4, atol=1e-7)
+  close(n(cent_f.grad), g['dcent_fine'], rtol=2e-4, atol=1e-7)
+  close(n(cent_c.grad), g['dcent_coarse'], rtol=2e-4, atol=1e-7)
+  close(n(nd_f.grad), g['dnd_fine'], rtol=2e-4, atol=1e-8)
+  close(n(nd_c.grad), g['dnd_coarse'], rtol=2e-4, atol=1e-8)
   # only one of the terms switched on, and a term with its own concentration (separate pass)
   me.fine_hrchy_loss = None
   me.coarse_hrchy_loss = L.SegSortLoss(10)
-  img2, hr2, _, _ = head.losses(me, datas, targets)
+  me.dmon_loss = me.centroid_cont_loss = None
+  img2, hr2, cl2, _ = head.losses(me, datas, targets)
+  assert cl2 is None
   close(n(img2), g['img_sim_loss'], rtol=2e-5)
   want = o_loss.segsort_loss(g['emb'], g['coarse_map'][g['cidx']], g['cidx'], g['protos'], g['coarse_map'], 10) * 0.1
   close(n(hr2), want, rtol=2e-5)
