@@ -858,3 +858,79 @@ def test_config2_full_size_properties(S):
     want = o_loss.calculate_log_likelihood(*args, dtype=np.float64).reshape(-1)
     tol = 1e-5 * np.abs(want) + 1e-6 * o_loss.nce_condition(*args) + 1e-6
     assert np.all(np.abs(n(ll[s][pick]) - want) <= tol), np.abs(n(ll[s][pick]) - want).max()
+
+
+# ---------------------------------------------------------------- the whole step, composed
+def test_whole_step_composes_and_differentiates(S):
+  """One training step of the hot path as pyscripts/train/train.py + MultiviewResnetFcn.generate_clusters
+  (resnet_fcn_hsg.py:862-968) + Hsg.losses drive it, built only from this package's drop-ins: k-means ->
+  per-pair prototypes -> fine / coarse clustering transformers -> per-pixel hierarchy ids -> (single-GPU)
+  gather -> the five losses -> backward to the backbone's embeddings and the transformer weights.
+  Every stage is checked against the oracle elsewhere; here: shapes, dtypes, index consistency, finite
+  gradients everywhere they must flow."""
+  import types
+  from hsg_b200.models import utils as MU
+  from hsg_b200.models.embeddings import hierarchy as H
+  from hsg_b200.models.embeddings.transformer_clusters import TransformerClustering
+  from hsg_b200.models.predictions import hsg as head
+  from hsg_b200.utils.graph import loss as GL
+  from hsg_b200.utils.segsort import loss as L
+  torch.manual_seed(235)
+  rng = np.random.RandomState(5)
+  b, c, hw, div, m = 4, 64, 16, 2048, 256
+  emb = torch.randn(b, c, hw, hw, device=dev(), requires_grad=True)
+  labels = t(_block_labels(rng, b, hw, hw, 4, div))
+  image_index = torch.tensor([0, 0, 1, 1], device=dev())
+  x, xloc, lab, ids, bat = S.segment_by_kmeans(emb, labels, [4, 4], iterations=5)
+  assert x.requires_grad and ids.dtype == torch.int64
+  pos = torch.randn(x.shape[0], c, device=dev())
+  protos, pos_protos, mask, plab, pbat, by_image = H.calculate_kmeans_prototypes(x, ids, bat, pos, lab, image_index, div, m)
+  assert protos.shape == (2, c, m) and mask.shape == (2, m) and by_image.shape == ids.shape
+  fine = TransformerClustering(8, c, 4, 2, 2, 2 * c, 0.0).to(dev())
+  coarse = TransformerClustering(4, c, 4, 2, 2, 2 * c, 0.0).to(dev())
+  q_fine = torch.nn.Parameter(torch.randn(8, c, device=dev()))
+  q_coarse = torch.nn.Parameter(torch.randn(4, c, device=dev()))
+  f_cent, f_feat, f_logit, _ = fine(src=protos, mask=mask, query_embed=q_fine, pos_embed=pos_protos)
+  f_prob = torch.softmax(f_logit, dim=1)                                      # :639-642
+  f_lab = torch.argmax(f_prob, dim=1)
+  f_pos = H.collect_nd_coarser_prototype(pos_protos, f_lab, mask, num_groups=8, normalized=False)
+  c_cent, _, c_logit, _ = coarse(src=f_feat, mask=None, query_embed=q_coarse, pos_embed=f_pos)
+  c_prob = torch.einsum('bij,bjk->bik', torch.softmax(c_logit, dim=1), f_prob)   # :664-672
+  c_lab = torch.argmax(c_prob, dim=1)
+  img_of_pixel = image_index[bat]
+  f_pix = H.collect_pixel_hierarchical_clustering_indices(by_image, img_of_pixel, f_lab)
+  c_pix = H.collect_pixel_hierarchical_clustering_indices(by_image, img_of_pixel, c_lab)
+  assert f_pix.shape == ids.shape and int(f_pix.max()) < 8 and int(c_pix.max()) < 4
+  # cross-GPU step on one GPU (train.py:187-228): global prototypes and updated pixel -> prototype ids
+  out = MU.gather_clustering_and_update_prototypes([x], [xloc], [ids], [bat], [lab // div], [lab % div])
+  g_protos, g_sem, g_inst, g_bat, g_ids = out[0][0], out[2][0], out[3][0], out[4][0], out[5][0]
+  assert torch.equal(g_ids, ids) and g_protos.shape[0] == int(ids.max()) + 1
+  fine_map = MU.gather_and_update_cluster_mappings([g_ids], [f_pix + 8 * img_of_pixel])[0]
+  coarse_map = MU.gather_and_update_cluster_mappings([g_ids], [c_pix + 4 * img_of_pixel])[0]
+  assert fine_map.shape[0] == g_protos.shape[0]
+  me = types.SimpleNamespace(
+      img_sim_loss=L.SegSortLoss(16), img_sim_loss_weight=1.0, fine_hrchy_loss=L.SegSortLoss(16),
+      fine_hrchy_loss_weight=0.1, coarse_hrchy_loss=L.SegSortLoss(16), coarse_hrchy_loss_weight=0.1,
+      dmon_loss=GL.DMonLoss(adj_knn=2), dmon_loss_weight=1.0, centroid_cont_loss=L.SegSortLoss(16),
+      centroid_cont_loss_weight=1.0, label_divisor=div)
+  datas = {'cluster_index': g_ids, 'cluster_embedding': x, 'cluster_batch_index': bat, 'cluster_instance_label': lab % div,
+           'finehrchy_nd_prototype_grouping_logit': f_prob, 'coarsehrchy_nd_prototype_grouping_logit': c_prob,
+           'nd_prototype': protos, 'nd_prototype_batch_index': pbat, 'nd_prototype_padding_mask': mask,
+           'finehrchy_nd_prototype_grouping_centroid': f_cent, 'coarsehrchy_nd_prototype_grouping_centroid': c_cent}
+  targets = {'image_index': image_index, 'prototype': g_protos, 'prototype_batch_index': g_bat,
+             'prototype_instance_label': g_inst, 'finehrchy_mapping_index': fine_map,
+             'coarsehrchy_mapping_index': coarse_map,
+             'finehrchy_nd_prototype_grouping_centroid': f_cent.detach(),
+             'coarsehrchy_nd_prototype_grouping_centroid': c_cent.detach()}
+  img, hr, cl, acc = head.losses(me, datas, targets)
+  total = img + hr + cl
+  assert torch.isfinite(total) and 0.0 <= float(acc) <= 1.0
+  total.backward()
+  assert emb.grad is not None and torch.isfinite(emb.grad).all() and float(emb.grad.abs().sum()) > 0
+  for name, net in (('fine', fine), ('coarse', coarse)):
+    missing = [k for k, p in net.named_parameters() if p.requires_grad and p.grad is None]
+    bad = [k for k, p in net.named_parameters() if p.grad is not None and not torch.isfinite(p.grad).all()]
+    assert not bad, (name, bad)
+    # the coarse head's centroid features feed nothing downstream (as in the reference); everything else trains
+    assert all(k.startswith('centroid_feat_fc') for k in missing) and (name == 'coarse' or not missing), (name, missing)
+  assert q_fine.grad is not None and q_coarse.grad is not None
