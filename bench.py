@@ -168,9 +168,13 @@ def run_ours(args):
   torch.cuda.set_device(local_rank)
   device = torch.device('cuda', local_rank)
   group = None
+  json_fd = None
   if world > 1:
-    # NCCL writes its version / debug lines to stdout by default; stdout is reserved for the one JSON line
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+    # NCCL prints its version line on file descriptor 1; stdout is reserved for the one JSON line, so
+    # everything any library writes to fd 1 goes to stderr and the JSON is written to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.distributed.init_process_group('nccl', device_id=device)
   import hsg_b200
   from hsg_b200 import _lib
@@ -331,7 +335,13 @@ def run_ours(args):
       'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
       'roofline': roofline, 'roofline_kmeans': roofline_kmeans, 'phases': per_phase, 'cpu_baseline': cpu, 'loss': float(loss),
   }
-  print(json.dumps(out))
+  line = json.dumps(out) + '\n'
+  if json_fd is not None:
+    sys.stdout.flush()
+    os.write(json_fd, line.encode())
+  else:
+    sys.stdout.write(line)
+    sys.stdout.flush()
   if world > 1:
     torch.distributed.destroy_process_group()
 
