@@ -1,0 +1,25 @@
+"""Latency of the k-means stage at the reference's TRAINING shapes (COCO stage 2: 12 images of 28x28, D=128,
+grid 4x4, 15 iterations; Cityscapes-like 16 x 48x48, D=256), where everything is launch-bound:
+    python tools/bench_training_shape.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from hsg_b200 import ops, _lib
+from hsg_b200.utils.segsort import common as S
+
+dev = torch.device('cuda:0')
+for (b, d, hw, grid, iters) in ((12, 128, 28, 4, 15), (32, 128, 14, 4, 15), (16, 256, 48, 4, 15)):
+  emb = torch.randn(b, d, hw, hw, device=dev)
+  for _ in range(3):
+    S.segment_by_kmeans(emb, None, [grid, grid], iterations=iters)
+  torch.cuda.synchronize()
+  t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  lib = _lib.load()
+  n0 = lib.hsg_launch_count()
+  t0.record()
+  reps = 20
+  for _ in range(reps):
+    S.segment_by_kmeans(emb, None, [grid, grid], iterations=iters)
+  t1.record(); torch.cuda.synchronize()
+  print('segment_by_kmeans %2d x %dx%d, D=%d, K=%d, T=%d: %.3f ms per call, %d kernel launches of the library'
+        % (b, hw, hw, d, grid * grid, iters, t0.elapsed_time(t1) / reps, (lib.hsg_launch_count() - n0) // reps))
