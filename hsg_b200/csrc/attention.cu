@@ -399,6 +399,16 @@ static int fill(AttnArgs& a, const float* q, const float* k, const float* v, con
   return HSG_OK;
 }
 
+// tensor-core forward (attention_tc.cu)
+bool attn_tc_supported(int B, int heads, int L, int S, int hd);
+bool attn_tc_profitable(int B, int heads, int L, int S, int hd);
+size_t attn_tc_workspace_bytes(int B, int heads, int L, int S);
+int attn_fwd_tc(const float* q, const float* k, const float* v, const unsigned char* mask, int B, int heads, int L,
+                int S, float scale, float drop_p, uint64_t seed, float* out, float* lse, void* workspace,
+                cudaStream_t st);
+extern int g_debug_flags;      // nce.cu; tests: bit 4 (16) keeps the attention forward on the CUDA-core kernel,
+                               // bit 5 (32) takes the tensor-core kernel for every shape it supports
+
 }  // namespace hsg
 
 using namespace hsg;
@@ -409,14 +419,23 @@ size_t hsg_mha_workspace_bytes(int B, int heads, int L, int S) {
   return (size_t)2 * B * heads * L * S * sizeof(float) + 256;
 }
 
+size_t hsg_mha_fwd_workspace_bytes(int B, int heads, int L, int S, int hd) {
+  const bool use = (g_debug_flags & 32) ? attn_tc_supported(B, heads, L, S, hd) : attn_tc_profitable(B, heads, L, S, hd);
+  return use && !(g_debug_flags & 16) ? attn_tc_workspace_bytes(B, heads, L, S) : 0;
+}
+
 int hsg_mha_fwd_f32(const float* q, const float* k, const float* v, const unsigned char* key_padding_mask,
                     int B, int heads, int L, int S, int hd, float scale, float dropout_p,
-                    unsigned long long seed, float* out, float* lse, void* stream) {
+                    unsigned long long seed, float* out, float* lse, void* workspace, size_t workspace_bytes,
+                    void* stream) {
   AttnArgs a;
   int rc = fill(a, q, k, v, key_padding_mask, B, heads, L, S, hd, scale, dropout_p, seed);
   if (rc) return rc;
   HSG_REQUIRE(out && lse, HSG_E_INVALID, "mha_fwd: null output");
   cudaStream_t st = (cudaStream_t)stream;
+  if (!(g_debug_flags & 16) && attn_tc_supported(B, heads, L, S, hd) && workspace &&
+      workspace_bytes >= attn_tc_workspace_bytes(B, heads, L, S))
+    return attn_fwd_tc(q, k, v, key_padding_mask, B, heads, L, S, scale, dropout_p, seed, out, lse, workspace, st);
   const int R = L >= 64 ? 4 : 1;                   // rows per warp (tiny L: keep the CTAs many)
   const size_t smem = (size_t)(2 * AT_TS * (hd + AT_PAD) + AT_WARPS * R * (hd + AT_TS)) * sizeof(float);
   dim3 grid((L + AT_WARPS * R - 1) / (AT_WARPS * R), a.BH);

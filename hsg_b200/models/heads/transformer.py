@@ -37,10 +37,13 @@ class _AttentionCore(torch.autograd.Function):
     out = torch.empty_like(q)
     lse = torch.empty((bh, l), dtype=torch.float32, device=q.device)
     scale = 1.0 / math.sqrt(hd)
+    lib = _lib.load()
+    nws = lib.hsg_mha_fwd_workspace_bytes(batch, heads, l, s, hd)      # > 0: the tcgen05 forward applies
+    ws = _workspace(nws, q.device) if nws else None
     with torch.cuda.device(q.device):
-      check(_lib.load().hsg_mha_fwd_f32(_ptr(q), _ptr(k), _ptr(v), _ptr(mask), batch, heads, l, s, hd,
-                                        scale, float(dropout_p), ctypes.c_ulonglong(seed), _ptr(out),
-                                        _ptr(lse), _stream()), 'mha_fwd')
+      check(lib.hsg_mha_fwd_f32(_ptr(q), _ptr(k), _ptr(v), _ptr(mask), batch, heads, l, s, hd,
+                                scale, float(dropout_p), ctypes.c_ulonglong(seed), _ptr(out),
+                                _ptr(lse), _ptr(ws), nws, _stream()), 'mha_fwd')
     ctx.save_for_backward(q, k, v, mask, out, lse)
     ctx.cfg = (batch, heads, float(dropout_p), seed, scale)
     return out

@@ -227,10 +227,13 @@ HSG_API int hsg_nce_bwd_f32(const float* e, const float* prototypes, int64_t N, 
  * parity with the reference is defined at p = 0).  A row whose keys are all
  * masked yields NaN, as in the reference. */
 HSG_API size_t hsg_mha_workspace_bytes(int B, int heads, int L, int S);
+/* forward workspace: with it (head dim 64, S <= 256) the two contractions run on tcgen05 (fp16 hi/lo split,
+ * fp32-grade); without it, or for other shapes, on CUDA cores.  0 bytes = not needed. */
+HSG_API size_t hsg_mha_fwd_workspace_bytes(int B, int heads, int L, int S, int hd);
 HSG_API int hsg_mha_fwd_f32(const float* q, const float* k, const float* v,
                             const unsigned char* key_padding_mask, int B, int heads, int L, int S,
                             int hd, float scale, float dropout_p, unsigned long long seed,
-                            float* out, float* lse, void* stream);
+                            float* out, float* lse, void* workspace, size_t workspace_bytes, void* stream);
 HSG_API int hsg_mha_bwd_f32(const float* q, const float* k, const float* v,
                             const unsigned char* key_padding_mask, int B, int heads, int L, int S,
                             int hd, float scale, float dropout_p, unsigned long long seed,

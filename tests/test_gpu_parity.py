@@ -695,6 +695,43 @@ def test_fused_attention_core_vs_float64():
   assert abs(float(od.mean()) - float(out.detach().mean())) < 0.05 and not torch.equal(od, out.detach())
 
 
+@pytest.mark.parametrize('b,l,s_', [(3, 37, 70), (2, 256, 256), (5, 8, 200), (1, 130, 64)])
+def test_attention_tensor_core_forward(b, l, s_):
+  """tcgen05 forward of the attention core (head dim 64): against float64, against the CUDA-core kernel
+  (same dropout mask), and through the CUDA-core backward (which consumes the saved log-sum-exp)."""
+  from hsg_b200 import _lib
+  from hsg_b200.models.heads.transformer import attention_core
+  lib = _lib.load()
+  rng = np.random.RandomState(b * 1000 + l)
+  h, hd = 4, 64
+  q, k, v = [rng.randn(b * h, m, hd).astype(np.float32) for m in (l, s_, s_)]
+  mask = np.zeros((b, s_), bool)
+  mask[0, s_ // 2:] = True
+  mask[-1, :3] = True
+  w = rng.randn(b * h, l, hd).astype(np.float32)
+  res = {}
+  for flags in (32, 16):          # tensor-core kernel for every supported shape / CUDA-core kernel
+    lib.hsg_debug_set_flags(flags)
+    try:
+      assert (lib.hsg_mha_fwd_workspace_bytes(b, 4, l, s_, 64) > 0) == (flags == 32)
+      qt, kt, vt = [t(a).requires_grad_(True) for a in (q, k, v)]
+      out = attention_core(qt, kt, vt, t(mask), b, h)
+      (out * t(w)).sum().backward()
+      torch.manual_seed(3)
+      dropped = attention_core(t(q), t(k), t(v), t(mask), b, h, dropout_p=0.3)
+    finally:
+      lib.hsg_debug_set_flags(0)
+    res[0 if flags == 32 else 16] = [n(out), n(qt.grad), n(kt.grad), n(vt.grad), n(dropped)]
+  sc = torch.einsum('zld,zsd->zls', torch.from_numpy(q).double() / hd ** 0.5, torch.from_numpy(k).double())
+  sc = sc.masked_fill(torch.from_numpy(np.repeat(mask, h, axis=0)).unsqueeze(1), float('-inf'))
+  want = torch.einsum('zls,zsd->zld', torch.softmax(sc, -1), torch.from_numpy(v).double()).numpy()
+  close(res[0][0], want, rtol=1e-5, atol=2e-6)
+  close(res[16][0], want, rtol=1e-5, atol=2e-6)
+  for a, c in zip(res[0][1:4], res[16][1:4]):               # same backward kernels, lse from two forwards
+    close(a, c, rtol=1e-4, atol=1e-5)
+  close(res[0][4], res[16][4], rtol=1e-5, atol=2e-6)        # dropout: the same counter-based mask in both kernels
+
+
 # ---------------------------------------------------------------- BASELINE.json configs 3-5 (shapes of the other configs)
 def _block_labels(rng, b, h, w, blk, divisor=2048):
   """block oversegmentation (~(h/blk)*(w/blk) regions per image) packed as sem*divisor + inst"""
