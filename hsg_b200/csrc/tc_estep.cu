@@ -343,8 +343,15 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       acc_phase ^= 1;
       par ^= 1;
       if (tile_many) asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");        // barrier 3
+      // one atomic per warp for the list slots (the counter is a single address shared by every SM)
+      const unsigned amb_mask = __ballot_sync(FULL, amb);
+      int slot_base = 0;
+      if (amb_mask) {
+        if (lane == 0) slot_base = atomicAdd(p.fix.count, __popc(amb_mask));
+        slot_base = __shfl_sync(FULL, slot_base, 0);
+      }
       if (amb) {
-        const int slot = atomicAdd(p.fix.count, 1);
+        const int slot = slot_base + __popc(amb_mask & ((1u << lane) - 1u));
         if (slot < p.fix.capacity) {
           p.fix.pixels[slot] = (int32_t)pix;
           uint16_t* cd = p.fix.cand + (int64_t)slot * FIX_MAX_CAND;
