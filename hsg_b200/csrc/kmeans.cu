@@ -533,6 +533,39 @@ int hsg_segment_reduce_f32(const float* x, int64_t N, int dim, const int64_t* la
   return sr_combine(p, P, seg_base, mode, out, sums_out, counts_out, st);
 }
 
+size_t hsg_segment_sum_exact_workspace_bytes(int64_t N, int dim, int64_t P, int S, int kmax, int64_t max_seg_len) {
+  (void)P;
+  return sr_workspace_bytes(N, dim, S > 0 ? S : 1, kmax, max_seg_len, true) + 1024;
+}
+
+int hsg_segment_sum_exact_i64(const float* x, int64_t N, int dim, const int64_t* labels, int64_t P,
+                              const int64_t* seg_offsets, int S, int64_t max_seg_len, const int64_t* seg_base,
+                              int kmax, long long* sums_out, void* workspace, size_t workspace_bytes, void* stream) {
+  HSG_REQUIRE(P >= 0 && dim > 0 && N >= 0, HSG_E_INVALID, "segment_sum_exact: bad shape");
+  HSG_REQUIRE(seg_offsets && seg_base && S > 0, HSG_E_INVALID, "segment_sum_exact: seg_offsets/seg_base are required");
+  if (P == 0) return HSG_OK;
+  HSG_REQUIRE(sums_out, HSG_E_INVALID, "segment_sum_exact: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) {
+    HSG_CUDA(cudaMemsetAsync(sums_out, 0, sizeof(long long) * P * dim, st));
+    return HSG_OK;
+  }
+  int rc = check_common(x, N, dim, seg_offsets, S, max_seg_len, kmax);
+  if (rc) return rc;
+  HSG_REQUIRE(labels, HSG_E_INVALID, "segment_sum_exact: null labels");
+  HSG_REQUIRE(workspace && workspace_bytes >= hsg_segment_sum_exact_workspace_bytes(N, dim, P, S, kmax, max_seg_len),
+              HSG_E_WORKSPACE, "segment_sum_exact: workspace too small");
+  Carver c(workspace);
+  SegReducePlan p;
+  sr_carve(c, p, N, dim, S, kmax, max_seg_len, true);
+  ProfRange prof(PROF_POOL, st);
+  ProfSuppress inner;
+  if ((rc = sr_build_tiles(p, seg_offsets, st))) return rc;
+  if ((rc = sr_labels_to_keys(p, labels, seg_base, st))) return rc;
+  if ((rc = sr_sort_and_sum(p, x, seg_offsets, st))) return rc;
+  return sr_combine_exact(p, P, seg_base, sums_out, st);
+}
+
 }  // extern "C"
 
 // backward: per-bin gradient of the finishing step, then a row gather

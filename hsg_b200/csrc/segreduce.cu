@@ -202,13 +202,20 @@ constexpr int GATHER_WARPS = 8;
 // DELTA = true : the sorted objects are the signed entries of a DeltaList (kmeans.cuh): entry
 //                e = eoff[s] + perm[j] adds (+) or removes (-) row off[s] + (erow[e] & 0x7fffffff)
 //                to / from key keys[e]; sums are accumulated and emitted in float64.
-template <int NV, bool DELTA>
+//                emitted in float64.
+// MODE 2 (exact): rows as in mode 0, but every element is converted to 2^-36 fixed point and summed in int64:
+//                integer sums do not depend on the order or on how the rows are split over launches / GPUs.
+constexpr float SR_FIXED_SCALE = 68719476736.f;     // 2^36: |x| <= 1 rows, up to 2^26 rows per bin
+
+template <int NV, int MODE>
 __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_sum_kernel(
     const float* __restrict__ x, int dim, int64_t N, const int64_t* __restrict__ off, int S,
     const int32_t* __restrict__ keys, const uint32_t* __restrict__ perm,
     float* __restrict__ pieces, int32_t* __restrict__ piece_cnt, Gate gate,
     const int64_t* __restrict__ eoff, const uint32_t* __restrict__ erow) {
-  typedef typename std::conditional<DELTA, double, float>::type acc_t;
+  constexpr bool DELTA = MODE == 1;
+  constexpr bool EXACT = MODE == 2;
+  typedef typename std::conditional<DELTA, double, typename std::conditional<EXACT, long long, float>::type>::type acc_t;
   if (gate.closed()) return;
   const int lane = threadIdx.x & 31;
   const int64_t run = (int64_t)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
@@ -290,6 +297,10 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_sum_kernel(
 #pragma unroll
           for (int m = 0; m < NV; ++m) acc[m] += (acc_t)(neg[u] ? -v[u][m] : v[u][m]);
           cnt += neg[u] ? -1 : 1;
+        } else if (EXACT) {
+#pragma unroll
+          for (int m = 0; m < NV; ++m) acc[m] += (acc_t)__float2ll_rn(v[u][m] * SR_FIXED_SCALE);
+          ++cnt;
         } else {
 #pragma unroll
           for (int m = 0; m < NV; ++m) acc[m] += v[u][m];
@@ -514,8 +525,8 @@ int64_t sr_tiles_bound(int64_t N, int S, int64_t tile) { return N / tile + S + 1
 
 static int64_t sr_num_pieces(int64_t N, int64_t bins) { return ceil_div64(N, SR_RUN) + bins + 2; }
 
-void sr_carve(Carver& c, SegReducePlan& p, int64_t N, int dim, int S, int kmax, int64_t max_seg_len) {
-  p.N = N; p.dim = dim; p.S = S; p.kmax = kmax; p.bins = (int64_t)S * kmax;
+void sr_carve(Carver& c, SegReducePlan& p, int64_t N, int dim, int S, int kmax, int64_t max_seg_len, bool exact) {
+  p.N = N; p.dim = dim; p.S = S; p.kmax = kmax; p.bins = (int64_t)S * kmax; p.exact = exact;
   p.tiles.tile = sr_tile_size(max_seg_len);
   p.tiles.bound = sr_tiles_bound(N, S, p.tiles.tile);
   p.tiles.seg = c.take<int32_t>(p.tiles.bound);
@@ -529,14 +540,14 @@ void sr_carve(Carver& c, SegReducePlan& p, int64_t N, int dim, int S, int kmax, 
   p.bin_start = c.take<int64_t>(p.bins);
   p.bin_count = c.take<int32_t>(p.bins);
   const int64_t np = sr_num_pieces(N, p.bins);
-  p.pieces = c.take<float>(np * dim);
+  p.pieces = c.take<float>(np * dim * (exact ? 2 : 1));      // int64 pieces in exact mode
   p.piece_cnt = c.take<int32_t>(np);
 }
 
-size_t sr_workspace_bytes(int64_t N, int dim, int S, int kmax, int64_t max_seg_len) {
+size_t sr_workspace_bytes(int64_t N, int dim, int S, int kmax, int64_t max_seg_len, bool exact) {
   Carver c(nullptr);
   SegReducePlan p;
-  sr_carve(c, p, N, dim, S, kmax, max_seg_len);
+  sr_carve(c, p, N, dim, S, kmax, max_seg_len, exact);
   return c.used() + 256;
 }
 
@@ -564,7 +575,7 @@ int sr_keys_to_labels(const SegReducePlan& p, const int32_t* keys, int64_t* labe
   return HSG_OK;
 }
 
-template <int NV, bool DELTA>
+template <int NV, int DELTA>
 static int launch_gather(const SegReducePlan& p, const float* x, const int64_t* off, Gate gate,
                          const int64_t* eoff, const uint32_t* erow, cudaStream_t st) {
   const int64_t runs = ceil_div64(p.N, SR_RUN);
@@ -574,7 +585,7 @@ static int launch_gather(const SegReducePlan& p, const float* x, const int64_t* 
   return HSG_OK;
 }
 
-template <bool DELTA>
+template <int DELTA>
 static int gather_dispatch(const SegReducePlan& p, const float* x, const int64_t* off, Gate gate,
                            const int64_t* eoff, const uint32_t* erow, cudaStream_t st) {
   const int nv = (p.dim + 31) / 32;
@@ -617,12 +628,47 @@ int sr_sort_and_sum_gated(const SegReducePlan& p, const float* x, const int64_t*
   HSG_LAUNCH_CHECK();
   }
   ProfRange prof(PROF_MSTEP_GATHER, st);
-  return eoff ? gather_dispatch<true>(p, x, off, gate, eoff, erow, st)
-              : gather_dispatch<false>(p, x, off, gate, nullptr, nullptr, st);
+  if (p.exact) return gather_dispatch<2>(p, x, off, gate, nullptr, nullptr, st);
+  return eoff ? gather_dispatch<1>(p, x, off, gate, eoff, erow, st)
+              : gather_dispatch<0>(p, x, off, gate, nullptr, nullptr, st);
 }
 
 int sr_sort_and_sum(const SegReducePlan& p, const float* x, const int64_t* off, cudaStream_t st) {
   return sr_sort_and_sum_gated(p, x, off, Gate{nullptr, 0}, nullptr, nullptr, st);
+}
+
+// exact sums: out[p, d] = sum of the int64 fixed-point pieces of bin p (see gather_sum_kernel, mode 2)
+__global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_exact_kernel(
+    int64_t P, int dim, int S, int kmax, const int64_t* __restrict__ seg_base,
+    const int64_t* __restrict__ bin_start, const int32_t* __restrict__ bin_count,
+    const long long* __restrict__ pieces, long long* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p = (int64_t)blockIdx.x * COMBINE_WARPS + (threadIdx.x >> 5);
+  if (p >= P) return;
+  int64_t key = p;
+  bool covered = true;
+  if (seg_base) {
+    const int s = upper_bound_i64(seg_base, S, p) - 1;
+    const int64_t k = s >= 0 ? p - seg_base[s] : kmax;
+    covered = s >= 0 && k < kmax;
+    key = covered ? (int64_t)s * kmax + k : 0;
+  }
+  const int cnt = covered ? bin_count[key] : 0;
+  const int64_t start = covered ? bin_start[key] : 0;
+  const int64_t r0 = start / SR_RUN, r1 = cnt > 0 ? (start + cnt - 1) / SR_RUN : r0 - 1;
+  for (int d = lane; d < dim; d += 32) {
+    long long a = 0;
+    for (int64_t r = r0; r <= r1; ++r) a += pieces[(r + key) * dim + d];
+    out[p * dim + d] = a;
+  }
+}
+
+int sr_combine_exact(const SegReducePlan& p, int64_t P, const int64_t* seg_base, long long* out, cudaStream_t st) {
+  if (P == 0) return HSG_OK;
+  combine_exact_kernel<<<(unsigned)ceil_div64(P, COMBINE_WARPS), COMBINE_WARPS * 32, 0, st>>>(
+      P, p.dim, p.S, p.kmax, seg_base, p.bin_start, p.bin_count, reinterpret_cast<const long long*>(p.pieces), out);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
 }
 
 int sr_combine64(const SegReducePlan& p, const float* pieces_full, const double* pieces_delta,

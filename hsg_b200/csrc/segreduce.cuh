@@ -46,6 +46,7 @@ struct SegReducePlan {
   int S;
   int kmax;
   int64_t bins;          // S * kmax
+  bool exact;            // pieces are int64 fixed-point sums (order / partition independent)
   Tiles tiles;
   int32_t* keys;         // [N] global key = s*kmax + local key
   uint32_t* perm;        // [N] row id relative to its segment start
@@ -69,9 +70,9 @@ struct Gate {
 
 int64_t sr_tile_size(int64_t max_seg_len);
 int64_t sr_tiles_bound(int64_t N, int S, int64_t tile);
-size_t sr_workspace_bytes(int64_t N, int dim, int S, int kmax, int64_t max_seg_len);
+size_t sr_workspace_bytes(int64_t N, int dim, int S, int kmax, int64_t max_seg_len, bool exact = false);
 // carve the plan's buffers out of `c`
-void sr_carve(Carver& c, SegReducePlan& p, int64_t N, int dim, int S, int kmax, int64_t max_seg_len);
+void sr_carve(Carver& c, SegReducePlan& p, int64_t N, int dim, int S, int kmax, int64_t max_seg_len, bool exact = false);
 
 int sr_build_tiles(const SegReducePlan& p, const int64_t* seg_offsets, cudaStream_t st);
 // keys[i] = s*kmax + clamp(labels[i] - base_s, 0, kmax-1); seg_base may be NULL (base 0)
@@ -97,6 +98,8 @@ int sr_combine64(const SegReducePlan& p, const float* pieces_full, const double*
 int sr_delta_build(const SegReducePlan& p, const int64_t* seg_offsets, int32_t* keys_prev,
                    int32_t* tile_entries, int64_t* eoff, int32_t* flag, int64_t cap, uint32_t* erow,
                    int32_t* ekey, cudaStream_t st);
+// exact mode: out[r,:] = int64 fixed-point (2^-36) sums of the rows of bin r
+int sr_combine_exact(const SegReducePlan& p, int64_t P, const int64_t* seg_base, long long* out, cudaStream_t st);
 // out[r,:] for r in [0,P): row r = key (seg_base == NULL) or the label whose
 // key it is; mode as in hsg_b200.h.  sums_out / counts_out optional.
 int sr_combine(const SegReducePlan& p, int64_t P, const int64_t* seg_base, int mode, float* out,

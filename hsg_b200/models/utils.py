@@ -166,10 +166,13 @@ def dist_gather_clustering_and_update_prototypes(embeddings, embeddings_with_loc
   return exchange_prototypes(ids, protos, protos_loc, psem, pinst, pbat, group)
 
 
-def dist_kmeans_with_initial_labels(embeddings, initial_labels, max_label, iterations=10, group=None):
-  """Flat spherical k-means over rows sharded across ranks: each iteration
-  all-reduces the [K,D] centroid sums (the one real exchange step of the path),
-  every rank normalises identically, then assigns its own rows."""
+def dist_kmeans_with_initial_labels(embeddings, initial_labels, max_label, iterations=10, group=None,
+                                    collective=True):
+  """Flat spherical k-means over rows sharded across ranks: each iteration all-reduces the [K,D] centroid
+  sums (the one real exchange step of the path), every rank normalises identically, then assigns its own
+  rows.  The sums are exact int64 fixed-point sums (ops.segment_sum_exact) and the all-reduce of integers is
+  exact, so centroids and labels are bit-identical at every rank count and for every way of sharding the
+  rows -- including the single-process run (`collective=False`: this process holds every row)."""
   x = embeddings.reshape(-1, embeddings.shape[-1]).detach()
   labels = initial_labels.reshape(-1).long()
   d16 = ops.tc_d16(x.shape[1], max_label)
@@ -178,9 +181,9 @@ def dist_kmeans_with_initial_labels(embeddings, initial_labels, max_label, itera
     xh, xerr = ops.make_half_copy(x, d16)
   with torch.no_grad():
     for _ in range(int(iterations)):
-      sums = ops.segment_reduce(x, labels, int(max_label), REDUCE_SUM)
-      if dist.is_initialized() and dist.get_world_size(group) > 1:
+      sums = ops.segment_sum_exact(x, labels, int(max_label))
+      if collective and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-      centroids = ops.normalize(sums)
+      centroids = ops.normalize((sums.double() * ops.FIXED_POINT_SCALE).float())
       labels = ops.kmeans_estep(x, centroids.view(1, int(max_label), -1), xh=xh, xerr=xerr)
   return labels

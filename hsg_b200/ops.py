@@ -251,6 +251,31 @@ def segment_reduce(x, labels, num_bins, mode, seg_offsets=None, max_seg_len=None
   return _SegmentReduce.apply(x2, labels, int(num_bins), mode, seg_offsets, max_seg_len, seg_base, kmax)
 
 
+FIXED_POINT_SCALE = 2.0 ** -36
+
+
+def segment_sum_exact(x, labels, num_bins):
+  """Exact bin sums as int64 fixed point (value = sum * FIXED_POINT_SCALE): independent of the row order and
+  of how the rows are split over calls or GPUs (hsg_segment_sum_exact_i64).  x rows with |x| <= 1."""
+  _need_cuda(x, labels)
+  x2 = _f32(x.reshape(-1, x.shape[-1]).detach())
+  labels = _i64(labels).reshape(-1)
+  n, dim = x2.shape
+  dev = x2.device
+  if num_bins > 49152:
+    raise _lib.HsgError('segment_sum_exact: more than 49152 bins')
+  out = torch.empty((num_bins, dim), dtype=torch.int64, device=dev)
+  seg_offsets = torch.tensor([0, n], dtype=torch.int64, device=dev)
+  seg_base = torch.zeros((1,), dtype=torch.int64, device=dev)
+  lib = _lib.load()
+  ws = _workspace(lib.hsg_segment_sum_exact_workspace_bytes(n, dim, num_bins, 1, num_bins, n), dev)
+  with torch.cuda.device(dev):
+    check(lib.hsg_segment_sum_exact_i64(_ptr(x2), n, dim, _ptr(labels), num_bins, _ptr(seg_offsets), 1, n,
+                                        _ptr(seg_base), int(num_bins), _ptr(out), _ptr(ws), ws.numel(), _stream()),
+          'segment_sum_exact')
+  return out
+
+
 # ---------------------------------------------------------------- K4 NCE
 class _Nce(torch.autograd.Function):
 

@@ -191,6 +191,17 @@ HSG_API int hsg_segment_reduce_bwd_f32(const float* grad_out, const float* out, 
                                int64_t P, int mode, float* grad_x, void* workspace,
                                size_t workspace_bytes, void* stream);
 
+/* Exact, order-independent bin sums: every element is converted to 2^-36 fixed point and summed in int64
+ * (rows with |x| <= 1, up to 2^26 rows per bin).  sums_out [P,dim] int64; sum * 2^-36 is the value.  Integer sums do
+ * not depend on how the rows are split over launches or GPUs, so a row-sharded k-means that all-reduces these
+ * (ncclSum on int64 is exact) yields bit-identical centroids and labels at every GPU count (SURVEY 8e notes). */
+HSG_API size_t hsg_segment_sum_exact_workspace_bytes(int64_t N, int dim, int64_t P, int S, int kmax,
+                                                     int64_t max_seg_len);
+HSG_API int hsg_segment_sum_exact_i64(const float* x, int64_t N, int dim, const int64_t* labels, int64_t P,
+                                      const int64_t* seg_offsets, int S, int64_t max_seg_len,
+                                      const int64_t* seg_base, int kmax, long long* sums_out,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K4: pixel-to-prototype NCE ("SegSort+") loss
  *      _calculate_log_likelihood (hsg/utils/segsort/loss.py:15-82).
  * e [N,dim], prototypes [P,dim], inst [N] (own prototype id), n_sets label

@@ -466,6 +466,40 @@ def test_kmeans_incremental_mstep_matches_full_resum(S):
       assert np.array_equal(n(lab9)[sl][sel], best[sel])
 
 
+def test_exact_sums_are_partition_invariant_and_flat_kmeans_is_shard_invariant():
+  """the row-sharded flat k-means all-reduces centroid sums.  The sums are int64 fixed point, so
+  (1) they equal the float64 sums to 2^-36 per row, (2) the sum over any split of the rows is bit-identical to
+  the sum over all rows, and therefore (3) the k-means labels do not depend on how many shards (GPUs) the rows
+  are split over -- emulated here on one GPU by running the loop with 1, 2 and 5 shards."""
+  from hsg_b200 import ops
+  from hsg_b200.models import utils as MU
+  rng = np.random.RandomState(9)
+  nn, d, k, iters = 60000, 130, 48, 8
+  x = o_ops.normalize_embedding(rng.randn(nn, d).astype(np.float32))
+  lab = rng.randint(0, k, nn).astype(np.int64)
+  xt, lt = t(x), t(lab)
+  whole = ops.segment_sum_exact(xt, lt, k)
+  assert whole.dtype == torch.int64
+  want = o_ops.scatter_sum(x.astype(np.float64), lab, k)
+  assert np.abs(n(whole).astype(np.float64) * ops.FIXED_POINT_SCALE - want).max() <= nn * 2.0 ** -37
+  for cuts in ([0, 31234, nn], [0, 1, 777, 20000, 41111, nn]):
+    parts = sum(ops.segment_sum_exact(xt[a:b], lt[a:b], k) for a, b in zip(cuts[:-1], cuts[1:]))
+    assert torch.equal(parts, whole)
+
+  def sharded_kmeans(cuts):
+    labels = lt.clone()
+    for _ in range(iters):
+      sums = sum(ops.segment_sum_exact(xt[a:b], labels[a:b], k) for a, b in zip(cuts[:-1], cuts[1:]))
+      cent = ops.normalize((sums.double() * ops.FIXED_POINT_SCALE).float())
+      labels = torch.cat([ops.kmeans_estep(xt[a:b], cent.view(1, k, -1)) for a, b in zip(cuts[:-1], cuts[1:])])
+    return labels
+
+  one = MU.dist_kmeans_with_initial_labels(xt, lt, k, iters)              # single process, no group
+  assert torch.equal(one, sharded_kmeans([0, nn]))
+  assert torch.equal(one, sharded_kmeans([0, 30000, nn]))
+  assert torch.equal(one, sharded_kmeans([0, 11111, 22222, 40000, 59999, nn]))
+
+
 # ---------------------------------------------------------------- tensor-core (tcgen05) E-step
 def _tc_case(nn, d16, loc, k, lens=None, seed=11):
   rng = np.random.RandomState(seed)

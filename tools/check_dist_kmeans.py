@@ -1,5 +1,6 @@
 """Flat spherical k-means with rows sharded over ranks and an NCCL all-reduce of the centroid sums per
-iteration (BASELINE configs[2]/[4] mode), against the single-GPU run of the same problem.
+iteration (BASELINE configs[2]/[4] mode), against the single-GPU run of the same problem: the exact int64
+fixed-point sums make the labels bit-identical at every GPU count.
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_dist_kmeans.py [N] [D] [K] [T]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -29,7 +30,7 @@ mine = MU.dist_kmeans_with_initial_labels(x[lo:hi], init[lo:hi], K, T)
 t1.record(); torch.cuda.synchronize()
 ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-full = S.kmeans_with_initial_labels(x, init, K, T)          # every rank: the whole problem on one GPU
+full = MU.dist_kmeans_with_initial_labels(x, init, K, T, collective=False)   # every rank alone: the whole problem on one GPU
 agree = (mine == full[lo:hi]).float().mean()
 dist.all_reduce(agree, op=dist.ReduceOp.SUM)
 if rank == 0:
