@@ -46,7 +46,8 @@ def parse():
   ap.add_argument('--steps', type=int, default=5)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-  ap.add_argument('--images', type=int, default=48)
+  ap.add_argument('--images', type=int, default=48, help='images of the GLOBAL batch (strong scaling) or per GPU (weak)')
+  ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
   ap.add_argument('--size', type=int, default=448)
   ap.add_argument('--dim', type=int, default=256)
   ap.add_argument('--grid', type=int, default=16)
@@ -182,6 +183,14 @@ def run_ours(args):
   from hsg_b200.models import utils as MU
   lib = hsg_b200.load_library()
 
+  # strong scaling (default): the job is BASELINE configs[1] itself -- 48 images in the global batch -- at every
+  # GPU count, each rank taking 48 / N images; weak: 48 images per GPU (the NCE then contrasts against N x 12288
+  # prototypes, i.e. the work per GPU grows with N)
+  global_images = args.images
+  if args.scaling == 'strong':
+    if args.images % world:
+      raise SystemExit('--images %d is not divisible by %d GPUs' % (args.images, world))
+    args.images = args.images // world
   n_pix = args.images * args.size * args.size
   dp = args.dim + 2
   # two resident input batches (each 9.9 GB >> 126 MB L2), alternated between steps
@@ -317,19 +326,24 @@ def run_ours(args):
       'metric': 'pixel-embeddings/sec spherical-kmeans+NCE (448^2, D=256, K=256)',
       'value': value, 'unit': 'pixel-embeddings/s', 'n_gpus': world, 'steps': args.steps,
       'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': 'configs[1]: %d images x %dx%d embeddings, D=%d, k-means grid %dx%d (K=%d), '
-                             '%d iterations + prototype pooling + NCE fwd (2 label sets, P=%d/GPU); %s values; '
+      'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': 'configs[1]: %d images per GPU x %dx%d embeddings, D=%d, k-means grid %dx%d (K=%d), '
+                             '%d iterations + prototype pooling + all-gather of prototypes + NCE fwd (2 label sets, P=%d/GPU); %s values; '
                              'inputs %.1f GB per step (> L2), two batches alternated'
                              % (args.images, args.size, args.size, args.dim, args.grid, args.grid,
                                 args.grid ** 2, args.iters, args.images * args.grid ** 2, args.dist,
                                 n_pix * args.dim * 4 / 1e9),
-                 'images_per_gpu': args.images, 'embedding_grid': [args.size, args.size], 'dim': args.dim,
+                 'images_per_gpu': args.images, 'global_images': args.images * world,
+                 'embedding_grid': [args.size, args.size], 'dim': args.dim,
                  'k': args.grid ** 2, 'iterations': args.iters, 'parallelism': 'images sharded over %d GPU(s)' % world,
                  'nce_prototypes_global': world * args.images * args.grid ** 2,
-                 'scaling_note': 'images (and their k-means) are sharded with no collective; the NCE contrasts every '
-                                 'pixel with the prototypes of the WHOLE global batch (all-gather), so NCE work per GPU '
-                                 'grows with the GPU count: see nce_pairs_per_s_per_gpu for the work-normalised rate'},
+                 'scaling_note': ('strong scaling: the global batch is configs[1] (%d images, %d prototypes) at every GPU '
+                                  'count; images and their k-means are sharded with no collective, the prototypes are '
+                                  'all-gathered before the NCE' % (global_images, global_images * args.grid ** 2))
+                                 if args.scaling == 'strong' else
+                                 ('weak scaling: %d images per GPU; the NCE contrasts every pixel with the prototypes of the '
+                                  'WHOLE global batch (all-gather), so NCE work per GPU grows with the GPU count: see '
+                                  'nce_pairs_per_s_per_gpu for the work-normalised rate' % args.images)},
       'nce_pairs_per_s_per_gpu': (n_pix * float(world * args.images * args.grid ** 2) /
                                   (phase_ms['nce_fwd'] / args.steps * 1e-3)) if phase_ms['nce_fwd'] > 0 else None,
       'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
