@@ -10,6 +10,8 @@ One "step" = one pass of the hot path over one synthetic batch:
 on BASELINE.json configs[1]: 48 images of 448x448 embeddings, D=256, k-means grid
 16x16 (K=256), 10 iterations.  Prints ONE JSON line (see the keys below).
 
+scaling : strong by default -- the global batch is configs[1] (48 images) at every GPU count, 48/N images per
+          rank (--scaling weak: 48 images per rank; the NCE then faces N x 12288 prototypes).
 value   : pixel-embeddings/s with the input embeddings already resident in HBM.
 e2e     : the same metric through the reference-facing Python operators with HOST
           (pinned) input, the host->device copy and the loss read-back inside the
