@@ -260,6 +260,7 @@ struct KmPlan {
   DeltaPlan d;
 };
 
+constexpr int64_t KM_DELTA_MIN_ROWS = 1 << 18;
 constexpr double KM_DELTA_MAX_FRACTION = 0.4;   // of the rows may have moved (2 entries each) for a delta pass
 
 static void km_carve(Carver& c, KmPlan& p, int64_t N, int dim, int S, int kmax, int64_t max_seg_len,
@@ -419,8 +420,10 @@ int hsg_kmeans_f32(const float* x, int64_t N, int dim, const void* xh, int d16, 
   ea.S = S; ea.seg_k = seg_k; ea.kmax = kmax; ea.tiles = p.sr.tiles; ea.keys_out = p.sr.keys;
   ea.fix = p.fix;
 
+  // below ~2.6e5 rows a full re-sum is cheaper than the dozen extra launches of the delta machinery
+  const bool incremental = !(flags & HSG_KMEANS_FULL_MSTEP) && N >= KM_DELTA_MIN_ROWS;
   for (int it = 0; it < iterations; ++it) {
-    if ((rc = km_mstep(p, x, seg_offsets, it, !(flags & HSG_KMEANS_FULL_MSTEP), st))) return rc;
+    if ((rc = km_mstep(p, x, seg_offsets, it, incremental, st))) return rc;
     if ((rc = run_estep(ea, p, use_tc, st))) return rc;
   }
   if ((rc = sr_keys_to_labels(p.sr, p.sr.keys, labels_out, st))) return rc;

@@ -433,7 +433,7 @@ def test_kmeans_incremental_mstep_matches_full_resum(S):
   exact zero centroid, and the result is bit-reproducible."""
   from hsg_b200 import ops, _lib
   rng = np.random.RandomState(5)
-  lens = [30000, 1, 0, 21111, 4097]
+  lens = [150000, 1, 0, 111111, 40970]          # > 2^18 rows: below that the library always re-sums
   d, k = 66, 24
   centres = o_ops.normalize_embedding(rng.randn(6, d).astype(np.float32))
   x = centres[rng.randint(0, 6, sum(lens))] + 0.35 * rng.randn(sum(lens), d).astype(np.float32)
