@@ -19,6 +19,8 @@
 
 #include <float.h>
 
+#include <algorithm>
+
 namespace hsg {
 
 constexpr int AT_WARPS = 8;           // query rows per CTA (one warp each)
@@ -406,8 +408,16 @@ size_t attn_tc_workspace_bytes(int B, int heads, int L, int S);
 int attn_fwd_tc(const float* q, const float* k, const float* v, const unsigned char* mask, int B, int heads, int L,
                 int S, float scale, float drop_p, uint64_t seed, float* out, float* lse, void* workspace,
                 cudaStream_t st);
+// tensor-core backward (attention_bwd_tc.cu)
+bool attn_bwd_tc_supported(int B, int heads, int L, int S, int hd);
+bool attn_bwd_tc_profitable(int B, int heads, int L, int S, int hd);
+size_t attn_bwd_tc_workspace_bytes(int B, int heads, int L, int S);
+int attn_bwd_tc(const float* q, const float* k, const float* v, const unsigned char* mask, int B, int heads, int L,
+                int S, float scale, float drop_p, uint64_t seed, const float* out, const float* lse, const float* dout,
+                float* dq, float* dk, float* dv, void* workspace, cudaStream_t st);
 extern int g_debug_flags;      // nce.cu; tests: bit 4 (16) keeps the attention forward on the CUDA-core kernel,
-                               // bit 5 (32) takes the tensor-core kernel for every shape it supports
+                               // bit 5 (32) takes the tensor-core kernel for every shape it supports;
+                               // bits 6 (64) / 7 (128): the same two switches for the backward
 
 }  // namespace hsg
 
@@ -415,8 +425,15 @@ using namespace hsg;
 
 extern "C" {
 
-size_t hsg_mha_workspace_bytes(int B, int heads, int L, int S) {
+static size_t mha_bwd_simt_bytes(int B, int heads, int L, int S) {
   return (size_t)2 * B * heads * L * S * sizeof(float) + 256;
+}
+
+// enough for either backward (the entry point has no head dim: the tensor-core layout is counted whenever L, S fit it)
+size_t hsg_mha_workspace_bytes(int B, int heads, int L, int S) {
+  size_t need = mha_bwd_simt_bytes(B, heads, L, S);
+  if (attn_bwd_tc_supported(B, heads, L, S, 64)) need = std::max(need, attn_bwd_tc_workspace_bytes(B, heads, L, S));
+  return need;
 }
 
 size_t hsg_mha_fwd_workspace_bytes(int B, int heads, int L, int S, int hd) {
@@ -460,9 +477,13 @@ int hsg_mha_bwd_f32(const float* q, const float* k, const float* v, const unsign
   int rc = fill(a, q, k, v, key_padding_mask, B, heads, L, S, hd, scale, dropout_p, seed);
   if (rc) return rc;
   HSG_REQUIRE(out && lse && dout && dq && dk && dv, HSG_E_INVALID, "mha_bwd: null pointer");
-  HSG_REQUIRE(workspace && workspace_bytes >= hsg_mha_workspace_bytes(B, heads, L, S), HSG_E_WORKSPACE,
+  HSG_REQUIRE(workspace && workspace_bytes >= mha_bwd_simt_bytes(B, heads, L, S), HSG_E_WORKSPACE,
               "mha_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  const bool tc = (g_debug_flags & 128) ? attn_bwd_tc_supported(B, heads, L, S, hd) : attn_bwd_tc_profitable(B, heads, L, S, hd);
+  if (tc && !(g_debug_flags & 64) && workspace_bytes >= attn_bwd_tc_workspace_bytes(B, heads, L, S))
+    return attn_bwd_tc(q, k, v, key_padding_mask, B, heads, L, S, scale, dropout_p, seed, out, lse, dout, dq, dk, dv,
+                       workspace, st);
   float* pd = (float*)workspace;
   float* ds = pd + (size_t)a.BH * L * S;
   const int R = L >= 64 ? 4 : 1;

@@ -12,7 +12,7 @@
 //   tcgen05  : O = P V     -> TMEM [128 x 64]
 //   epilogue : O / row sum -> out, log-sum-exp -> lse (the CUDA-core backward reuses both)
 // The [L,S] score matrix never exists in memory.
-#include "tc_common.cuh"
+#include "attention_tc.cuh"
 
 #include <float.h>
 
@@ -20,10 +20,7 @@
 
 namespace hsg {
 
-constexpr int AC_BM = 128;
-constexpr int AC_HD = 64;
 constexpr int AC_THREADS = 192;           // warp0: TMA + MMA issue, warp1: TMEM allocation, warps 2-5: softmax / epilogue
-constexpr int AC_SLAB = AC_BM * 64 * 2;   // [128 rows x 64 fp16] = 16 KiB
 
 struct AttnTcParams {
   int BH, heads, L, S, Sp;        // Sp = S rounded up to 64
@@ -33,20 +30,6 @@ struct AttnTcParams {
   float* out;                     // [BH,L,64]
   float* lse;                     // [BH,L]
 };
-
-__device__ __forceinline__ bool attn_dropout_keep(uint64_t seed, uint32_t bh, uint32_t row, uint32_t col, float p) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (((uint64_t)bh << 40) ^ ((uint64_t)row << 20) ^ col);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (float)(z >> 40) * (1.0f / 16777216.0f) >= p;
-}
-
-__device__ __forceinline__ float ex2f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 __global__ void __launch_bounds__(AC_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -238,9 +221,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 }
 
 // ---------------------------------------------------------------- operand preparation
+__device__ __forceinline__ float attn_mul(float mul, const float* amax) {
+  if (!amax) return mul;
+  const float m = *amax;
+  return m > 0.f ? mul / m : 0.f;
+}
+
 // rows [R, 64] fp32 -> [R, 128] fp16 (hi | lo) of mul * x
 __global__ void __launch_bounds__(256) attn_split_rows_kernel(const float* __restrict__ src, int64_t R, float mul,
-                                                              __half* __restrict__ dst) {
+                                                              const float* __restrict__ amax, __half* __restrict__ dst) {
+  mul = attn_mul(mul, amax);
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= R * AC_HD) return;
   const int64_t r = i / AC_HD;
@@ -257,29 +247,45 @@ __global__ void __launch_bounds__(256) attn_split_rows_kernel(const float* __res
   *reinterpret_cast<uint2*>(dst + r * 2 * AC_HD + AC_HD + d) = *reinterpret_cast<const uint2*>(lo);
 }
 
-// v [BH, S, 64] -> vt [BH, 64, 2*Sp]: vt[bh, d, s] = hi(v[bh, s, d]), vt[bh, d, Sp + s] = lo; zero for s >= S
-__global__ void __launch_bounds__(256) attn_split_vt_kernel(const float* __restrict__ v, int S, int Sp,
-                                                            __half* __restrict__ vt) {
+// x [BH, n, 64] -> xt [BH, 64, 2*np]: xt[bh, d, s] = hi(mul x[bh, s, d]), xt[bh, d, np + s] = lo; zero for s >= n
+__global__ void __launch_bounds__(256) attn_split_transposed_kernel(const float* __restrict__ x, int n, int np, float mul,
+                                                                    const float* __restrict__ amax,
+                                                                    __half* __restrict__ xt) {
   __shared__ float tile[32][33];
+  mul = attn_mul(mul, amax);
   const int bh = blockIdx.z;
   const int s0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const float* src = v + (int64_t)bh * S * AC_HD;
+  const float* src = x + (int64_t)bh * n * AC_HD;
   for (int k = ty; k < 32; k += 8) {
     const int s = s0 + k;
-    tile[k][tx] = s < S ? src[(int64_t)s * AC_HD + d0 + tx] : 0.f;
+    tile[k][tx] = s < n ? src[(int64_t)s * AC_HD + d0 + tx] * mul : 0.f;
   }
   __syncthreads();
-  __half* dst = vt + (int64_t)bh * AC_HD * 2 * Sp;
+  __half* dst = xt + (int64_t)bh * AC_HD * 2 * np;
   for (int k = ty; k < 32; k += 8) {
     const int d = d0 + k, s = s0 + tx;
-    if (s < Sp) {
-      const float x = tile[tx][k];
-      const __half hi = __float2half_rn(x);
-      dst[(int64_t)d * 2 * Sp + s] = hi;
-      dst[(int64_t)d * 2 * Sp + Sp + s] = __float2half_rn(x - __half2float(hi));
+    if (s < np) {
+      const float v = tile[tx][k];
+      const __half hi = __float2half_rn(v);
+      dst[(int64_t)d * 2 * np + s] = hi;
+      dst[(int64_t)d * 2 * np + np + s] = __float2half_rn(v - __half2float(hi));
     }
   }
+}
+
+int attn_split_rows(const float* src, int64_t R, float mul, const float* amax, __half* dst, cudaStream_t st) {
+  attn_split_rows_kernel<<<(unsigned)ceil_div64(R * AC_HD, 1024), 256, 0, st>>>(src, R, mul, amax, dst);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+int attn_split_transposed(const float* src, int64_t BH, int n, int np, float mul, const float* amax, __half* dst,
+                          cudaStream_t st) {
+  dim3 grid((unsigned)(np / 32), AC_HD / 32, (unsigned)BH);
+  attn_split_transposed_kernel<<<grid, 256, 0, st>>>(src, n, np, mul, amax, dst);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
 }
 
 // ---------------------------------------------------------------- host side
@@ -294,7 +300,7 @@ bool attn_tc_profitable(int B, int heads, int L, int S, int hd) {
   return attn_tc_supported(B, heads, L, S, hd) && L >= 96 && (int64_t)B * heads * ((L + AC_BM - 1) / AC_BM) >= 96;
 }
 
-static int attn_sp(int S) { return (S + 63) / 64 * 64; }
+static int attn_sp(int S) { return attn_pad64(S); }
 
 size_t attn_tc_workspace_bytes(int B, int heads, int L, int S) {
   const int64_t bh = (int64_t)B * heads;
@@ -314,19 +320,15 @@ int attn_fwd_tc(const float* q, const float* k, const float* v, const unsigned c
   __half* q2 = c.take<__half>((size_t)(bh * L + AC_BM) * 2 * AC_HD);
   __half* k2 = c.take<__half>((size_t)(bh * S + 256) * 2 * AC_HD);
   __half* vt2 = c.take<__half>((size_t)bh * AC_HD * 2 * Sp);
-  attn_split_rows_kernel<<<(unsigned)ceil_div64(bh * L * AC_HD, 1024), 256, 0, st>>>(q, bh * L, scale * 1.4426950408889634f, q2);
-  HSG_LAUNCH_CHECK();
-  attn_split_rows_kernel<<<(unsigned)ceil_div64(bh * S * AC_HD, 1024), 256, 0, st>>>(k, bh * S, 1.f, k2);
-  HSG_LAUNCH_CHECK();
-  dim3 gv((unsigned)(Sp / 32), AC_HD / 32, (unsigned)bh);
-  attn_split_vt_kernel<<<gv, 256, 0, st>>>(v, S, Sp, vt2);
-  HSG_LAUNCH_CHECK();
+  int rc;
+  if ((rc = attn_split_rows(q, bh * L, scale * 1.4426950408889634f, nullptr, q2, st))) return rc;
+  if ((rc = attn_split_rows(k, bh * S, 1.f, nullptr, k2, st))) return rc;
+  if ((rc = attn_split_transposed(v, bh, S, Sp, 1.f, nullptr, vt2, st))) return rc;
 
   AttnTcParams p;
   p.BH = (int)bh; p.heads = heads; p.L = L; p.S = S; p.Sp = Sp; p.mask = mask; p.drop_p = drop_p; p.seed = seed;
   p.out = out; p.lse = lse;
   CUtensorMap mq, mk, mv;
-  int rc;
   if ((rc = encode_2d_f16(&mq, q2, (uint64_t)(bh * L), 2 * AC_HD, 64, AC_BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = encode_2d_f16(&mk, k2, (uint64_t)(bh * S), 2 * AC_HD, 64, (uint32_t)Sp, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = encode_2d_f16(&mv, vt2, (uint64_t)(bh * AC_HD), (uint64_t)2 * Sp, 64, AC_HD, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;

@@ -766,6 +766,50 @@ def test_attention_tensor_core_forward(b, l, s_):
   close(res[0][4], res[16][4], rtol=1e-5, atol=2e-6)        # dropout: the same counter-based mask in both kernels
 
 
+@pytest.mark.parametrize('b,l,s_', [(3, 37, 70), (2, 256, 256), (5, 8, 200), (1, 130, 64), (2, 200, 129)])
+def test_attention_tensor_core_backward(b, l, s_):
+  """tcgen05 backward of the attention core (head dim 64, L, S <= 256): dq, dk, dv against float64 autograd,
+  against the CUDA-core backward under the same dropout mask, and with a tiny upstream gradient (the fp16
+  operand split is normalised by max |dout|)."""
+  from hsg_b200 import _lib
+  from hsg_b200.models.heads.transformer import attention_core
+  lib = _lib.load()
+  rng = np.random.RandomState(b * 1000 + l + 7)
+  h, hd = 4, 64
+  q, k, v = [rng.randn(b * h, m, hd).astype(np.float32) for m in (l, s_, s_)]
+  mask = np.zeros((b, s_), bool)
+  mask[0, s_ // 2:] = True
+  mask[-1, :3] = True
+  w = rng.randn(b * h, l, hd).astype(np.float32)
+  res = {}
+  for flags in (128, 64):         # tensor-core backward for every supported shape / CUDA-core backward
+    lib.hsg_debug_set_flags(flags)
+    try:
+      grads = []
+      for p_drop, mul in ((0.0, 1.0), (0.3, 1.0), (0.0, 1e-7)):
+        qt, kt, vt = [t(a).requires_grad_(True) for a in (q, k, v)]
+        torch.manual_seed(3)
+        out = attention_core(qt, kt, vt, t(mask), b, h, dropout_p=p_drop)
+        (out * t(w * np.float32(mul))).sum().backward()
+        grads.append([n(qt.grad), n(kt.grad), n(vt.grad)])
+    finally:
+      lib.hsg_debug_set_flags(0)
+    res[flags] = grads
+  q64, k64, v64 = [torch.from_numpy(a).double().requires_grad_(True) for a in (q, k, v)]
+  sc = torch.einsum('zld,zsd->zls', q64 / hd ** 0.5, k64)
+  sc = sc.masked_fill(torch.from_numpy(np.repeat(mask, h, axis=0)).unsqueeze(1), float('-inf'))
+  ref = torch.einsum('zls,zsd->zld', torch.softmax(sc, -1), v64)
+  (ref * torch.from_numpy(w).double()).sum().backward()
+  want = [a.grad.numpy() for a in (q64, k64, v64)]
+  for got, ref_g in zip(res[128][0], want):
+    close(got, ref_g, rtol=1e-4, atol=1e-5)
+    assert np.linalg.norm(got - ref_g) <= 1e-5 * np.linalg.norm(ref_g)
+  for got, ref_g in zip(res[128][2], want):                    # upstream gradient of 1e-7: still fp32-grade
+    assert np.linalg.norm(got - 1e-7 * ref_g) <= 1e-5 * np.linalg.norm(1e-7 * ref_g)
+  for a, c in zip(res[128][1], res[64][1]):                    # dropout: both backward kernels see the same mask
+    close(a, c, rtol=1e-4, atol=2e-5)
+
+
 # ---------------------------------------------------------------- BASELINE.json configs 3-5 (shapes of the other configs)
 def _block_labels(rng, b, h, w, blk, divisor=2048):
   """block oversegmentation (~(h/blk)*(w/blk) regions per image) packed as sem*divisor + inst"""

@@ -5,7 +5,10 @@ our fused kernel (fwd, fwd+bwd) against torch's nn.MultiheadAttention core as th
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from hsg_b200 import _lib
 from hsg_b200.models.heads.transformer import attention_core
+
+lib = _lib.load()
 
 dev = torch.device('cuda:0')
 torch.backends.cuda.matmul.allow_tf32 = False
@@ -32,8 +35,9 @@ def timeit(fn, reps=20):
 
 
 lines = ['# attention core, fp32, 4 heads x hd 64 (C=256); us per call; flop = 4*B*h*L*S*hd (fwd)',
-         '%5s %4s %4s %12s %12s %9s %14s %14s %10s' % ('B', 'L', 'S', 'ours fwd', 'torch fwd', 'speed-up', 'ours fwd+bwd', 'torch fwd+bwd',
-                                                      'GFLOP/s')]
+         '# fwd+bwd columns: default dispatch | backward forced to the CUDA-core kernels | backward forced to tcgen05 | torch',
+         '%5s %4s %4s %12s %12s %9s %14s %14s %14s %14s %10s' % ('B', 'L', 'S', 'ours fwd', 'torch fwd', 'speed-up', 'ours fwd+bwd',
+                                                                'simt bwd', 'tc bwd', 'torch fwd+bwd', 'GFLOP/s')]
 for b in (8, 16, 64, 256, 1024):
   for (l, s) in ((256, 256), (64, 256), (16, 64)):
     h, hd = 4, 64
@@ -54,9 +58,14 @@ for b in (8, 16, 64, 256, 1024):
         (fn(q, k, v, mask, b, h) * w).sum().backward()
       return run
     fb_ours = timeit(fb(attention_core))
+    lib.hsg_debug_set_flags(64)
+    fb_simt = timeit(fb(attention_core))
+    lib.hsg_debug_set_flags(128)
+    fb_tc = timeit(fb(attention_core))
+    lib.hsg_debug_set_flags(0)
     fb_torch = timeit(fb(torch_core))
-    lines.append('%5d %4d %4d %12.1f %12.1f %9.2f %14.1f %14.1f %10.0f' % (b, l, s, f_ours, f_torch, f_torch / f_ours, fb_ours,
-                                                                            fb_torch, 4.0 * b * h * l * s * hd / f_ours / 1e3))
+    lines.append('%5d %4d %4d %12.1f %12.1f %9.2f %14.1f %14.1f %14.1f %14.1f %10.0f' % (
+        b, l, s, f_ours, f_torch, f_torch / f_ours, fb_ours, fb_simt, fb_tc, fb_torch, 4.0 * b * h * l * s * hd / f_ours / 1e3))
 text = '\n'.join(lines)
 print(text)
 if len(sys.argv) > 1:
