@@ -237,6 +237,8 @@ HSG_API int hsg_nce_bwd_f32(const float* e, const float* prototypes, int64_t N, 
  * drops probabilities with a counter-based generator keyed by `seed` (train-mode
  * parity with the reference is defined at p = 0).  A row whose keys are all
  * masked yields NaN, as in the reference. */
+/* backward workspace: large enough for either backward -- tcgen05 (head dim 64, L, S <= 256, where the shape
+ * pays for the operand preparation: dq and dk/dv kernels, scores recomputed in TMEM) or CUDA cores. */
 HSG_API size_t hsg_mha_workspace_bytes(int B, int heads, int L, int S);
 /* forward workspace: with it (head dim 64, S <= 256) the two contractions run on tcgen05 (fp16 hi/lo split,
  * fp32-grade); without it, or for other shapes, on CUDA cores.  0 bytes = not needed. */
