@@ -217,10 +217,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 }
 
 // ===================================================================== dk, dv
-// One CTA per (batch*head, 128 keys, 128 query rows); with L > 128 the two row halves add their partial dk / dv
-// onto a zeroed output (two addends: the fp32 sum does not depend on their order).
+// One CTA per (batch*head, 128 keys); the query rows go by in halves of 128 (shared memory holds the operands of
+// one half), dk / dv accumulate in TMEM across the halves.
 // shared memory, phase 1: K hi|lo, V hi|lo tiles (4 x 16 KiB), Q hi|lo, dO hi|lo of the row half (4 x qbox*128 B)
 //                phase 2: dS^T hi, lo, P~^T hi, lo (4*nls slabs of 16 KiB), then Q^T hi, lo, dO^T hi, lo (4*nls x 8 KiB)
+// Every barrier completes one phase per half (parity = half & 1).
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                        const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
@@ -229,12 +230,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const gbase = smem_raw + (base - smem_u32(smem_raw));
-  const int l0 = blockIdx.z * AC_BM;                            // first query row of this CTA's half
-  const int width = min(AC_BM, p.Lp - l0);                      // 64 or 128 (padded) query rows
-  const int nls = width / 64;
+  const int halves = (p.Lp + AC_BM - 1) / AC_BM;
   const uint32_t q_bytes = (uint32_t)qbox * 128u;               // the TMA box of Q / dO: qbox = min(128, Lp) rows
   const uint32_t sK = base, sV = sK + 2 * AC_SLAB, sQ = sV + 2 * AC_SLAB, sDO = sQ + 2 * q_bytes;
-  const uint32_t oDS = 0, oPD = 2u * nls * AC_SLAB, oQT = 4u * nls * AC_SLAB, oDOT = oQT + 2u * nls * AC_TSLAB;
   uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + region);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* s_l2 = reinterpret_cast<float*>(tmem_slot + 4);        // [128] log2-domain log-sum-exp of the query rows
@@ -260,48 +258,58 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bar_in, 4 * AC_SLAB + 4 * q_bytes);
-      tma_load_2d(sK, &tmap_k, 0, bh * p.S + key0, bar_in);
-      tma_load_2d(sK + AC_SLAB, &tmap_k, AC_HD, bh * p.S + key0, bar_in);
-      tma_load_2d(sV, &tmap_v, 0, bh * p.S + key0, bar_in);
-      tma_load_2d(sV + AC_SLAB, &tmap_v, AC_HD, bh * p.S + key0, bar_in);
-      tma_load_2d(sQ, &tmap_q, 0, bh * p.L + l0, bar_in);
-      tma_load_2d(sQ + q_bytes, &tmap_q, AC_HD, bh * p.L + l0, bar_in);
-      tma_load_2d(sDO, &tmap_do, 0, bh * p.L + l0, bar_in);
-      tma_load_2d(sDO + q_bytes, &tmap_do, AC_HD, bh * p.L + l0, bar_in);
-      mbar_wait(bar_in, 0);
-      tc_fence_after();
-      {
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(width >> 3) << 17) | ((uint32_t)(AC_BM >> 4) << 24);
-        mma3(t_s, umma_desc(sK, 1024, 2), umma_desc(sK + AC_SLAB, 1024, 2), umma_desc(sQ, 1024, 2),
-             umma_desc(sQ + q_bytes, 1024, 2), idesc, true);
-        mma3(t_dp, umma_desc(sV, 1024, 2), umma_desc(sV + AC_SLAB, 1024, 2), umma_desc(sDO, 1024, 2),
-             umma_desc(sDO + q_bytes, 1024, 2), idesc, true);
-        tc_commit(bar_s);
-      }
-      // the phase-1 operands are dead once the products have completed: bring Q^T, dO^T into their place
-      mbar_wait(bar_s, 0);
-      mbar_expect_tx(bar_t, 4 * nls * AC_TSLAB);
-      for (int ls = 0; ls < nls; ++ls) {
-        tma_load_2d(base + oQT + ls * AC_TSLAB, &tmap_qt, l0 + ls * 64, bh * AC_HD, bar_t);
-        tma_load_2d(base + oQT + (nls + ls) * AC_TSLAB, &tmap_qt, p.Lp + l0 + ls * 64, bh * AC_HD, bar_t);
-        tma_load_2d(base + oDOT + ls * AC_TSLAB, &tmap_dot, l0 + ls * 64, bh * AC_HD, bar_t);
-        tma_load_2d(base + oDOT + (nls + ls) * AC_TSLAB, &tmap_dot, p.Lp + l0 + ls * 64, bh * AC_HD, bar_t);
-      }
-      mbar_wait(bar_p, 0);
-      mbar_wait(bar_t, 0);
-      tc_fence_after();
-      {
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(AC_HD >> 3) << 17) | ((uint32_t)(AC_BM >> 4) << 24);
-        for (int ls = 0; ls < nls; ++ls) {
-          mma3(t_dk, umma_desc(base + oDS + ls * AC_SLAB, 1024, 2), umma_desc(base + oDS + (nls + ls) * AC_SLAB, 1024, 2),
-               umma_desc(base + oQT + ls * AC_TSLAB, 1024, 2), umma_desc(base + oQT + (nls + ls) * AC_TSLAB, 1024, 2),
-               idesc, ls == 0);
-          mma3(t_dv, umma_desc(base + oPD + ls * AC_SLAB, 1024, 2), umma_desc(base + oPD + (nls + ls) * AC_SLAB, 1024, 2),
-               umma_desc(base + oDOT + ls * AC_TSLAB, 1024, 2), umma_desc(base + oDOT + (nls + ls) * AC_TSLAB, 1024, 2),
-               idesc, ls == 0);
+      for (int half = 0; half < halves; ++half) {
+        const uint32_t ph = half & 1;
+        const int l0 = half * AC_BM;
+        const int width = min(AC_BM, p.Lp - l0);                // 64 or 128 (padded) query rows
+        const int nls = width / 64;
+        const uint32_t oDS = 0, oPD = 2u * nls * AC_SLAB, oQT = 4u * nls * AC_SLAB, oDOT = oQT + 2u * nls * AC_TSLAB;
+        // the previous half's second products still read the shared memory the loads below overwrite
+        if (half > 0) mbar_wait(bar_o, ph ^ 1u);
+        mbar_expect_tx(bar_in, 4 * AC_SLAB + 4 * q_bytes);
+        tma_load_2d(sK, &tmap_k, 0, bh * p.S + key0, bar_in);
+        tma_load_2d(sK + AC_SLAB, &tmap_k, AC_HD, bh * p.S + key0, bar_in);
+        tma_load_2d(sV, &tmap_v, 0, bh * p.S + key0, bar_in);
+        tma_load_2d(sV + AC_SLAB, &tmap_v, AC_HD, bh * p.S + key0, bar_in);
+        tma_load_2d(sQ, &tmap_q, 0, bh * p.L + l0, bar_in);
+        tma_load_2d(sQ + q_bytes, &tmap_q, AC_HD, bh * p.L + l0, bar_in);
+        tma_load_2d(sDO, &tmap_do, 0, bh * p.L + l0, bar_in);
+        tma_load_2d(sDO + q_bytes, &tmap_do, AC_HD, bh * p.L + l0, bar_in);
+        mbar_wait(bar_in, ph);
+        tc_fence_after();
+        {
+          const uint32_t idesc = (1u << 4) | ((uint32_t)(width >> 3) << 17) | ((uint32_t)(AC_BM >> 4) << 24);
+          mma3(t_s, umma_desc(sK, 1024, 2), umma_desc(sK + AC_SLAB, 1024, 2), umma_desc(sQ, 1024, 2),
+               umma_desc(sQ + q_bytes, 1024, 2), idesc, true);
+          mma3(t_dp, umma_desc(sV, 1024, 2), umma_desc(sV + AC_SLAB, 1024, 2), umma_desc(sDO, 1024, 2),
+               umma_desc(sDO + q_bytes, 1024, 2), idesc, true);
+          tc_commit(bar_s);
         }
-        tc_commit(bar_o);
+        // the phase-1 operands are dead once the products have completed: bring Q^T, dO^T into their place
+        mbar_wait(bar_s, ph);
+        mbar_expect_tx(bar_t, 4 * nls * AC_TSLAB);
+        for (int ls = 0; ls < nls; ++ls) {
+          tma_load_2d(base + oQT + ls * AC_TSLAB, &tmap_qt, l0 + ls * 64, bh * AC_HD, bar_t);
+          tma_load_2d(base + oQT + (nls + ls) * AC_TSLAB, &tmap_qt, p.Lp + l0 + ls * 64, bh * AC_HD, bar_t);
+          tma_load_2d(base + oDOT + ls * AC_TSLAB, &tmap_dot, l0 + ls * 64, bh * AC_HD, bar_t);
+          tma_load_2d(base + oDOT + (nls + ls) * AC_TSLAB, &tmap_dot, p.Lp + l0 + ls * 64, bh * AC_HD, bar_t);
+        }
+        mbar_wait(bar_p, ph);
+        mbar_wait(bar_t, ph);
+        tc_fence_after();
+        {
+          const uint32_t idesc = (1u << 4) | ((uint32_t)(AC_HD >> 3) << 17) | ((uint32_t)(AC_BM >> 4) << 24);
+          for (int ls = 0; ls < nls; ++ls) {
+            const bool fresh = half == 0 && ls == 0;
+            mma3(t_dk, umma_desc(base + oDS + ls * AC_SLAB, 1024, 2), umma_desc(base + oDS + (nls + ls) * AC_SLAB, 1024, 2),
+                 umma_desc(base + oQT + ls * AC_TSLAB, 1024, 2), umma_desc(base + oQT + (nls + ls) * AC_TSLAB, 1024, 2),
+                 idesc, fresh);
+            mma3(t_dv, umma_desc(base + oPD + ls * AC_SLAB, 1024, 2), umma_desc(base + oPD + (nls + ls) * AC_SLAB, 1024, 2),
+                 umma_desc(base + oDOT + ls * AC_TSLAB, 1024, 2), umma_desc(base + oDOT + (nls + ls) * AC_TSLAB, 1024, 2),
+                 idesc, fresh);
+          }
+          tc_commit(bar_o);
+        }
       }
     }
   } else if (warp >= 2) {
@@ -313,55 +321,62 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
     const bool in_s = key < p.S;
     const bool live = in_s && !(p.mask && p.mask[(int64_t)b * p.S + key]);
     const uint32_t trow = ((uint32_t)(32 * q) << 16);
-    {
-      const int t = threadIdx.x - 64;                            // 0..255; the first 128 fetch one query row each
-      if (t < AC_BM) {
-        const bool in_l = l0 + t < p.L;
-        s_l2[t] = in_l ? p.lse[(int64_t)bh * p.L + l0 + t] * LOG2E : 0.f;
-        s_dl[t] = in_l ? p.delta[(int64_t)bh * p.L + l0 + t] : 0.f;
+    const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    for (int half = 0; half < halves; ++half) {
+      const uint32_t ph = half & 1;
+      const int l0 = half * AC_BM;
+      const int width = min(AC_BM, p.Lp - l0);
+      const int nls = width / 64;
+      const uint32_t oDS = 0, oPD = 2u * nls * AC_SLAB;
+      asm volatile("bar.sync 1, 256;" ::: "memory");             // every sweep thread is done with the previous half's rows
+      {
+        const int t = threadIdx.x - 64;                          // 0..255; the first 128 fetch one query row each
+        if (t < AC_BM) {
+          const bool in_l = l0 + t < p.L;
+          s_l2[t] = in_l ? p.lse[(int64_t)bh * p.L + l0 + t] * LOG2E : 0.f;
+          s_dl[t] = in_l ? p.delta[(int64_t)bh * p.L + l0 + t] : 0.f;
+        }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
-    const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    const int nchunk = width / 16;                               // 4 or 8
-    const int c_lo = h * (nchunk >> 1), c_hi = c_lo + (nchunk >> 1);
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
-    for (int c = c_lo; c < c_hi; ++c) {
-      uint32_t v[16], w[16];
-      tc_ld16(t_s + trow + c * 16, v);
-      tc_ld16(t_dp + trow + c * 16, w);
-      tc_ld_wait();
-      float l2[16], dl[16];
+      const int nchunk = width / 16;                             // 4 or 8
+      const int c_lo = h * (nchunk >> 1), c_hi = c_lo + (nchunk >> 1);
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      for (int c = c_lo; c < c_hi; ++c) {
+        uint32_t v[16], w[16];
+        tc_ld16(t_s + trow + c * 16, v);
+        tc_ld16(t_dp + trow + c * 16, w);
+        tc_ld_wait();
+        float l2[16], dl[16];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        *reinterpret_cast<float4*>(l2 + 4 * u) = *reinterpret_cast<const float4*>(s_l2 + c * 16 + 4 * u);
-        *reinterpret_cast<float4*>(dl + 4 * u) = *reinterpret_cast<const float4*>(s_dl + c * 16 + 4 * u);
-      }
-      float xs[16], xp[16];
+        for (int u = 0; u < 4; ++u) {
+          *reinterpret_cast<float4*>(l2 + 4 * u) = *reinterpret_cast<const float4*>(s_l2 + c * 16 + 4 * u);
+          *reinterpret_cast<float4*>(dl + 4 * u) = *reinterpret_cast<const float4*>(s_dl + c * 16 + 4 * u);
+        }
+        float xs[16], xp[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int row = l0 + c * 16 + j;
-        const bool ok = live && row < p.L;
-        const float pj = ex2f(__uint_as_float(v[j]) - l2[j]);
-        float kf = 1.f;
-        if (p.drop_p > 0.f) kf = attn_dropout_keep(p.seed, bh, row, key, p.drop_p) ? keep_scale : 0.f;
-        xp[j] = ok ? pj * kf : 0.f;
-        xs[j] = ok ? pj * (__uint_as_float(w[j]) * kf - dl[j]) : 0.f;
+        for (int j = 0; j < 16; ++j) {
+          const int row = l0 + c * 16 + j;
+          const bool ok = live && row < p.L;
+          const float pj = ex2f(__uint_as_float(v[j]) - l2[j]);
+          float kf = 1.f;
+          if (p.drop_p > 0.f) kf = attn_dropout_keep(p.seed, bh, row, key, p.drop_p) ? keep_scale : 0.f;
+          xp[j] = ok ? pj * kf : 0.f;
+          xs[j] = ok ? pj * (__uint_as_float(w[j]) * kf - dl[j]) : 0.f;
+        }
+        const int ls = c >> 2;
+        store16_split(gbase + oDS + ls * AC_SLAB, gbase + oDS + (nls + ls) * AC_SLAB, r, c & 3, xs);
+        store16_split(gbase + oPD + ls * AC_SLAB, gbase + oPD + (nls + ls) * AC_SLAB, r, c & 3, xp);
       }
-      const int ls = c >> 2;
-      store16_split(gbase + oDS + ls * AC_SLAB, gbase + oDS + (nls + ls) * AC_SLAB, r, c & 3, xs);
-      store16_split(gbase + oPD + ls * AC_SLAB, gbase + oPD + (nls + ls) * AC_SLAB, r, c & 3, xp);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_p);
-    mbar_wait(bar_o, 0);
+    mbar_wait(bar_o, (uint32_t)(halves - 1) & 1u);
     tc_fence_after();
     const float am = *p.amax;
     const float mk = am * LN2;                                   // q was pre-scaled by scale * log2(e)
-    const bool add = gridDim.z > 1;
 #pragma unroll 1
     for (int c = 2 * h; c < 2 * h + 2; ++c) {
       uint32_t v[16], w[16];
@@ -369,22 +384,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
       tc_ld16(t_dv + trow + c * 16, w);
       tc_ld_wait();
       if (in_s) {
-        float* dk = p.dk + ((int64_t)bh * p.S + key) * AC_HD + c * 16;
-        float* dv = p.dv + ((int64_t)bh * p.S + key) * AC_HD + c * 16;
-        if (add) {
+        float4* dk = reinterpret_cast<float4*>(p.dk + ((int64_t)bh * p.S + key) * AC_HD + c * 16);
+        float4* dv = reinterpret_cast<float4*>(p.dv + ((int64_t)bh * p.S + key) * AC_HD + c * 16);
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            atomicAdd(dk + u, __uint_as_float(v[u]) * mk);
-            atomicAdd(dv + u, __uint_as_float(w[u]) * am);
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            reinterpret_cast<float4*>(dk)[u] = make_float4(__uint_as_float(v[4 * u]) * mk, __uint_as_float(v[4 * u + 1]) * mk,
-                                                           __uint_as_float(v[4 * u + 2]) * mk, __uint_as_float(v[4 * u + 3]) * mk);
-            reinterpret_cast<float4*>(dv)[u] = make_float4(__uint_as_float(w[4 * u]) * am, __uint_as_float(w[4 * u + 1]) * am,
-                                                           __uint_as_float(w[4 * u + 2]) * am, __uint_as_float(w[4 * u + 3]) * am);
-          }
+        for (int u = 0; u < 4; ++u) {
+          dk[u] = make_float4(__uint_as_float(v[4 * u]) * mk, __uint_as_float(v[4 * u + 1]) * mk,
+                              __uint_as_float(v[4 * u + 2]) * mk, __uint_as_float(v[4 * u + 3]) * mk);
+          dv[u] = make_float4(__uint_as_float(w[4 * u]) * am, __uint_as_float(w[4 * u + 1]) * am,
+                              __uint_as_float(w[4 * u + 2]) * am, __uint_as_float(w[4 * u + 3]) * am);
         }
       }
     }
@@ -511,13 +518,8 @@ int attn_bwd_tc(const float* q, const float* k, const float* v, const unsigned c
     attn_bwd_dq_tc_kernel<<<grid, AB_THREADS, smem, st>>>(mq, mdo, mk, mv, mkt, p, region);
     HSG_LAUNCH_CHECK();
   }
-  // dk / dv: 128-key tiles of k / v against 128-row halves of the queries
+  // dk / dv: 128-key tiles of k / v against the queries, 128 rows at a time
   const int qbox = std::min(AC_BM, Lp);
-  const int halves = (Lp + AC_BM - 1) / AC_BM;
-  if (halves > 1) {
-    HSG_CUDA(cudaMemsetAsync(dk, 0, (size_t)bh * S * AC_HD * sizeof(float), st));
-    HSG_CUDA(cudaMemsetAsync(dv, 0, (size_t)bh * S * AC_HD * sizeof(float), st));
-  }
   if ((rc = encode_2d_f16(&mk, w.k2, (uint64_t)(bh * S), 2 * AC_HD, 64, AC_BM, sw))) return rc;
   if ((rc = encode_2d_f16(&mv, w.v2, (uint64_t)(bh * S), 2 * AC_HD, 64, AC_BM, sw))) return rc;
   if ((rc = encode_2d_f16(&mq, w.q2, (uint64_t)(bh * L), 2 * AC_HD, 64, (uint32_t)qbox, sw))) return rc;
@@ -530,7 +532,7 @@ int attn_bwd_tc(const float* q, const float* k, const float* v, const unsigned c
     const uint32_t region = (uint32_t)std::max(p1, p2);
     const size_t smem = 1024 + region + 64 + 32 + 2 * AC_BM * sizeof(float) + 64;
     HSG_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((S + AC_BM - 1) / AC_BM), (unsigned)bh, (unsigned)halves);
+    dim3 grid((unsigned)((S + AC_BM - 1) / AC_BM), (unsigned)bh);
     attn_bwd_dkv_tc_kernel<<<grid, AB_THREADS, smem, st>>>(mk, mv, mq, mdo, mqt, mdot, p, region, qbox);
     HSG_LAUNCH_CHECK();
   }
