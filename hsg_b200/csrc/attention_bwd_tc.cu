@@ -406,35 +406,64 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
 }
 
 // ---------------------------------------------------------------- operand preparation
-// dout rows -> fp16 (hi | lo) of dout / amax, and delta[row] = <dout, out> / amax  (16 threads per row of 64)
-__global__ void __launch_bounds__(256) attn_split_dout_kernel(const float* __restrict__ dout, const float* __restrict__ out,
-                                                              int64_t R, const float* __restrict__ amax,
-                                                              __half* __restrict__ dst, float* __restrict__ delta) {
-  const float m = *amax;
-  const float mul = m > 0.f ? 1.f / m : 0.f;
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const bool in = i < R * AC_HD;
-  const int64_t r = i / AC_HD;
-  const int d = (int)(i - r * AC_HD);
-  float4 g = make_float4(0.f, 0.f, 0.f, 0.f), o = g;
-  if (in) {
-    g = *reinterpret_cast<const float4*>(dout + i);
-    o = *reinterpret_cast<const float4*>(out + i);
-  }
-  float dot = g.x * o.x + g.y * o.y + g.z * o.z + g.w * o.w;
+// One pass over x [BH, n, 64]: rows [(BH*n), 128] = fp16 (hi | lo) of mul * x, and the transposed copy
+// xt [BH, 64, 2*np] (xt[bh, d, s] = hi, xt[bh, d, np + s] = lo, zero for n <= s < np).  With DELTA also
+// delta[bh*n + s] = mul * <x[s], o[s]> (x = dout, o = out, mul = 1 / max|dout|).  One CTA per 32 rows.
+template <bool DELTA>
+__global__ void __launch_bounds__(256) attn_split_both_kernel(const float* __restrict__ x, const float* __restrict__ o,
+                                                              int n, int np, float mul, const float* __restrict__ amax,
+                                                              __half* __restrict__ rows, __half* __restrict__ xt,
+                                                              float* __restrict__ delta) {
+  __shared__ float tile[32][AC_HD + 1];
+  mul = attn_mul(mul, amax);
+  const int bh = blockIdx.y;
+  const int s0 = blockIdx.x * 32;
 #pragma unroll
-  for (int s = 8; s > 0; s >>= 1) dot += __shfl_xor_sync(FULL, dot, s);
-  if (!in) return;
-  const float v[4] = {g.x * mul, g.y * mul, g.z * mul, g.w * mul};
-  __align__(8) __half hi[4], lo[4];
+  for (int rep = 0; rep < 2; ++rep) {
+    const int idx = threadIdx.x + 256 * rep;                     // 512 float4 of the [32 x 64] tile
+    const int r = idx >> 4, c = (idx & 15) << 2;
+    const int s = s0 + r;
+    const bool in = s < n;
+    const int64_t off = ((int64_t)bh * n + s) * AC_HD + c;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in) g = *reinterpret_cast<const float4*>(x + off);
+    const float v[4] = {g.x * mul, g.y * mul, g.z * mul, g.w * mul};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    hi[j] = __float2half_rn(v[j]);
-    lo[j] = __float2half_rn(v[j] - __half2float(hi[j]));
+    for (int j = 0; j < 4; ++j) tile[r][c + j] = v[j];
+    if (in) {
+      __align__(8) __half hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hi[j] = __float2half_rn(v[j]);
+        lo[j] = __float2half_rn(v[j] - __half2float(hi[j]));
+      }
+      __half* dst = rows + ((int64_t)bh * n + s) * 2 * AC_HD + c;
+      *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(dst + AC_HD) = *reinterpret_cast<const uint2*>(lo);
+    }
+    if (DELTA) {                                                 // the 16 threads of a row are 16 consecutive lanes
+      float4 ov = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (in) ov = *reinterpret_cast<const float4*>(o + off);
+      float dot = v[0] * ov.x + v[1] * ov.y + v[2] * ov.z + v[3] * ov.w;
+#pragma unroll
+      for (int sh = 8; sh > 0; sh >>= 1) dot += __shfl_xor_sync(FULL, dot, sh);
+      if (in && (idx & 15) == 0) delta[(int64_t)bh * n + s] = dot;
+    }
   }
-  *reinterpret_cast<uint2*>(dst + r * 2 * AC_HD + d) = *reinterpret_cast<const uint2*>(hi);
-  *reinterpret_cast<uint2*>(dst + r * 2 * AC_HD + AC_HD + d) = *reinterpret_cast<const uint2*>(lo);
-  if (d == 0) delta[r] = dot * mul;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = s0 + lane;
+  if (s < np) {
+    __half* dst = xt + (int64_t)bh * AC_HD * 2 * np;
+#pragma unroll
+    for (int k = 0; k < AC_HD / 8; ++k) {
+      const int d = warp + 8 * k;
+      const float v = tile[lane][d];
+      const __half hi = __float2half_rn(v);
+      dst[(int64_t)d * 2 * np + s] = hi;
+      dst[(int64_t)d * 2 * np + np + s] = __float2half_rn(v - __half2float(hi));
+    }
+  }
 }
 
 // ---------------------------------------------------------------- host side
@@ -445,7 +474,7 @@ bool attn_bwd_tc_supported(int B, int heads, int L, int S, int hd) {
          (int64_t)B * heads * 256 < (1ll << 31);
 }
 
-// Where it pays (measured, profiles/r1_attention_core.txt): the two kernels are preceded by eight small
+// Where it pays (measured, profiles/r1_attention_core.txt): the two kernels are preceded by five small
 // operand-preparation launches, and a tile of mostly padding (L = 16, S = 64) is slower than the CUDA-core kernels.
 bool attn_bwd_tc_profitable(int B, int heads, int L, int S, int hd) {
   return attn_bwd_tc_supported(B, heads, L, S, hd) && L >= 64 && S >= 96 &&
@@ -488,14 +517,16 @@ int attn_bwd_tc(const float* q, const float* k, const float* v, const unsigned c
   const BwdCarve w = bwd_carve(workspace, bh, L, S);
   int rc;
   if ((rc = absmax(dout, bh * L * AC_HD, w.amax, st))) return rc;
-  if ((rc = attn_split_rows(q, bh * L, scale * LOG2E, nullptr, w.q2, st))) return rc;
-  if ((rc = attn_split_rows(k, bh * S, 1.f, nullptr, w.k2, st))) return rc;
-  if ((rc = attn_split_rows(v, bh * S, 1.f, nullptr, w.v2, st))) return rc;
-  attn_split_dout_kernel<<<(unsigned)ceil_div64(bh * L * AC_HD, 1024), 256, 0, st>>>(dout, out, bh * L, w.amax, w.do2, w.delta);
-  HSG_LAUNCH_CHECK();
-  if ((rc = attn_split_transposed(k, bh, S, Sp, 1.f, nullptr, w.kt2, st))) return rc;
-  if ((rc = attn_split_transposed(q, bh, L, Lp, scale * LOG2E, nullptr, w.qt2, st))) return rc;
-  if ((rc = attn_split_transposed(dout, bh, L, Lp, 1.f, w.amax, w.dot2, st))) return rc;
+  {
+    dim3 gq((unsigned)(Lp / 32), (unsigned)bh), gk((unsigned)(Sp / 32), (unsigned)bh);
+    attn_split_both_kernel<false><<<gq, 256, 0, st>>>(q, nullptr, L, Lp, scale * LOG2E, nullptr, w.q2, w.qt2, nullptr);
+    HSG_LAUNCH_CHECK();
+    attn_split_both_kernel<false><<<gk, 256, 0, st>>>(k, nullptr, S, Sp, 1.f, nullptr, w.k2, w.kt2, nullptr);
+    HSG_LAUNCH_CHECK();
+    if ((rc = attn_split_rows(v, bh * S, 1.f, nullptr, w.v2, st))) return rc;
+    attn_split_both_kernel<true><<<gq, 256, 0, st>>>(dout, out, L, Lp, 1.f, w.amax, w.do2, w.dot2, w.delta);
+    HSG_LAUNCH_CHECK();
+  }
 
   AttnBwdTcParams p;
   p.BH = (int)bh; p.heads = heads; p.L = L; p.S = S; p.Lp = Lp; p.Sp = Sp; p.mask = mask; p.drop_p = drop_p; p.seed = seed;

@@ -221,12 +221,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 }
 
 // ---------------------------------------------------------------- operand preparation
-__device__ __forceinline__ float attn_mul(float mul, const float* amax) {
-  if (!amax) return mul;
-  const float m = *amax;
-  return m > 0.f ? mul / m : 0.f;
-}
-
 // rows [R, 64] fp32 -> [R, 128] fp16 (hi | lo) of mul * x
 __global__ void __launch_bounds__(256) attn_split_rows_kernel(const float* __restrict__ src, int64_t R, float mul,
                                                               const float* __restrict__ amax, __half* __restrict__ dst) {

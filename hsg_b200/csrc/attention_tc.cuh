@@ -25,6 +25,13 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// multiplier of an operand split: mul, or mul / *amax (0 when *amax == 0) when a device-side normaliser is given
+__device__ __forceinline__ float attn_mul(float mul, const float* amax) {
+  if (!amax) return mul;
+  const float m = *amax;
+  return m > 0.f ? mul / m : 0.f;
+}
+
 // byte offset of the 16-byte chunk holding columns [8*chunk, 8*chunk+8) of row r in a 128B-swizzled
 // K-major slab of 64 fp16 columns (rows of 128 bytes, 8-row groups 1024 bytes apart)
 __device__ __forceinline__ uint32_t swz128_off(int r, int chunk) {
