@@ -59,15 +59,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 4); mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // TMEM: Sp columns of scores + 64 of output, as a power of two (short key sets leave room for more CTAs per SM)
+  const uint32_t ncols = p.Sp + AC_HD <= 128 ? 128u : p.Sp + AC_HD <= 256 ? 256u : 512u;
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t t_s = tmem_base, t_o = tmem_base + 256;
+  const uint32_t t_s = tmem_base, t_o = tmem_base + (uint32_t)p.Sp;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -216,7 +218,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols));
   }
 }
 
@@ -288,10 +290,10 @@ bool attn_tc_supported(int B, int heads, int L, int S, int hd) {
          (int64_t)B * heads * (int64_t)(L > S ? L : S) < (1ll << 31);
 }
 
-// Where it pays (measured, profiles/r1_attention_core.txt): the 128-row tiles must be mostly real rows and
-// there must be enough of them to amortise the three operand-preparation launches.
+// Where it pays (measured, profiles/r1_attention_core.txt): three operand-preparation launches put a floor of
+// ~50 us under the tensor-core path; the CUDA-core kernel costs ~20 us per 2^20 (row, key) pairs.
 bool attn_tc_profitable(int B, int heads, int L, int S, int hd) {
-  return attn_tc_supported(B, heads, L, S, hd) && L >= 96 && (int64_t)B * heads * ((L + AC_BM - 1) / AC_BM) >= 96;
+  return attn_tc_supported(B, heads, L, S, hd) && (int64_t)B * heads * L * S >= 3 * (1ll << 20);
 }
 
 static int attn_sp(int S) { return attn_pad64(S); }

@@ -36,8 +36,9 @@ def timeit(fn, reps=20):
 
 lines = ['# attention core, fp32, 4 heads x hd 64 (C=256); us per call; flop = 4*B*h*L*S*hd (fwd)',
          '# fwd+bwd columns: default dispatch | backward forced to the CUDA-core kernels | backward forced to tcgen05 | torch',
-         '%5s %4s %4s %12s %12s %9s %14s %14s %14s %14s %10s' % ('B', 'L', 'S', 'ours fwd', 'torch fwd', 'speed-up', 'ours fwd+bwd',
-                                                                'simt bwd', 'tc bwd', 'torch fwd+bwd', 'GFLOP/s')]
+         '# fwd columns: default dispatch | forced to the CUDA-core kernel | forced to tcgen05 | torch',
+         '%5s %4s %4s %10s %10s %10s %10s %9s %14s %12s %12s %14s %10s' % ('B', 'L', 'S', 'ours fwd', 'simt fwd', 'tc fwd', 'torch fwd', 'speed-up',
+                                                                          'ours fwd+bwd', 'simt bwd', 'tc bwd', 'torch fwd+bwd', 'GFLOP/s')]
 for b in (8, 16, 64, 256, 1024):
   for (l, s) in ((256, 256), (64, 256), (16, 64)):
     h, hd = 4, 64
@@ -49,6 +50,11 @@ for b in (8, 16, 64, 256, 1024):
     w = torch.randn(b * h, l, hd, device=dev)
     with torch.no_grad():
       f_ours = timeit(lambda: attention_core(q, k, v, mask, b, h))
+      lib.hsg_debug_set_flags(16)
+      f_simt = timeit(lambda: attention_core(q, k, v, mask, b, h))
+      lib.hsg_debug_set_flags(32)
+      f_tc = timeit(lambda: attention_core(q, k, v, mask, b, h))
+      lib.hsg_debug_set_flags(0)
       f_torch = timeit(lambda: torch_core(q, k, v, mask, b, h))
 
     def fb(fn):
@@ -64,8 +70,9 @@ for b in (8, 16, 64, 256, 1024):
     fb_tc = timeit(fb(attention_core))
     lib.hsg_debug_set_flags(0)
     fb_torch = timeit(fb(torch_core))
-    lines.append('%5d %4d %4d %12.1f %12.1f %9.2f %14.1f %14.1f %14.1f %14.1f %10.0f' % (
-        b, l, s, f_ours, f_torch, f_torch / f_ours, fb_ours, fb_simt, fb_tc, fb_torch, 4.0 * b * h * l * s * hd / f_ours / 1e3))
+    lines.append('%5d %4d %4d %10.1f %10.1f %10.1f %10.1f %9.2f %14.1f %12.1f %12.1f %14.1f %10.0f' % (
+        b, l, s, f_ours, f_simt, f_tc, f_torch, f_torch / f_ours, fb_ours, fb_simt, fb_tc, fb_torch,
+        4.0 * b * h * l * s * hd / f_ours / 1e3))
 text = '\n'.join(lines)
 print(text)
 if len(sys.argv) > 1:
