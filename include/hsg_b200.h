@@ -79,7 +79,10 @@ HSG_API int hsg_profile_collect(double* total_ms_host, long long* counts_host, i
 /* test hook: the next tensor-core E-steps also write their screening
  * similarities to sims [N,kmax] (device); NULL switches the dump off. */
 HSG_API int hsg_debug_set_tc_dump(float* sims);
-/* test hook: bit 0 keeps the NCE forward on the fp32 CUDA-core kernel */
+/* test hook, a bit mask that pins a path to one of its two implementations (0 = the library decides):
+ *   1 NCE forward on the fp32 CUDA-core kernel      4 NCE backward GEMMs on CUDA cores     8 NCE backward G chunk on CUDA cores
+ *  16 attention forward on CUDA cores              32 attention forward on tcgen05 for every shape it supports
+ *  64 attention backward on CUDA cores            128 attention backward on tcgen05 for every shape it supports */
 HSG_API int hsg_debug_set_flags(int flags);
 
 /* ---- a1: normalize_embedding  (hsg/utils/general/common.py:101-120) -------
