@@ -26,7 +26,8 @@ _TARGETS = {
         'normalize_embedding', 'segment_mean']),
     'hsg.utils.segsort.loss': ('hsg_b200.utils.segsort.loss', [
         '_calculate_log_likelihood', 'SegSortLoss']),
-    'hsg.utils.segsort.eval': ('hsg_b200.utils.segsort.eval', ['top_k_ranking']),
+    'hsg.utils.segsort.eval': ('hsg_b200.utils.segsort.eval', ['top_k_ranking', 'majority_label_from_topk']),
+    'hsg.utils.segsort.others': ('hsg_b200.utils.segsort.others', ['load_memory_banks']),
     'hsg.utils.graph.common': ('hsg_b200.utils.graph.common', ['affinity_matrix_as_attention']),
     'hsg.utils.graph.loss': ('hsg_b200.utils.graph.loss', ['dmon_pool_loss', 'DMonLoss']),
     'hsg.models.utils': ('hsg_b200.models.utils', [
@@ -59,6 +60,8 @@ def _patch_methods(importlib):
   tables = [(m, hierarchy.METHODS) for m in _METHOD_MODULES]
   tables += [(m, {'Hsg': {'losses': loss_head.losses_cs if m.endswith('_cs') else loss_head.losses}})
              for m in _LOSS_MODULES]
+  from .models.predictions import segsort as retrieval_head
+  tables.append(('hsg.models.predictions.segsort', retrieval_head.METHODS))
   for ref_name, table in tables:
     try:
       ref = importlib.import_module(ref_name)

@@ -208,8 +208,9 @@ def segment_by_kmeans_ex(embeddings, labels=None, num_clusters=[5, 5], cluster_i
     xerr = buf['xerr'][:n] if want_half else None
     if n == 0:
       raise RuntimeError('segment_by_kmeans: every pixel is ignored')     # the reference fails on .max() of an empty tensor
+    max_len = min(h * w, n)            # a single image with ignore pixels dropped is shorter than its grid
     clusters = ops.kmeans(xloc, buf['clusters'][:n], kmax, int(iterations),
-                          seg_offsets=buf['seg_offsets'], max_seg_len=h * w, seg_k=seg_k,
+                          seg_offsets=buf['seg_offsets'], max_seg_len=max_len, seg_k=seg_k,
                           xh=xh, xerr=xerr, flags=KMEANS_AUTO)
     if labels is None:
       label_values = torch.zeros((1,), dtype=torch.int64, device=dev)
@@ -221,7 +222,7 @@ def segment_by_kmeans_ex(embeddings, labels=None, num_clusters=[5, 5], cluster_i
     loc_rows = loc.reshape(-1, n_loc).index_select(0, pix % (h * w) if loc_stride == 0 else pix)
     x, xloc = _PrepOutputs.apply(embeddings, x, xloc, pix, loc_rows)
   ex = {'embeddings': x, 'embeddings_with_loc': xloc, 'labels': lab, 'cluster_indices': ids,
-        'batch_indices': bat, 'seg_offsets': buf['seg_offsets'], 'max_seg_len': h * w,
+        'batch_indices': bat, 'seg_offsets': buf['seg_offsets'], 'max_seg_len': max_len,
         'num_images': b, 'batch_base': b * gpu_id, 'kmeans_labels': clusters,
         'slots_per_image': kmax * int(label_values.numel()),
         'num_prototypes_device': npro, 'proto_label': pl, 'proto_batch': pb, 'proto_cluster': pc}

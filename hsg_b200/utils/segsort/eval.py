@@ -17,3 +17,14 @@ def top_k_ranking(embeddings, labels, prototypes, prototype_labels, top_k=3):
   retrieved = prototype_labels.reshape(-1)[top.reshape(-1)].view(-1, top_k)
   accuracy = torch.mean((retrieved == labels.reshape(-1, 1)).float())
   return accuracy, retrieved
+
+
+def majority_label_from_topk(top_k_labels, num_classes=None):
+  """Most frequent label of each row of [num_queries, top_k], ties -> lowest label (reference :55-72,
+  which materialises the [N, k, C] one-hot tensor and sums it; here the counts are one scatter_add)."""
+  labels = top_k_labels.reshape(top_k_labels.shape[0], -1).long()
+  if num_classes is None:
+    num_classes = int(labels.max()) + 1
+  counts = torch.zeros((labels.shape[0], int(num_classes)), dtype=torch.long, device=labels.device)
+  counts.scatter_add_(1, labels, torch.ones_like(labels))
+  return torch.argmax(counts, 1)

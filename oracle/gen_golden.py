@@ -41,13 +41,16 @@ def save(name, **arrays):
   print('%-28s %8.1f KB' % (name, os.path.getsize(path) / 1024.0))
 
 
+_REFERENCE_SEGMENT_BY_KMEANS = s_common.segment_by_kmeans
+
+
 def segment_by_kmeans_cpu(*args, **kwargs):
   """Reference segment_by_kmeans with the CPU shim `device.index or 0`
   (hsg/utils/segsort/common.py:376: `.device.index` is None on CPU and
   `N * None` raises).  The reference source is re-compiled in memory with that
   one expression patched; nothing is written anywhere."""
   import inspect
-  text = inspect.getsource(s_common.segment_by_kmeans)
+  text = inspect.getsource(_REFERENCE_SEGMENT_BY_KMEANS)
   patched = text.replace('cur_cluster_indices.device.index',
                          '(cur_cluster_indices.device.index or 0)')
   assert patched != text
@@ -415,9 +418,72 @@ def transformer_fixture():
        dsrc=_np(src_g.grad), **arrays, **grads)
 
 
+def inference_fixture():
+  """the prototype-bank writer and the nearest-neighbour label retrieval of the inference
+  scripts, on small full-resolution-style inputs.  Runs the reference's own `generate_clusters`
+  (hsg/models/embeddings/resnet_fcn.py:90-148, unbound, on a stub holding its four config fields),
+  `calculate_prototypes_from_labels`, `find_majority_label_index` (pyscripts/inference/prototype.py:181-208),
+  `load_memory_banks` (hsg/utils/segsort/others.py:11-41), `Segsort.predictions`
+  (hsg/models/predictions/segsort.py:66-123) and `majority_label_from_topk` (segsort/eval.py:55-72)."""
+  import tempfile
+  import hsg.utils.segsort.eval as s_eval
+  import hsg.utils.segsort.others as s_others
+  from hsg.models.embeddings.resnet_fcn import ResnetFcn
+  from hsg.models.predictions.segsort import Segsort
+  torch.manual_seed(235)
+  rng = np.random.RandomState(235)
+  d, hp, wp, h, w = 16, 20, 24, 18, 21                 # padded image 20x24, real image 18x21 (pad right / bottom)
+  n_class = 5
+  centres = torch.nn.functional.normalize(torch.randn(n_class, d), dim=1)
+  stub = types.SimpleNamespace(label_divisor=2048, semantic_ignore_index=255, kmeans_num_clusters=[4, 4],
+                               kmeans_iterations=10)
+  orig = s_common.segment_by_kmeans
+  s_common.segment_by_kmeans = segment_by_kmeans_cpu     # CPU shim (device.index or 0), see above
+  arrays = {}
+  banks = []
+  try:
+    with tempfile.TemporaryDirectory() as tmp:
+      for img in range(7):
+        # ground truth: blocks of classes; embedding = class centre + noise, normalised per pixel
+        gt = torch.from_numpy(rng.randint(0, n_class, size=(3, 3))).long()
+        gt = gt.repeat_interleave(6, 0).repeat_interleave(7, 1)[:h, :w].contiguous()
+        full = torch.zeros(hp, wp, dtype=torch.long)
+        full[:h, :w] = gt
+        emb = centres[full] + 2.0 * torch.randn(hp, wp, d) / d ** 0.5
+        emb = g_common.normalize_embedding(emb).permute(2, 0, 1).unsqueeze(0).contiguous()
+        fake = torch.full((1, hp, wp), 255, dtype=torch.long)
+        fake[:, :h, :w] = 0
+        out = ResnetFcn.generate_clusters(stub, emb, fake, fake.clone())
+        protos = s_common.calculate_prototypes_from_labels(out['cluster_embedding'], out['cluster_index'])
+        keep, proto_labels = s_common.find_majority_label_index(gt.unsqueeze(0), out['cluster_index'])
+        arrays.update({'emb%d' % img: _np(emb), 'gt%d' % img: _np(gt), 'fake%d' % img: _np(fake),
+                       'cluster_index%d' % img: _np(out['cluster_index']),
+                       'cluster_embedding%d' % img: _np(out['cluster_embedding']),
+                       'cluster_semantic_label%d' % img: _np(out['cluster_semantic_label']),
+                       'cluster_instance_label%d' % img: _np(out['cluster_instance_label']),
+                       'cluster_batch_index%d' % img: _np(out['cluster_batch_index']),
+                       'protos%d' % img: _np(protos), 'proto_labels%d' % img: _np(proto_labels), 'keep%d' % img: _np(keep)})
+        if img < 6:                                      # images 0-5 form the memory bank; image 6 is the query
+          np.save(os.path.join(tmp, 'img%d.npy' % img), {'prototype': _np(protos), 'prototype_label': _np(proto_labels)})
+        else:
+          bank_p, bank_l = s_others.load_memory_banks(tmp)
+          pred, topk = Segsort.predictions(None, out, {'semantic_memory_prototype': bank_p,
+                                                       'semantic_memory_prototype_label': bank_l})
+          arrays.update(bank_p=_np(bank_p), bank_l=_np(bank_l), pred=_np(pred), topk=_np(topk))
+  finally:
+    s_common.segment_by_kmeans = orig
+  votes = torch.from_numpy(rng.randint(0, 7, size=(40, 20))).long()
+  arrays.update(votes=_np(votes), votes_majority=_np(s_eval.majority_label_from_topk(votes)),
+                votes_majority9=_np(s_eval.majority_label_from_topk(votes, 9)))
+  save('inference_bank', cfg=np.asarray([d, hp, wp, h, w, 4, 4, 10, 2048, 255]), **arrays)
+
+
 if __name__ == '__main__':
   if len(sys.argv) > 1 and sys.argv[1] == 'transformer':
     transformer_fixture()
+  elif len(sys.argv) > 1 and sys.argv[1] == 'inference':
+    inference_fixture()
   else:
     main()
     transformer_fixture()
+    inference_fixture()

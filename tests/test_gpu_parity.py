@@ -1049,3 +1049,33 @@ def test_whole_step_composes_and_differentiates(S):
     # the coarse head's centroid features feed nothing downstream (as in the reference); everything else trains
     assert all(k.startswith('centroid_feat_fc') for k in missing) and (name == 'coarse' or not missing), (name, missing)
   assert q_fine.grad is not None and q_coarse.grad is not None
+
+
+# ---------------------------------------------------------------- inference: prototype bank + nearest-neighbour labels (8f rank 4)
+@pytest.mark.xfail(strict=False, reason='written after the round-1 GPU budget ran out: its one run on a B200 exposed the '
+                   'single-image max_seg_len bug fixed in segment_by_kmeans_ex, and the fixed path has not been run on a GPU yet; '
+                   'the host logic and the oracle are covered by tests/test_host_inference.py and test_oracle_golden.py')
+def test_inference_prototype_bank_and_retrieval(golden, tmp_path):
+  """generate_clusters -> bank entry per image -> bank on disk -> nearest-neighbour labels of a query image,
+  against the reference's CPU run (pyscripts/inference/prototype.py:181-208, inference.py:207-224)."""
+  from hsg_b200 import inference
+  g = golden('inference_bank')
+  d, hp, wp, h, w, ky, kx, iters, div, ignore = [int(v) for v in g['cfg']]
+  for img in range(7):
+    fake = t(g['fake%d' % img])
+    out = inference.generate_clusters(t(g['emb%d' % img]), fake, fake.clone(), div, ignore, [ky, kx], iters)
+    for key in ('cluster_index', 'cluster_semantic_label', 'cluster_instance_label', 'cluster_batch_index'):
+      assert out[key].dtype == torch.int64 and np.array_equal(n(out[key]), g['%s%d' % (key, img)]), (key, img)
+    close(n(out['cluster_embedding']), g['cluster_embedding%d' % img])
+    protos, labels = inference.prototype_bank(out['cluster_embedding'], out['cluster_index'], t(g['gt%d' % img]))
+    close(n(protos), g['protos%d' % img])
+    assert np.array_equal(n(labels), g['proto_labels%d' % img])
+    if img < 6:
+      inference.save_memory_bank(str(tmp_path / ('img%d.npy' % img)), protos, labels)
+  bank_p, bank_l = inference.load_memory_banks(str(tmp_path))
+  close(n(bank_p), g['bank_p'])
+  assert np.array_equal(n(bank_l), g['bank_l'])
+  pred, topk = inference.nearest_neighbor_labels(out, bank_p, bank_l)          # the bank is moved to the GPU inside
+  assert pred.dtype == torch.int64 and topk.shape == (g['pred'].shape[0], 20)
+  assert np.array_equal(n(pred), g['pred']) and np.array_equal(n(topk), g['topk'])
+  assert inference.nearest_neighbor_labels({}, bank_p, bank_l) == (None, None)  # reference :70-84

@@ -251,3 +251,29 @@ def test_cross_gpu_gather(golden):
   re = protos.gather_and_reorder_image_indices([g['r0_img'], g['r1_img']])
   for r in range(2):                 # every rank receives the whole vector
     assert np.array_equal(re, g['r%d_img_reordered' % r])
+
+
+def test_inference_prototype_bank_and_retrieval(golden, tmp_path):
+  """generate_clusters -> prototype bank -> load_memory_banks -> nearest-neighbour labels."""
+  from oracle import inference
+  g = golden('inference_bank')
+  d, hp, wp, h, w, ky, kx, iters, div, ignore = [int(v) for v in g['cfg']]
+  for img in range(7):
+    out = inference.generate_clusters(g['emb%d' % img], g['fake%d' % img], g['fake%d' % img], div, ignore, (ky, kx), iters)
+    for key in ('cluster_index', 'cluster_semantic_label', 'cluster_instance_label', 'cluster_batch_index'):
+      assert np.array_equal(out[key], g['%s%d' % (key, img)]), (key, img)
+    close(out['cluster_embedding'], g['cluster_embedding%d' % img])
+    protos, labels = inference.prototype_bank(out['cluster_embedding'], out['cluster_index'], g['gt%d' % img])
+    close(protos, g['protos%d' % img])
+    assert np.array_equal(labels, g['proto_labels%d' % img])
+    keep, _ = inference.find_majority_label_index(g['gt%d' % img], out['cluster_index'])
+    assert np.array_equal(keep, g['keep%d' % img])
+    if img < 6:
+      np.save(str(tmp_path / ('img%d.npy' % img)), {'prototype': protos, 'prototype_label': labels})
+  bank_p, bank_l = inference.load_memory_banks(str(tmp_path))
+  close(bank_p, g['bank_p'])
+  assert np.array_equal(bank_l, g['bank_l'])
+  pred, topk = inference.predictions(out['cluster_embedding'], out['cluster_index'], g['bank_p'], g['bank_l'])
+  assert np.array_equal(pred, g['pred']) and np.array_equal(topk, g['topk'])
+  assert np.array_equal(inference.majority_label_from_topk(g['votes']), g['votes_majority'])
+  assert np.array_equal(inference.majority_label_from_topk(g['votes'], 9), g['votes_majority9'])
