@@ -13,18 +13,20 @@ import numpy as np
 import torch
 
 
+def _entries(memory_dir):
+  files = sorted(glob.glob(os.path.join(memory_dir, '*.npy')))
+  if not files:
+    raise AssertionError('No memory stored in the directory')          # the reference asserts here
+  return [np.load(f, allow_pickle=True).item() for f in files]
+
+
 def load_memory_banks(memory_dir):
-  """(prototypes float32 [num_prototypes, C], labels int64 [num_prototypes]) of every *.npy in the directory."""
-  memory_paths = sorted(glob.glob(os.path.join(memory_dir, '*.npy')))
-  assert len(memory_paths) > 0, 'No memory stored in the directory'
-  prototypes, prototype_labels = [], []
-  for memory_path in memory_paths:
-    datas = np.load(memory_path, allow_pickle=True).item()
-    prototypes.append(datas['prototype'])
-    prototype_labels.append(datas['prototype_label'])
-  prototypes = torch.from_numpy(np.concatenate(prototypes, 0).astype(np.float32))
-  prototype_labels = torch.from_numpy(np.concatenate(prototype_labels, 0).astype(np.int64))
-  return prototypes, prototype_labels
+  """(prototypes float32 [num_prototypes, C], labels int64 [num_prototypes]): the entries of every *.npy file of
+  the directory, files in sorted order."""
+  entries = _entries(memory_dir)
+  bank = torch.cat([torch.as_tensor(np.asarray(e['prototype'], dtype=np.float32)) for e in entries], 0)
+  labels = torch.cat([torch.as_tensor(np.asarray(e['prototype_label'], dtype=np.int64)).reshape(-1) for e in entries], 0)
+  return bank, labels
 
 
 def save_memory_bank(path, prototypes, prototype_labels):
