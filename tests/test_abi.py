@@ -117,9 +117,25 @@ def test_patch_rebinds_the_reference_operators(lib):
         was = hsg_b200._PATCHED[('hsg.models.embeddings.resnet_fcn_hsg', cls + '.' + name)]
         assert list(inspect.signature(was).parameters) == list(inspect.signature(now).parameters), (cls, name)
       method_orig = hsg_b200._PATCHED[('hsg.models.embeddings.resnet_fcn_hsg', 'ResnetFcn._calculate_kmeans_prototypes')]
+      # inference row: memory bank loader, top-k vote and the retrieval method of the SegSort head
+      import hsg.utils.segsort.others as ref_others
+      import hsg.utils.segsort.eval as ref_eval
+      import hsg.models.predictions.segsort as ref_head
+      assert ref_others.load_memory_banks.__module__.startswith('hsg_b200')
+      for mod, name in (('hsg.utils.segsort.others', 'load_memory_banks'), ('hsg.utils.segsort.eval', 'majority_label_from_topk'),
+                        ('hsg.utils.segsort.eval', 'top_k_ranking'), ('hsg.utils.segsort.common', 'find_majority_label_index')):
+        was = inspect.signature(hsg_b200._PATCHED[(mod, name)])
+        now = inspect.signature(getattr(sys.modules[mod], name))
+        assert list(was.parameters) == list(now.parameters), name
+      now = ref_head.Segsort.__dict__['predictions']
+      was = hsg_b200._PATCHED[('hsg.models.predictions.segsort', 'Segsort.predictions')]
+      assert now.__module__.startswith('hsg_b200') and list(inspect.signature(was).parameters) == list(inspect.signature(now).parameters)
+      retrieval_orig = was
     finally:
       hsg_b200.unpatch()
     assert ref_common.segment_by_kmeans is orig
     assert ref_model.ResnetFcn.__dict__['_calculate_kmeans_prototypes'] is method_orig
+    assert ref_head.Segsort.__dict__['predictions'] is retrieval_orig
+    assert ref_others.load_memory_banks.__module__ == 'hsg.utils.segsort.others'
   finally:
     sys.path.remove('/root/reference')
