@@ -24,6 +24,7 @@
 #include "tc_common.cuh"
 
 #include <float.h>
+#include <stdlib.h>
 
 namespace hsg {
 
@@ -385,6 +386,293 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------- single-pass kernel (K <= 256 per image)
+// Same TMA / MMA pipeline as estep_tc_kernel, different epilogue.  The sorted top-3 with packed
+// indices costs ~6.5 ALU-pipe instructions per similarity and made the ALU pipe the limiter of the
+// whole k-means iteration (profiles/r1_estep_tc.txt: ALU 70 %, tensor 41 %).  Here one thread owns one
+// pixel row and sweeps its accumulator lane ONCE, 32 columns at a time:
+//
+//   chunk max        16 FMNMX3                      (ALU pipe, 0.5 per similarity)
+//   running max      run = max(run, chunk max)
+//   hit bits         v - (run - thr) on the FMA pipe, its sign funnel-shifted into a 32-bit mask
+//                    (one SHF per similarity, ALU pipe)
+//
+// A chunk's bits are taken against the running maximum at that point, which can only be lower than
+// the final one, so they flag a superset of the columns within `thr` of the row maximum; after the
+// sweep a chunk whose own maximum is below (final max - thr) is dropped whole.  What is left is exact
+// for every chunk from the one holding the maximum onwards and a superset before it -- and an earlier
+// chunk only survives when it really holds a second candidate, so no row is sent to the float64
+// re-decision that the exact rule would not send (lists can only be longer).  A row with exactly one
+// surviving bit is decided; the others are listed with every surviving column as candidate.
+// 1.5 ALU-pipe instructions per similarity instead of 6.5, no cross-thread merge, no named barriers.
+constexpr int TC1_THREADS = 384;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
+constexpr float TC1_EPS_CONST = 3.3e-5f; // accumulation (3e-5) + split tail (1e-6) + slack for the fp32 threshold arithmetic
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+
+// load chunk c (32 columns; the last chunk may be 16 wide: kpad is a multiple of 16)
+__device__ __forceinline__ void tc1_load(uint32_t trow, int c, int kpad, uint32_t (&v)[32]) {
+  if (c * 32 + 32 <= kpad) {
+    tc_ld32(trow + c * 32, v);
+  } else {
+    uint32_t lo[16];
+    tc_ld16(trow + c * 32, lo);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { v[j] = lo[j]; v[16 + j] = 0xFF800000u; }    // -inf: never a hit
+  }
+}
+
+template <bool DUMP>
+__global__ void __launch_bounds__(TC1_THREADS, 1)
+estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_xt,
+                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_ct,
+                 const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nslab = p.d16 / TC_BK;
+  const uint32_t slab_b_bytes = (uint32_t)p.kpad * 128u;
+  const uint32_t tail_b_bytes = (uint32_t)p.kpad * 32u;
+  const uint32_t sB = base;                                   // centroids, main slabs
+  const uint32_t sBT = sB + nslab * slab_b_bytes;             // centroids, tail slab
+  const uint32_t sAT = sBT + 256 * 32;                        // pixel tail slab, 2 buffers
+  const uint32_t sA = sAT + 2 * TC_TAIL_BYTES;                // pixel main slabs, nst stages
+  const uint32_t sMisc = sA + p.nst * TC_STAGE_BYTES;
+  uint8_t* misc = smem_raw + (sMisc - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+  const uint32_t bar_full = smem_u32(bars);                   // [12]
+  const uint32_t bar_empty = bar_full + 12 * 8;               // [12]
+  const uint32_t bar_tlfull = bar_empty + 12 * 8;             // [2] tail slab landed
+  const uint32_t bar_tlempty = bar_tlfull + 16;               // [2]
+  const uint32_t bar_bfull = bar_tlempty + 16;                // [1] centroids landed
+  const uint32_t bar_tfull = bar_bfull + 8;                   // [2] accumulator ready
+  const uint32_t bar_tempty = bar_tfull + 16;                 // [2] accumulator drained
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.nst; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tlfull + 8 * i, 1); mbar_init(bar_tlempty + 8 * i, 1);
+      mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4);
+    }
+    mbar_init(bar_bfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_xt) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_c) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_ct) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int count = *p.tiles.count;
+  const long long i_begin = p.items * blockIdx.x / gridDim.x;
+  const long long i_end = p.items * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0, cur_seg = -1, tl = 0, last_tl = 0;
+      uint32_t phase = 0, tl_phase = 0, last_tl_phase = 0;
+      for (long long item = i_begin; item < i_end; ++item) {
+        int seg, np; int64_t row0;
+        if (!item_rows(p, item, count, seg, row0, np)) continue;
+        if (seg != cur_seg) {
+          // the tail MMA is the last one of a tile: once it retired, nothing reads the old centroids
+          if (cur_seg >= 0) mbar_wait(bar_tlempty + 8 * last_tl, last_tl_phase);
+          mbar_expect_tx(bar_bfull, nslab * slab_b_bytes + tail_b_bytes);
+          for (int j = 0; j < nslab; ++j)
+            tma_load_2d(sB + j * slab_b_bytes, &tmap_c, j * TC_BK, seg * p.kpad_total, bar_bfull);
+          tma_load_2d(sBT, &tmap_ct, p.d16, seg * p.kpad_total, bar_bfull);
+          cur_seg = seg;
+        }
+        for (int j = 0; j < nslab; ++j) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
+          tma_load_2d(sA + stage * TC_STAGE_BYTES, &tmap_x, j * TC_BK, (int)row0, bar_full + 8 * stage);
+          if (++stage == p.nst) { stage = 0; phase ^= 1; }
+        }
+        mbar_wait(bar_tlempty + 8 * tl, tl_phase ^ 1);
+        mbar_expect_tx(bar_tlfull + 8 * tl, TC_TAIL_BYTES);
+        tma_load_2d(sAT + tl * TC_TAIL_BYTES, &tmap_xt, p.d16, (int)row0, bar_tlfull + 8 * tl);
+        last_tl = tl; last_tl_phase = tl_phase;
+        if (++tl == 2) { tl = 0; tl_phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.kpad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0, cur_seg = -1, acc = 0, tl = 0;
+      uint32_t phase = 0, bcount = 0, tl_phase = 0, acc_phase0 = 0, acc_phase1 = 0;
+      for (long long item = i_begin; item < i_end; ++item) {
+        int seg, np; int64_t row0;
+        if (!item_rows(p, item, count, seg, row0, np)) continue;
+        if (seg != cur_seg) {
+          mbar_wait(bar_bfull, bcount & 1);
+          ++bcount;
+          cur_seg = seg;
+        }
+        mbar_wait(bar_tempty + 8 * acc, (acc ? acc_phase1 : acc_phase0) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int j = 0; j < nslab; ++j) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t ad = umma_desc(sA + stage * TC_STAGE_BYTES, 1024, 2);
+          const uint64_t bd = umma_desc(sB + j * slab_b_bytes, 1024, 2);
+#pragma unroll
+          for (int k4 = 0; k4 < TC_BK / 16; ++k4)
+            tc_mma_f16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (j | k4) ? 1u : 0u);
+          tc_commit(bar_empty + 8 * stage);
+          if (++stage == p.nst) { stage = 0; phase ^= 1; }
+        }
+        mbar_wait(bar_tlfull + 8 * tl, tl_phase);
+        tc_fence_after();
+        tc_mma_f16(d_tmem, umma_desc(sAT + tl * TC_TAIL_BYTES, 256, 6), umma_desc(sBT, 256, 6), idesc, 1u);
+        tc_commit(bar_tlempty + 8 * tl);
+        if (++tl == 2) { tl = 0; tl_phase ^= 1; }
+        tc_commit(bar_tfull + 8 * acc);
+        if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+        acc ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: one thread per pixel row =====================
+    const int e = warp - 4;
+    const int q = warp & 3;                        // TMEM lane quadrant of this warp
+    const int g = e >> 2;                          // accumulator / tile parity
+    const int r = 32 * q + lane;                   // accumulator row = pixel within the tile
+    const int kpad = p.kpad;
+    int cur_seg = -1, seq = 0;
+    uint32_t acc_phase = 0;
+    float cerrmax = 0.f;
+    for (long long item = i_begin; item < i_end; ++item) {
+      int seg, np; int64_t row0;
+      if (!item_rows(p, item, count, seg, row0, np)) continue;
+      if (((seq++) & 1) != g) continue;
+      if (seg != cur_seg) { cerrmax = p.cerr_max[seg]; cur_seg = seg; }
+      const int64_t pix = row0 + r;
+      const bool inb = r < np;
+      const float xe = inb ? p.xerr[pix] : 0.f;
+      const float thr = 2.f * (xe * 1.001f + cerrmax * 1.001f + TC1_EPS_CONST);
+
+      mbar_wait(bar_tfull + 8 * g, acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + g * 256 + ((uint32_t)(32 * q) << 16);
+      float run = -FLT_MAX;
+      float cm[8];
+      uint32_t mk[8];
+      uint32_t va[32], vb[32];
+      tc1_load(trow, 0, kpad, va);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        cm[c] = -FLT_MAX; mk[c] = 0xFFFFFFFFu;
+        if (c * 32 < kpad) {                                     // warp-uniform
+          uint32_t (&v)[32] = (c & 1) ? vb : va;
+          uint32_t (&nx)[32] = (c & 1) ? va : vb;
+          tc_ld_wait();
+          if ((c + 1) * 32 < kpad) tc1_load(trow, c + 1, kpad, nx);   // in flight while chunk c is reduced
+          if (DUMP) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int k = c * 32 + j;
+              if (inb && k < p.kmax) p.dbg_sims[pix * p.kmax + k] = __uint_as_float(v[j]);
+            }
+          }
+          float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]);
+#pragma unroll
+          for (int j = 2; j < 32; j += 4) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+            if (j + 3 < 32) m1 = fmaxf(m1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+          }
+          const float cmax = fmaxf(m0, m1);
+          cm[c] = cmax;
+          run = fmaxf(run, cmax);
+          const float tp = run - thr;
+          uint32_t ma = 0xFFFFFFFFu, mb = 0xFFFFFFFFu;           // two chains of 16
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            ma = __funnelshift_l(__float_as_uint(__uint_as_float(v[j]) - tp), ma, 1);
+            mb = __funnelshift_l(__float_as_uint(__uint_as_float(v[16 + j]) - tp), mb, 1);
+          }
+          mk[c] = (ma << 16) | (mb & 0xFFFFu);                   // bit 31-j clear = column c*32+j is a hit
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * g);
+      acc_phase ^= 1;
+
+      const float t_final = run - thr;
+      int cnt = 0, first = 0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t hits = (c * 32 < kpad && cm[c] >= t_final) ? ~mk[c] : 0u;
+        mk[c] = hits;
+        if (cnt == 0 && hits) first = c * 32 + __clz(hits);
+        cnt += __popc(hits);
+      }
+      const bool amb = inb && cnt > 1;
+      if (inb) p.keys_out[pix] = seg * p.kmax + first;
+      // one atomic per warp for the list slots (the counter is a single address shared by every SM)
+      const unsigned amb_mask = __ballot_sync(FULL, amb);
+      if (amb_mask) {
+        int slot_base = 0;
+        if (lane == 0) slot_base = atomicAdd(p.fix.count, __popc(amb_mask));
+        slot_base = __shfl_sync(FULL, slot_base, 0);
+        if (amb) {
+          const int slot = slot_base + __popc(amb_mask & ((1u << lane) - 1u));
+          if (slot < p.fix.capacity) {
+            p.fix.pixels[slot] = (int32_t)pix;
+            uint16_t* cd = p.fix.cand + (int64_t)slot * FIX_MAX_CAND;
+            if (cnt > FIX_MAX_CAND) {
+              cd[0] = 0xFFFF;                        // too many to list: scan every cluster
+              atomicAdd(p.fix.count + 1, 1);
+            } else {
+              int w = 0;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                uint32_t hits = mk[c];
+                while (hits) {
+                  const int j = __clz(hits);
+                  hits &= ~(0x80000000u >> j);
+                  cd[w++] = (uint16_t)(c * 32 + j);
+                }
+              }
+              if (w < FIX_MAX_CAND) cd[w] = 0xFFFF;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+  }
+}
+
 // ---------------------------------------------------------------- centroid conversion
 __global__ void tc_convert_kernel(const float* __restrict__ cent, const int32_t* __restrict__ seg_k, int S,
                                   int kmax, int kpad, int dim, int d16, __half* __restrict__ ch,
@@ -538,6 +826,25 @@ int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
   long long grid = num_sms();
   if (grid > p.items) grid = p.items;
   if (grid < 1) grid = 1;
+  static const bool legacy = getenv("HSG_ESTEP_LEGACY") != nullptr;     // A/B switch for profiling only
+  if (p.n_pass == 1 && !legacy) {
+    // single-pass shapes (K <= 256 per image): one thread per pixel row, single sweep (estep_tc1_kernel)
+    const size_t fixed1 = (size_t)nslab * t.kpad * 128 + 256 * 32 + 2 * TC_TAIL_BYTES + 40 * 8 + 64;
+    int nst1 = (int)((227 * 1024 - 1024 - 1024 - fixed1) / TC_STAGE_BYTES);
+    if (nst1 > 12) nst1 = 12;
+    HSG_REQUIRE(nst1 >= 2, HSG_E_UNSUPPORTED, "tensor-core E-step: shared memory budget (kpad=%d d16=%d)", t.kpad, t.d16);
+    p.nst = nst1;
+    const size_t smem1 = 1024 + fixed1 + (size_t)nst1 * TC_STAGE_BYTES;
+    if (p.dbg_sims) {
+      HSG_CUDA(cudaFuncSetAttribute(estep_tc1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      estep_tc1_kernel<true><<<(unsigned)grid, TC1_THREADS, smem1, st>>>(mx, mxt, mc, mct, p);
+    } else {
+      HSG_CUDA(cudaFuncSetAttribute(estep_tc1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      estep_tc1_kernel<false><<<(unsigned)grid, TC1_THREADS, smem1, st>>>(mx, mxt, mc, mct, p);
+    }
+    HSG_LAUNCH_CHECK();
+    return HSG_OK;
+  }
   for (p.pass = 0; p.pass < p.n_pass; ++p.pass) {
     if (p.dbg_sims) {
       HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
