@@ -58,6 +58,7 @@ def parse():
   ap.add_argument('--dist', default='iid', choices=['iid', 'planted'])
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--no-cpu', action='store_true')
+  ap.add_argument('--no-extra', action='store_true', help='skip the reference-signature and NCE-backward legs')
   ap.add_argument('--cpu-images', type=int, default=3)
   return ap.parse_args()
 
@@ -161,6 +162,51 @@ def hot_path(torch, S, L, MU, emb, args, world, group):
   pid = torch.arange(protos.shape[0], device=emb.device, dtype=torch.int64)
   losses = L.segsort_loss_multi(x, ids, [bat, ids], protos, [pbatch, pid], args.concentration)
   return losses[0] + losses[1], x.shape[0]
+
+
+def hot_path_reference_signatures(torch, S, L, MU, emb, args):
+  """The same step through the REFERENCE signatures only -- exactly what hsg_b200.patch() installs and
+  the unchanged train loop calls: segment_by_kmeans -> calculate_prototypes_from_labels -> two SegSortLoss
+  calls (one [N,P] pass each; the reference has no multi-label-set entry point).  Single GPU."""
+  x, xloc, lab, ids, bat = S.segment_by_kmeans(emb, None, [args.grid, args.grid], iterations=args.iters)
+  protos = S.calculate_prototypes_from_labels(x, ids)          # host read of ids.max(), as in the reference
+  pid = torch.arange(protos.shape[0], device=emb.device, dtype=torch.int64)
+  pbatch = torch.div(pid, args.grid ** 2, rounding_mode='floor') + int(bat[0])
+  crit = L.SegSortLoss(args.concentration, group_mode='segsort+', reduction='mean')
+  return crit(x, bat, ids, protos, pbatch) + crit(x, ids, ids, protos, pid)
+
+
+def nce_backward_leg(torch, S, L, emb, args, lib, steps):
+  """NCE forward + backward on the step's own embeddings and prototypes (reported separately,
+  `value` stays forward-only).  Returns (ms per fwd+bwd, ms in the backward kernels, pixels, prototypes)."""
+  with torch.no_grad():
+    ex = S.segment_by_kmeans_ex(emb, None, [args.grid, args.grid], iterations=args.iters, count_prototypes=True)
+    protos = S.pool_prototypes(ex).detach()
+  x, ids, bat, pbatch = ex['embeddings'].detach(), ex['cluster_indices'], ex['batch_indices'], ex['proto_batch']
+  pid = torch.arange(protos.shape[0], device=emb.device, dtype=torch.int64)
+  times = []
+  bwd_ms = 0.0
+  for i in range(steps + 1):
+    xe = x.clone().requires_grad_(True)
+    pe = protos.clone().requires_grad_(True)
+    torch.cuda.synchronize()
+    if i == 1:
+      lib.hsg_profile_enable(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    losses = L.segsort_loss_multi(xe, ids, [bat, ids], pe, [pbatch, pid], args.concentration)
+    (losses[0] + losses[1]).backward()
+    ev1.record()
+    torch.cuda.synchronize()
+    if i >= 1:
+      times.append(ev0.elapsed_time(ev1))
+    del xe, pe, losses
+  tot = (ctypes.c_double * len(PHASES))()
+  cnt = (ctypes.c_longlong * len(PHASES))()
+  lib.hsg_profile_collect(tot, cnt, len(PHASES))
+  lib.hsg_profile_enable(0)
+  bwd_ms = tot[PHASES.index('nce_bwd')] / max(1, steps)
+  return float(np.mean(times)), bwd_ms, int(x.shape[0]), int(protos.shape[0])
 
 
 def run_ours(args):
@@ -274,6 +320,36 @@ def run_ours(args):
     e2e = {'value': world * n_pix * e_steps / float(dt), 'unit': 'pixel-embeddings/s',
            'h2d_bytes_per_step': int(host.numel() * 4), 'd2h_bytes_per_step': 4, 'steps': e_steps}
 
+  # ---- the same step through the reference signatures only (what patch() installs), single GPU
+  ref_sig_ms = None
+  if world == 1 and not args.no_extra:
+    with torch.no_grad():
+      hot_path_reference_signatures(torch, S, L, MU, embs[0], args)
+      torch.cuda.synchronize()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      for i in range(2):
+        hot_path_reference_signatures(torch, S, L, MU, embs[i % 2], args)
+      e1.record()
+      torch.cuda.synchronize()
+      ref_sig_ms = e0.elapsed_time(e1) / 2
+
+  # ---- NCE backward (reported separately)
+  nce_bwd = None
+  if world == 1 and not args.no_extra:
+    del embs[1]
+    torch.cuda.empty_cache()
+    fb_ms, bwd_ms, n_b, p_b = nce_backward_leg(torch, S, L, embs[0], args, lib, 2)
+    pk_b, _ = peaks()
+    flops_b = 6.0 * n_b * p_b * args.dim          # dE = G.P, dP = G^T.E (4 N P D) + recomputing S (2 N P D)
+    peak_b = pk_b.get('bf16_tflops_sustained', pk_b['bf16_tflops'])
+    tf_b = flops_b / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0
+    nce_bwd = {'kernel': 'NCE backward (recompute S tile-wise, G chunk, dE = G.P, dP = G^T.E; all on tcgen05, three fp16 passes each)',
+               'bound': 'tensor', 'achieved': tf_b, 'peak': peak_b, 'unit': 'TFLOP/s', 'frac': tf_b / peak_b,
+               'algorithmic_flops_per_launch': flops_b, 'ms_per_launch': bwd_ms, 'ms_forward_plus_backward': fb_ms,
+               'executed_tflops': 3.0 * tf_b, 'pixels': n_b, 'prototypes': p_b,
+               'note': 'not part of `value` (SURVEY 8d: forward is the metric, backward reported separately)'}
+
   if rank != 0:
     if world > 1:
       torch.distributed.destroy_process_group()
@@ -323,7 +399,7 @@ def run_ours(args):
                       'flop because the loss needs fp32-grade similarities, so executed/peak = %.2f' % (3.0 * nce_tf / peak_tf)}
   per_phase = {k: {'ms_per_step': phase_ms[k] / args.steps, 'ranges': phase_n[k]} for k in PHASES if phase_n[k]}
 
-  cpu = None if args.no_cpu else cpu_baseline(args)
+  cpu = None if (args.no_cpu or world > 1) else cpu_baseline(args, global_images * args.grid ** 2)
   out = {
       'metric': 'pixel-embeddings/sec spherical-kmeans+NCE (448^2, D=256, K=256)',
       'value': value, 'unit': 'pixel-embeddings/s', 'n_gpus': world, 'steps': args.steps,
@@ -349,7 +425,12 @@ def run_ours(args):
       'nce_pairs_per_s_per_gpu': (n_pix * float(world * args.images * args.grid ** 2) /
                                   (phase_ms['nce_fwd'] / args.steps * 1e-3)) if phase_ms['nce_fwd'] > 0 else None,
       'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
-      'roofline': roofline, 'roofline_kmeans': roofline_kmeans, 'phases': per_phase, 'cpu_baseline': cpu, 'loss': float(loss),
+      'roofline': roofline, 'roofline_kmeans': roofline_kmeans, 'roofline_nce_bwd': nce_bwd,
+      'reference_signature_path': ({'ms_per_step': ref_sig_ms, 'value': n_pix / (ref_sig_ms * 1e-3), 'unit': 'pixel-embeddings/s',
+                                    'note': 'same step through segment_by_kmeans / calculate_prototypes_from_labels / SegSortLoss x2 '
+                                            '(the signatures patch() installs); the default path uses the extended entry points'}
+                                   if ref_sig_ms else None),
+      'phases': per_phase, 'cpu_baseline': cpu, 'loss': float(loss),
   }
   line = json.dumps(out) + '\n'
   if json_fd is not None:
@@ -362,58 +443,103 @@ def run_ours(args):
     torch.distributed.destroy_process_group()
 
 
-# ------------------------------------------------------------------ CPU arm (oracle port)
-def cpu_workload(args, images):
-  """The same path on the host cores through the numpy restatement of the
-  reference (oracle/), on a bounded sample: `images` images for the k-means +
-  pooling part, 4096 pixels against all prototypes for the NCE part."""
-  from oracle import ops as o_ops, loss as o_loss
-  rng = np.random.RandomState(235)
-  s, d, g = args.size, args.dim, args.grid
-  emb = rng.standard_normal((images, d, s, s)).astype(np.float32)
-  t0 = time.perf_counter()
-  x, xloc, lab, ids, bat = o_ops.segment_by_kmeans(emb, None, (g, g), iterations=args.iters)
-  protos = o_ops.calculate_prototypes_from_labels(x, ids)
-  t_cluster = time.perf_counter() - t0
-  p_total = args.images * g * g
-  pr = o_ops.normalize_embedding(rng.standard_normal((p_total, d)).astype(np.float32))
-  pr[:protos.shape[0]] = protos
-  pb = np.arange(p_total) // (g * g)
-  n_s = 4096
-  t0 = time.perf_counter()
-  o_loss.calculate_log_likelihood(x[:n_s], bat[:n_s], ids[:n_s], pr, pb, args.concentration)
-  o_loss.calculate_log_likelihood(x[:n_s], ids[:n_s], ids[:n_s], pr, np.arange(p_total), args.concentration)
-  t_nce = time.perf_counter() - t0
-  per_pixel = t_cluster / (images * s * s) + t_nce / n_s
-  return 1.0 / per_pixel, t_cluster, t_nce
+# ------------------------------------------------------------------ CPU arm
+def _reference_cpu_ops():
+  """The reference's own functions from baseline/_ref (tools/install_reference.py), or None."""
+  sys.path.insert(0, os.path.join(ROOT, 'tests'))
+  try:
+    import refenv
+    if not refenv.available():
+      return None
+    refenv.activate()
+    import hsg.utils.segsort.common as rc
+    import hsg.utils.segsort.loss as rl
+    if rc.calculate_prototypes_from_labels.__module__.startswith('hsg_b200'):
+      return None
+    return {'segment_by_kmeans': refenv.cpu_segment_by_kmeans(), 'prototypes': rc.calculate_prototypes_from_labels,
+            'loss': rl.SegSortLoss}
+  except Exception as e:                       # noqa: BLE001 -- fall back to the port and say so
+    sys.stderr.write('reference CPU arm unavailable (%s): timing the oracle port\n' % e)
+    return None
 
 
-def cpu_baseline(args):
+def cpu_workload(args, images, p_total):
+  """The same path on the host cores, on a bounded sample of the workload: `images` images for the
+  k-means + pooling part, 4096 pixels against all `p_total` prototypes for the NCE part (two label sets).
+  Runs the reference's own torch-CPU functions (kind "reference") when baseline/_ref is present, else the
+  numpy restatement under oracle/ (kind "port").  Returns (pixel-embeddings/s, t_cluster, t_nce, kind, threads)."""
   import torch
-  value, t_c, t_n = cpu_workload(args, args.cpu_images)
-  return {'value': value, 'unit': 'pixel-embeddings/s', 'cores': os.cpu_count(), 'kind': 'port',
-          'threads': torch.get_num_threads(),
-          'sample': 'oracle (numpy restatement of the reference, BLAS threads = host cores): k-means+pooling on '
-                    '%d image(s) of the workload (%.1f s), NCE (2 label sets) on 4096 pixels x %d prototypes '
-                    '(%.1f s); per-pixel times added' % (args.cpu_images, t_c, args.images * args.grid ** 2, t_n)}
+  s, d, g = args.size, args.dim, args.grid
+  n_s = 4096
+  ref = _reference_cpu_ops()
+  if ref is not None:
+    torch.set_num_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1
+    gen = torch.Generator().manual_seed(235)
+    emb = torch.randn((images, d, s, s), generator=gen)
+    with torch.no_grad():
+      t0 = time.perf_counter()
+      x, xloc, lab, ids, bat = ref['segment_by_kmeans'](emb, None, [g, g], iterations=args.iters)
+      protos = ref['prototypes'](x, ids)
+      t_cluster = time.perf_counter() - t0
+      pr = torch.nn.functional.normalize(torch.randn((p_total, d), generator=gen), dim=1)
+      pr[:protos.shape[0]] = protos
+      pb = torch.arange(p_total) // (g * g)
+      crit = ref['loss'](args.concentration, group_mode='segsort+', reduction='mean')
+      t0 = time.perf_counter()
+      crit(x[:n_s], bat[:n_s], ids[:n_s], pr, pb)
+      crit(x[:n_s], ids[:n_s], ids[:n_s], pr, torch.arange(p_total))
+      t_nce = time.perf_counter() - t0
+    kind, threads = 'reference', torch.get_num_threads()
+  else:
+    from oracle import ops as o_ops, loss as o_loss
+    rng = np.random.RandomState(235)
+    emb = rng.standard_normal((images, d, s, s)).astype(np.float32)
+    t0 = time.perf_counter()
+    x, xloc, lab, ids, bat = o_ops.segment_by_kmeans(emb, None, (g, g), iterations=args.iters)
+    protos = o_ops.calculate_prototypes_from_labels(x, ids)
+    t_cluster = time.perf_counter() - t0
+    pr = o_ops.normalize_embedding(rng.standard_normal((p_total, d)).astype(np.float32))
+    pr[:protos.shape[0]] = protos
+    pb = np.arange(p_total) // (g * g)
+    t0 = time.perf_counter()
+    o_loss.calculate_log_likelihood(x[:n_s], bat[:n_s], ids[:n_s], pr, pb, args.concentration)
+    o_loss.calculate_log_likelihood(x[:n_s], ids[:n_s], ids[:n_s], pr, np.arange(p_total), args.concentration)
+    t_nce = time.perf_counter() - t0
+    kind, threads = 'port', os.cpu_count()
+  per_pixel = t_cluster / (images * s * s) + t_nce / n_s
+  return 1.0 / per_pixel, t_cluster, t_nce, kind, threads
+
+
+def _cpu_sample_text(kind, images, p_total, t_c, t_n):
+  who = ('the reference\'s own torch-CPU functions (baseline/_ref: segment_by_kmeans, calculate_prototypes_from_labels, '
+         'SegSortLoss)' if kind == 'reference' else 'oracle (numpy restatement of the reference)')
+  return ('%s: k-means+pooling on %d image(s) of the workload (%.1f s), NCE (2 label sets) on 4096 pixels x %d '
+          'prototypes (%.1f s); per-pixel times added' % (who, images, t_c, p_total, t_n))
+
+
+def cpu_baseline(args, p_total):
+  value, t_c, t_n, kind, threads = cpu_workload(args, args.cpu_images, p_total)
+  return {'value': value, 'unit': 'pixel-embeddings/s', 'cores': os.cpu_count(), 'kind': kind, 'threads': threads,
+          'sample': _cpu_sample_text(kind, args.cpu_images, p_total, t_c, t_n)}
 
 
 def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
+  p_total = args.images * args.grid ** 2                  # configs[1]: the whole global batch's prototypes
   vals = []
   for i in range(args.warmup + args.steps):
     t0 = time.perf_counter()
-    v, t_c, t_n = cpu_workload(args, args.cpu_images)
+    v, t_c, t_n, kind, threads = cpu_workload(args, args.cpu_images, p_total)
     if i >= args.warmup:
       vals.append((v, time.perf_counter() - t0, t_c, t_n))
   value = float(np.mean([v[0] for v in vals]))
   ms = float(np.mean([v[1] for v in vals])) * 1e3
   n_pix = args.images * args.size * args.size
-  cpu = {'value': value, 'unit': 'pixel-embeddings/s', 'cores': os.cpu_count(), 'kind': 'port',
-         'sample': 'each step = oracle k-means+pooling on %d image(s) + NCE on 4096 pixels x %d prototypes; '
-                   'per-pixel times added' % (args.cpu_images, args.images * args.grid ** 2)}
+  cpu = {'value': value, 'unit': 'pixel-embeddings/s', 'cores': os.cpu_count(), 'kind': kind, 'threads': threads,
+         'sample': 'each step = ' + _cpu_sample_text(kind, args.cpu_images, p_total, float(np.mean([v[2] for v in vals])),
+                                                     float(np.mean([v[3] for v in vals])))}
   out = {
       'impl': 'reference',
       'metric': 'pixel-embeddings/sec spherical-kmeans+NCE (448^2, D=256, K=256)',

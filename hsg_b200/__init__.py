@@ -57,7 +57,7 @@ _LOSS_MODULES = ['hsg.models.predictions.hsg', 'hsg.models.predictions.hsg_cs']
 def _patch_methods(importlib):
   from .models.embeddings import hierarchy
   from .models.predictions import hsg as loss_head
-  tables = [(m, hierarchy.METHODS) for m in _METHOD_MODULES]
+  tables = [(m, hierarchy.METHODS_CS if m.endswith('_cs') else hierarchy.METHODS) for m in _METHOD_MODULES]
   tables += [(m, {'Hsg': {'losses': loss_head.losses_cs if m.endswith('_cs') else loss_head.losses}})
              for m in _LOSS_MODULES]
   from .models.predictions import segsort as retrieval_head

@@ -45,6 +45,7 @@ SIGNATURES = {
     'hsg_profile_enable': (_i, [_i]),
     'hsg_profile_collect': (_i, [_p, _p, _i]),
     'hsg_debug_set_tc_dump': (_i, [_p]),
+    'hsg_debug_set_tc_clock': (_i, [_p]),
     'hsg_debug_set_flags': (_i, [_i]),
     'hsg_normalize_f32': (_i, [_p, _p, _l, _i, _p]),
     'hsg_normalize_bwd_f32': (_i, [_p, _p, _p, _l, _i, _p]),

@@ -12,6 +12,7 @@
 #include "kmeans.cuh"
 
 #include <float.h>
+#include <stdlib.h>
 
 namespace hsg {
 
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(ES_THREADS) estep_simt_kernel(const EStepArgs 
       const int slot = atomicAdd(a.fix.count, 1);
       if (slot < a.fix.capacity) {
         a.fix.pixels[slot] = (int32_t)pix;
+        a.fix.segs[slot] = seg;
         if (a.fix.cand) a.fix.cand[(int64_t)slot * FIX_MAX_CAND] = 0xFFFF;
         atomicAdd(a.fix.count + 1, 1);
       }
@@ -209,6 +211,125 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) estep_fixup_kernel(const EStep
   }
 }
 
+// Eight lanes per listed pixel, four pixels per warp.  The warp-per-pixel kernel above is latency
+// bound (r2 measurement at the benchmark shape: 1.3 pixels/ns = 1.4 TB/s of row reads, each warp
+// walking pixel id -> segment search -> row -> candidate rows one dependent round trip after the
+// other).  Here the segment comes with the list entry, a warp has four rows and their candidate
+// centroid rows in flight at once, and rows are read as float2 when dim is even.  Same rule: fixed
+// order float64 dot products (lane-strided partials, xor tree over the 8 lanes), ties to the lowest
+// index.  Entries that ask for a scan of every cluster are handed to the whole warp afterwards.
+template <int NV, int VEC>
+__device__ __forceinline__ void fix8_load(const float* __restrict__ row, int dim, int sub, bool on, float (&v)[NV * VEC]) {
+#pragma unroll
+  for (int m = 0; m < NV; ++m) {
+    const int i = (sub + 8 * m) * VEC;
+    if (VEC == 2) {
+      float2 t = make_float2(0.f, 0.f);
+      if (on && i < dim) t = *reinterpret_cast<const float2*>(row + i);     // dim even: i + 1 < dim too
+      v[2 * m] = t.x; v[2 * m + 1] = t.y;
+    } else {
+      v[m] = (on && i < dim) ? row[i] : 0.f;
+    }
+  }
+}
+
+// fp32 dot product and sum of |x_d c_d| over the 8 lanes of a group (lane-strided FMA chains, xor tree)
+template <int NV, int VEC>
+__device__ __forceinline__ void fix8_dot32(const float (&x)[NV * VEC], const float (&c)[NV * VEC], float& dot, float& mag) {
+  float s = 0.f, a = 0.f;
+#pragma unroll
+  for (int m = 0; m < NV * VEC; ++m) { s = fmaf(x[m], c[m], s); a = fmaf(fabsf(x[m]), fabsf(c[m]), a); }
+  s += __shfl_xor_sync(FULL, s, 4); a += __shfl_xor_sync(FULL, a, 4);
+  s += __shfl_xor_sync(FULL, s, 2); a += __shfl_xor_sync(FULL, a, 2);
+  s += __shfl_xor_sync(FULL, s, 1); a += __shfl_xor_sync(FULL, a, 1);
+  dot = s; mag = a;
+}
+
+// Two stages.  (1) fp32: every candidate's dot product comes with a rigorous bound on its rounding error,
+// gamma_n * sum|x_d c_d| with n = the longest chain of roundings (NV*VEC fused multiply-adds + 3 tree adds),
+// computed from the actual rows (no unit-norm assumption).  When the best candidate's interval lies strictly
+// above every other one's, it is the arg-max of the exact -- hence of the float64 -- products and the row is
+// decided without a single fp32->fp64 conversion (r2: those conversions, 816 per row on the quarter-rate XU
+// pipe, were 45 % of this kernel).  (2) the few rows that stay undecided (gap below ~5e-6, exact duplicates,
+// "scan every cluster" entries) go through fixed-order float64 dot products, ties to the lowest index.
+template <int NV, int VEC>
+__global__ void __launch_bounds__(FIX_WARPS * 32, 4) estep_fixup8_kernel(const EStepArgs a, const int exp_flags) {
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  const int total = (int)min((int64_t)*a.fix.count, a.fix.capacity);
+  const int stride = gridDim.x * FIX_WARPS * 4;
+  constexpr float GAMMA = (float)(NV * VEC + 3 + 2) * 5.9604645e-8f * 1.01f;   // +2: the bound itself is computed in fp32
+  for (int e0 = (blockIdx.x * FIX_WARPS + (threadIdx.x >> 5)) * 4; e0 < total; e0 += stride) {
+    const int e = e0 + grp;
+    const bool act = e < total;
+    const int64_t pix = act ? a.fix.pixels[e] : 0;
+    const int seg = act ? a.fix.segs[e] : 0;
+    float xr[NV * VEC];
+    fix8_load<NV, VEC>(a.x + pix * a.dim, a.dim, sub, act && !(exp_flags & 1), xr);
+    const uint16_t* cand = a.fix.cand + (int64_t)e * FIX_MAX_CAND;
+    // the eight candidate slots of the entry: lane `sub` of the group reads slot `sub`
+    int mine = (act && a.fix.cand) ? (int)cand[sub] : 0xFFFF;
+    const int first = __shfl_sync(FULL, mine, grp * 8);
+    const bool all = act && first == 0xFFFF;
+    // slots after the first 0xFFFF are not part of the list
+    const unsigned ends = __ballot_sync(FULL, mine == 0xFFFF) >> (grp * 8) & 0xFFu;
+    const int ncand = all ? 0 : (ends ? __ffs(ends) - 1 : FIX_MAX_CAND);
+    const int K = a.seg_k ? a.seg_k[seg] : a.kmax;
+    const float* cbase = a.centroids + (int64_t)seg * a.kmax * a.dim;
+    float bv = -FLT_MAX, be = 0.f, others_hi = -FLT_MAX;     // best value, its error bound, upper end of the rest
+    int bi = 0x7fffffff;
+    for (int c = 0; c < FIX_MAX_CAND; c += 2) {
+      if (!__any_sync(FULL, c < ncand)) break;
+      const int k0 = __shfl_sync(FULL, mine, grp * 8 + c);
+      const int k1 = __shfl_sync(FULL, mine, grp * 8 + c + 1);
+      const bool on0 = c < ncand && k0 < K, on1 = c + 1 < ncand && k1 < K;
+      float c0[NV * VEC], c1[NV * VEC];
+      fix8_load<NV, VEC>(cbase + (int64_t)min(k0, K - 1) * a.dim, a.dim, sub, on0 && !(exp_flags & 2), c0);
+      fix8_load<NV, VEC>(cbase + (int64_t)min(k1, K - 1) * a.dim, a.dim, sub, on1 && !(exp_flags & 2), c1);
+      float s0, a0, s1, a1;
+      fix8_dot32<NV, VEC>(xr, c0, s0, a0);
+      fix8_dot32<NV, VEC>(xr, c1, s1, a1);
+      const float e0b = a0 * GAMMA + 1e-37f, e1b = a1 * GAMMA + 1e-37f;
+      if (on0) {
+        if (s0 > bv) { others_hi = fmaxf(others_hi, bv + be); bv = s0; be = e0b; bi = k0; }
+        else others_hi = fmaxf(others_hi, s0 + e0b);
+      }
+      if (on1) {
+        if (s1 > bv) { others_hi = fmaxf(others_hi, bv + be); bv = s1; be = e1b; bi = k1; }
+        else others_hi = fmaxf(others_hi, s1 + e1b);
+      }
+    }
+    const bool decided = act && !all && bi != 0x7fffffff && (bv - be > others_hi);
+    if (decided && sub == 0) a.keys_out[pix] = seg * a.kmax + bi;
+
+    // the rest (rare): float64, the whole warp on one entry at a time
+    unsigned slow = __ballot_sync(FULL, act && !decided && sub == 0);
+    while (slow) {
+      const int src = __ffs(slow) - 1;
+      slow &= slow - 1;
+      const int64_t apix = __shfl_sync(FULL, pix, src);
+      const int aseg = __shfl_sync(FULL, seg, src);
+      const bool aall = __shfl_sync(FULL, (int)all, src) != 0;
+      const int anc = __shfl_sync(FULL, ncand, src);
+      const int aK = a.seg_k ? a.seg_k[aseg] : a.kmax;
+      const float* ab = a.centroids + (int64_t)aseg * a.kmax * a.dim;
+      const float* xrow = a.x + apix * a.dim;
+      double abv = -DBL_MAX;
+      int abi = 0x7fffffff;
+      const int n_it = aall ? aK : anc;
+      for (int it = 0; it < n_it; ++it) {
+        const int k = aall ? it : __shfl_sync(FULL, mine, src + it);      // src is lane 0 of its group
+        if (k >= aK) continue;                                             // warp-uniform
+        const float* cr = ab + (int64_t)k * a.dim;
+        double sacc = 0.0;
+        for (int d = lane; d < a.dim; d += 32) sacc = fma((double)xrow[d], (double)cr[d], sacc);
+        sacc = warp_sum(sacc);
+        if (sacc > abv || (sacc == abv && k < abi)) { abv = sacc; abi = k; }
+      }
+      if (lane == 0) a.keys_out[apix] = aseg * a.kmax + abi;
+    }
+  }
+}
+
 int estep_simt(const EStepArgs& a, cudaStream_t st) {
   // |fl(dot) - dot| <= gamma_dim * sum|x_d c_d| <= dim*2^-24*(1+tiny) for unit rows;
   // two such errors can reorder a pair, so re-decide below twice that (plus slack).
@@ -220,6 +341,19 @@ int estep_simt(const EStepArgs& a, cudaStream_t st) {
 }
 
 int estep_fixup(const EStepArgs& a, cudaStream_t st) {
+  static const bool legacy = getenv("HSG_FIXUP_LEGACY") != nullptr;     // A/B switch for profiling only
+  static const int fexp = getenv("HSG_FIXUP_EXP") ? atoi(getenv("HSG_FIXUP_EXP")) : 0;     // timing experiments only
+  const bool aligned8 = (a.dim % 2 == 0) && ((uintptr_t)a.x % 8 == 0) && ((uintptr_t)a.centroids % 8 == 0);
+  if (!legacy && a.fix.cand && aligned8 && a.dim <= 272) {
+    estep_fixup8_kernel<17, 2><<<num_sms() * 4, FIX_WARPS * 32, 0, st>>>(a, fexp);
+    HSG_LAUNCH_CHECK();
+    return HSG_OK;
+  }
+  if (!legacy && a.fix.cand && a.dim <= 136) {
+    estep_fixup8_kernel<17, 1><<<num_sms() * 4, FIX_WARPS * 32, 0, st>>>(a, fexp);
+    HSG_LAUNCH_CHECK();
+    return HSG_OK;
+  }
   if (a.dim <= 32 * 9)
     estep_fixup_kernel<9><<<num_sms() * 16, FIX_WARPS * 32, 0, st>>>(a);
   else
@@ -270,6 +404,7 @@ static void km_carve(Carver& c, KmPlan& p, int64_t N, int dim, int S, int kmax, 
   p.fix.count = c.take<int32_t>(2);    // [0] listed pixels, [1] of those: scans over every cluster
   p.fix.capacity = N;
   p.fix.pixels = c.take<int32_t>(N);
+  p.fix.segs = c.take<int32_t>(N);
   p.fix.cand = c.take<uint16_t>(N * FIX_MAX_CAND);
   tc_carve(c, p.tc, S, kmax, d16 > 0 ? d16 : 64, N);
   // delta plan: own tiles / keys / float64 pieces, everything else aliases the full plan (only

@@ -9,6 +9,7 @@ namespace hsg {
 struct FixList {
   int32_t* count;      // [1]
   int32_t* pixels;     // [capacity]
+  int32_t* segs;       // [capacity] segment of each listed pixel
   uint16_t* cand;      // [capacity * FIX_MAX_CAND] candidate local ids, 0xFFFF-terminated;
                        // first entry 0xFFFF = "all clusters"; NULL = always all
   int64_t capacity;
@@ -51,6 +52,8 @@ struct TcState {
   unsigned char tmap_xt[128];//   centroid main slabs / tail slab
   unsigned char tmap_c[128];
   unsigned char tmap_ct[128];
+  unsigned char tmap_c2[128];  // centroid boxes of kpad/2 rows (CTA-pair kernel)
+  unsigned char tmap_ct2[128];
 };
 bool tc_shape_supported(int dim, int d16, int kmax);
 void tc_carve(Carver& c, TcState& t, int S, int kmax, int d16, int64_t N);

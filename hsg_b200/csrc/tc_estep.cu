@@ -25,6 +25,7 @@
 
 #include <float.h>
 #include <stdlib.h>
+#include <cfloat>
 
 namespace hsg {
 
@@ -54,6 +55,13 @@ struct TcParams {
   FixList fix;
   int nst;                   // pipeline stages
   float* dbg_sims;           // optional [N,kmax] dump of the screening values
+  const __half* xh;          // the fp16 side copy itself (L2 prefetch of whole tiles)
+  const float* x32;          // fp32 rows [N,dim32] and centroids [S,kmax,dim32] for the in-kernel re-decision
+  const float* c32;          //   (dim32 <= 288; NULL = list everything)
+  int dim32;
+  long long* dbg_clk;        // [grid,4 roles,3] cycle counters of the timing experiment
+  int exp_flags;             // timing experiments (HSG_TC_EXP), 0 in production
+  int pf_dist;               // single-pass kernel: pixel tiles prefetched into L2 ahead of the ring
 };
 
 __device__ __forceinline__ bool item_rows(const TcParams& p, long long item, int count, int& seg,
@@ -355,6 +363,7 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int slot = slot_base + __popc(amb_mask & ((1u << lane) - 1u));
         if (slot < p.fix.capacity) {
           p.fix.pixels[slot] = (int32_t)pix;
+            p.fix.segs[slot] = seg;
           uint16_t* cd = p.fix.cand + (int64_t)slot * FIX_MAX_CAND;
           if (!many) {                               // everything but the top two is provably out of reach
             cd[0] = (uint16_t)kb; cd[1] = (uint16_t)ks; cd[2] = 0xFFFF;
@@ -406,6 +415,8 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 // surviving bit is decided; the others are listed with every surviving column as candidate.
 // 1.5 ALU-pipe instructions per similarity instead of 6.5, no cross-thread merge, no named barriers.
 constexpr int TC1_THREADS = 384;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
+constexpr int TC1_PF_DIST = 0;          // pixel tiles prefetched into L2 ahead of the ring (4 x 70 KB x 148 SMs = 41 MB)
+constexpr int TC1_INLINE = 2;           // ambiguous rows a warp settles itself per tile (the rest is listed)
 constexpr float TC1_EPS_CONST = 3.3e-5f; // accumulation (3e-5) + split tail (1e-6) + slack for the fp32 threshold arithmetic
 
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -483,15 +494,33 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   const int count = *p.tiles.count;
-  const long long i_begin = p.items * blockIdx.x / gridDim.x;
-  const long long i_end = p.items * (blockIdx.x + 1) / gridDim.x;
+  // CTA -> tiles: one contiguous range per CTA (fewest centroid reloads), or, with HSG_TC_EXP & 4, interleaved
+  // (CTA b takes tiles b, b + grid, ...; measured 5 % slower at the benchmark shape)
+  const bool contiguous = (p.exp_flags & 4) == 0;
+  const long long i_begin = contiguous ? p.items * blockIdx.x / gridDim.x : blockIdx.x;
+  const long long i_end = contiguous ? p.items * (blockIdx.x + 1) / gridDim.x : p.items;
+  const long long i_step = contiguous ? 1 : gridDim.x;
+  // timing experiment (HSG_TC_EXP & 2, tools/estep_timeline.py): cycles each role spends waiting
+  const bool timing = (p.exp_flags & 2) && p.dbg_clk;
+  long long t_wait0 = 0, t_wait1 = 0;
+  const long long t_begin = timing ? clock64() : 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0, cur_seg = -1, tl = 0, last_tl = 0;
       uint32_t phase = 0, tl_phase = 0, last_tl_phase = 0;
-      for (long long item = i_begin; item < i_end; ++item) {
+      // The shared-memory ring (4 stages next to 136 KiB of centroids) holds too few bytes to cover DRAM
+      // latency at full bandwidth (r2 ncu: tensor 58 %, DRAM 51 %, the MMA warp waiting on `full`), so the
+      // tiles TC1_PF_DIST ahead are pulled into L2 first: the ring then only has to cover L2 latency.
+      auto prefetch_item = [&](long long it2) {
+        int seg2, np2; int64_t r2;
+        if (it2 < i_end && item_rows(p, it2, count, seg2, r2, np2))      // the tile's rows are one contiguous range
+          bulk_prefetch_l2(p.xh + r2 * (p.d16 + HSG_XH_TAIL), (uint32_t)np2 * (uint32_t)(p.d16 + HSG_XH_TAIL) * 2u);
+      };
+      for (int d = 0; d < p.pf_dist; ++d) prefetch_item(i_begin + d * i_step);
+      for (long long item = i_begin; item < i_end; item += i_step) {
+        if (p.pf_dist > 0) prefetch_item(item + p.pf_dist * i_step);
         int seg, np; int64_t row0;
         if (!item_rows(p, item, count, seg, row0, np)) continue;
         if (seg != cur_seg) {
@@ -504,14 +533,20 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           cur_seg = seg;
         }
         for (int j = 0; j < nslab; ++j) {
+          const long long c0 = timing ? clock64() : 0;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (timing) t_wait0 += clock64() - c0;
           mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
           tma_load_2d(sA + stage * TC_STAGE_BYTES, &tmap_x, j * TC_BK, (int)row0, bar_full + 8 * stage);
           if (++stage == p.nst) { stage = 0; phase ^= 1; }
         }
         mbar_wait(bar_tlempty + 8 * tl, tl_phase ^ 1);
-        mbar_expect_tx(bar_tlfull + 8 * tl, TC_TAIL_BYTES);
-        tma_load_2d(sAT + tl * TC_TAIL_BYTES, &tmap_xt, p.d16, (int)row0, bar_tlfull + 8 * tl);
+        if (p.exp_flags & 1) {                         // timing experiment only: no tail slab
+          mbar_arrive(bar_tlfull + 8 * tl);
+        } else {
+          mbar_expect_tx(bar_tlfull + 8 * tl, TC_TAIL_BYTES);
+          tma_load_2d(sAT + tl * TC_TAIL_BYTES, &tmap_xt, p.d16, (int)row0, bar_tlfull + 8 * tl);
+        }
         last_tl = tl; last_tl_phase = tl_phase;
         if (++tl == 2) { tl = 0; tl_phase ^= 1; }
       }
@@ -522,7 +557,7 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.kpad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0, cur_seg = -1, acc = 0, tl = 0;
       uint32_t phase = 0, bcount = 0, tl_phase = 0, acc_phase0 = 0, acc_phase1 = 0;
-      for (long long item = i_begin; item < i_end; ++item) {
+      for (long long item = i_begin; item < i_end; item += i_step) {
         int seg, np; int64_t row0;
         if (!item_rows(p, item, count, seg, row0, np)) continue;
         if (seg != cur_seg) {
@@ -530,11 +565,15 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           ++bcount;
           cur_seg = seg;
         }
+        long long c0 = timing ? clock64() : 0;
         mbar_wait(bar_tempty + 8 * acc, (acc ? acc_phase1 : acc_phase0) ^ 1);
+        if (timing) t_wait1 += clock64() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int j = 0; j < nslab; ++j) {
+          c0 = timing ? clock64() : 0;
           mbar_wait(bar_full + 8 * stage, phase);
+          if (timing) t_wait0 += clock64() - c0;
           tc_fence_after();
           const uint64_t ad = umma_desc(sA + stage * TC_STAGE_BYTES, 1024, 2);
           const uint64_t bd = umma_desc(sB + j * slab_b_bytes, 1024, 2);
@@ -546,7 +585,8 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
         mbar_wait(bar_tlfull + 8 * tl, tl_phase);
         tc_fence_after();
-        tc_mma_f16(d_tmem, umma_desc(sAT + tl * TC_TAIL_BYTES, 256, 6), umma_desc(sBT, 256, 6), idesc, 1u);
+        if (!(p.exp_flags & 1))
+          tc_mma_f16(d_tmem, umma_desc(sAT + tl * TC_TAIL_BYTES, 256, 6), umma_desc(sBT, 256, 6), idesc, 1u);
         tc_commit(bar_tlempty + 8 * tl);
         if (++tl == 2) { tl = 0; tl_phase ^= 1; }
         tc_commit(bar_tfull + 8 * acc);
@@ -564,7 +604,7 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     int cur_seg = -1, seq = 0;
     uint32_t acc_phase = 0;
     float cerrmax = 0.f;
-    for (long long item = i_begin; item < i_end; ++item) {
+    for (long long item = i_begin; item < i_end; item += i_step) {
       int seg, np; int64_t row0;
       if (!item_rows(p, item, count, seg, row0, np)) continue;
       if (((seq++) & 1) != g) continue;
@@ -574,9 +614,12 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const float xe = inb ? p.xerr[pix] : 0.f;
       const float thr = 2.f * (xe * 1.001f + cerrmax * 1.001f + TC1_EPS_CONST);
 
+      long long c0 = timing ? clock64() : 0;
       mbar_wait(bar_tfull + 8 * g, acc_phase);
+      if (timing) { const long long c1 = clock64(); t_wait0 += c1 - c0; c0 = c1; }
       tc_fence_after();
       const uint32_t trow = tmem_base + g * 256 + ((uint32_t)(32 * q) << 16);
+      const int kpad_eff = (p.exp_flags & 8) ? kpad / 2 : kpad;   // timing experiment: half of the TMEM sweep
       float run = -FLT_MAX;
       float cm[8];
       uint32_t mk[8];
@@ -585,11 +628,12 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         cm[c] = -FLT_MAX; mk[c] = 0xFFFFFFFFu;
-        if (c * 32 < kpad) {                                     // warp-uniform
+        if (c * 32 < kpad_eff) {                                 // warp-uniform
           uint32_t (&v)[32] = (c & 1) ? vb : va;
           uint32_t (&nx)[32] = (c & 1) ? va : vb;
           tc_ld_wait();
-          if ((c + 1) * 32 < kpad) tc1_load(trow, c + 1, kpad, nx);   // in flight while chunk c is reduced
+          if ((c + 1) * 32 < kpad_eff) tc1_load(trow, c + 1, kpad, nx);   // in flight while chunk c is reduced
+          if ((p.exp_flags & 16) && (c & 1)) continue;            // timing experiment: TMEM loads without the arithmetic
           if (DUMP) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -620,6 +664,7 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * g);
       acc_phase ^= 1;
+      if (timing) t_wait1 += clock64() - c0;          // sweep
 
       const float t_final = run - thr;
       int cnt = 0, first = 0;
@@ -630,8 +675,43 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (cnt == 0 && hits) first = c * 32 + __clz(hits);
         cnt += __popc(hits);
       }
-      const bool amb = inb && cnt > 1;
+      bool amb = inb && cnt > 1;
       if (inb) p.keys_out[pix] = seg * p.kmax + first;
+      // Ambiguous rows.  The kernel is paced by the tensor pipe and this warp idles ~2/3 of a tile period, so up
+      // to TC1_INLINE rows per warp and tile are settled right here (same rule as estep_fixup: float64 dot
+      // products of the fp32 row with the fp32 centroids of the listed candidates, fixed order, ties to the
+      // lowest index); the rest -- the bulk of the first two iterations -- goes to the list as before.
+      if (p.x32) {
+        unsigned todo = __ballot_sync(FULL, amb && cnt <= FIX_MAX_CAND);
+        for (int n_in = 0; todo && n_in < TC1_INLINE; ++n_in) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int64_t apix = __shfl_sync(FULL, pix, src);
+          const float* xrow = p.x32 + apix * p.dim32;
+          const float* cbase = p.c32 + (int64_t)seg * p.kmax * p.dim32;
+          float xr[9];
+#pragma unroll
+          for (int m = 0; m < 9; ++m) { const int d = lane + 32 * m; xr[m] = d < p.dim32 ? ld_stream(xrow + d) : 0.f; }
+          double bv = -DBL_MAX;
+          int bi = 0x7fffffff;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t hits = __shfl_sync(FULL, mk[c], src);
+            while (hits) {
+              const int jb = __clz(hits);
+              hits &= ~(0x80000000u >> jb);
+              const int k = c * 32 + jb;
+              const float* cr = cbase + (int64_t)min(k, p.kmax - 1) * p.dim32;
+              double sacc = 0.0;
+#pragma unroll
+              for (int m = 0; m < 9; ++m) { const int d = lane + 32 * m; if (d < p.dim32) sacc = fma((double)xr[m], (double)cr[d], sacc); }
+              sacc = warp_sum(sacc);
+              if (k < p.kmax && (sacc > bv || (sacc == bv && k < bi))) { bv = sacc; bi = k; }
+            }
+          }
+          if (lane == src) { p.keys_out[pix] = seg * p.kmax + bi; amb = false; }
+        }
+      }
       // one atomic per warp for the list slots (the counter is a single address shared by every SM)
       const unsigned amb_mask = __ballot_sync(FULL, amb);
       if (amb_mask) {
@@ -642,6 +722,7 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           const int slot = slot_base + __popc(amb_mask & ((1u << lane) - 1u));
           if (slot < p.fix.capacity) {
             p.fix.pixels[slot] = (int32_t)pix;
+            p.fix.segs[slot] = seg;
             uint16_t* cd = p.fix.cand + (int64_t)slot * FIX_MAX_CAND;
             if (cnt > FIX_MAX_CAND) {
               cd[0] = 0xFFFF;                        // too many to list: scan every cluster
@@ -665,11 +746,301 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
   }
 
+  if (timing && lane == 0 && (warp <= 1 || warp == 4 || warp == 8)) {
+    const int role = warp <= 1 ? warp : (warp == 4 ? 2 : 3);     // producer, MMA, epilogue acc 0, epilogue acc 1
+    long long* o = p.dbg_clk + ((long long)blockIdx.x * 4 + role) * 3;
+    o[0] = clock64() - t_begin; o[1] = t_wait0; o[2] = t_wait1;
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+  }
+}
+
+// ---------------------------------------------------------------- CTA-pair kernel (kpad a multiple of 32)
+// r2 timeline of the single-CTA kernel above (tools/estep_timeline.py): the MMA issuer waits < 12 % of the
+// time, the epilogue can be cut in half without changing the tile time, and yet a tile takes 3 850 cycles
+// instead of the 2 176 seventeen 128x256x16 MMAs need: every MMA streams 12 KB of operands out of shared
+// memory (4 KB of pixels + 8 KB of centroids) and that read rate, not the tensor pipe, paces it.  A
+// cta_group::2 tile of 256 pixels x 256 centroids reads 8 KB per CTA instead: each CTA keeps its own 128
+// pixel rows and HALF of the centroids, the tensor cores fetch the other half from the peer's shared
+// memory.  It also frees 68 KB for the pixel ring (9 stages instead of 4).  Plumbing as in the NCE forward
+// (nce_tc.cu): the leader (cluster rank 0) issues every MMA, both CTAs run a TMA producer crediting the
+// leader's "full" barriers, commits are multicast, each CTA's epilogue drains its own 128 TMEM lanes.
+__device__ __forceinline__ bool pair_item_rows(const TcParams& p, long long item, int count, uint32_t rank,
+                                               int& seg, int64_t& row0, int& np) {
+  const int sub2 = p.sub >> 1;                       // 256-pixel items per tile
+  const int ti = (int)(item / sub2);
+  if (ti >= count) return false;
+  const int64_t b = p.tiles.begin[ti] + (int64_t)(item % sub2) * (2 * TC_BM);
+  const int64_t e = p.tiles.end[ti];
+  if (b >= e) return false;                          // decided on the pair's first row: both CTAs agree
+  seg = p.tiles.seg[ti];
+  row0 = b + (int64_t)rank * TC_BM;
+  const int64_t left = e - row0;
+  np = left <= 0 ? 0 : (int)min((int64_t)TC_BM, left);
+  return true;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC1_THREADS, 1)
+estep_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_xt,
+                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_ct,
+                 const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nslab = p.d16 / TC_BK;
+  const int khalf = p.kpad >> 1;                              // centroid rows held by this CTA
+  const uint32_t slab_b_bytes = (uint32_t)khalf * 128u;
+  const uint32_t tail_b_bytes = (uint32_t)khalf * 32u;
+  const uint32_t sB = base;                                   // centroids (own half), main slabs
+  const uint32_t sBT = sB + nslab * slab_b_bytes;             // centroids (own half), tail slab
+  const uint32_t sAT = sBT + 128 * 32;                        // pixel tail slab, 2 buffers
+  const uint32_t sA = sAT + 2 * TC_TAIL_BYTES;                // pixel main slabs, nst stages
+  const uint32_t sMisc = sA + p.nst * TC_STAGE_BYTES;
+  uint8_t* misc = smem_raw + (sMisc - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+  const uint32_t bar_full = smem_u32(bars);                   // [12] (waited on in the leader only)
+  const uint32_t bar_empty = bar_full + 12 * 8;               // [12]
+  const uint32_t bar_tlfull = bar_empty + 12 * 8;             // [2] tail slab landed (leader)
+  const uint32_t bar_tlempty = bar_tlfull + 16;               // [2]
+  const uint32_t bar_bfull = bar_tlempty + 16;                // [1] centroids landed (leader)
+  const uint32_t bar_tfull = bar_bfull + 8;                   // [2] accumulator ready
+  const uint32_t bar_tempty = bar_tfull + 16;                 // [2] accumulator drained (leader; 8 arrivals)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.nst; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tlfull + 8 * i, 1); mbar_init(bar_tlempty + 8 * i, 1);
+      mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8);
+    }
+    mbar_init(bar_bfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_xt) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_c) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_ct) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                         // the peer's barriers exist before anything remote touches them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int count = *p.tiles.count;
+  const long long pitems = p.items >> 1;                      // 256-pixel items
+  const long long i_begin = blockIdx.x >> 1, i_step = gridDim.x >> 1;
+  const bool timing = (p.exp_flags & 2) && p.dbg_clk;
+  long long t_wait0 = 0, t_wait1 = 0;
+  const long long t_begin = timing ? clock64() : 0;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      const uint32_t l_full = mapa_cluster(bar_full, 0);
+      const uint32_t l_tlfull = mapa_cluster(bar_tlfull, 0);
+      const uint32_t l_bfull = mapa_cluster(bar_bfull, 0);
+      int stage = 0, cur_seg = -1, tl = 0, last_tl = 0;
+      uint32_t phase = 0, tl_phase = 0, last_tl_phase = 0;
+      for (long long item = i_begin; item < pitems; item += i_step) {
+        int seg, np; int64_t row0;
+        if (!pair_item_rows(p, item, count, rank, seg, row0, np)) continue;
+        if (seg != cur_seg) {
+          // the tail MMA is the last one of a tile: once it retired, nothing reads the old centroids
+          if (cur_seg >= 0) mbar_wait(bar_tlempty + 8 * last_tl, last_tl_phase);
+          if (leader) mbar_expect_tx(bar_bfull, 2 * (nslab * slab_b_bytes + tail_b_bytes));
+          const int crow = seg * p.kpad_total + (int)rank * khalf;
+          for (int j = 0; j < nslab; ++j) tma_load_2d_pair(sB + j * slab_b_bytes, &tmap_c, j * TC_BK, crow, l_bfull);
+          tma_load_2d_pair(sBT, &tmap_ct, p.d16, crow, l_bfull);
+          cur_seg = seg;
+        }
+        for (int j = 0; j < nslab; ++j) {
+          const long long c0 = timing ? clock64() : 0;
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (timing) t_wait0 += clock64() - c0;
+          if (leader) mbar_expect_tx(bar_full + 8 * stage, 2 * TC_STAGE_BYTES);
+          tma_load_2d_pair(sA + stage * TC_STAGE_BYTES, &tmap_x, j * TC_BK, (int)row0, l_full + 8 * stage);
+          if (++stage == p.nst) { stage = 0; phase ^= 1; }
+        }
+        mbar_wait(bar_tlempty + 8 * tl, tl_phase ^ 1);
+        if (leader) mbar_expect_tx(bar_tlfull + 8 * tl, 2 * TC_TAIL_BYTES);
+        tma_load_2d_pair(sAT + tl * TC_TAIL_BYTES, &tmap_xt, p.d16, (int)row0, l_tlfull + 8 * tl);
+        last_tl = tl; last_tl_phase = tl_phase;
+        if (++tl == 2) { tl = 0; tl_phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (lane == 0 && leader) {
+      // instruction descriptor: D=f32, A=B=f16, both K-major, N=kpad, M=256 (two CTAs x 128)
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.kpad >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      int stage = 0, cur_seg = -1, acc = 0, tl = 0;
+      uint32_t phase = 0, bcount = 0, tl_phase = 0, acc_phase0 = 0, acc_phase1 = 0;
+      for (long long item = i_begin; item < pitems; item += i_step) {
+        int seg, np; int64_t row0;
+        if (!pair_item_rows(p, item, count, rank, seg, row0, np)) continue;
+        if (seg != cur_seg) {
+          mbar_wait(bar_bfull, bcount & 1);
+          ++bcount;
+          cur_seg = seg;
+        }
+        long long c0 = timing ? clock64() : 0;
+        mbar_wait(bar_tempty + 8 * acc, (acc ? acc_phase1 : acc_phase0) ^ 1);
+        if (timing) t_wait1 += clock64() - c0;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int j = 0; j < nslab; ++j) {
+          c0 = timing ? clock64() : 0;
+          mbar_wait(bar_full + 8 * stage, phase);
+          if (timing) t_wait0 += clock64() - c0;
+          tc_fence_after();
+          const uint64_t ad = umma_desc(sA + stage * TC_STAGE_BYTES, 1024, 2);
+          const uint64_t bd = umma_desc(sB + j * slab_b_bytes, 1024, 2);
+#pragma unroll
+          for (int k4 = 0; k4 < TC_BK / 16; ++k4)
+            tc_mma_f16_pair(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (j | k4) ? 1u : 0u);
+          tc_commit_pair(bar_empty + 8 * stage);
+          if (++stage == p.nst) { stage = 0; phase ^= 1; }
+        }
+        mbar_wait(bar_tlfull + 8 * tl, tl_phase);
+        tc_fence_after();
+        tc_mma_f16_pair(d_tmem, umma_desc(sAT + tl * TC_TAIL_BYTES, 256, 6), umma_desc(sBT, 256, 6), idesc, 1u);
+        tc_commit_pair(bar_tlempty + 8 * tl);
+        if (++tl == 2) { tl = 0; tl_phase ^= 1; }
+        tc_commit_pair(bar_tfull + 8 * acc);
+        if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
+        acc ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 TMEM lanes): one thread per pixel row =====================
+    const int e = warp - 4;
+    const int q = warp & 3;
+    const int g = e >> 2;
+    const int r = 32 * q + lane;
+    const int kpad = p.kpad;
+    const uint32_t l_tempty = mapa_cluster(bar_tempty, 0);
+    int cur_seg = -1, seq = 0;
+    uint32_t acc_phase = 0;
+    float cerrmax = 0.f;
+    for (long long item = i_begin; item < pitems; item += i_step) {
+      int seg, np; int64_t row0;
+      if (!pair_item_rows(p, item, count, rank, seg, row0, np)) continue;
+      if (((seq++) & 1) != g) continue;
+      if (seg != cur_seg) { cerrmax = p.cerr_max[seg]; cur_seg = seg; }
+      const int64_t pix = row0 + r;
+      const bool inb = r < np;
+      const float xe = inb ? p.xerr[pix] : 0.f;
+      const float thr = 2.f * (xe * 1.001f + cerrmax * 1.001f + TC1_EPS_CONST);
+
+      long long c0 = timing ? clock64() : 0;
+      mbar_wait(bar_tfull + 8 * g, acc_phase);
+      if (timing) { const long long c1 = clock64(); t_wait0 += c1 - c0; c0 = c1; }
+      tc_fence_after();
+      const uint32_t trow = tmem_base + g * 256 + ((uint32_t)(32 * q) << 16);
+      float run = -FLT_MAX;
+      float cm[8];
+      uint32_t mk[8];
+      uint32_t va[32], vb[32];
+      tc_ld32(trow, va);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        cm[c] = -FLT_MAX; mk[c] = 0xFFFFFFFFu;
+        if (c * 32 < kpad) {                                     // warp-uniform; kpad is a multiple of 32 here
+          uint32_t (&v)[32] = (c & 1) ? vb : va;
+          uint32_t (&nx)[32] = (c & 1) ? va : vb;
+          tc_ld_wait();
+          if ((c + 1) * 32 < kpad) tc_ld32(trow + (c + 1) * 32, nx);
+          float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]);
+#pragma unroll
+          for (int j = 2; j < 32; j += 4) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+            if (j + 3 < 32) m1 = fmaxf(m1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+          }
+          const float cmax = fmaxf(m0, m1);
+          cm[c] = cmax;
+          run = fmaxf(run, cmax);
+          const float tp = run - thr;
+          uint32_t ma = 0xFFFFFFFFu, mb = 0xFFFFFFFFu;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            ma = __funnelshift_l(__float_as_uint(__uint_as_float(v[j]) - tp), ma, 1);
+            mb = __funnelshift_l(__float_as_uint(__uint_as_float(v[16 + j]) - tp), mb, 1);
+          }
+          mk[c] = (ma << 16) | (mb & 0xFFFFu);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(l_tempty + 8 * g);
+      acc_phase ^= 1;
+      if (timing) t_wait1 += clock64() - c0;
+
+      const float t_final = run - thr;
+      int cnt = 0, first = 0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t hits = (c * 32 < kpad && cm[c] >= t_final) ? ~mk[c] : 0u;
+        mk[c] = hits;
+        if (cnt == 0 && hits) first = c * 32 + __clz(hits);
+        cnt += __popc(hits);
+      }
+      const bool amb = inb && cnt > 1;
+      if (inb) p.keys_out[pix] = seg * p.kmax + first;
+      const unsigned amb_mask = __ballot_sync(FULL, amb);
+      if (amb_mask) {
+        int slot_base = 0;
+        if (lane == 0) slot_base = atomicAdd(p.fix.count, __popc(amb_mask));
+        slot_base = __shfl_sync(FULL, slot_base, 0);
+        if (amb) {
+          const int slot = slot_base + __popc(amb_mask & ((1u << lane) - 1u));
+          if (slot < p.fix.capacity) {
+            p.fix.pixels[slot] = (int32_t)pix;
+            p.fix.segs[slot] = seg;
+            uint16_t* cd = p.fix.cand + (int64_t)slot * FIX_MAX_CAND;
+            if (cnt > FIX_MAX_CAND) {
+              cd[0] = 0xFFFF;
+              atomicAdd(p.fix.count + 1, 1);
+            } else {
+              int w = 0;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                uint32_t hits = mk[c];
+                while (hits) {
+                  const int j = __clz(hits);
+                  hits &= ~(0x80000000u >> j);
+                  cd[w++] = (uint16_t)(c * 32 + j);
+                }
+              }
+              if (w < FIX_MAX_CAND) cd[w] = 0xFFFF;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  if (timing && lane == 0 && (warp <= 1 || warp == 4 || warp == 8)) {
+    const int role = warp <= 1 ? warp : (warp == 4 ? 2 : 3);
+    long long* o = p.dbg_clk + ((long long)blockIdx.x * 4 + role) * 3;
+    o[0] = clock64() - t_begin; o[1] = t_wait0; o[2] = t_wait1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // neither CTA leaves (or frees TMEM) while the pair still works
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
   }
 }
 
@@ -787,6 +1158,10 @@ int tc_prepare(TcState& t, int64_t N, int S) {
   if ((rc = encode_2d_f16(t.tmap_xt, t.xh, (uint64_t)N, wx, HSG_XH_TAIL, TC_BM, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   if ((rc = encode_2d_f16(t.tmap_c, t.ch, (uint64_t)S * t.kpad_total, wx, TC_BK, (uint32_t)t.kpad, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = encode_2d_f16(t.tmap_ct, t.ch, (uint64_t)S * t.kpad_total, wx, HSG_XH_TAIL, (uint32_t)t.kpad, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if (t.n_pass == 1 && t.kpad % 32 == 0) {         // CTA-pair kernel: each CTA loads half of the centroid rows
+    if ((rc = encode_2d_f16(t.tmap_c2, t.ch, (uint64_t)S * t.kpad_total, wx, TC_BK, (uint32_t)t.kpad / 2, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = encode_2d_f16(t.tmap_ct2, t.ch, (uint64_t)S * t.kpad_total, wx, HSG_XH_TAIL, (uint32_t)t.kpad / 2, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  }
   t.enabled = true;
   return HSG_OK;
 }
@@ -800,7 +1175,8 @@ int tc_convert_centroids(const EStepArgs& a, const TcState& t, cudaStream_t st) 
   return HSG_OK;
 }
 
-float* g_tc_debug_sims = nullptr;   // set by hsg_debug_set_tc_dump (tests only)
+float* g_tc_debug_sims = nullptr;
+long long* g_tc_debug_clk = nullptr;   // set by hsg_debug_set_tc_clock (tools only)   // set by hsg_debug_set_tc_dump (tests only)
 
 int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
   HSG_REQUIRE(t.enabled, HSG_E_INVALID, "tensor-core E-step used before tc_prepare");
@@ -808,7 +1184,9 @@ int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
   p.d16 = t.d16; p.kmax = a.kmax; p.kpad = t.kpad; p.kpad_total = t.kpad_total; p.n_pass = t.n_pass; p.pass = 0;
   p.st_val = t.st_val; p.st_tile = t.st_tile; p.xerr = t.xerr; p.cerr_max = t.cerr_max;
   p.tiles = a.tiles; p.sub = (int)(a.tiles.tile / TC_BM); p.items = (long long)a.tiles.bound * p.sub;
-  p.keys_out = a.keys_out; p.fix = a.fix; p.dbg_sims = g_tc_debug_sims;
+  p.keys_out = a.keys_out; p.fix = a.fix; p.dbg_sims = g_tc_debug_sims; p.xh = t.xh; p.pf_dist = 0; p.exp_flags = 0; p.dbg_clk = g_tc_debug_clk;
+  static const bool no_inline = getenv("HSG_ESTEP_INLINE") == nullptr;      // opt-in: measured 2x SLOWER
+  p.x32 = (a.dim <= 288 && !no_inline) ? a.x : nullptr; p.c32 = a.centroids; p.dim32 = a.dim;
   const int nslab = t.d16 / TC_BK;
   const size_t fixed = (size_t)nslab * t.kpad * 128 + 256 * 32 + 2 * TC_TAIL_BYTES   // centroids + tails
                        + TC_EX_BYTES + 32 * 8 + 64;                                  // exchange, barriers, tmem slot
@@ -827,6 +1205,31 @@ int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
   if (grid > p.items) grid = p.items;
   if (grid < 1) grid = 1;
   static const bool legacy = getenv("HSG_ESTEP_LEGACY") != nullptr;     // A/B switch for profiling only
+  static const bool no_pair = getenv("HSG_ESTEP_PAIR") == nullptr;         // the pair kernel is opt-in (profiling): see DESIGN.md
+  static const int exp_all = getenv("HSG_TC_EXP") ? atoi(getenv("HSG_TC_EXP")) : 0;
+  if (p.n_pass == 1 && !legacy && !no_pair && !p.dbg_sims && t.kpad >= 64 && t.kpad % 32 == 0 && p.sub % 2 == 0 &&
+      num_sms() >= 2) {
+    // CTA pairs: half of the centroids per CTA (estep_tc2_kernel)
+    const int khalf = t.kpad / 2;
+    const size_t fixed2 = (size_t)nslab * khalf * 128 + 128 * 32 + 2 * TC_TAIL_BYTES + 40 * 8 + 64;
+    int nst2 = (int)((227 * 1024 - 1024 - 1024 - fixed2) / TC_STAGE_BYTES);
+    if (nst2 > 12) nst2 = 12;
+    HSG_REQUIRE(nst2 >= 2, HSG_E_UNSUPPORTED, "tensor-core E-step: shared memory budget (kpad=%d d16=%d)", t.kpad, t.d16);
+    p.nst = nst2;
+    p.exp_flags = exp_all;
+    const size_t smem2 = 1024 + fixed2 + (size_t)nst2 * TC_STAGE_BYTES;
+    CUtensorMap mc2, mct2;
+    memcpy(&mc2, t.tmap_c2, sizeof(mc2));
+    memcpy(&mct2, t.tmap_ct2, sizeof(mct2));
+    long long grid2 = num_sms() & ~1;
+    const long long pitems = p.items / 2;
+    if (grid2 > 2 * pitems) grid2 = 2 * pitems;
+    if (grid2 < 2) grid2 = 2;
+    HSG_CUDA(cudaFuncSetAttribute(estep_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    estep_tc2_kernel<<<(unsigned)grid2, TC1_THREADS, smem2, st>>>(mx, mxt, mc2, mct2, p);
+    HSG_LAUNCH_CHECK();
+    return HSG_OK;
+  }
   if (p.n_pass == 1 && !legacy) {
     // single-pass shapes (K <= 256 per image): one thread per pixel row, single sweep (estep_tc1_kernel)
     const size_t fixed1 = (size_t)nslab * t.kpad * 128 + 256 * 32 + 2 * TC_TAIL_BYTES + 40 * 8 + 64;
@@ -834,6 +1237,10 @@ int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
     if (nst1 > 12) nst1 = 12;
     HSG_REQUIRE(nst1 >= 2, HSG_E_UNSUPPORTED, "tensor-core E-step: shared memory budget (kpad=%d d16=%d)", t.kpad, t.d16);
     p.nst = nst1;
+    static const int pf_env = getenv("HSG_TC_PF") ? atoi(getenv("HSG_TC_PF")) : TC1_PF_DIST;    // tuning knob
+    p.pf_dist = pf_env < 0 ? 0 : (pf_env > 16 ? 16 : pf_env);
+    static const int exp_env = getenv("HSG_TC_EXP") ? atoi(getenv("HSG_TC_EXP")) : 0;
+    p.exp_flags = exp_env;
     const size_t smem1 = 1024 + fixed1 + (size_t)nst1 * TC_STAGE_BYTES;
     if (p.dbg_sims) {
       HSG_CUDA(cudaFuncSetAttribute(estep_tc1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
@@ -862,6 +1269,11 @@ int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
 
 // test hook: dump the screening similarities of the next tensor-core E-steps into
 // a caller buffer [N,kmax] (NULL switches it off)
+extern "C" int hsg_debug_set_tc_clock(long long* clk) {
+  hsg::g_tc_debug_clk = clk;
+  return HSG_OK;
+}
+
 extern "C" int hsg_debug_set_tc_dump(float* sims) {
   hsg::g_tc_debug_sims = sims;
   return HSG_OK;

@@ -36,7 +36,8 @@ def calculate_kmeans_prototypes(cluster_embeddings, cluster_indices, cluster_bat
                                 label_divisor=2048, max_num_clusters=256):
   """Returns (prototypes [G,C,M], pos_prototypes [G,C,M] or None, padding_masks [G,M] bool,
   prototype_labels [G,M], prototype_batch_indices [G,M] (pad -1), cluster_indices_by_image [N]),
-  G = image groups in increasing id order, M = max_num_clusters (reference :1005-1136).
+  G = image groups in increasing id order, M = max_num_clusters (reference :1005-1136), or the largest
+  number of prototypes of a group when max_num_clusters is None (the `_cs` model).
   `cluster_indices` are the dense ids of segment_by_kmeans (one id = one (image, cluster,
   label) triple), as in the reference's call sites (:243-252, :906-916)."""
   emb = cluster_embeddings
@@ -45,7 +46,6 @@ def calculate_kmeans_prototypes(cluster_embeddings, cluster_indices, cluster_bat
   bidx = cluster_batch_indices.reshape(-1).long()
   labs = cluster_labels.reshape(-1).long()
   n = cidx.shape[0]
-  m = int(max_num_clusters)
   if n == 0:
     raise ValueError('calculate_kmeans_prototypes: no pixels')
   group_of_pixel = image_indices.to(dev).long()[bidx] if image_indices is not None else bidx
@@ -72,6 +72,8 @@ def calculate_kmeans_prototypes(cluster_embeddings, cluster_indices, cluster_bat
   stats = torch.stack([is_new.sum(), torch.where(valid_sorted, local_sorted, torch.zeros_like(local_sorted)).max(),
                        grouped.long()]).tolist()                        # host read 2: output sizes
   g_count, biggest, grouped = int(stats[0]), int(stats[1]) + 1, bool(stats[2])
+  # the Cityscapes model pads to the largest group of the batch (resnet_fcn_hsg_cs.py:499-502, 1061-1064)
+  m = biggest if max_num_clusters is None else int(max_num_clusters)
   if biggest > m:
     raise HsgError('calculate_kmeans_prototypes: %d prototypes in one image group, max_num_clusters is %d '
                    '(the reference scatters out of bounds here, resnet_fcn_hsg.py:1090-1091)' % (biggest, m))
@@ -169,6 +171,20 @@ def _collect_pixel_hierarchical_clustering_indices(self, cluster_indices_by_batc
                                                        finehrchy_prototype_grouping_labels)
 
 
+def _calculate_kmeans_prototypes_single_cs(self, cluster_embeddings, cluster_indices, cluster_batch_indices,
+                                           cluster_pos_embeddings, cluster_labels):
+  """resnet_fcn_hsg_cs.py:455-560: pads to the largest per-image cluster count of the batch."""
+  return calculate_kmeans_prototypes(cluster_embeddings, cluster_indices, cluster_batch_indices,
+                                     cluster_pos_embeddings, cluster_labels, None, self.label_divisor, None)
+
+
+def _calculate_kmeans_prototypes_multiview_cs(self, cluster_embeddings, cluster_indices, cluster_batch_indices,
+                                              cluster_pos_embeddings, cluster_labels, image_indices):
+  """resnet_fcn_hsg_cs.py:1010-1135: pads to the largest per-image-pair cluster count of the batch."""
+  return calculate_kmeans_prototypes(cluster_embeddings, cluster_indices, cluster_batch_indices,
+                                     cluster_pos_embeddings, cluster_labels, image_indices, self.label_divisor, None)
+
+
 METHODS = {
     'ResnetFcn': {
         '_calculate_kmeans_prototypes': _calculate_kmeans_prototypes_single,
@@ -177,5 +193,13 @@ METHODS = {
     },
     'MultiviewResnetFcn': {
         '_calculate_kmeans_prototypes': _calculate_kmeans_prototypes_multiview,
+    },
+}
+
+# hsg/models/embeddings/resnet_fcn_hsg_cs.py (Cityscapes): same classes, prototypes padded to the batch's largest group
+METHODS_CS = {
+    'ResnetFcn': dict(METHODS['ResnetFcn'], _calculate_kmeans_prototypes=_calculate_kmeans_prototypes_single_cs),
+    'MultiviewResnetFcn': {
+        '_calculate_kmeans_prototypes': _calculate_kmeans_prototypes_multiview_cs,
     },
 }

@@ -196,6 +196,12 @@ def segment_by_kmeans_ex(embeddings, labels=None, num_clusters=[5, 5], cluster_i
 
   lab_in = labels.long().contiguous() if labels is not None else None
   ign = int(ignore_index) if ignore_index is not None else None           # may be a 0-dim tensor
+  if lab_in is None and ign is not None:
+    # the reference treats missing labels as all-zero (:325-327), so an ignore_index of 0 drops every pixel
+    # and any other value drops none
+    if ign == 0:
+      raise RuntimeError('segment_by_kmeans: every pixel is ignored')
+    ign = None
   gpu_id = dev.index or 0
   want_half = ops.tc_d16(c + n_loc, kmax) == c and iterations >= 1
   with torch.no_grad():

@@ -79,6 +79,10 @@ HSG_API int hsg_profile_collect(double* total_ms_host, long long* counts_host, i
 /* test hook: the next tensor-core E-steps also write their screening
  * similarities to sims [N,kmax] (device); NULL switches the dump off. */
 HSG_API int hsg_debug_set_tc_dump(float* sims);
+/* profiling hook (tools/estep_timeline.py): with HSG_TC_EXP=2 in the environment the single-pass
+ * tensor-core E-step writes, per CTA and role (TMA producer, MMA issuer, epilogue of accumulator 0 / 1),
+ * {cycles alive, cycles in its first wait, cycles in its second wait} to clk [grid,4,3] (device). */
+HSG_API int hsg_debug_set_tc_clock(long long* clk);
 /* test hook, a bit mask that pins a path to one of its two implementations (0 = the library decides):
  *   1 NCE forward on the fp32 CUDA-core kernel      4 NCE backward GEMMs on CUDA cores     8 NCE backward G chunk on CUDA cores
  *  16 attention forward on CUDA cores              32 attention forward on tcgen05 for every shape it supports

@@ -311,6 +311,23 @@ def test_kmeans_prototypes_per_image_batched(golden):
     H.calculate_kmeans_prototypes(t(g['emb']), t(g['cluster']), t(g['batch']), None, t(g['labels']), None, 2048, 4)
 
 
+def test_kmeans_prototypes_cityscapes_model_pads_to_largest_group(golden):
+  """the `_cs` model pads to the largest per-image(-pair) cluster count of the batch
+  (resnet_fcn_hsg_cs.py:499-502, 1061-1064), not to 256; patch() gives that module its own method table."""
+  from hsg_b200.models.embeddings import hierarchy as H
+  import types
+  g, c = golden('kmeans_prototypes'), golden('kmeans_prototypes_cs')
+  me = types.SimpleNamespace(label_divisor=2048, max_num_clusters=256)
+  args = (t(g['emb']), t(g['cluster']), t(g['batch']), t(g['pos']), t(g['labels']))
+  for prefix, out in (('mv', H.METHODS_CS['MultiviewResnetFcn']['_calculate_kmeans_prototypes'](me, *args, t(g['image_indices']))),
+                      ('sv', H.METHODS_CS['ResnetFcn']['_calculate_kmeans_prototypes'](me, *args))):
+    assert tuple(out[0].shape) == c[prefix + '0'].shape and out[0].shape[-1] < 256
+    close(n(out[0]), c[prefix + '0'], rtol=1e-5, atol=1e-7)
+    close(n(out[1]), c[prefix + '1'], rtol=1e-5, atol=1e-6)
+    for i in (2, 3, 4, 5):
+      assert np.array_equal(n(out[i]), c[prefix + str(i)])
+
+
 def test_hierarchy_helpers(golden):
   """a12: coarser-prototype pooling (fwd + bwd) and per-pixel hierarchy ids."""
   from hsg_b200.models.embeddings import hierarchy as H
@@ -1052,9 +1069,6 @@ def test_whole_step_composes_and_differentiates(S):
 
 
 # ---------------------------------------------------------------- inference: prototype bank + nearest-neighbour labels (8f rank 4)
-@pytest.mark.xfail(strict=False, reason='written after the round-1 GPU budget ran out: its one run on a B200 exposed the '
-                   'single-image max_seg_len bug fixed in segment_by_kmeans_ex, and the fixed path has not been run on a GPU yet; '
-                   'the host logic and the oracle are covered by tests/test_host_inference.py and test_oracle_golden.py')
 def test_inference_prototype_bank_and_retrieval(golden, tmp_path):
   """generate_clusters -> bank entry per image -> bank on disk -> nearest-neighbour labels of a query image,
   against the reference's CPU run (pyscripts/inference/prototype.py:181-208, inference.py:207-224)."""
