@@ -52,10 +52,16 @@ SIGNATURES = {
     'hsg_prep_workspace_bytes': (_z, [_i, _i, _i]),
     'hsg_prep_f32': (_i, [_p, _i, _i, _i, _i, _p, _i, _l, _p, _i, _l, _p, _l, _l,
                           _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
+    'hsg_prep_bwd_f32': (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _l, _p, _p, _p, _p, _p]),
+    'hsg_prep_runs_per_image': (_l, [_i, _i]),
+    'hsg_prep_sums_f32': (_i, [_p, _i, _i, _i, _i, _p, _i, _l, _p, _i, _l, _p, _l, _l,
+                               _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p, _p, _p, _p, _p]),
     'hsg_make_half_copy_f32': (_i, [_p, _l, _i, _i, _p, _p, _p]),
     'hsg_kmeans_workspace_bytes': (_z, [_l, _i, _i, _i, _l]),
     'hsg_kmeans_f32': (_i, [_p, _l, _i, _p, _i, _p, _p, _i, _l, _p, _i, _p, _i, _p, _p, _i,
                             _p, _z, _p]),
+    'hsg_kmeans_presummed_f32': (_i, [_p, _l, _i, _p, _i, _p, _p, _i, _l, _p, _i, _p, _i, _p, _p, _i,
+                                      _p, _z, _p, _p, _p, _p, _l, _p]),
     'hsg_kmeans_mstep_f32': (_i, [_p, _l, _i, _p, _i, _l, _p, _i, _p, _p, _p, _z, _p]),
     'hsg_kmeans_estep_f32': (_i, [_p, _l, _i, _p, _i, _p, _p, _i, _l, _p, _i, _p, _p, _p, _i,
                                   _p, _z, _p]),
@@ -75,6 +81,7 @@ SIGNATURES = {
     'hsg_segment_sum_exact_workspace_bytes': (_z, [_l, _i, _l, _i, _i, _l]),
     'hsg_segment_sum_exact_i64': (_i, [_p, _l, _i, _p, _l, _p, _i, _l, _p, _i, _p, _p, _z, _p]),
     'hsg_knn_adjacency_f32': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    'hsg_topk_affinity_f32': (_i, [_p, _l, _p, _l, _i, _i, _p, _p, _p]),
     'hsg_relabel_workspace_bytes': (_z, [_i, _i, _l]),
     'hsg_relabel_i64': (_i, [_p, _p, _p, _l, _l, _i, _i, _p, _l, _p, _p, _p, _p, _p, _p, _z, _p]),
 }

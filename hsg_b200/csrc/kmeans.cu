@@ -434,11 +434,101 @@ static void km_carve(Carver& c, KmPlan& p, int64_t N, int dim, int S, int kmax, 
   d.members = c.take<int32_t>(p.sr.bins);
 }
 
+// First M-step from the run sums the prep kernel emitted (hsg_prep_sums_f32): one warp per (segment, cluster)
+// scans the segment's run table in slot order and adds the matching partial sums in float64 -- fixed order,
+// no re-read of the rows.  Runs only when the table is complete (*overflow == 0); otherwise the gated
+// ordinary pass has produced the sums.
+struct RunSums {
+  const float* sums;        // [S*runs_per_segment, dim]
+  const int32_t* cluster;   // [S*runs_per_segment]
+  const int32_t* count;     // [S*runs_per_segment]
+  const int32_t* overflow;  // [1]
+  int64_t runs_per_segment;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(256) runsum_combine_kernel(const RunSums r, int S, int kmax, int dim,
+                                                             double* __restrict__ sums, int32_t* __restrict__ members,
+                                                             float* __restrict__ out) {
+  if (*r.overflow != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t key = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (key >= (int64_t)S * kmax) return;
+  const int seg = (int)(key / kmax), k = (int)(key % kmax);
+  const int64_t base = (int64_t)seg * r.runs_per_segment;
+  double acc[NV];
+#pragma unroll
+  for (int m = 0; m < NV; ++m) acc[m] = 0.0;
+  int mem = 0;
+  // four slots per lane and step (runs_per_segment is a multiple of HSG_PREP_RUNS = 4: 16-byte loads)
+  for (int64_t j0 = 0; j0 < r.runs_per_segment; j0 += 128) {
+    const int64_t j = j0 + 4 * lane;
+    int4 c4 = make_int4(-1, -1, -1, -1);
+    if (j < r.runs_per_segment) c4 = *reinterpret_cast<const int4*>(r.cluster + base + j);
+    const int cs[4] = {c4.x, c4.y, c4.z, c4.w};
+    unsigned any = __ballot_sync(FULL, cs[0] == k || cs[1] == k || cs[2] == k || cs[3] == k);
+    while (any) {                                  // lanes in slot order, their four slots in order
+      const int b = __ffs(any) - 1;
+      any &= any - 1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (__shfl_sync(FULL, cs[u], b) != k) continue;
+        const int64_t slot = base + j0 + 4 * b + u;
+        mem += r.count[slot];
+        const float* row = r.sums + slot * dim;
+#pragma unroll
+        for (int m = 0; m < NV; ++m) {
+          const int d = lane + 32 * m;
+          if (d < dim) acc[m] += (double)row[d];
+        }
+      }
+    }
+  }
+  if (lane == 0) members[key] = mem;
+  float ss = 0.f;
+  float f[NV];
+#pragma unroll
+  for (int m = 0; m < NV; ++m) {
+    const int d = lane + 32 * m;
+    f[m] = 0.f;
+    if (d < dim) {
+      const double a = mem == 0 ? 0.0 : acc[m];
+      sums[key * dim + d] = a;
+      f[m] = (float)a;
+      ss = fmaf(f[m], f[m], ss);
+    }
+  }
+  const float n = safe_norm(warp_sum(ss));
+#pragma unroll
+  for (int m = 0; m < NV; ++m) {
+    const int d = lane + 32 * m;
+    if (d < dim) out[key * dim + d] = f[m] / n;
+  }
+}
+
 // one M-step of the k-means loop: full pass on the first iteration, afterwards delta or full
 // as decided on the device
 static int km_mstep(KmPlan& p, const float* x, const int64_t* seg_offsets, int it, bool incremental,
-                    cudaStream_t st) {
+                    cudaStream_t st, const RunSums* runs = nullptr) {
   int rc;
+  if (it == 0 && runs) {
+    // usual case: the run table is complete and only the combine below does any work
+    const Gate fallback{runs->overflow, 1};
+    if ((rc = sr_sort_and_sum_gated(p.sr, x, seg_offsets, fallback, nullptr, nullptr, st))) return rc;
+    if ((rc = sr_combine64(p.sr, p.sr.pieces, nullptr, nullptr, p.d.sums, p.d.members, p.centroids, st, fallback))) return rc;
+    {
+      ProfRange prof(PROF_MSTEP_COMBINE, st);
+      const unsigned grid = (unsigned)ceil_div64(p.sr.bins, 8);
+      if (p.sr.dim <= 32 * 9)
+        runsum_combine_kernel<9><<<grid, 256, 0, st>>>(*runs, p.sr.S, p.sr.kmax, p.sr.dim, p.d.sums, p.d.members, p.centroids);
+      else
+        runsum_combine_kernel<20><<<grid, 256, 0, st>>>(*runs, p.sr.S, p.sr.kmax, p.sr.dim, p.d.sums, p.d.members, p.centroids);
+      HSG_LAUNCH_CHECK();
+    }
+    if (incremental)
+      HSG_CUDA(cudaMemcpyAsync(p.d.keys_prev, p.sr.keys, sizeof(int32_t) * p.sr.N, cudaMemcpyDeviceToDevice, st));
+    return HSG_OK;
+  }
   if (it == 0 || !incremental) {
     if ((rc = sr_sort_and_sum(p.sr, x, seg_offsets, st))) return rc;
     if ((rc = sr_combine64(p.sr, p.sr.pieces, nullptr, nullptr, p.d.sums, p.d.members, p.centroids, st))) return rc;
@@ -522,11 +612,11 @@ size_t hsg_kmeans_workspace_bytes(int64_t N, int dim, int S, int kmax, int64_t m
   return need + 1024;
 }
 
-int hsg_kmeans_f32(const float* x, int64_t N, int dim, const void* xh, int d16, const float* xerr,
-                   const int64_t* seg_offsets, int S, int64_t max_seg_len, const int32_t* seg_k,
-                   int kmax, const int64_t* init_labels, int iterations, int64_t* labels_out,
-                   float* centroids_out, int flags, void* workspace, size_t workspace_bytes,
-                   void* stream) {
+static int kmeans_impl(const float* x, int64_t N, int dim, const void* xh, int d16, const float* xerr,
+                       const int64_t* seg_offsets, int S, int64_t max_seg_len, const int32_t* seg_k,
+                       int kmax, const int64_t* init_labels, int iterations, int64_t* labels_out,
+                       float* centroids_out, int flags, void* workspace, size_t workspace_bytes,
+                       void* stream, const RunSums* runs) {
   int rc = check_common(x, N, dim, seg_offsets, S, max_seg_len, kmax);
   if (rc) return rc;
   HSG_REQUIRE(iterations >= 0, HSG_E_INVALID, "kmeans: iterations=%d", iterations);
@@ -558,7 +648,7 @@ int hsg_kmeans_f32(const float* x, int64_t N, int dim, const void* xh, int d16, 
   // below ~2.6e5 rows a full re-sum is cheaper than the dozen extra launches of the delta machinery
   const bool incremental = !(flags & HSG_KMEANS_FULL_MSTEP) && N >= KM_DELTA_MIN_ROWS;
   for (int it = 0; it < iterations; ++it) {
-    if ((rc = km_mstep(p, x, seg_offsets, it, incremental, st))) return rc;
+    if ((rc = km_mstep(p, x, seg_offsets, it, incremental, st, runs))) return rc;
     if ((rc = run_estep(ea, p, use_tc, st))) return rc;
   }
   if ((rc = sr_keys_to_labels(p.sr, p.sr.keys, labels_out, st))) return rc;
@@ -566,6 +656,28 @@ int hsg_kmeans_f32(const float* x, int64_t N, int dim, const void* xh, int d16, 
     HSG_CUDA(cudaMemcpyAsync(centroids_out, p.centroids, sizeof(float) * S * kmax * dim,
                              cudaMemcpyDeviceToDevice, st));
   return HSG_OK;
+}
+
+int hsg_kmeans_f32(const float* x, int64_t N, int dim, const void* xh, int d16, const float* xerr,
+                   const int64_t* seg_offsets, int S, int64_t max_seg_len, const int32_t* seg_k,
+                   int kmax, const int64_t* init_labels, int iterations, int64_t* labels_out,
+                   float* centroids_out, int flags, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  return kmeans_impl(x, N, dim, xh, d16, xerr, seg_offsets, S, max_seg_len, seg_k, kmax, init_labels, iterations,
+                     labels_out, centroids_out, flags, workspace, workspace_bytes, stream, nullptr);
+}
+
+int hsg_kmeans_presummed_f32(const float* x, int64_t N, int dim, const void* xh, int d16, const float* xerr,
+                             const int64_t* seg_offsets, int S, int64_t max_seg_len, const int32_t* seg_k,
+                             int kmax, const int64_t* init_labels, int iterations, int64_t* labels_out,
+                             float* centroids_out, int flags, void* workspace, size_t workspace_bytes,
+                             const float* run_sums, const int32_t* run_cluster, const int32_t* run_count,
+                             const int32_t* run_overflow, int64_t runs_per_segment, void* stream) {
+  HSG_REQUIRE(run_sums && run_cluster && run_count && run_overflow && runs_per_segment > 0, HSG_E_INVALID,
+              "kmeans_presummed: null run buffers");
+  RunSums r{run_sums, run_cluster, run_count, run_overflow, runs_per_segment};
+  return kmeans_impl(x, N, dim, xh, d16, xerr, seg_offsets, S, max_seg_len, seg_k, kmax, init_labels, iterations,
+                     labels_out, centroids_out, flags, workspace, workspace_bytes, stream, &r);
 }
 
 int hsg_kmeans_mstep_f32(const float* x, int64_t N, int dim, const int64_t* seg_offsets, int S,

@@ -197,11 +197,18 @@ struct PrepArgs {
   int64_t* pixel_out;         // optional: flat source pixel b*HW+p of each row
   const int64_t* tile_base;   // NULL when nothing is dropped
   int tiles_per_image;
+  // optional: partial sums of the xloc rows over runs of equal initial cluster id inside each tile
+  // (the first k-means M-step without re-reading xloc; see hsg_prep_sums_f32)
+  float* run_sums;            // [B*tiles_per_image*HSG_PREP_RUNS, D+L]
+  int32_t* run_cluster;       // [B*tiles_per_image*HSG_PREP_RUNS] local cluster id, -1 = unused
+  int32_t* run_count;         // [B*tiles_per_image*HSG_PREP_RUNS] pixels in the run
+  int32_t* run_overflow;      // [1] set to 1 when a tile has more runs than slots
 };
 
 __global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs a) {
-  extern __shared__ float tile[];                 // [D][PREP_LD]
+  extern __shared__ float tile[];                 // [D][PREP_LD] ([D+L] when run sums are wanted)
   __shared__ int64_t rows[PREP_TPX];
+  __shared__ int ck[PREP_TPX];                    // initial cluster of each kept pixel, -1 = dropped
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int t = blockIdx.x;
@@ -243,9 +250,11 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs 
                                      : (int64_t)b * a.HW + p0;
     const int64_t row = valid ? base + before + __popc(m & ((1u << lane) - 1u)) : -1;
     rows[px] = row;
+    const int64_t c0 = valid ? a.init[(int64_t)b * a.init_image_stride + p] : -1;
+    ck[px] = (int)c0;
     if (valid) {
       a.labels_out[row] = lab;
-      a.clusters_out[row] = a.init[(int64_t)b * a.init_image_stride + p];
+      a.clusters_out[row] = c0;
       a.batch_out[row] = a.batch_base + b;
       if (a.pixel_out) a.pixel_out[row] = (int64_t)b * a.HW + p;
     }
@@ -257,7 +266,10 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs 
   for (int i = 0; i < PREP_TPX / (PREP_THREADS / 32); ++i) {
     const int px = warp * (PREP_TPX / (PREP_THREADS / 32)) + i;
     const int64_t row = rows[px];
-    if (row < 0) continue;                          // warp-uniform
+    if (row < 0) {                                  // warp-uniform
+      if (a.run_sums) for (int d = lane; d < a.D + a.L; d += 32) tile[d * PREP_LD + px] = 0.f;
+      continue;
+    }
     float ss = 0.f;
     for (int d = lane; d < a.D; d += 32) {
       const float v = tile[d * PREP_LD + px];
@@ -288,6 +300,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs 
       const float z = div_rn_by(y, n2, r2);
       xr[d] = y;
       xl[d] = z;
+      if (a.run_sums) tile[d * PREP_LD + px] = z;
       if (a.xh) {
         const __half h = __float2half_rn(z);
         const float r = z - __half2float(h);
@@ -295,7 +308,10 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs 
         a.xh[row * (a.D + HSG_XH_TAIL) + d] = h;
       }
     }
-    if (lane < a.L) xl[a.D + lane] = lv / n2;
+    if (lane < a.L) {
+      xl[a.D + lane] = lv / n2;
+      if (a.run_sums) tile[(a.D + lane) * PREP_LD + px] = lv / n2;
+    }
     if (a.xh) {
       const int l = lane / 3;
       const float vl = __shfl_sync(FULL, lv / n2, l < a.L ? l : 0);
@@ -304,6 +320,140 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs 
     if (a.xh && a.xerr) {
       e2 = warp_sum(e2);
       if (lane == 0) a.xerr[row] = sqrtf(e2) * 1.0001f + 1e-30f;
+    }
+  }
+
+  if (a.run_sums) {
+    // The tile now holds the xloc rows (zero columns for dropped pixels).  Thread 0 finds the runs of equal
+    // initial cluster among the kept pixels, then one thread per feature sums each run's pixel range -- fixed
+    // order, so the sums do not depend on scheduling.
+    __shared__ int run_lo[HSG_PREP_RUNS + 1];
+    __shared__ int n_runs_s;
+    const int64_t slot0 = ((int64_t)b * a.tiles_per_image + t) * HSG_PREP_RUNS;
+    if (threadIdx.x == 0) {
+      int run = -1, cur = -2, cnt = 0;
+      for (int px = 0; px < PREP_TPX; ++px) {
+        const int c = ck[px];
+        if (c < 0) continue;
+        if (c != cur) {
+          if (run >= 0 && run < HSG_PREP_RUNS) { a.run_cluster[slot0 + run] = cur; a.run_count[slot0 + run] = cnt; }
+          ++run; cur = c; cnt = 0;
+          if (run <= HSG_PREP_RUNS) run_lo[run] = px;
+        }
+        ++cnt;
+      }
+      if (run >= 0 && run < HSG_PREP_RUNS) { a.run_cluster[slot0 + run] = cur; a.run_count[slot0 + run] = cnt; }
+      for (int r = run + 1; r < HSG_PREP_RUNS; ++r) a.run_cluster[slot0 + r] = -1;
+      if (run >= HSG_PREP_RUNS) *a.run_overflow = 1;
+      const int nr = min(run + 1, HSG_PREP_RUNS);
+      run_lo[nr] = PREP_TPX;                       // dropped pixels inside a range hold zeros
+      n_runs_s = nr;
+    }
+    __syncthreads();
+    const int nr = n_runs_s;
+    for (int d = threadIdx.x; d < Dp; d += PREP_THREADS) {
+      const float* col = tile + d * PREP_LD;
+      for (int r = 0; r < nr; ++r) {
+        float acc = 0.f;
+        for (int px = run_lo[r]; px < run_lo[r + 1]; ++px) acc += col[px];
+        a.run_sums[(slot0 + r) * Dp + d] = acc;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------ backward of the prep chain
+// Reference autograd chain (hsg/utils/segsort/common.py:305-365): permute -> normalize -> cat(loc) ->
+// normalize -> index_select.  With r the raw pixel row, y = r/n1, z = [y, loc]/n2:
+//   g_cat = (g_z - z <z,g_z>) / n2          (g_z / n2 when ||cat|| < eps)
+//   g_y   = g_x + g_cat[:D]
+//   g_r   = (g_y - y <y,g_y>) / n1          (g_y / eps when ||r|| < eps)
+// scattered back NHWC -> NCHW, zero for dropped pixels.  One CTA per 64 source pixels, like the forward:
+// the raw tile comes in by cp.async, the gradient tile leaves through the same transposed shared tile, so
+// both NCHW accesses are coalesced; y, g_x, g_z are read twice (dot products, then the update), the second
+// time from L1/L2.
+struct PrepBwdArgs {
+  const float* emb;           // [B,D,HW] raw input of the forward
+  int B, D, HW, L;
+  const float* x;             // [N,D]   forward output (y)
+  const float* loc;           // local features as in the forward
+  int64_t loc_image_stride;
+  const int64_t* row_of_pixel;// [B*HW] output row of each source pixel, -1 = dropped; NULL = identity
+  const float* gx;            // [N,D] or NULL
+  const float* gz;            // [N,D+L] or NULL
+  float* gemb;                // [B,D,HW]
+};
+
+__global__ void __launch_bounds__(PREP_THREADS) prep_bwd_kernel(const PrepBwdArgs a) {
+  extern __shared__ float tile[];                 // [D][PREP_LD]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y, t = blockIdx.x, p0 = t * PREP_TPX;
+  const float* src = a.emb + (int64_t)b * a.D * a.HW;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  for (int d = warp; d < a.D; d += PREP_THREADS / 32) {
+    const float* cr = src + (int64_t)d * a.HW + p0;
+#pragma unroll
+    for (int u = 0; u < PREP_TPX / 32; ++u) {
+      const int px = 32 * u + lane;
+      const bool in = p0 + px < a.HW;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(tile_s + 4u * (uint32_t)(d * PREP_LD + px)),
+                   "l"(in ? cr + px : src), "r"(in ? 4 : 0) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int Dp = a.D + a.L;
+  for (int i = 0; i < PREP_TPX / (PREP_THREADS / 32); ++i) {
+    const int px = warp * (PREP_TPX / (PREP_THREADS / 32)) + i;
+    const int p = p0 + px;
+    int64_t row = -1;
+    if (p < a.HW) row = a.row_of_pixel ? a.row_of_pixel[(int64_t)b * a.HW + p] : (int64_t)b * a.HW + p;
+    if (row < 0) {                                   // warp-uniform: dropped (or out of range) pixel
+      for (int d = lane; d < a.D; d += 32) tile[d * PREP_LD + px] = 0.f;
+      continue;
+    }
+    const float* yr = a.x + row * a.D;
+    const float* gxr = a.gx ? a.gx + row * a.D : nullptr;
+    const float* gzr = a.gz ? a.gz + row * Dp : nullptr;
+    float s_rr = 0.f, s_yy = 0.f, s_ygx = 0.f, s_ygz = 0.f;
+    for (int d = lane; d < a.D; d += 32) {
+      const float r = tile[d * PREP_LD + px], y = yr[d];
+      s_rr = fmaf(r, r, s_rr);
+      s_yy = fmaf(y, y, s_yy);
+      if (gxr) s_ygx = fmaf(y, gxr[d], s_ygx);
+      if (gzr) s_ygz = fmaf(y, gzr[d], s_ygz);
+    }
+    float lv = 0.f, s_ll = 0.f, s_lg = 0.f;
+    if (lane < a.L) {
+      lv = a.loc[(int64_t)b * a.loc_image_stride + (int64_t)p * a.L + lane];
+      s_ll = lv * lv;
+      if (gzr) s_lg = lv * gzr[a.D + lane];
+    }
+    s_rr = warp_sum(s_rr); s_yy = warp_sum(s_yy); s_ygx = warp_sum(s_ygx); s_ygz = warp_sum(s_ygz);
+    s_ll = warp_sum(s_ll); s_lg = warp_sum(s_lg);
+    const float raw1 = sqrtf(s_rr), raw2 = sqrtf(s_yy + s_ll);
+    const bool big1 = raw1 >= 1e-12f, big2 = raw2 >= 1e-12f;
+    const float n1 = big1 ? raw1 : 1e-12f, n2 = big2 ? raw2 : 1e-12f;
+    const float dotz = (s_ygz + s_lg) / n2;                          // <z, g_z>
+    const float y_gcat = big2 ? (s_ygz - (s_yy / n2) * dotz) / n2 : s_ygz / n2;
+    const float doty = s_ygx + y_gcat;                               // <y, g_y>
+    for (int d = lane; d < a.D; d += 32) {
+      const float y = yr[d];
+      const float gzv = gzr ? gzr[d] : 0.f;
+      const float gcat = big2 ? (gzv - (y / n2) * dotz) / n2 : gzv / n2;
+      const float gy = (gxr ? gxr[d] : 0.f) + gcat;
+      tile[d * PREP_LD + px] = big1 ? (gy - y * doty) / n1 : gy / n1;
+    }
+  }
+  __syncthreads();
+  float* dst = a.gemb + (int64_t)b * a.D * a.HW;
+  for (int d = warp; d < a.D; d += PREP_THREADS / 32) {
+#pragma unroll
+    for (int u = 0; u < PREP_TPX / 32; ++u) {
+      const int px = 32 * u + lane;
+      if (p0 + px < a.HW) dst[(int64_t)d * a.HW + p0 + px] = tile[d * PREP_LD + px];
     }
   }
 }
@@ -352,15 +502,16 @@ size_t hsg_prep_workspace_bytes(int B, int H, int W) {
   return align_up((size_t)B * tpi * sizeof(int32_t), 256) + align_up((size_t)B * tpi * sizeof(int64_t), 256) + 512;
 }
 
-int hsg_prep_f32(const float* emb_nchw, int B, int D, int H, int W,
-                 const float* loc, int L, int64_t loc_image_stride,
-                 const int64_t* labels, int use_ignore, int64_t ignore_index,
-                 const int64_t* init_clusters, int64_t init_image_stride,
-                 int64_t batch_index_base,
-                 float* x_out, float* xloc_out, void* xh_out, float* xerr_out,
-                 int64_t* labels_out, int64_t* clusters_out, int64_t* batch_out,
-                 int64_t* pixel_out, int64_t* seg_offsets, void* workspace, size_t workspace_bytes,
-                 void* stream) {
+static int prep_impl(const float* emb_nchw, int B, int D, int H, int W,
+                     const float* loc, int L, int64_t loc_image_stride,
+                     const int64_t* labels, int use_ignore, int64_t ignore_index,
+                     const int64_t* init_clusters, int64_t init_image_stride,
+                     int64_t batch_index_base,
+                     float* x_out, float* xloc_out, void* xh_out, float* xerr_out,
+                     int64_t* labels_out, int64_t* clusters_out, int64_t* batch_out,
+                     int64_t* pixel_out, int64_t* seg_offsets, void* workspace, size_t workspace_bytes,
+                     float* run_sums, int32_t* run_cluster, int32_t* run_count, int32_t* run_overflow,
+                     void* stream) {
   HSG_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, HSG_E_INVALID, "prep: bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
   HSG_REQUIRE(L >= 0 && L <= 32, HSG_E_UNSUPPORTED, "prep: %d local-feature channels (max 32)", L);
   HSG_REQUIRE(emb_nchw && (loc || L == 0) && init_clusters && x_out && xloc_out && labels_out &&
@@ -369,8 +520,9 @@ int hsg_prep_f32(const float* emb_nchw, int B, int D, int H, int W,
   HSG_REQUIRE(!xh_out || L <= HSG_XH_MAX_TRAILING, HSG_E_UNSUPPORTED,
               "prep: the fp16 side copy holds at most %d local-feature channels", HSG_XH_MAX_TRAILING);
   HSG_REQUIRE((int64_t)H * W < (1ll << 31) && B <= 65535, HSG_E_UNSUPPORTED, "prep: image too large");
-  const size_t smem = (size_t)D * PREP_LD * sizeof(float);
+  const size_t smem = (size_t)(D + (run_sums ? L : 0)) * PREP_LD * sizeof(float);
   HSG_REQUIRE(smem <= 200 * 1024, HSG_E_UNSUPPORTED, "prep: embedding_dim %d too large", D);
+  HSG_REQUIRE(!run_sums || (run_cluster && run_count && run_overflow), HSG_E_INVALID, "prep: run sums need all four buffers");
   cudaStream_t st = (cudaStream_t)stream;
   const int HW = H * W;
   const int tpi = (HW + PREP_TPX - 1) / PREP_TPX;
@@ -402,9 +554,65 @@ int hsg_prep_f32(const float* emb_nchw, int B, int D, int H, int W,
   a.batch_base = batch_index_base; a.x = x_out; a.xloc = xloc_out; a.xh = (__half*)xh_out;
   a.xerr = xerr_out; a.labels_out = labels_out; a.clusters_out = clusters_out;
   a.batch_out = batch_out; a.pixel_out = pixel_out; a.tile_base = tile_base; a.tiles_per_image = tpi;
+  a.run_sums = run_sums; a.run_cluster = run_cluster; a.run_count = run_count; a.run_overflow = run_overflow;
+  if (run_sums) HSG_CUDA(cudaMemsetAsync(run_overflow, 0, sizeof(int32_t), (cudaStream_t)stream));
   if (smem > 48 * 1024)
     HSG_CUDA(cudaFuncSetAttribute(prep_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prep_main_kernel<<<dim3(tpi, B), PREP_THREADS, smem, st>>>(a);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+int hsg_prep_f32(const float* emb_nchw, int B, int D, int H, int W,
+                 const float* loc, int L, int64_t loc_image_stride,
+                 const int64_t* labels, int use_ignore, int64_t ignore_index,
+                 const int64_t* init_clusters, int64_t init_image_stride,
+                 int64_t batch_index_base,
+                 float* x_out, float* xloc_out, void* xh_out, float* xerr_out,
+                 int64_t* labels_out, int64_t* clusters_out, int64_t* batch_out,
+                 int64_t* pixel_out, int64_t* seg_offsets, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  return prep_impl(emb_nchw, B, D, H, W, loc, L, loc_image_stride, labels, use_ignore, ignore_index, init_clusters,
+                   init_image_stride, batch_index_base, x_out, xloc_out, xh_out, xerr_out, labels_out, clusters_out,
+                   batch_out, pixel_out, seg_offsets, workspace, workspace_bytes, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int64_t hsg_prep_runs_per_image(int H, int W) {
+  return ceil_div64((int64_t)H * W, PREP_TPX) * HSG_PREP_RUNS;
+}
+
+int hsg_prep_sums_f32(const float* emb_nchw, int B, int D, int H, int W,
+                      const float* loc, int L, int64_t loc_image_stride,
+                      const int64_t* labels, int use_ignore, int64_t ignore_index,
+                      const int64_t* init_clusters, int64_t init_image_stride,
+                      int64_t batch_index_base,
+                      float* x_out, float* xloc_out, void* xh_out, float* xerr_out,
+                      int64_t* labels_out, int64_t* clusters_out, int64_t* batch_out,
+                      int64_t* pixel_out, int64_t* seg_offsets, void* workspace, size_t workspace_bytes,
+                      float* run_sums, int32_t* run_cluster, int32_t* run_count, int32_t* run_overflow,
+                      void* stream) {
+  HSG_REQUIRE(run_sums && run_cluster && run_count && run_overflow, HSG_E_INVALID, "prep_sums: null run buffers");
+  return prep_impl(emb_nchw, B, D, H, W, loc, L, loc_image_stride, labels, use_ignore, ignore_index, init_clusters,
+                   init_image_stride, batch_index_base, x_out, xloc_out, xh_out, xerr_out, labels_out, clusters_out,
+                   batch_out, pixel_out, seg_offsets, workspace, workspace_bytes, run_sums, run_cluster, run_count,
+                   run_overflow, stream);
+}
+
+int hsg_prep_bwd_f32(const float* emb_nchw, int B, int D, int H, int W, const float* x, const float* loc, int L,
+                     int64_t loc_image_stride, const int64_t* row_of_pixel, const float* grad_x,
+                     const float* grad_xloc, float* grad_emb_nchw, void* stream) {
+  HSG_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && L >= 0 && L <= 32, HSG_E_INVALID, "prep_bwd: bad shape");
+  HSG_REQUIRE(emb_nchw && x && grad_emb_nchw && (loc || L == 0), HSG_E_INVALID, "prep_bwd: null pointer");
+  HSG_REQUIRE((int64_t)H * W < (1ll << 31) && B <= 65535, HSG_E_UNSUPPORTED, "prep_bwd: image too large");
+  const size_t smem = (size_t)D * PREP_LD * sizeof(float);
+  HSG_REQUIRE(smem <= 200 * 1024, HSG_E_UNSUPPORTED, "prep_bwd: embedding_dim %d too large", D);
+  PrepBwdArgs a;
+  a.emb = emb_nchw; a.B = B; a.D = D; a.HW = H * W; a.L = L; a.x = x; a.loc = loc; a.loc_image_stride = loc_image_stride;
+  a.row_of_pixel = row_of_pixel; a.gx = grad_x; a.gz = grad_xloc; a.gemb = grad_emb_nchw;
+  if (smem > 48 * 1024)
+    HSG_CUDA(cudaFuncSetAttribute(prep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tpi = (a.HW + PREP_TPX - 1) / PREP_TPX;
+  prep_bwd_kernel<<<dim3(tpi, B), PREP_THREADS, smem, (cudaStream_t)stream>>>(a);
   HSG_LAUNCH_CHECK();
   return HSG_OK;
 }

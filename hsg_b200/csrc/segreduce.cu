@@ -361,10 +361,10 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine64_kernel(
     int64_t bins, int dim, const int64_t* __restrict__ bin_start, const int32_t* __restrict__ bin_count,
     const float* __restrict__ pieces, const double* __restrict__ p64, const int32_t* __restrict__ piece_cnt,
     const int32_t* __restrict__ delta_flag, double* __restrict__ sums, int32_t* __restrict__ members,
-    float* __restrict__ out) {
+    float* __restrict__ out, Gate gate) {
   const int lane = threadIdx.x & 31;
   const int64_t key = (int64_t)blockIdx.x * COMBINE_WARPS + (threadIdx.x >> 5);
-  if (key >= bins) return;
+  if (gate.closed() || key >= bins) return;
   const bool delta = delta_flag && *delta_flag == 1;
   const int cnt = bin_count[key];
   const int64_t start = bin_start[key];
@@ -672,10 +672,10 @@ int sr_combine_exact(const SegReducePlan& p, int64_t P, const int64_t* seg_base,
 }
 
 int sr_combine64(const SegReducePlan& p, const float* pieces_full, const double* pieces_delta,
-                 const int32_t* delta_flag, double* sums, int32_t* members, float* out, cudaStream_t st) {
+                 const int32_t* delta_flag, double* sums, int32_t* members, float* out, cudaStream_t st, Gate gate) {
   ProfRange prof(PROF_MSTEP_COMBINE, st);
   combine64_kernel<<<(unsigned)ceil_div64(p.bins, COMBINE_WARPS), COMBINE_WARPS * 32, 0, st>>>(
-      p.bins, p.dim, p.bin_start, p.bin_count, pieces_full, pieces_delta, p.piece_cnt, delta_flag, sums, members, out);
+      p.bins, p.dim, p.bin_start, p.bin_count, pieces_full, pieces_delta, p.piece_cnt, delta_flag, sums, members, out, gate);
   HSG_LAUNCH_CHECK();
   return HSG_OK;
 }

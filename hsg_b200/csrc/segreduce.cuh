@@ -91,7 +91,8 @@ int sr_sort_and_sum_gated(const SegReducePlan& p, const float* x, const int64_t*
 // k-means finish on running float64 sums: *delta_flag == 1 adds the (float64) pieces of a delta
 // pass, otherwise the sums are set from the float pieces of a full pass; out = normalised rows
 int sr_combine64(const SegReducePlan& p, const float* pieces_full, const double* pieces_delta,
-                 const int32_t* delta_flag, double* sums, int32_t* members, float* out, cudaStream_t st);
+                 const int32_t* delta_flag, double* sums, int32_t* members, float* out, cudaStream_t st,
+                 Gate gate = Gate{nullptr, 0});
 // rows of p whose key differs from keys_prev -> signed entries (erow/ekey, per-segment offsets
 // eoff[S+1]); flag[0] = 1 when they fit `cap` entries (else 0: take the full pass), flag[1] =
 // changed rows; keys_prev is brought up to date either way

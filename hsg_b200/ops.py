@@ -76,9 +76,10 @@ def normalize(x):
 
 # ---------------------------------------------------------------- K0 prep
 def prep(embeddings, loc, loc_image_stride, labels, ignore_index, init_clusters, init_image_stride,
-         batch_index_base, want_half):
+         batch_index_base, want_half, want_run_sums=False):
   """Front half of segment_by_kmeans.  Returns a dict of max-size buffers plus
-  the device offsets; the caller slices with N = seg_offsets[-1]."""
+  the device offsets; the caller slices with N = seg_offsets[-1].  With want_run_sums the kernel
+  also emits the partial sums of the first k-means M-step (out['runs'], for kmeans(run_sums=...))."""
   _need_cuda(embeddings, loc, labels, init_clusters)
   emb = _f32(embeddings)
   b, d, h, w = emb.shape
@@ -99,15 +100,40 @@ def prep(embeddings, loc, loc_image_stride, labels, ignore_index, init_clusters,
   lib = _lib.load()
   ws = _workspace(lib.hsg_prep_workspace_bytes(b, h, w), dev)
   use_ignore = ignore_index is not None
+  args = (_ptr(emb), b, d, h, w, _ptr(loc), l, int(loc_image_stride),
+          _ptr(labels), int(use_ignore), int(ignore_index) if use_ignore else 0,
+          _ptr(init_clusters), int(init_image_stride), int(batch_index_base),
+          _ptr(out['x']), _ptr(out['xloc']), _ptr(out['xh']), _ptr(out['xerr']),
+          _ptr(out['labels']), _ptr(out['clusters']), _ptr(out['batch']), _ptr(out['pixel']), _ptr(out['seg_offsets']),
+          _ptr(ws), ws.numel())
   with torch.cuda.device(dev):
-    check(lib.hsg_prep_f32(
-        _ptr(emb), b, d, h, w, _ptr(loc), l, int(loc_image_stride),
-        _ptr(labels), int(use_ignore), int(ignore_index) if use_ignore else 0,
-        _ptr(init_clusters), int(init_image_stride), int(batch_index_base),
-        _ptr(out['x']), _ptr(out['xloc']), _ptr(out['xh']), _ptr(out['xerr']),
-        _ptr(out['labels']), _ptr(out['clusters']), _ptr(out['batch']), _ptr(out['pixel']), _ptr(out['seg_offsets']),
-        _ptr(ws), ws.numel(), _stream()), 'prep')
+    if want_run_sums:
+      rpi = int(lib.hsg_prep_runs_per_image(h, w))
+      runs = {'sums': torch.empty((b * rpi, d + l), dtype=torch.float32, device=dev),
+              'cluster': torch.empty((b * rpi,), dtype=torch.int32, device=dev),
+              'count': torch.empty((b * rpi,), dtype=torch.int32, device=dev),
+              'overflow': torch.empty((1,), dtype=torch.int32, device=dev), 'per_segment': rpi}
+      check(lib.hsg_prep_sums_f32(*args, _ptr(runs['sums']), _ptr(runs['cluster']), _ptr(runs['count']),
+                                  _ptr(runs['overflow']), _stream()), 'prep_sums')
+      out['runs'] = runs
+    else:
+      check(lib.hsg_prep_f32(*args, _stream()), 'prep')
   return out
+
+
+def prep_backward(embeddings, x, loc, loc_image_stride, row_of_pixel, grad_x, grad_xloc):
+  """Gradient of the prep chain w.r.t. the NCHW embeddings (hsg_prep_bwd_f32); either gradient may be None."""
+  _need_cuda(embeddings, x, loc, row_of_pixel, grad_x, grad_xloc)
+  emb = _f32(embeddings)
+  b, d, h, w = emb.shape
+  l = loc.shape[-1]
+  gemb = torch.empty_like(emb)
+  gx = _f32(grad_x) if grad_x is not None else None
+  gz = _f32(grad_xloc) if grad_xloc is not None else None
+  with torch.cuda.device(emb.device):
+    check(_lib.load().hsg_prep_bwd_f32(_ptr(emb), b, d, h, w, _ptr(_f32(x)), _ptr(loc), l, int(loc_image_stride),
+                                       _ptr(row_of_pixel), _ptr(gx), _ptr(gz), _ptr(gemb), _stream()), 'prep_bwd')
+  return gemb
 
 
 def make_half_copy(x, d16):
@@ -138,7 +164,7 @@ def tc_d16(dim, kmax):
 
 
 def kmeans(x, init_labels, kmax, iterations, seg_offsets=None, max_seg_len=None, seg_k=None,
-           xh=None, xerr=None, flags=_lib.KMEANS_AUTO, return_centroids=False):
+           xh=None, xerr=None, flags=_lib.KMEANS_AUTO, return_centroids=False, run_sums=None):
   _need_cuda(x, init_labels, seg_offsets, seg_k, xh, xerr)
   x = _f32(x)
   n, dim = x.shape
@@ -152,11 +178,15 @@ def kmeans(x, init_labels, kmax, iterations, seg_offsets=None, max_seg_len=None,
   lib = _lib.load()
   ws = _workspace(lib.hsg_kmeans_workspace_bytes(n, dim, s, kmax, max_seg_len), x.device)
   d16 = xh.shape[1] - XH_TAIL if xh is not None else 0
+  args = (_ptr(x), n, dim, _ptr(xh), d16, _ptr(xerr), _ptr(seg_offsets), s, max_seg_len, _ptr(seg_k), kmax,
+          _ptr(init_labels), iterations, _ptr(labels), _ptr(cent), flags, _ptr(ws), ws.numel())
   with torch.cuda.device(x.device):
-    check(lib.hsg_kmeans_f32(_ptr(x), n, dim, _ptr(xh), d16, _ptr(xerr), _ptr(seg_offsets), s,
-                             max_seg_len, _ptr(seg_k), kmax, _ptr(init_labels), iterations,
-                             _ptr(labels), _ptr(cent), flags, _ptr(ws), ws.numel(), _stream()),
-          'kmeans')
+    if run_sums is not None:
+      r = run_sums
+      check(lib.hsg_kmeans_presummed_f32(*args, _ptr(r['sums']), _ptr(r['cluster']), _ptr(r['count']),
+                                         _ptr(r['overflow']), int(r['per_segment']), _stream()), 'kmeans_presummed')
+    else:
+      check(lib.hsg_kmeans_f32(*args, _stream()), 'kmeans')
   return (labels, cent) if return_centroids else labels
 
 
@@ -362,3 +392,16 @@ def relabel(batch, cluster, label, batch_base, num_images, kmax, label_values):
                               kmax, _ptr(label_values), nl, _ptr(ids), _ptr(pl), _ptr(pb), _ptr(pc),
                               _ptr(npro), _ptr(ws), ws.numel(), _stream()), 'relabel')
   return ids, pl, pb, pc, npro
+
+
+# ---------------------------------------------------------------- f3 top-k retrieval
+def topk_affinity(embeddings, prototypes, k):
+  """Indices [N,k] (int64, best first) of the k prototypes with the largest inner product per row."""
+  _need_cuda(embeddings, prototypes)
+  e = _f32(embeddings.detach().reshape(-1, embeddings.shape[-1]))
+  p = _f32(prototypes.detach().reshape(-1, prototypes.shape[-1]))
+  idx = torch.empty((e.shape[0], int(k)), dtype=torch.int64, device=e.device)
+  with torch.cuda.device(e.device):
+    check(_lib.load().hsg_topk_affinity_f32(_ptr(e), e.shape[0], _ptr(p), p.shape[0], e.shape[1], int(k), _ptr(idx), None,
+                                            _stream()), 'topk')
+  return idx

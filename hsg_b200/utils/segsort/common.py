@@ -14,6 +14,7 @@ from ... import ops
 from ..._lib import REDUCE_NORMALIZE, KMEANS_AUTO
 
 _GRID_CACHE = {}
+_RUN_SUMS_MIN_PIXELS = 1 << 18     # below this the k-means loop re-sums every row anyway (launch-bound regime)
 
 
 def calculate_prototypes_from_labels(embeddings, labels, max_label=None):
@@ -102,34 +103,26 @@ def find_majority_label_index(semantic_labels, cluster_labels):
 class _PrepOutputs(torch.autograd.Function):
   """Makes the two float outputs of the prep kernel differentiable in the input
   embeddings (the reference's permute/normalize/cat/normalize/index_select chain
-  is; the NCE loss back-propagates through `cluster_embedding`)."""
+  is; the NCE loss back-propagates through `cluster_embedding`).  Backward = one
+  kernel (hsg_prep_bwd_f32)."""
 
   @staticmethod
-  def forward(ctx, embeddings, x, xloc, pixel, loc_rows):
-    ctx.save_for_backward(embeddings, x, xloc, pixel, loc_rows)
-    ctx.mark_non_differentiable(pixel)
+  def forward(ctx, embeddings, x, xloc, pixel, loc, loc_stride, dropped):
+    ctx.save_for_backward(embeddings, x, pixel, loc)
+    ctx.loc_stride = loc_stride
+    ctx.dropped = dropped
     return x.view_as(x), xloc.view_as(xloc)
 
   @staticmethod
   def backward(ctx, gx, gxloc):
-    emb, y, z, pixel, loc_rows = ctx.saved_tensors
+    emb, y, pixel, loc = ctx.saved_tensors
     b, d, h, w = emb.shape
-    rows = emb.permute(0, 2, 3, 1).reshape(-1, d).index_select(0, pixel)
-    n1 = rows.norm(dim=1, keepdim=True)
-    n1 = torch.where(n1 >= 1e-12, n1, torch.full_like(n1, 1e-12))
-    gy = gx.clone() if gx is not None else torch.zeros_like(y)
-    if gxloc is not None:
-      cat = torch.cat([y, loc_rows], 1)
-      n2 = cat.norm(dim=1, keepdim=True)
-      big = n2 >= 1e-12
-      n2 = torch.where(big, n2, torch.full_like(n2, 1e-12))
-      gcat = torch.where(big, gxloc - z * (z * gxloc).sum(1, keepdim=True), gxloc) / n2
-      gy += gcat[:, :d]
-    big1 = rows.norm(dim=1, keepdim=True) >= 1e-12
-    grow = torch.where(big1, gy - y * (y * gy).sum(1, keepdim=True), gy) / n1
-    gemb = torch.zeros((b * h * w, d), dtype=emb.dtype, device=emb.device)
-    gemb.index_copy_(0, pixel, grow)
-    return gemb.view(b, h, w, d).permute(0, 3, 1, 2), None, None, None, None
+    row_of_pixel = None
+    if ctx.dropped:                                   # inverse of the compaction: source pixel -> output row
+      row_of_pixel = torch.full((b * h * w,), -1, dtype=torch.int64, device=emb.device)
+      row_of_pixel[pixel] = torch.arange(pixel.shape[0], device=emb.device, dtype=torch.int64)
+    gemb = ops.prep_backward(emb, y, loc, ctx.loc_stride, row_of_pixel, gx, gxloc)
+    return gemb, None, None, None, None, None, None
 
 
 def _grid_init(num_clusters, hw, device):
@@ -205,8 +198,11 @@ def segment_by_kmeans_ex(embeddings, labels=None, num_clusters=[5, 5], cluster_i
   gpu_id = dev.index or 0
   want_half = ops.tc_d16(c + n_loc, kmax) == c and iterations >= 1
   with torch.no_grad():
+    # at full-resolution sizes the prep kernel also emits the first M-step's partial sums (the rows are on
+    # chip anyway), so k-means does not start by re-reading every row it has just written
+    want_runs = int(iterations) >= 1 and b * h * w >= _RUN_SUMS_MIN_PIXELS
     buf = ops.prep(embeddings.detach(), loc, loc_stride, lab_in, ign, init, init_stride,
-                   b * gpu_id, want_half)                                 # :376-377 batch offset
+                   b * gpu_id, want_half, want_run_sums=want_runs)        # :376-377 batch offset
     n = b * h * w if ign is None else int(buf['seg_offsets'][-1])         # one sync when pixels are dropped
     x, xloc = buf['x'][:n], buf['xloc'][:n]
     lab, bat, pix = buf['labels'][:n], buf['batch'][:n], buf['pixel'][:n]
@@ -217,7 +213,7 @@ def segment_by_kmeans_ex(embeddings, labels=None, num_clusters=[5, 5], cluster_i
     max_len = min(h * w, n)            # a single image with ignore pixels dropped is shorter than its grid
     clusters = ops.kmeans(xloc, buf['clusters'][:n], kmax, int(iterations),
                           seg_offsets=buf['seg_offsets'], max_seg_len=max_len, seg_k=seg_k,
-                          xh=xh, xerr=xerr, flags=KMEANS_AUTO)
+                          xh=xh, xerr=xerr, flags=KMEANS_AUTO, run_sums=buf.get('runs'))
     if labels is None:
       label_values = torch.zeros((1,), dtype=torch.int64, device=dev)
     else:
@@ -225,8 +221,7 @@ def segment_by_kmeans_ex(embeddings, labels=None, num_clusters=[5, 5], cluster_i
     ids, pl, pb, pc, npro = ops.relabel(bat, clusters, lab, b * gpu_id, b, kmax, label_values)   # :397-405
 
   if embeddings.requires_grad and torch.is_grad_enabled():
-    loc_rows = loc.reshape(-1, n_loc).index_select(0, pix % (h * w) if loc_stride == 0 else pix)
-    x, xloc = _PrepOutputs.apply(embeddings, x, xloc, pix, loc_rows)
+    x, xloc = _PrepOutputs.apply(embeddings, x, xloc, pix, loc, loc_stride, ign is not None)
   ex = {'embeddings': x, 'embeddings_with_loc': xloc, 'labels': lab, 'cluster_indices': ids,
         'batch_indices': bat, 'seg_offsets': buf['seg_offsets'], 'max_seg_len': max_len,
         'num_images': b, 'batch_base': b * gpu_id, 'kmeans_labels': clusters,

@@ -124,6 +124,39 @@ HSG_API int hsg_prep_f32(const float* emb_nchw, int B, int D, int H, int W,
                  int64_t* pixel_out, int64_t* seg_offsets, void* workspace, size_t workspace_bytes,
                  void* stream);
 
+/* hsg_prep_f32 that also emits the partial sums of the FIRST k-means M-step while the rows are on chip
+ * (segment_by_kmeans starts k-means from the grid labels it has just written, common.py:337-372, so the
+ * first calculate_prototypes_from_labels would re-read every xloc row): for each tile of 64 consecutive
+ * source pixels of an image, one partial sum per run of equal initial cluster id among the kept pixels,
+ * at most HSG_PREP_RUNS runs per tile.
+ *   run_sums    [B*R, D+L] fp32, R = hsg_prep_runs_per_image(H,W); slot (b*tiles + t)*HSG_PREP_RUNS + run
+ *   run_cluster [B*R] int32 initial cluster id of the run, -1 = unused slot (its sum row is not written)
+ *   run_count   [B*R] int32 pixels in the run
+ *   run_overflow[1]   int32, 1 when some tile had more runs than slots: the sums are then incomplete and
+ *               hsg_kmeans_presummed_f32 falls back to the ordinary first M-step (decided on the device) */
+#define HSG_PREP_RUNS 4
+HSG_API int64_t hsg_prep_runs_per_image(int H, int W);
+HSG_API int hsg_prep_sums_f32(const float* emb_nchw, int B, int D, int H, int W,
+                 const float* loc, int L, int64_t loc_image_stride,
+                 const int64_t* labels, int use_ignore, int64_t ignore_index,
+                 const int64_t* init_clusters, int64_t init_image_stride,
+                 int64_t batch_index_base,
+                 float* x_out, float* xloc_out, void* xh_out, float* xerr_out,
+                 int64_t* labels_out, int64_t* clusters_out, int64_t* batch_out,
+                 int64_t* pixel_out, int64_t* seg_offsets, void* workspace, size_t workspace_bytes,
+                 float* run_sums, int32_t* run_cluster, int32_t* run_count, int32_t* run_overflow,
+                 void* stream);
+
+/* Backward of the prep chain (the reference's autograd through permute / normalize / cat / normalize /
+ * index_select, hsg/utils/segsort/common.py:305-365): gradients w.r.t. the two float outputs of hsg_prep_f32
+ * (either may be NULL) -> gradient w.r.t. the NCHW input, zero at dropped pixels.  One pass.
+ *   x            [N,D]   the forward's x_out
+ *   row_of_pixel [B*H*W] output row of every source pixel, -1 = dropped; NULL = nothing was dropped */
+HSG_API int hsg_prep_bwd_f32(const float* emb_nchw, int B, int D, int H, int W,
+                 const float* x, const float* loc, int L, int64_t loc_image_stride,
+                 const int64_t* row_of_pixel, const float* grad_x, const float* grad_xloc,
+                 float* grad_emb_nchw, void* stream);
+
 /* fp16 side copy used by the tensor-core E-step, for callers that did not go
  * through hsg_prep_f32: xh [rows, d16+HSG_XH_TAIL] fp16, xerr[r] = rounding norm
  * of the first d16 columns; dim - d16 <= HSG_XH_MAX_TRAILING */
@@ -157,6 +190,19 @@ HSG_API int hsg_kmeans_f32(const float* x, int64_t N, int dim,
                    const int64_t* init_labels, int iterations,
                    int64_t* labels_out, float* centroids_out, int flags,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* hsg_kmeans_f32 whose first M-step takes the run sums of hsg_prep_sums_f32 (the init labels must be the
+ * clusters that call wrote, segment s = image s, runs_per_segment = hsg_prep_runs_per_image) instead of
+ * re-reading every row; falls back to the ordinary first M-step on the device when *run_overflow != 0. */
+HSG_API int hsg_kmeans_presummed_f32(const float* x, int64_t N, int dim,
+                   const void* xh, int d16, const float* xerr,
+                   const int64_t* seg_offsets, int S, int64_t max_seg_len,
+                   const int32_t* seg_k, int kmax,
+                   const int64_t* init_labels, int iterations,
+                   int64_t* labels_out, float* centroids_out, int flags,
+                   void* workspace, size_t workspace_bytes,
+                   const float* run_sums, const int32_t* run_cluster, const int32_t* run_count,
+                   const int32_t* run_overflow, int64_t runs_per_segment, void* stream);
 
 /* single steps, for per-iteration (teacher-forced) parity:
  * M-step == calculate_prototypes_from_labels per segment (common.py:11-41),
@@ -289,6 +335,13 @@ HSG_API int hsg_relabel_i64(const int64_t* batch, const int64_t* cluster, const 
                     int64_t* ids_out, int64_t* proto_label_out, int64_t* proto_batch_out,
                     int64_t* proto_cluster_out, int64_t* n_protos_out,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- f3: top_k_ranking  (hsg/utils/segsort/eval.py:9-52)
+ * indices_out[r, 0..k) = the k prototypes with the largest inner product with embeddings[r,:], best first
+ * (ties: lower index first), k <= 8.  fp32 products; the [N,M] affinity matrix is never written.
+ * values_out optional [N,k].  The caller gathers the labels / averages the hits (tiny tensors). */
+HSG_API int hsg_topk_affinity_f32(const float* embeddings, int64_t N, const float* prototypes, int64_t M,
+                                  int dim, int k, int64_t* indices_out, float* values_out, void* stream);
 
 #ifdef __cplusplus
 }

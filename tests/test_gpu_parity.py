@@ -614,6 +614,88 @@ def test_segment_by_kmeans_tc_equals_simt(S):
   assert np.mean(n(res[3]) == ref[3]) > 0.99
 
 
+def test_prep_backward_matches_reference_autograd(S, golden):
+  """hsg_prep_bwd_f32 against the reference's own autograd through the prep chain (D = 256, dropped pixels,
+  a zero pixel that takes the eps branch of both normalisations) -- oracle/gen_golden_prep_bwd.py."""
+  g = golden('prep_backward')
+  emb = t(g['emb']).requires_grad_(True)
+  x, xloc, lab, ids, bat = S.segment_by_kmeans(emb, t(g['labels']), [2, 2], ignore_index=7, iterations=1)
+  close(n(x), g['x'], rtol=1e-5, atol=1e-7)
+  close(n(xloc), g['xloc'], rtol=1e-5, atol=1e-7)
+  ((x * t(g['gx'])).sum() + (xloc * t(g['gz'])).sum()).backward()
+  scale = np.abs(g['demb']).max()
+  zero_px = np.abs(g['emb'][1, :, 2, 3]).max() == 0          # its gradient is g / 1e-12: compare relatively
+  assert zero_px
+  mask = np.ones(g['demb'].shape, dtype=bool)
+  mask[1, :, 2, 3] = False
+  scale_rest = np.abs(g['demb'][mask]).max()
+  assert np.abs(n(emb.grad)[mask] - g['demb'][mask]).max() <= 1e-5 * scale_rest
+  close(n(emb.grad)[1, :, 2, 3], g['demb'][1, :, 2, 3], rtol=1e-5, atol=1e-5 * scale * 1e-6)
+  emb.grad = None
+  x, xloc, _, _, _ = S.segment_by_kmeans(emb, t(g['labels']), [2, 2], ignore_index=7, iterations=1)
+  (x * t(g['gx'])).sum().backward()
+  assert np.abs(n(emb.grad)[mask] - g['demb_x_only'][mask]).max() <= 1e-5 * np.abs(g['demb_x_only'][mask]).max()
+
+
+@pytest.mark.parametrize('nq,m,d,k', [(1000, 333, 128, 5), (257, 4096, 256, 5), (64, 7, 32, 3), (12288, 12288, 256, 5)])
+def test_top_k_ranking_kernel(nq, m, d, k):
+  """f3: hsg_topk_affinity_f32 (running top-k over register-tiled fp32 products, no [N,P] matrix) against the
+  reference's mm + argsort (hsg/utils/segsort/eval.py:32-34).  Rows whose k-th / (k+1)-th affinities are closer
+  than fp32 summation-order noise may legitimately differ; they are excluded by their float64 margin."""
+  from hsg_b200.utils.segsort import eval as E
+  rng = np.random.RandomState(7)
+  e = o_ops.normalize_embedding(rng.randn(nq, d).astype(np.float32))
+  p = o_ops.normalize_embedding(rng.randn(m, d).astype(np.float32))
+  lab = rng.randint(0, 9, nq).astype(np.int64)
+  plab = rng.randint(0, 9, m).astype(np.int64)
+  acc, got = E.top_k_ranking(t(e), t(lab), t(p), t(plab), k)
+  aff = e.astype(np.float64) @ p.astype(np.float64).T
+  order = np.argsort(-aff, axis=1, kind='stable')[:, :k + 1]
+  srt = np.take_along_axis(aff, order, 1)
+  gaps = np.abs(np.diff(srt, axis=1)).min(1) if m > k else np.abs(np.diff(srt[:, :k], axis=1)).min(1)
+  sure = gaps > 1e-5
+  assert sure.mean() > 0.9
+  want = plab[order[:, :k]]
+  assert np.array_equal(n(got)[sure], want[sure])
+  want_acc = float((want == lab[:, None]).mean())
+  assert abs(float(acc) - want_acc) <= (1.0 - sure.mean()) + 1e-6
+
+
+def test_first_mstep_from_prep_run_sums(S):
+  """The prep kernel can emit the first M-step's partial sums (hsg_prep_sums_f32 -> hsg_kmeans_presummed_f32).
+  Same labels as the ordinary path (up to float64 near-ties: the fp32 partial sums are formed in another fixed
+  order), including ignored pixels, and the device-side fallback when a tile has more runs than slots."""
+  from hsg_b200.utils.segsort import common as C
+  rng = np.random.RandomState(17)
+  saved = C._RUN_SUMS_MIN_PIXELS
+  try:
+    for shape, grid, labelled in (((3, 64, 48, 160), [3, 4], True),      # 40-pixel wide clusters: <= 3 runs per tile
+                                  ((2, 32, 24, 16), [6, 8], False)):     # 2-pixel wide clusters: overflow -> fallback
+      emb = t(rng.randn(*shape).astype(np.float32))
+      lab = None
+      if labelled:
+        lab = rng.randint(0, 3, (shape[0], shape[2], shape[3]))
+        lab[0, :5, :] = 9
+        lab = t(lab.astype(np.int64))
+      out = {}
+      for name, thr in (('plain', 1 << 60), ('fused', 0)):
+        C._RUN_SUMS_MIN_PIXELS = thr
+        out[name] = C.segment_by_kmeans_ex(emb, lab, grid, ignore_index=9 if labelled else None, iterations=3)
+      a, b = out['plain'], out['fused']
+      assert torch.equal(a['embeddings_with_loc'], b['embeddings_with_loc'])
+      assert torch.equal(a['batch_indices'], b['batch_indices'])
+      agree = float((a['kmeans_labels'] == b['kmeans_labels']).float().mean())
+      assert agree > 0.999, agree
+      # one iteration: centroids of the first M-step agree to fp32 accuracy -> check through the labels of E-step 1
+      C._RUN_SUMS_MIN_PIXELS = 1 << 60
+      one_a = C.segment_by_kmeans_ex(emb, lab, grid, ignore_index=9 if labelled else None, iterations=1)['kmeans_labels']
+      C._RUN_SUMS_MIN_PIXELS = 0
+      one_b = C.segment_by_kmeans_ex(emb, lab, grid, ignore_index=9 if labelled else None, iterations=1)['kmeans_labels']
+      assert float((one_a == one_b).float().mean()) > 0.9995
+  finally:
+    C._RUN_SUMS_MIN_PIXELS = saved
+
+
 # ---------------------------------------------------------------- tensor-core NCE forward
 @pytest.mark.parametrize('nn,pp,d,conc', [(3000, 300, 64, 16.0), (1500, 1100, 256, 16.0), (700, 37, 128, 10.0)])
 def test_nce_tensor_core_forward(nn, pp, d, conc):
