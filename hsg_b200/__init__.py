@@ -80,12 +80,35 @@ def _patch_methods(importlib):
         setattr(cls, n, fn)
 
 
-def patch():
+_SYNCBN_TARGETS = ['lib.nn.sync_batchnorm.batchnorm', 'lib.nn.sync_batchnorm', 'lib.nn.sync_batchnorm.replicate']
+
+
+def _patch_sync_batchnorm(importlib):
+  """One process per GPU (torchrun): SyncBN statistics cross the ranks of the default process group instead of
+  the replicas of a thread-per-GPU DataParallel (lib/nn/sync_batchnorm/batchnorm.py:353-393, replicate.py:69-94)."""
+  from .nn import sync_batchnorm as ours
+  for ref_name in _SYNCBN_TARGETS:
+    try:
+      ref = importlib.import_module(ref_name)
+    except ImportError:
+      continue
+    for n, fn in (('convert_model', ours.convert_model), ('patch_replication_callback', ours.patch_replication_callback)):
+      if hasattr(ref, n):
+        if (ref_name, n) not in _PATCHED:
+          _PATCHED[(ref_name, n)] = getattr(ref, n)
+        setattr(ref, n, fn)
+
+
+def patch(sync_batchnorm=False):
   """Rebind the reference's hot-path operators to this package.  The reference
   resolves them late through module attributes (e.g. segsort_common.segment_by_kmeans
-  in hsg/models/embeddings/resnet_fcn_hsg.py:206), so nothing else changes."""
+  in hsg/models/embeddings/resnet_fcn_hsg.py:206), so nothing else changes.
+  sync_batchnorm=True also rebinds lib.nn.sync_batchnorm's convert_model / patch_replication_callback to the
+  torch.distributed form (for one-process-per-GPU launches only)."""
   import importlib
   load_library()                       # fail loudly before touching anything
+  if sync_batchnorm:
+    _patch_sync_batchnorm(importlib)
   for ref_name, (our_name, names) in _TARGETS.items():
     try:
       ref = importlib.import_module(ref_name)

@@ -81,6 +81,8 @@ SIGNATURES = {
     'hsg_segment_sum_exact_workspace_bytes': (_z, [_l, _i, _l, _i, _i, _l]),
     'hsg_segment_sum_exact_i64': (_i, [_p, _l, _i, _p, _l, _p, _i, _l, _p, _i, _p, _p, _z, _p]),
     'hsg_knn_adjacency_f32': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    'hsg_bn_stats_f32': (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    'hsg_bn_apply_f32': (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _p, _p]),
     'hsg_topk_affinity_f32': (_i, [_p, _l, _p, _l, _i, _i, _p, _p, _p]),
     'hsg_relabel_workspace_bytes': (_z, [_i, _i, _l]),
     'hsg_relabel_i64': (_i, [_p, _p, _p, _l, _l, _i, _i, _p, _l, _p, _p, _p, _p, _p, _p, _z, _p]),

@@ -324,30 +324,46 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_main_kernel(const PrepArgs 
   }
 
   if (a.run_sums) {
-    // The tile now holds the xloc rows (zero columns for dropped pixels).  Thread 0 finds the runs of equal
+    // The tile now holds the xloc rows (zero columns for dropped pixels).  Warp 0 finds the runs of equal
     // initial cluster among the kept pixels, then one thread per feature sums each run's pixel range -- fixed
     // order, so the sums do not depend on scheduling.
     __shared__ int run_lo[HSG_PREP_RUNS + 1];
     __shared__ int n_runs_s;
     const int64_t slot0 = ((int64_t)b * a.tiles_per_image + t) * HSG_PREP_RUNS;
-    if (threadIdx.x == 0) {
-      int run = -1, cur = -2, cnt = 0;
-      for (int px = 0; px < PREP_TPX; ++px) {
-        const int c = ck[px];
-        if (c < 0) continue;
-        if (c != cur) {
-          if (run >= 0 && run < HSG_PREP_RUNS) { a.run_cluster[slot0 + run] = cur; a.run_count[slot0 + run] = cnt; }
-          ++run; cur = c; cnt = 0;
-          if (run <= HSG_PREP_RUNS) run_lo[run] = px;
+    if (warp == 0) {
+      // run starts among the kept pixels, found with two 32-pixel ballots (no serial walk)
+      const int ca = ck[lane], cb = ck[lane + 32];
+      const uint64_t kept = (uint64_t)__ballot_sync(FULL, ca >= 0) | ((uint64_t)__ballot_sync(FULL, cb >= 0) << 32);
+      auto prev_cluster = [&](int px) {
+        const uint64_t below = kept & ((1ull << px) - 1ull);
+        return below ? ck[63 - __clzll((long long)below)] : -2;
+      };
+      const bool sa = ca >= 0 && ca != prev_cluster(lane);
+      const bool sb = cb >= 0 && cb != prev_cluster(lane + 32);
+      const uint64_t starts = (uint64_t)__ballot_sync(FULL, sa) | ((uint64_t)__ballot_sync(FULL, sb) << 32);
+      const int n_all = __popcll(starts);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int px = lane + 32 * h;
+        if (h ? sb : sa) {
+          const int run = __popcll(starts & ((1ull << px) - 1ull));
+          if (run < HSG_PREP_RUNS) {
+            const uint64_t later = px == 63 ? 0ull : (starts >> (px + 1)) << (px + 1);
+            const int end = later ? __ffsll((long long)later) - 1 : PREP_TPX;
+            const uint64_t range = (end == 64 ? ~0ull : ((1ull << end) - 1ull)) & ~((1ull << px) - 1ull);
+            run_lo[run] = px;
+            a.run_cluster[slot0 + run] = h ? cb : ca;
+            a.run_count[slot0 + run] = __popcll(kept & range);
+          }
         }
-        ++cnt;
       }
-      if (run >= 0 && run < HSG_PREP_RUNS) { a.run_cluster[slot0 + run] = cur; a.run_count[slot0 + run] = cnt; }
-      for (int r = run + 1; r < HSG_PREP_RUNS; ++r) a.run_cluster[slot0 + r] = -1;
-      if (run >= HSG_PREP_RUNS) *a.run_overflow = 1;
-      const int nr = min(run + 1, HSG_PREP_RUNS);
-      run_lo[nr] = PREP_TPX;                       // dropped pixels inside a range hold zeros
-      n_runs_s = nr;
+      const int nr0 = min(n_all, HSG_PREP_RUNS);
+      if (lane >= nr0 && lane < HSG_PREP_RUNS) a.run_cluster[slot0 + lane] = -1;
+      if (lane == 0) {
+        if (n_all > HSG_PREP_RUNS) *a.run_overflow = 1;
+        run_lo[nr0] = PREP_TPX;                    // dropped pixels inside a range hold zeros
+        n_runs_s = nr0;
+      }
     }
     __syncthreads();
     const int nr = n_runs_s;

@@ -144,11 +144,74 @@ def all_gather_varlen(t, group=None, sizes=None):
   return _AllGatherVarlen.apply(t, sizes, dist.get_rank(group), group)
 
 
+class _PackedPrototypeExchange(torch.autograd.Function):
+  """ONE all-gather for the whole prototype exchange: every rank sends a fixed-capacity record
+  [count | prototypes | prototypes_with_loc | sem | inst | batch] (bytes), so there is no size exchange before
+  the collective and no host synchronisation until the counts -- which ride in the payload -- are read to size
+  the outputs.  Backward: one all-reduce of the two float gradients, then this rank's slice."""
+
+  @staticmethod
+  def forward(ctx, prototypes, prototypes_with_loc, proto_sem, proto_inst, proto_batch, capacity, group):
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n, d = prototypes.shape
+    d2 = prototypes_with_loc.shape[1]
+    if n > capacity:
+      raise ValueError('exchange_prototypes: %d prototypes on this rank, capacity %d' % (n, capacity))
+    dev = prototypes.device
+    floats = capacity * (d + d2)
+    record = torch.zeros((8 + 4 * floats + 3 * 8 * capacity,), dtype=torch.uint8, device=dev)
+    record[:8].view(torch.int64)[0] = n
+    fl = record[8:8 + 4 * floats].view(torch.float32)
+    fl[:capacity * d].view(capacity, d)[:n] = prototypes.detach().float()
+    fl[capacity * d:].view(capacity, d2)[:n] = prototypes_with_loc.detach().float()
+    ints = record[8 + 4 * floats:].view(torch.int64).view(3, capacity)
+    ints[0, :n], ints[1, :n], ints[2, :n] = proto_sem.long(), proto_inst.long(), proto_batch.long()
+    gathered = torch.empty((world * record.numel(),), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, record, group=group)
+    gathered = gathered.view(world, record.numel())
+    sizes = gathered[:, :8].contiguous().view(torch.int64).view(-1).tolist()          # the one host read
+    fl_all = gathered[:, 8:8 + 4 * floats].contiguous().view(torch.float32).view(world, floats)
+    in_all = gathered[:, 8 + 4 * floats:].contiguous().view(torch.int64).view(world, 3, capacity)
+    protos = torch.cat([fl_all[r, :capacity * d].view(capacity, d)[:sizes[r]] for r in range(world)], 0)
+    protos_loc = torch.cat([fl_all[r, capacity * d:].view(capacity, d2)[:sizes[r]] for r in range(world)], 0)
+    labels = [torch.cat([in_all[r, j, :sizes[r]] for r in range(world)], 0) for j in range(3)]
+    ctx.sizes, ctx.rank, ctx.group = sizes, rank, group
+    ctx.mark_non_differentiable(*labels)
+    offset = torch.tensor(sum(sizes[:rank]), dtype=torch.int64, device=dev)
+    ctx.mark_non_differentiable(offset)
+    return (protos, protos_loc) + tuple(labels) + (offset,)
+
+  @staticmethod
+  def backward(ctx, gp, gpl, *_unused):
+    start, n = sum(ctx.sizes[:ctx.rank]), ctx.sizes[ctx.rank]
+    parts = [g.contiguous().reshape(-1) for g in (gp, gpl) if g is not None]
+    flat = torch.cat(parts) if parts else None
+    if flat is not None:
+      dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=ctx.group)
+    out, at = [], 0
+    for g in (gp, gpl):
+      if g is None:
+        out.append(None)
+        continue
+      out.append(flat[at:at + g.numel()].view_as(g)[start:start + n])
+      at += g.numel()
+    return out[0], out[1], None, None, None, None, None
+
+
 def exchange_prototypes(local_ids, prototypes, prototypes_with_loc, proto_sem, proto_inst, proto_batch,
-                        group=None):
+                        group=None, capacity=None):
   """All-gather the per-rank prototypes and labels (rank order == the
   reference's global order) and shift this rank's pixel -> prototype ids by the
-  number of prototypes on lower ranks.  Pure torch.distributed (gloo or nccl)."""
+  number of prototypes on lower ranks.  Pure torch.distributed (gloo or nccl).
+
+  capacity: a host-known upper bound on the prototypes of ANY rank, the same value on every rank (e.g. images
+  per rank x slots per image).
+  With it the exchange is one packed all-gather and one host read; without it, a size all-gather (with its
+  host read) followed by five padded all-gathers."""
+  if capacity is not None:
+    res = _PackedPrototypeExchange.apply(prototypes, prototypes_with_loc, proto_sem, proto_inst, proto_batch,
+                                         int(capacity), group)
+    return res[0], res[1], res[2], res[3], res[4], local_ids + res[5]
   sizes = all_gather_sizes(prototypes.shape[0], prototypes.device, group)
   rank = dist.get_rank(group)
   out = [all_gather_varlen(t, group, sizes)

@@ -343,6 +343,17 @@ HSG_API int hsg_relabel_i64(const int64_t* batch, const int64_t* cluster, const 
 HSG_API int hsg_topk_affinity_f32(const float* embeddings, int64_t N, const float* prototypes, int64_t M,
                                   int dim, int k, int64_t* indices_out, float* values_out, void* stream);
 
+/* ---- f2: SynchronizedBatchNorm for one process per GPU  (lib/nn/sync_batchnorm/batchnorm.py:55-118)
+ * x viewed as [B,C,L].  Forward: stats_out[0..C) = sum x, [C..2C) = sum x^2 (grad NULL); the caller all-reduces
+ * them over the ranks, forms mean / inv_std and calls hsg_bn_apply_f32 (grad NULL): y = (x-mean)*inv_std*w + b.
+ * Backward: hsg_bn_stats_f32 with grad -> sum g and sum g*xhat; all-reduce; hsg_bn_apply_f32 with grad ->
+ * gx = (g - mean_g - xhat*mean_gx) * w * inv_std, mean_* = grad_stats * inv_count. */
+HSG_API int hsg_bn_stats_f32(const float* x, const float* grad_or_null, const float* mean, const float* inv_std,
+                             int B, int C, int L, float* stats_out, void* stream);
+HSG_API int hsg_bn_apply_f32(const float* x, const float* grad_or_null, const float* mean, const float* inv_std,
+                             const float* weight, const float* bias, const float* grad_stats, float inv_count,
+                             int B, int C, int L, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

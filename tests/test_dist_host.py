@@ -36,6 +36,15 @@ def _worker(rank, world, port, golden_path, out_dir):
   # every rank's "loss" touches every prototype; d/d(local protos) must be the sum over ranks
   weight = torch.arange(out[0].numel(), dtype=torch.float32).view_as(out[0]) * (rank + 1)
   (out[0] * weight).sum().backward()
+  # the packed single-collective form must give the same tensors and the same gradient
+  protos2 = torch.from_numpy(res[0]).requires_grad_(True)
+  out2 = mu.exchange_prototypes(torch.from_numpy(res[5][0]), protos2, torch.from_numpy(res[1]),
+                                torch.from_numpy(res[2]), torch.from_numpy(res[3]),
+                                torch.from_numpy(res[4]), capacity=64)
+  (out2[0] * weight).sum().backward()
+  for a_, b_ in zip(out, out2):
+    assert torch.equal(a_.detach(), b_.detach())
+  assert torch.equal(protos.grad, protos2.grad)
   np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), prototypes=out[0].detach().numpy(),
            prototypes_loc=out[1].numpy(), sem=out[2].numpy(), inst=out[3].numpy(), batch=out[4].numpy(),
            updated=out[5].numpy(), grad=protos.grad.numpy(), n_local=np.asarray(res[0].shape[0]))
