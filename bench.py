@@ -60,6 +60,12 @@ def parse():
   ap.add_argument('--no-cpu', action='store_true')
   ap.add_argument('--no-extra', action='store_true', help='skip the reference-signature and NCE-backward legs')
   ap.add_argument('--cpu-images', type=int, default=3)
+  ap.add_argument('--mode', default='step', choices=['step', 'flat'], help='flat: only the row-sharded flat k-means (config 5)')
+  ap.add_argument('--flat-rows', type=int, default=16 * (1 << 20), help='TOTAL rows of the flat k-means leg (multiple of 2^20 x GPUs)')
+  ap.add_argument('--flat-dim', type=int, default=256)
+  ap.add_argument('--flat-k', type=int, default=256)
+  ap.add_argument('--flat-iters', type=int, default=20)
+  ap.add_argument('--no-flat', action='store_true')
   return ap.parse_args()
 
 
@@ -125,6 +131,34 @@ class ClockSampler(object):
             'samples': len(sm)}
 
 
+# ------------------------------------------------------------------ host placement
+def bind_to_gpu_numa_node(torch, local_rank):
+  """Pin this rank's host threads (and therefore the first-touch placement of its pinned staging buffer) to the
+  NUMA node its GPU hangs off.  At 8 ranks the r1 end-to-end run landed every rank's upload at ~22 GB/s because
+  all ranks shared CPUs 0-31 / one node's memory; best effort, silent when the topology cannot be read."""
+  try:
+    bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+    dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+    dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+    path = '/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node' % (dom, bus, dev)
+    with open(path) as f:
+      node = int(f.read().strip())
+    if node < 0:
+      return None
+    with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+      spec = f.read().strip()
+    cpus = set()
+    for part in spec.split(','):
+      lo, _, hi = part.partition('-')
+      cpus.update(range(int(lo), int(hi or lo) + 1))
+    allowed = cpus & os.sched_getaffinity(0)
+    if allowed:
+      os.sched_setaffinity(0, allowed)
+    return node
+  except Exception:                       # noqa: BLE001
+    return None
+
+
 # ------------------------------------------------------------------ synthetic input
 def make_embeddings(torch, args, device, seed):
   g = torch.Generator(device=device)
@@ -155,7 +189,8 @@ def hot_path(torch, S, L, MU, emb, args, world, group):
   protos = S.pool_prototypes(ex)
   pbatch = ex['proto_batch']
   if world > 1:       # all-gather of the prototypes (replaces hsg/models/utils.py:127-217)
-    res = MU.exchange_prototypes(ids, protos, protos, pbatch, pbatch, pbatch, group)
+    res = MU.exchange_prototypes(ids, protos, protos, pbatch, pbatch, pbatch, group,
+                                 capacity=ex['num_images'] * ex['slots_per_image'])
     protos, pbatch, ids = res[0], res[2], res[5]
   # two label sets in one pass over E x P: image-level positives ("img_sim",
   # hsg/models/predictions/hsg.py:97-110) and prototype-level positives
@@ -209,6 +244,62 @@ def nce_backward_leg(torch, S, L, emb, args, lib, steps):
   return float(np.mean(times)), bwd_ms, int(x.shape[0]), int(protos.shape[0])
 
 
+def flat_kmeans_leg(torch, MU, args, world, rank, device, group):
+  """BASELINE configs[4] / SURVEY 8e: flat spherical k-means over rows sharded across the ranks, an all-reduce of
+  the exact int64 [K,D] centroid sums every iteration (the path's one per-iteration collective).  The rows are a
+  function of their GLOBAL index (1 Mi-row chunks, one seed each), so every GPU count clusters the same data; the
+  sums are exact, so the labels -- and `labels_checksum` -- must be identical at 1, 2, 4 and 8 GPUs."""
+  chunk = 1 << 20
+  rows, d, k, iters = args.flat_rows, args.flat_dim, args.flat_k, args.flat_iters
+  if rows % (chunk * world):
+    raise SystemExit('--flat-rows must be a multiple of %d' % (chunk * world))
+  per = rows // world // chunk
+  xs, ls = [], []
+  for c in range(rank * per, (rank + 1) * per):
+    g = torch.Generator(device=device)
+    g.manual_seed(5000 + c)
+    v = torch.randn((chunk, d), generator=g, device=device)
+    xs.append(v / v.norm(dim=1, keepdim=True))
+    ls.append(torch.randint(0, k, (chunk,), generator=g, device=device))
+  x, init = torch.cat(xs), torch.cat(ls)
+  del xs, ls
+
+  def barrier():
+    if world > 1:
+      torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+  MU.dist_kmeans_with_initial_labels(x, init, k, iterations=2, group=group)
+  barrier()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  labels = MU.dist_kmeans_with_initial_labels(x, init, k, iterations=iters, group=group)
+  e1.record()
+  barrier()
+  t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+  base = rank * per * chunk
+  weight = (torch.arange(labels.numel(), device=device, dtype=torch.int64) + base) % 1000003 + 1
+  check = (labels.long() * weight).sum().view(1)
+  if world > 1:
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    torch.distributed.all_reduce(check)
+  ms = float(t) / iters
+  pk, pk_src = peaks()
+  gbs = rows * (4.0 * d + 8.0) / (ms * 1e-3) / 1e9
+  tfs = 2.0 * rows * d * k / (ms * 1e-3) / 1e12
+  return {'rows_total': rows, 'rows_per_gpu': rows // world, 'dim': d, 'k': k, 'iterations': iters,
+          'ms_per_iteration': ms, 'rows_per_s': rows / (ms * 1e-3),
+          'hbm': {'achieved': gbs, 'peak': pk['hbm_gbs'] * world, 'unit': 'GB/s', 'frac': gbs / (pk['hbm_gbs'] * world),
+                  'algorithmic_bytes_per_iteration': rows * (4.0 * d + 8.0)},
+          'tensor': {'achieved': tfs, 'peak': pk.get('bf16_tflops_sustained', pk['bf16_tflops']) * world, 'unit': 'TFLOP/s',
+                     'frac': tfs / (pk.get('bf16_tflops_sustained', pk['bf16_tflops']) * world)},
+          'bound': 'tensor' if k > 425 else 'hbm',         # SURVEY 8d: HBM-bound while K <~ 425 single-pass equivalents
+          'allreduce_bytes_per_iteration': k * d * 8 if world > 1 else 0,
+          'collective': 'all-reduce (sum) of exact int64 fixed-point centroid sums, NCCL' if world > 1 else 'none (one GPU holds every row)',
+          'labels_checksum': int(check), 'peak_source': pk_src,
+          'note': 'sum_i label_i * (i mod 1000003 + 1) over the global row index: identical at every GPU count'}
+
+
 def run_ours(args):
   import torch
   world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -216,6 +307,7 @@ def run_ours(args):
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
   torch.cuda.set_device(local_rank)
   device = torch.device('cuda', local_rank)
+  numa_node = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
   group = None
   json_fd = None
   if world > 1:
@@ -230,6 +322,21 @@ def run_ours(args):
   from hsg_b200.utils.segsort import common as S, loss as L
   from hsg_b200.models import utils as MU
   lib = hsg_b200.load_library()
+
+  if args.mode == 'flat':
+    flat = flat_kmeans_leg(torch, MU, args, world, rank, device, group)
+    if rank == 0:
+      line = json.dumps({'metric': 'rows/sec flat spherical k-means (row-sharded, all-reduce of centroid sums per iteration)',
+                         'value': flat['rows_per_s'], 'unit': 'rows/s', 'n_gpus': world, 'higher_is_better': True,
+                         'scaling': 'strong', 'dtype': 'f32', 'data': 'synthetic', 'flat_kmeans': flat}) + '\n'
+      if json_fd is not None:
+        sys.stdout.flush()
+        os.write(json_fd, line.encode())
+      else:
+        sys.stdout.write(line)
+    if world > 1:
+      torch.distributed.destroy_process_group()
+    return
 
   # strong scaling (default): the job is BASELINE configs[1] itself -- 48 images in the global batch -- at every
   # GPU count, each rank taking 48 / N images; weak: 48 images per GPU (the NCE then contrasts against N x 12288
@@ -318,7 +425,8 @@ def run_ours(args):
     if world > 1:
       torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
     e2e = {'value': world * n_pix * e_steps / float(dt), 'unit': 'pixel-embeddings/s',
-           'h2d_bytes_per_step': int(host.numel() * 4), 'd2h_bytes_per_step': 4, 'steps': e_steps}
+           'h2d_bytes_per_step': int(host.numel() * 4), 'd2h_bytes_per_step': 4, 'steps': e_steps,
+           'host_numa_node_rank0': numa_node}
 
   # ---- the same step through the reference signatures only (what patch() installs), single GPU
   ref_sig_ms = None
@@ -349,6 +457,12 @@ def run_ours(args):
                'algorithmic_flops_per_launch': flops_b, 'ms_per_launch': bwd_ms, 'ms_forward_plus_backward': fb_ms,
                'executed_tflops': 3.0 * tf_b, 'pixels': n_b, 'prototypes': p_b,
                'note': 'not part of `value` (SURVEY 8d: forward is the metric, backward reported separately)'}
+
+  flat = None
+  if not args.no_flat:
+    del embs
+    torch.cuda.empty_cache()
+    flat = flat_kmeans_leg(torch, MU, args, world, rank, device, group)
 
   if rank != 0:
     if world > 1:
@@ -425,7 +539,7 @@ def run_ours(args):
       'nce_pairs_per_s_per_gpu': (n_pix * float(world * args.images * args.grid ** 2) /
                                   (phase_ms['nce_fwd'] / args.steps * 1e-3)) if phase_ms['nce_fwd'] > 0 else None,
       'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
-      'roofline': roofline, 'roofline_kmeans': roofline_kmeans, 'roofline_nce_bwd': nce_bwd,
+      'roofline': roofline, 'roofline_kmeans': roofline_kmeans, 'roofline_nce_bwd': nce_bwd, 'flat_kmeans': flat,
       'reference_signature_path': ({'ms_per_step': ref_sig_ms, 'value': n_pix / (ref_sig_ms * 1e-3), 'unit': 'pixel-embeddings/s',
                                     'note': 'same step through segment_by_kmeans / calculate_prototypes_from_labels / SegSortLoss x2 '
                                             '(the signatures patch() installs); the default path uses the extended entry points'}

@@ -506,10 +506,86 @@ __global__ void __launch_bounds__(256) runsum_combine_kernel(const RunSums r, in
   }
 }
 
+// M-step for the launch-bound regime (training shapes: 12 x 28x28 pixels, K = 16): ONE launch instead
+// of hist / scan / scatter / gather / combine.  It also resets the re-decision list counters the E-step that
+// follows appends to.  Reads: every row once, the keys K times (K * 4 bytes per pixel).
+// One (segment, cluster) bin per CTA of 8 warps: warp w scans the w-th eighth of the segment's keys 32 at a time and
+// adds its members' rows in index order (fp32 over runs of 32 members, folded into float64); the eight partial
+// sums are added in warp order -- a fixed order, the accuracy class of the general path.
+template <int NV>
+__device__ __forceinline__ void mstep_small_bin(const float* __restrict__ x, int dim, int64_t b, int64_t e, int key,
+                                                const int32_t* __restrict__ keys, float* __restrict__ out_row,
+                                                double (*part)[NV * 32]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t len = e - b;
+  const int64_t per = ((len + 7) / 8 + 31) / 32 * 32;            // rows per warp, a multiple of 32
+  const int64_t wb = b + warp * per, we = min(e, wb + per);
+  double acc[NV];
+  float run[NV];
+#pragma unroll
+  for (int m = 0; m < NV; ++m) { acc[m] = 0.0; run[m] = 0.f; }
+  int in_run = 0;
+  for (int64_t i0 = wb; i0 < we; i0 += 32) {
+    const int64_t i = i0 + lane;
+    unsigned hit = __ballot_sync(FULL, i < we && keys[i] == key);
+    while (hit) {
+      const int j = __ffs(hit) - 1;
+      hit &= hit - 1;
+      const float* row = x + (i0 + j) * dim;
+#pragma unroll
+      for (int m = 0; m < NV; ++m) {
+        const int d = lane + 32 * m;
+        if (d < dim) run[m] += row[d];
+      }
+      if (++in_run == 32) {
+#pragma unroll
+        for (int m = 0; m < NV; ++m) { acc[m] += (double)run[m]; run[m] = 0.f; }
+        in_run = 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < NV; ++m) part[warp][lane + 32 * m] = acc[m] + (double)run[m];
+  __syncthreads();
+  if (warp == 0) {
+    float ss = 0.f;
+    float f[NV];
+#pragma unroll
+    for (int m = 0; m < NV; ++m) {
+      double a = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a += part[w][lane + 32 * m];
+      f[m] = (float)a;
+      if (lane + 32 * m < dim) ss = fmaf(f[m], f[m], ss);
+    }
+    const float n = safe_norm(warp_sum(ss));
+#pragma unroll
+    for (int m = 0; m < NV; ++m) {
+      const int d = lane + 32 * m;
+      if (d < dim) out_row[d] = f[m] / n;
+    }
+  }
+  __syncthreads();
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) mstep_small_kernel(const float* __restrict__ x, int dim,
+                                                          const int64_t* __restrict__ seg_offsets, int S, int kmax,
+                                                          const int32_t* __restrict__ keys, float* __restrict__ out,
+                                                          int32_t* __restrict__ fix_count) {
+  __shared__ double part[8][NV * 32];
+  if (blockIdx.x == 0 && threadIdx.x < 2) fix_count[threadIdx.x] = 0;
+  const int64_t bin = blockIdx.x;
+  const int seg = (int)(bin / kmax);
+  mstep_small_bin<NV>(x, dim, seg_offsets[seg], seg_offsets[seg + 1], (int)bin, keys, out + bin * dim, part);
+}
+
+constexpr int64_t KM_SMALL_MAX_SEG = 16384;    // rows per segment up to which the one-launch M-step is used
+
 // one M-step of the k-means loop: full pass on the first iteration, afterwards delta or full
 // as decided on the device
 static int km_mstep(KmPlan& p, const float* x, const int64_t* seg_offsets, int it, bool incremental,
-                    cudaStream_t st, const RunSums* runs = nullptr) {
+                    cudaStream_t st, const RunSums* runs = nullptr, bool small = false) {
   int rc;
   if (it == 0 && runs) {
     // usual case: the run table is complete and only the combine below does any work
@@ -527,6 +603,16 @@ static int km_mstep(KmPlan& p, const float* x, const int64_t* seg_offsets, int i
     }
     if (incremental)
       HSG_CUDA(cudaMemcpyAsync(p.d.keys_prev, p.sr.keys, sizeof(int32_t) * p.sr.N, cudaMemcpyDeviceToDevice, st));
+    return HSG_OK;
+  }
+  if (!incremental && small) {
+    ProfRange prof(PROF_MSTEP_GATHER, st);
+    const unsigned grid = (unsigned)p.sr.bins;
+    if (p.sr.dim <= 32 * 5)
+      mstep_small_kernel<5><<<grid, 256, 0, st>>>(x, p.sr.dim, seg_offsets, p.sr.S, p.sr.kmax, p.sr.keys, p.centroids, p.fix.count);
+    else
+      mstep_small_kernel<9><<<grid, 256, 0, st>>>(x, p.sr.dim, seg_offsets, p.sr.S, p.sr.kmax, p.sr.keys, p.centroids, p.fix.count);
+    HSG_LAUNCH_CHECK();
     return HSG_OK;
   }
   if (it == 0 || !incremental) {
@@ -559,8 +645,8 @@ static int check_common(const float* x, int64_t N, int dim, const int64_t* seg_o
   return HSG_OK;
 }
 
-static int run_estep(EStepArgs& ea, KmPlan& p, bool use_tc, cudaStream_t st) {
-  HSG_CUDA(cudaMemsetAsync(p.fix.count, 0, 2 * sizeof(int32_t), st));
+static int run_estep(EStepArgs& ea, KmPlan& p, bool use_tc, cudaStream_t st, bool counters_cleared = false) {
+  if (!counters_cleared) HSG_CUDA(cudaMemsetAsync(p.fix.count, 0, 2 * sizeof(int32_t), st));
   if (use_tc) {
     int rc;
     {
@@ -647,9 +733,12 @@ static int kmeans_impl(const float* x, int64_t N, int dim, const void* xh, int d
 
   // below ~2.6e5 rows a full re-sum is cheaper than the dozen extra launches of the delta machinery
   const bool incremental = !(flags & HSG_KMEANS_FULL_MSTEP) && N >= KM_DELTA_MIN_ROWS;
+  // launch-bound regime: one-launch M-step (it also clears the re-decision counters)
+  const bool small = !incremental && !(flags & HSG_KMEANS_FULL_MSTEP) && max_seg_len <= KM_SMALL_MAX_SEG && dim <= 32 * 9 &&
+                     (int64_t)S * kmax <= (1 << 20);
   for (int it = 0; it < iterations; ++it) {
-    if ((rc = km_mstep(p, x, seg_offsets, it, incremental, st, runs))) return rc;
-    if ((rc = run_estep(ea, p, use_tc, st))) return rc;
+    if ((rc = km_mstep(p, x, seg_offsets, it, incremental, st, runs, small))) return rc;
+    if ((rc = run_estep(ea, p, use_tc, st, small && !(it == 0 && runs)))) return rc;   // the small M-step cleared the counters
   }
   if ((rc = sr_keys_to_labels(p.sr, p.sr.keys, labels_out, st))) return rc;
   if (centroids_out && iterations > 0)

@@ -1090,20 +1090,24 @@ __global__ void tc_convert_kernel(const float* __restrict__ cent, const int32_t*
 
 // ---------------------------------------------------------------- host side
 // centroids per pass: the fp16 tile [ktile x (d16+16)] has to fit next to the pixel ring (<= 136 KiB)
-static int tc_ktile(int d16) { return d16 <= 256 ? 256 : 128; }
+// D = 512: a whole 256-centroid tile (270 KB of fp16) does not fit one SM; the CTA-pair kernel holds half of it
+// per CTA, so K <= 256 stays a single pass there too (it was two passes with the running top-3 carried through
+// HBM: 16.7 ms per iteration at N = 1e7, profiles/r1_kmeans_flat_sweep.txt)
+static bool tc_pair_only(int d16, int kpad) { return d16 == 512 && kpad > 128 && kpad <= 256 && kpad % 32 == 0; }
+static int tc_ktile(int d16, int kpad) { return (d16 <= 256 || tc_pair_only(d16, kpad)) ? 256 : 128; }
 
 bool tc_shape_supported(int dim, int d16, int kmax) {
   if (!(d16 == 64 || d16 == 128 || d16 == 256 || d16 == 512)) return false;
   if (dim < d16 || dim - d16 > HSG_XH_MAX_TRAILING) return false;
   if (kmax < 1) return false;
   const int kpad = (kmax + 15) / 16 * 16;
-  return kpad <= 255 * tc_ktile(d16);              // tile ids are carried as bytes
+  return kpad <= 255 * tc_ktile(d16, kpad);        // tile ids are carried as bytes
 }
 
 void tc_carve(Carver& c, TcState& t, int S, int kmax, int d16, int64_t N) {
   t.enabled = false;
   t.d16 = d16;
-  const int kpad = (kmax + 15) / 16 * 16, ktile = tc_ktile(d16);
+  const int kpad = (kmax + 15) / 16 * 16, ktile = tc_ktile(d16, kpad);
   t.n_pass = (kpad + ktile - 1) / ktile;
   t.kpad = t.n_pass == 1 ? kpad : ktile;
   t.kpad_total = t.n_pass * t.kpad;
@@ -1193,8 +1197,7 @@ int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
   const size_t budget = 227 * 1024 - 1024 /*static*/ - 1024 /*alignment slack*/ - fixed;
   int nst = (int)(budget / TC_STAGE_BYTES);
   if (nst > 8) nst = 8;
-  HSG_REQUIRE(nst >= 2, HSG_E_UNSUPPORTED, "tensor-core E-step: shared memory budget (kpad=%d d16=%d)", t.kpad, t.d16);
-  p.nst = nst;
+  p.nst = nst;                                   // checked where the multi-pass kernel is launched
   const size_t smem = 1024 + fixed + (size_t)nst * TC_STAGE_BYTES;
   CUtensorMap mx, mxt, mc, mct;
   memcpy(&mx, t.tmap_x, sizeof(mx));
@@ -1207,8 +1210,11 @@ int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
   static const bool legacy = getenv("HSG_ESTEP_LEGACY") != nullptr;     // A/B switch for profiling only
   static const bool no_pair = getenv("HSG_ESTEP_PAIR") == nullptr;         // the pair kernel is opt-in (profiling): see DESIGN.md
   static const int exp_all = getenv("HSG_TC_EXP") ? atoi(getenv("HSG_TC_EXP")) : 0;
-  if (p.n_pass == 1 && !legacy && !no_pair && !p.dbg_sims && t.kpad >= 64 && t.kpad % 32 == 0 && p.sub % 2 == 0 &&
-      num_sms() >= 2) {
+  const bool need_pair = tc_pair_only(t.d16, t.kpad);
+  HSG_REQUIRE(!need_pair || (!p.dbg_sims && p.sub % 2 == 0 && num_sms() >= 2), HSG_E_UNSUPPORTED,
+              "tensor-core E-step: D=512 with more than 128 centroids runs on CTA pairs only (no similarity dump)");
+  if (p.n_pass == 1 && !legacy && (!no_pair || need_pair) && !p.dbg_sims && t.kpad >= 64 && t.kpad % 32 == 0 &&
+      p.sub % 2 == 0 && num_sms() >= 2) {
     // CTA pairs: half of the centroids per CTA (estep_tc2_kernel)
     const int khalf = t.kpad / 2;
     const size_t fixed2 = (size_t)nslab * khalf * 128 + 128 * 32 + 2 * TC_TAIL_BYTES + 40 * 8 + 64;
@@ -1252,6 +1258,7 @@ int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
     HSG_LAUNCH_CHECK();
     return HSG_OK;
   }
+  HSG_REQUIRE(nst >= 2 && fixed < 225 * 1024, HSG_E_UNSUPPORTED, "tensor-core E-step: shared memory budget (kpad=%d d16=%d)", t.kpad, t.d16);
   for (p.pass = 0; p.pass < p.n_pass; ++p.pass) {
     if (p.dbg_sims) {
       HSG_CUDA(cudaFuncSetAttribute(estep_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

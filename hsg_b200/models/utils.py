@@ -235,18 +235,38 @@ def dist_kmeans_with_initial_labels(embeddings, initial_labels, max_label, itera
   sums (the one real exchange step of the path), every rank normalises identically, then assigns its own
   rows.  The sums are exact int64 fixed-point sums (ops.segment_sum_exact) and the all-reduce of integers is
   exact, so centroids and labels are bit-identical at every rank count and for every way of sharding the
-  rows -- including the single-process run (`collective=False`: this process holds every row)."""
+  rows -- including the single-process run (`collective=False`: this process holds every row).
+
+  Because the sums are exact integers they can also be UPDATED exactly: from the third iteration on only the
+  rows whose label changed are touched (sum[new] += x, sum[old] -= x), which leaves the result bit-identical
+  to re-summing every row and removes most of the M-step traffic (r2: 8.9 -> see profiles/)."""
   x = embeddings.reshape(-1, embeddings.shape[-1]).detach()
   labels = initial_labels.reshape(-1).long()
-  d16 = ops.tc_d16(x.shape[1], max_label)
+  k = int(max_label)
+  d16 = ops.tc_d16(x.shape[1], k)
   xh = xerr = None
   if d16 and x.shape[0] >= 16384:
     xh, xerr = ops.make_half_copy(x, d16)
+  n = x.shape[0]
+  local = prev = None
   with torch.no_grad():
-    for _ in range(int(iterations)):
-      sums = ops.segment_sum_exact(x, labels, int(max_label))
+    for it in range(int(iterations)):
+      changed = None
+      if local is not None and it >= 2:
+        changed = torch.nonzero(labels != prev).view(-1)                 # one host read per iteration
+        if changed.numel() > 0.3 * n:
+          changed = None
+      if changed is None:
+        local = ops.segment_sum_exact(x, labels, k)
+      elif changed.numel() > 0:
+        rows = x.index_select(0, changed)
+        local = local + ops.segment_sum_exact(rows, labels.index_select(0, changed), k) \
+            - ops.segment_sum_exact(rows, prev.index_select(0, changed), k)
+      sums = local
       if collective and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        sums = local.clone()
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
       centroids = ops.normalize((sums.double() * ops.FIXED_POINT_SCALE).float())
-      labels = ops.kmeans_estep(x, centroids.view(1, int(max_label), -1), xh=xh, xerr=xerr)
+      prev = labels
+      labels = ops.kmeans_estep(x, centroids.view(1, k, -1), xh=xh, xerr=xerr)
   return labels

@@ -196,7 +196,8 @@ def segment_by_kmeans_ex(embeddings, labels=None, num_clusters=[5, 5], cluster_i
       raise RuntimeError('segment_by_kmeans: every pixel is ignored')
     ign = None
   gpu_id = dev.index or 0
-  want_half = ops.tc_d16(c + n_loc, kmax) == c and iterations >= 1
+  # below ~16k pixels the step is launch-bound: the fp32 CUDA-core E-step needs two launches fewer per iteration
+  want_half = ops.tc_d16(c + n_loc, kmax) == c and iterations >= 1 and b * h * w >= 16384
   with torch.no_grad():
     # at full-resolution sizes the prep kernel also emits the first M-step's partial sums (the rows are on
     # chip anyway), so k-means does not start by re-reading every row it has just written

@@ -11,6 +11,9 @@ Bars (north_star / SURVEY.md section 8c):
   * fp32 values within 1e-5 relative (written next to each check).
 """
 
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -49,7 +52,11 @@ def labels_match_certified(mine, ref, x, protos):
   bad = np.nonzero(mine != ref)[0]
   if bad.size:
     assert gap[bad].max() < TAU, 'differs from the reference outside near-ties'
+  CERTIFIED.append((int(np.sum(gap > TAU)), int(gap.size), int(bad.size)))
   return bad.size
+
+
+CERTIFIED = []     # per teacher-forced E-step: (pixels with float64 margin > TAU, pixels, labels that differ from the reference)
 
 
 @pytest.fixture(scope='module')
@@ -119,6 +126,12 @@ def test_kmeans_kat1_teacher_forced(golden, S):
     assert new.dtype == torch.int64
     flips += labels_match_certified(n(new), g['labels'][it + 1], g['x'], g['prototypes'][it])
   assert flips <= 4
+  # report the certified fraction (pixels whose float64 top-2 margin exceeds TAU: there the label must be
+  # -- and, by the asserts above, is -- bit-identical to the reference's); expected >= 99.97 % on iid data
+  cert, total = sum(c[0] for c in CERTIFIED[-10:]), sum(c[1] for c in CERTIFIED[-10:])
+  print('KAT1 teacher-forced: certified fraction %.5f (%d of %d pixel-iterations), %d labels differ from the fp32 '
+        'reference, all inside the uncertified near-ties' % (cert / total, cert, total, flips))
+  assert cert / total >= 0.9997
   final = S.kmeans_with_initial_labels(x, t(g['labels'][0]), 16, 10)
   agree = np.mean(n(final) == g['labels'][10])
   assert agree > 0.995, agree
@@ -544,6 +557,8 @@ def _tc_case(nn, d16, loc, k, lens=None, seed=11):
     (64, 0, 2048, [6000]),                # eight centroid tiles
     (512, 2, 40, [4000, 3000]),           # D = 512: eight slabs per pixel tile, 128-centroid tiles
     (512, 0, 300, [5000]),                # both
+    (512, 2, 256, [5000, 3000, 100]),     # D = 512, K = 256 in ONE pass: CTA pairs (cta_group::2), half the centroids per CTA
+    (512, 0, 160, [4100]),                # CTA pairs with a partial centroid tile
 ])
 def test_tc_estep_exact_and_equal_to_simt(d16, loc, k, lens):
   from hsg_b200 import ops, _lib
@@ -781,8 +796,9 @@ def test_transformer_clustering_matches_reference(golden):
   net.eval()
   with torch.no_grad():
     ev = net(*args)
-  # a 4-layer fp32 chain on the GPU (cuBLAS GEMMs + our attention) against the reference on the CPU:
-  # agreement to ~1e-4 of the O(1) activations
+  # a 4-layer fp32 chain on the GPU (cuBLAS GEMMs + our attention) against the reference on the CPU.  The
+  # tolerance is the reference's OWN CUDA-vs-CPU spread on this fixture, measured by the next test on the same
+  # GPU (profiles/r2_transformer_spread.txt); against the reference's CUDA run ours sits at 4x that spread or less
   for i, out in enumerate(ev):
     close(n(out), g['eval%d' % i], rtol=5e-4, atol=1e-4)
   net.train()                                             # dropout 0: train-mode parity is defined
@@ -798,6 +814,68 @@ def test_transformer_clustering_matches_reference(golden):
       ref = g[key]
       # (biases feeding a BatchNorm have an exactly-zero gradient: both sides hold ~1e-5 rounding noise)
       assert np.abs(n(p.grad) - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-4, name
+
+
+def test_transformer_clustering_tolerance_is_the_references_own_cuda_spread(golden):
+  """Where the 5e-4 / 1e-4 of the fixture test above comes from ("derive it").  The REFERENCE module
+  (baseline/_ref, unpatched) runs on this GPU from the fixture's weights and inputs; its distance to its own CPU
+  run (the fixture) is the reference-CUDA-vs-reference-CPU spread of a 4-layer fp32 chain with train-mode
+  BatchNorm.  Ours is then held to max(1e-5, 4 x that spread) against the reference's CUDA run, per output and
+  per gradient tensor (max-norm relative, gradients floored at 1e-3 of the largest gradient)."""
+  sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+  import refenv
+  if not refenv.available():
+    pytest.skip('baseline/_ref is not installed (tools/install_reference.py)')
+  refenv.activate()
+  hsg_b200.unpatch()
+  from hsg.models.embeddings.transformer_clusters import TransformerClustering as RefTC
+  g = golden('transformer_clustering')
+  b, c, s_, q, k = [int(v) for v in g['cfg']]
+  ref_net = RefTC(num_clusters=k, d_model=c, nhead=4, num_encoder_layers=2, num_decoder_layers=2,
+                  dim_feedforward=2 * c, dropout=0.0)
+  state = {key[3:].replace('__', '.'): torch.from_numpy(val) for key, val in g.items() if key.startswith('w__')}
+  ref_net.load_state_dict(state, strict=True)
+  ref_net = ref_net.to(dev())
+  ours_net = _load_transformer(g)
+
+  def run(net):
+    net.train()
+    src = t(g['src']).requires_grad_(True)
+    outs = net(src, t(g['mask']), t(g['query']), t(g['pos']))
+    for p_ in net.parameters():
+      p_.grad = None
+    sum((o * t(g['w%d' % i])).sum() for i, o in enumerate(outs)).backward()
+    grads = {'dsrc': src.grad.detach().clone()}
+    grads.update({name: p_.grad.detach().clone() for name, p_ in net.named_parameters() if p_.grad is not None})
+    return [o.detach() for o in outs], grads
+
+  def rel(a, b, floor=0.0):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), floor, 1e-30)
+
+  ref_out, ref_g = run(ref_net)
+  our_out, our_g = run(ours_net)
+  worst = 0.0
+  print('\n%-34s %14s %14s' % ('tensor', 'ours vs ref(CUDA)', 'ref CUDA vs CPU'))
+  for i, (a, r_) in enumerate(zip(our_out, ref_out)):
+    spread = rel(n(r_), g['train%d' % i])
+    mine = rel(n(a), n(r_))
+    print('%-34s %14.3e %14.3e' % ('train output %d' % i, mine, spread))
+    assert mine <= max(1e-5, 4.0 * spread), (i, mine, spread)
+    worst = max(worst, spread)
+  scale = max(float(v.abs().max()) for v in ref_g.values())
+  rows = []
+  for name, rg in ref_g.items():
+    key = 'dsrc' if name == 'dsrc' else 'g__' + name.replace('.', '__')
+    spread = rel(n(rg), g[key], 1e-3 * scale) if key in g else 0.0
+    rows.append((rel(n(our_g[name]), n(rg), 1e-3 * scale), spread, name))
+  rows.sort(reverse=True)
+  for mine, spread, name in rows[:6]:
+    print('%-34s %14.3e %14.3e' % (name[-34:], mine, spread))
+  g_spread = max(r_[1] for r_ in rows)
+  for mine, spread, name in rows:
+    assert mine <= max(1e-5, 4.0 * max(spread, 0.25 * g_spread)), (name, mine, spread, g_spread)
+  print('reference CUDA-vs-CPU spread: outputs %.2e, gradients %.2e' % (worst, g_spread))
 
 
 def test_fused_attention_core_vs_float64():
@@ -1008,7 +1086,8 @@ def test_config5_flat_kmeans_sweep_points(S, nn, d, k):
 
 
 # ---------------------------------------------------------------- BASELINE.json configs[1] at FULL size: properties
-def test_config2_full_size_properties(S):
+@pytest.mark.parametrize('dist', ['iid', 'planted'])
+def test_config2_full_size_properties(S, dist):
   """48 images x 448x448, D=256, grid 16x16 (K=256), 10 iterations, P=12288: the oracle cannot run
   this size, so the check is through size-independent properties on the full result --
   (1) run-to-run identical ids, (2) the dense ids are exactly the ranks of the (image, cluster)
@@ -1022,9 +1101,15 @@ def test_config2_full_size_properties(S):
   free, _ = torch.cuda.mem_get_info()
   if free < 90 * (1 << 30):
     pytest.skip('needs ~90 GB of free HBM')
-  g = torch.Generator(device=dev())
-  g.manual_seed(235)
-  emb = torch.randn((b, d, hw, hw), generator=g, device=dev(), dtype=torch.float32)
+  if dist == 'iid':
+    g = torch.Generator(device=dev())
+    g.manual_seed(235)
+    emb = torch.randn((b, d, hw, hw), generator=g, device=dev(), dtype=torch.float32)
+  else:       # 64 unit centres per image on an 8x8 block layout + noise -- near-duplicate
+    import types      # centroids inside a block are what stresses the float64 re-decision
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    emb = bench.make_embeddings(torch, types.SimpleNamespace(images=b, dim=d, size=hw, dist='planted'), dev(), 235)
   ex = S.segment_by_kmeans_ex(emb, None, [grid, grid], iterations=iters, count_prototypes=True)
   ex2 = S.segment_by_kmeans_ex(emb, None, [grid, grid], iterations=iters, count_prototypes=True)
   assert torch.equal(ex['cluster_indices'], ex2['cluster_indices'])                               # (1)
@@ -1034,11 +1119,9 @@ def test_config2_full_size_properties(S):
   assert torch.equal(inv, ids) and int(uniq.numel()) == ex['num_prototypes']                      # (2)
   n_img = hw * hw
   xloc = ex['embeddings_with_loc']
-  init = S._grid_init([grid, grid], (hw, hw), emb.device)[0].repeat(b)
-  xh, xerr = ops.make_half_copy(xloc, d)
-  prev = ops.kmeans(xloc, init, grid * grid, iters - 1, seg_offsets=ex['seg_offsets'], max_seg_len=n_img,
-                    xh=xh, xerr=xerr)
-  del xh, xerr
+  # the labels that entered the last M-step: the same operator one iteration short (same path, so the same
+  # trajectory bit for bit -- the first M-step comes from the prep kernel's run sums at this size)
+  prev = S.segment_by_kmeans_ex(emb, None, [grid, grid], iterations=iters - 1)['kmeans_labels']
   rng = np.random.RandomState(1)
   for img in (0, 17, 47):                                                                          # (3)
     sl = slice(img * n_img, (img + 1) * n_img)
@@ -1055,7 +1138,7 @@ def test_config2_full_size_properties(S):
   protos = S.pool_prototypes(ex)
   x = ex['embeddings']
   ids_h = n(ids[:3 * n_img])
-  for pid in rng.choice(3 * grid * grid, 40, replace=False):                                       # (4)
+  for pid in rng.choice(np.unique(ids_h), 40, replace=False):      # (4) (planted data leaves clusters empty: ids are dense)
     members = np.nonzero(ids_h == pid)[0]
     want = o_ops.calculate_prototypes_from_labels(n(x[torch.from_numpy(members).to(x.device)]),
                                                   np.zeros(members.size, np.int64), 1)[0]
@@ -1070,7 +1153,10 @@ def test_config2_full_size_properties(S):
   for s in range(2):                                                                               # (5)
     args = (xe, n(sets[s][pick]), xi, n(protos), n(psets[s]), 16.0)
     want = o_loss.calculate_log_likelihood(*args, dtype=np.float64).reshape(-1)
-    tol = 1e-5 * np.abs(want) + 1e-6 * o_loss.nce_condition(*args) + 1e-6
+    # third term: d loss / d similarity = concentration, and ANY fp32 dot product of D terms (the reference's sgemm
+    # included) carries ~sqrt(D) * 2^-24 of rounding at |s| ~ 1.  It only shows on planted data, where |l| ~ 1 (iid: 11)
+    # and the own-prototype similarity is ~1: 16 * 16 * 6e-8 = 1.5e-5
+    tol = 1e-5 * np.abs(want) + 1e-6 * o_loss.nce_condition(*args) + 16.0 * np.sqrt(d) * 2.0 ** -24
     assert np.all(np.abs(n(ll[s][pick]) - want) <= tol), np.abs(n(ll[s][pick]) - want).max()
 
 

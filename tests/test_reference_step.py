@@ -127,6 +127,8 @@ def _runs(stage):
   else:
     pytest.fail('no synthetic input with certified grouping decisions')
   ref, ref2, ref3 = refs
+  if stage == 2:      # the gradient test compares medians over five runs of the reference (see _check_gradients)
+    refs = refs + [ref_step.run_step(ref_models[0], ref_models[1], inputs, dev) for _ in range(2)]
   exact = _nce_terms_float64(ref[0], ref[1], cfg)
   launches = hsg_b200.load_library().hsg_launch_count()
   hsg_b200.patch()
@@ -141,7 +143,7 @@ def _runs(stage):
   finally:
     hsg_b200.unpatch()
   launched = hsg_b200.load_library().hsg_launch_count() - launches
-  return {'ref': ref, 'ref2': ref2, 'ref3': ref3, 'ours': ours, 'launched': launched, 'exact_nce': exact}
+  return {'ref': ref, 'ref2': ref2, 'ref3': ref3, 'refs': refs, 'ours': ours, 'launched': launched, 'exact_nce': exact}
 
 
 @pytest.fixture(scope='module')
@@ -209,8 +211,15 @@ def _check_gradients(r, title, per_tensor=True):
     num = sum(float((x[3][n_].double() - y[3][n_].double()).pow(2).sum()) for n_ in names)
     den = sum(float(y[3][n_].double().pow(2).sum()) for n_ in names)
     return (num / den) ** 0.5
-  d_ours, d_ref = dist(ours, ref), max(dist(ref2, ref), dist(ref3, ref))
-  print('all gradients as one vector, relative l2 distance to the reference: ours %.3e, reference run-to-run %.3e' % (d_ours, d_ref))
+  # Both distances are heavy-tailed (a near-tie flipping inside a BatchNorm batch of 8 tokens moves the whole vector), so
+  # a single distance against the max of two is a coin toss.  Under the hypothesis "the patched step is one more run of
+  # the reference" the distances ours<->ref_i are distributed like the pairwise distances ref_i<->ref_j: compare medians.
+  refs = r['refs']
+  d_ours = float(np.median([dist(ours, x) for x in refs]))
+  pair = [dist(refs[i], refs[j]) for i in range(len(refs)) for j in range(len(refs)) if i != j]
+  d_ref = float(np.median(pair))
+  print('all gradients as one vector, relative l2 distance: median ours<->reference run %.3e over %d runs, median reference '
+        'run<->run %.3e (min %.3e, max %.3e)' % (d_ours, len(refs), d_ref, min(pair), max(pair)))
   assert d_ours <= max(1e-5, SPREAD_FACTOR * d_ref), (d_ours, d_ref)
 
 
