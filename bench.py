@@ -166,6 +166,8 @@ def make_embeddings(torch, args, device, seed):
   b, d, s = args.images, args.dim, args.size
   if args.dist == 'iid':
     return torch.randn((b, d, s, s), generator=g, device=device, dtype=torch.float32)
+  if args.dist == 'const':      # every pixel the same vector: a power experiment (tools/kmeans_iter_stats.py), not a workload
+    return torch.randn((1, d, 1, 1), generator=g, device=device, dtype=torch.float32).expand(b, d, s, s).contiguous()
   # planted: per image 64 unit centres on an 8x8 block layout + noise
   out = torch.empty((b, d, s, s), device=device, dtype=torch.float32)
   blk = (s + 7) // 8

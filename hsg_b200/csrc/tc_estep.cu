@@ -577,15 +577,17 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           tc_fence_after();
           const uint64_t ad = umma_desc(sA + stage * TC_STAGE_BYTES, 1024, 2);
           const uint64_t bd = umma_desc(sB + j * slab_b_bytes, 1024, 2);
+          if (!(p.exp_flags & 32)) {                       // timing experiment (32): the data path without the products
 #pragma unroll
-          for (int k4 = 0; k4 < TC_BK / 16; ++k4)
-            tc_mma_f16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (j | k4) ? 1u : 0u);
+            for (int k4 = 0; k4 < TC_BK / 16; ++k4)
+              tc_mma_f16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (j | k4) ? 1u : 0u);
+          }
           tc_commit(bar_empty + 8 * stage);
           if (++stage == p.nst) { stage = 0; phase ^= 1; }
         }
         mbar_wait(bar_tlfull + 8 * tl, tl_phase);
         tc_fence_after();
-        if (!(p.exp_flags & 1))
+        if (!(p.exp_flags & (1 | 32)))
           tc_mma_f16(d_tmem, umma_desc(sAT + tl * TC_TAIL_BYTES, 256, 6), umma_desc(sBT, 256, 6), idesc, 1u);
         tc_commit(bar_tlempty + 8 * tl);
         if (++tl == 2) { tl = 0; tl_phase ^= 1; }
@@ -665,6 +667,7 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (lane == 0) mbar_arrive(bar_tempty + 8 * g);
       acc_phase ^= 1;
       if (timing) t_wait1 += clock64() - c0;          // sweep
+      if (p.exp_flags & 64) continue;                 // timing experiment: no labels, no list
 
       const float t_final = run - thr;
       int cnt = 0, first = 0;
@@ -838,8 +841,15 @@ estep_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   const int count = *p.tiles.count;
-  const long long pitems = p.items >> 1;                      // 256-pixel items
-  const long long i_begin = blockIdx.x >> 1, i_step = gridDim.x >> 1;
+  const long long pitems_all = p.items >> 1;                  // 256-pixel items
+  // pair -> items: one contiguous range per pair, as in the single-CTA kernel.  Interleaved (pair b takes items b,
+  // b + pairs, ...: HSG_TC_EXP & 4) every pair walks through EVERY image, and each image boundary drains the MMA
+  // pipeline and reloads 68 KB of centroids per CTA -- 48 times per pair at the benchmark shape.
+  const bool contiguous = (p.exp_flags & 4) == 0;
+  const long long n_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
+  const long long i_begin = contiguous ? pitems_all * pair_id / n_pairs : pair_id;
+  const long long pitems = contiguous ? pitems_all * (pair_id + 1) / n_pairs : pitems_all;
+  const long long i_step = contiguous ? 1 : n_pairs;
   const bool timing = (p.exp_flags & 2) && p.dbg_clk;
   long long t_wait0 = 0, t_wait1 = 0;
   const long long t_begin = timing ? clock64() : 0;
