@@ -271,7 +271,7 @@ def flat_kmeans_leg(torch, MU, args, world, rank, device, group):
       torch.distributed.barrier()
     torch.cuda.synchronize()
 
-  MU.dist_kmeans_with_initial_labels(x, init, k, iterations=2, group=group)
+  MU.dist_kmeans_with_initial_labels(x, init, k, iterations=3, group=group)       # full pass, delta pass, allocator
   barrier()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()

@@ -78,6 +78,10 @@ SIGNATURES = {
     'hsg_mha_fwd_f32': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, ctypes.c_ulonglong, _p, _p, _p, _z, _p]),
     'hsg_mha_bwd_f32': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, ctypes.c_ulonglong, _p, _p, _p,
                              _p, _p, _p, _p, _z, _p]),
+    'hsg_kmeans_dist_workspace_bytes': (_z, [_l, _i, _i]),
+    'hsg_kmeans_dist_local_i64': (_i, [_p, _l, _i, _i, _p, _i, _i, _p, _p, _p, _z, _p]),
+    'hsg_kmeans_dist_assign_f32': (_i, [_p, _l, _i, _p, _i, _p, _p, _i, _p, _i, _p, _z, _p]),
+    'hsg_kmeans_dist_labels_i64': (_i, [_l, _i, _i, _i, _p, _p, _z, _p]),
     'hsg_segment_sum_exact_workspace_bytes': (_z, [_l, _i, _l, _i, _i, _l]),
     'hsg_segment_sum_exact_i64': (_i, [_p, _l, _i, _p, _l, _p, _i, _l, _p, _i, _p, _p, _z, _p]),
     'hsg_knn_adjacency_f32': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),

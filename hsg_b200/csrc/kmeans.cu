@@ -384,6 +384,7 @@ struct DeltaPlan {
   int64_t cap;
   double* sums;            // [S*kmax*dim] running sums
   int32_t* members;        // [S*kmax]
+  long long* local_sums;   // [S*kmax*dim] exact mode: this shard's running int64 sums
 };
 
 struct KmPlan {
@@ -398,8 +399,9 @@ constexpr int64_t KM_DELTA_MIN_ROWS = 1 << 18;
 constexpr double KM_DELTA_MAX_FRACTION = 0.4;   // of the rows may have moved (2 entries each) for a delta pass
 
 static void km_carve(Carver& c, KmPlan& p, int64_t N, int dim, int S, int kmax, int64_t max_seg_len,
-                     int d16) {
-  sr_carve(c, p.sr, N, dim, S, kmax, max_seg_len);
+                     int d16, bool exact = false) {
+  // exact: int64 fixed-point sums (the row-sharded loop, hsg_kmeans_dist_*)
+  sr_carve(c, p.sr, N, dim, S, kmax, max_seg_len, exact);
   p.centroids = c.take<float>((int64_t)S * kmax * dim);
   p.fix.count = c.take<int32_t>(2);    // [0] listed pixels, [1] of those: scans over every cluster
   p.fix.capacity = N;
@@ -432,6 +434,7 @@ static void km_carve(Carver& c, KmPlan& p, int64_t N, int dim, int S, int kmax, 
   d.sr.pieces = reinterpret_cast<float*>(c.take<double>((ceil_div64(d.cap, SR_RUN) + p.sr.bins + 2) * dim));
   d.sums = c.take<double>(p.sr.bins * dim);
   d.members = c.take<int32_t>(p.sr.bins);
+  d.local_sums = exact ? c.take<long long>(p.sr.bins * dim) : nullptr;
 }
 
 // First M-step from the run sums the prep kernel emitted (hsg_prep_sums_f32): one warp per (segment, cluster)
@@ -830,6 +833,150 @@ int hsg_kmeans_estep_f32(const float* x, int64_t N, int dim, const void* xh, int
     HSG_LAUNCH_CHECK();
   }
   return sr_keys_to_labels(p.sr, p.sr.keys, labels_out, st);
+}
+
+// ---------------------------------------------------------------- row-sharded flat k-means, one iteration at a time
+// (kmeans_with_initial_labels over rows sharded across GPUs, SURVEY 8e / BASELINE configs[4]): the caller all-reduces
+// the int64 sums between `local` and `assign`; everything else (keys, previous keys, tiles) lives in the workspace,
+// which the caller keeps untouched between the calls of one loop.
+size_t hsg_kmeans_dist_workspace_bytes(int64_t N, int dim, int kmax) {
+  size_t need = 0;
+  for (int d16 = 64; d16 <= 512; d16 *= 2) {
+    Carver c(nullptr);
+    KmPlan p;
+    km_carve(c, p, N, dim, 1, kmax, N, d16, true);
+    if (c.used() > need) need = c.used();
+  }
+  return need + 1024;
+}
+
+}  // extern "C"
+
+namespace hsg {
+// centroids = normalise(sums * 2^-36); an empty cluster has an exactly zero sum and gets the zero centroid
+__global__ void __launch_bounds__(256) dist_centroids_kernel(const long long* __restrict__ sums, int kmax, int dim,
+                                                             float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (k >= kmax) return;
+  float ss = 0.f;
+  for (int d = lane; d < dim; d += 32) {
+    const float f = (float)((double)sums[(int64_t)k * dim + d] * (1.0 / 68719476736.0));
+    out[(int64_t)k * dim + d] = f;
+    ss = fmaf(f, f, ss);
+  }
+  const float n = safe_norm(warp_sum(ss));
+  for (int d = lane; d < dim; d += 32) out[(int64_t)k * dim + d] /= n;
+}
+
+// This shard's contribution to the running sums of the loop, whichever pass ran (flag[0] == 1: the delta pass over
+// the rows that moved, its pieces ARE the contribution; otherwise the full pass: contribution = new sums - the
+// shard's previous sums).  Integer arithmetic: both give the same numbers.  `local` keeps the shard's own sums.
+__global__ void __launch_bounds__(256) dist_contribution_kernel(
+    int64_t bins, int dim, const int64_t* __restrict__ bin_start, const int32_t* __restrict__ bin_count,
+    const long long* __restrict__ pieces_full, const long long* __restrict__ pieces_delta,
+    const int32_t* __restrict__ flag, long long* __restrict__ local, long long* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t key = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (key >= bins) return;
+  const bool delta = flag[0] == 1;
+  const long long* pieces = delta ? pieces_delta : pieces_full;
+  const int cnt = bin_count[key];
+  const int64_t start = bin_start[key];
+  const int64_t r0 = start / SR_RUN, r1 = cnt > 0 ? (start + cnt - 1) / SR_RUN : r0 - 1;
+  for (int d = lane; d < dim; d += 32) {
+    long long a = 0;
+    for (int64_t r = r0; r <= r1; ++r) a += pieces[(r + key) * dim + d];
+    const long long before = local[key * dim + d];
+    out[key * dim + d] = delta ? a : a - before;
+    local[key * dim + d] = delta ? before + a : a;
+  }
+}
+}  // namespace hsg
+
+extern "C" {
+
+// phase 0: this shard's contribution to the running sums.  first != 0: keys from init_labels, full exact pass
+// (sums_out = the shard's sums).  Otherwise: exact sums over the rows whose label changed in the last `assign`
+// (sum[new] += x, sum[old] -= x), to be ADDED to the running sums after the all-reduce.
+int hsg_kmeans_dist_local_i64(const float* x, int64_t N, int dim, int d16, const int64_t* seg_offsets /* {0,N} on the device */,
+                              int kmax, int first, const int64_t* init_labels, long long* sums_out,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(x, N, dim, seg_offsets, 1, N, kmax);
+  if (rc) return rc;
+  HSG_REQUIRE(sums_out, HSG_E_INVALID, "kmeans_dist_local: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) {
+    HSG_CUDA(cudaMemsetAsync(sums_out, 0, sizeof(long long) * kmax * dim, st));
+    return HSG_OK;
+  }
+  HSG_REQUIRE(workspace && workspace_bytes >= hsg_kmeans_dist_workspace_bytes(N, dim, kmax), HSG_E_WORKSPACE,
+              "kmeans_dist_local: workspace too small");
+  Carver c(workspace);
+  KmPlan p;
+  km_carve(c, p, N, dim, 1, kmax, N, d16, true);       // the three calls of a loop carve the same layout (same d16)
+  if (first) {
+    HSG_REQUIRE(init_labels, HSG_E_INVALID, "kmeans_dist_local: null labels");
+    if ((rc = sr_build_tiles(p.sr, seg_offsets, st))) return rc;
+    if ((rc = sr_labels_to_keys(p.sr, init_labels, nullptr, st))) return rc;
+    if ((rc = sr_sort_and_sum(p.sr, x, seg_offsets, st))) return rc;
+    if ((rc = sr_combine_exact(p.sr, kmax, nullptr, sums_out, st))) return rc;
+    HSG_CUDA(cudaMemcpyAsync(p.d.local_sums, sums_out, sizeof(long long) * kmax * dim, cudaMemcpyDeviceToDevice, st));
+    HSG_CUDA(cudaMemcpyAsync(p.d.keys_prev, p.sr.keys, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, st));
+    return HSG_OK;
+  }
+  // delta or full pass, decided on the device as in the per-image loop (both enqueued, one returns at once)
+  DeltaPlan& d = p.d;
+  if ((rc = sr_delta_build(p.sr, seg_offsets, d.keys_prev, d.tile_entries, d.eoff, d.flag, d.cap, d.erow, d.ekey, st))) return rc;
+  if ((rc = sr_build_tiles(d.sr, d.eoff, st))) return rc;
+  if ((rc = sr_sort_and_sum_gated(p.sr, x, seg_offsets, Gate{d.flag, 0}, nullptr, nullptr, st))) return rc;
+  if ((rc = sr_sort_and_sum_gated(d.sr, x, seg_offsets, Gate{d.flag, 1}, d.eoff, d.erow, st))) return rc;
+  dist_contribution_kernel<<<(unsigned)ceil_div64(p.sr.bins, 8), 256, 0, st>>>(
+      p.sr.bins, dim, p.sr.bin_start, p.sr.bin_count, reinterpret_cast<const long long*>(p.sr.pieces),
+      reinterpret_cast<const long long*>(d.sr.pieces), d.flag, d.local_sums, sums_out);
+  HSG_LAUNCH_CHECK();
+  return HSG_OK;
+}
+
+// phase 1: centroids from the all-reduced running sums, then the E-step; the new keys stay in the workspace
+int hsg_kmeans_dist_assign_f32(const float* x, int64_t N, int dim, const void* xh, int d16, const float* xerr,
+                               const int64_t* seg_offsets, int kmax, const long long* sums, int flags,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(x, N, dim, seg_offsets, 1, N, kmax);
+  if (rc) return rc;
+  if (N == 0) return HSG_OK;
+  HSG_REQUIRE(sums, HSG_E_INVALID, "kmeans_dist_assign: null sums");
+  HSG_REQUIRE(workspace && workspace_bytes >= hsg_kmeans_dist_workspace_bytes(N, dim, kmax), HSG_E_WORKSPACE,
+              "kmeans_dist_assign: workspace too small");
+  bool use_tc = false;
+  if ((rc = decide_tc(flags, dim, xh, d16, xerr, kmax, &use_tc))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c(workspace);
+  KmPlan p;
+  km_carve(c, p, N, dim, 1, kmax, N, d16, true);
+  if (use_tc) {
+    p.tc.xh = (const __half*)xh; p.tc.xerr = xerr; p.tc.d16 = d16;
+    if ((rc = tc_prepare(p.tc, N, 1))) return rc;
+  }
+  dist_centroids_kernel<<<(unsigned)ceil_div64(kmax, 8), 256, 0, st>>>(sums, kmax, dim, p.centroids);
+  HSG_LAUNCH_CHECK();
+  EStepArgs ea;
+  ea.x = x; ea.N = N; ea.dim = dim; ea.centroids = p.centroids; ea.seg_offsets = seg_offsets;
+  ea.S = 1; ea.seg_k = nullptr; ea.kmax = kmax; ea.tiles = p.sr.tiles; ea.keys_out = p.sr.keys;
+  ea.fix = p.fix;
+  return run_estep(ea, p, use_tc, st);
+}
+
+// phase 2: the labels of the last `assign`
+int hsg_kmeans_dist_labels_i64(int64_t N, int dim, int d16, int kmax, int64_t* labels_out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (N == 0) return HSG_OK;
+  HSG_REQUIRE(labels_out && workspace && workspace_bytes >= hsg_kmeans_dist_workspace_bytes(N, dim, kmax), HSG_E_WORKSPACE,
+              "kmeans_dist_labels: workspace too small");
+  Carver c(workspace);
+  KmPlan p;
+  km_carve(c, p, N, dim, 1, kmax, N, d16, true);
+  return sr_keys_to_labels(p.sr, p.sr.keys, labels_out, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------- K3 segmented reduction

@@ -213,9 +213,9 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_sum_kernel(
     const int32_t* __restrict__ keys, const uint32_t* __restrict__ perm,
     float* __restrict__ pieces, int32_t* __restrict__ piece_cnt, Gate gate,
     const int64_t* __restrict__ eoff, const uint32_t* __restrict__ erow) {
-  constexpr bool DELTA = MODE == 1;
-  constexpr bool EXACT = MODE == 2;
-  typedef typename std::conditional<DELTA, double, typename std::conditional<EXACT, long long, float>::type>::type acc_t;
+  constexpr bool DELTA = MODE == 1 || MODE == 3;       // MODE 3: signed entries AND int64 fixed point (exact delta)
+  constexpr bool EXACT = MODE == 2 || MODE == 3;
+  typedef typename std::conditional<EXACT, long long, typename std::conditional<DELTA, double, float>::type>::type acc_t;
   if (gate.closed()) return;
   const int lane = threadIdx.x & 31;
   const int64_t run = (int64_t)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
@@ -293,7 +293,14 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_sum_kernel(
 #pragma unroll
           for (int m = 0; m < NV; ++m) acc[m] = 0;
         }
-        if (DELTA) {
+        if (DELTA && EXACT) {
+#pragma unroll
+          for (int m = 0; m < NV; ++m) {
+            const long long q = __float2ll_rn(v[u][m] * SR_FIXED_SCALE);
+            acc[m] += (acc_t)(neg[u] ? -q : q);
+          }
+          cnt += neg[u] ? -1 : 1;
+        } else if (DELTA) {
 #pragma unroll
           for (int m = 0; m < NV; ++m) acc[m] += (acc_t)(neg[u] ? -v[u][m] : v[u][m]);
           cnt += neg[u] ? -1 : 1;
@@ -628,7 +635,8 @@ int sr_sort_and_sum_gated(const SegReducePlan& p, const float* x, const int64_t*
   HSG_LAUNCH_CHECK();
   }
   ProfRange prof(PROF_MSTEP_GATHER, st);
-  if (p.exact) return gather_dispatch<2>(p, x, off, gate, nullptr, nullptr, st);
+  if (p.exact) return eoff ? gather_dispatch<3>(p, x, off, gate, eoff, erow, st)
+                           : gather_dispatch<2>(p, x, off, gate, nullptr, nullptr, st);
   return eoff ? gather_dispatch<1>(p, x, off, gate, eoff, erow, st)
               : gather_dispatch<0>(p, x, off, gate, nullptr, nullptr, st);
 }

@@ -237,36 +237,29 @@ def dist_kmeans_with_initial_labels(embeddings, initial_labels, max_label, itera
   exact, so centroids and labels are bit-identical at every rank count and for every way of sharding the
   rows -- including the single-process run (`collective=False`: this process holds every row).
 
-  Because the sums are exact integers they can also be UPDATED exactly: from the third iteration on only the
-  rows whose label changed are touched (sum[new] += x, sum[old] -= x), which leaves the result bit-identical
-  to re-summing every row and removes most of the M-step traffic (r2: 8.9 -> see profiles/)."""
+  Because the sums are exact integers they can also be UPDATED exactly: after the first iteration a shard only
+  touches the rows whose label changed (sum[new] += x, sum[old] -= x), the all-reduce carries the integer
+  corrections, and every rank adds them to its copy of the running sums -- bit-identical to re-summing every row.
+  One iteration is two library calls around the collective (ops.DistKMeans / hsg_kmeans_dist_*), no host
+  synchronisation."""
   x = embeddings.reshape(-1, embeddings.shape[-1]).detach()
   labels = initial_labels.reshape(-1).long()
   k = int(max_label)
+  if int(iterations) <= 0:
+    return labels.clone()
   d16 = ops.tc_d16(x.shape[1], k)
   xh = xerr = None
   if d16 and x.shape[0] >= 16384:
     xh, xerr = ops.make_half_copy(x, d16)
-  n = x.shape[0]
-  local = prev = None
+  shard = ops.DistKMeans(x, labels, k, xh=xh, xerr=xerr)
+  exchange = collective and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+  running = None
   with torch.no_grad():
     for it in range(int(iterations)):
-      changed = None
-      if local is not None and it >= 2:
-        changed = torch.nonzero(labels != prev).view(-1)                 # one host read per iteration
-        if changed.numel() > 0.3 * n:
-          changed = None
-      if changed is None:
-        local = ops.segment_sum_exact(x, labels, k)
-      elif changed.numel() > 0:
-        rows = x.index_select(0, changed)
-        local = local + ops.segment_sum_exact(rows, labels.index_select(0, changed), k) \
-            - ops.segment_sum_exact(rows, prev.index_select(0, changed), k)
-      sums = local
-      if collective and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        sums = local.clone()
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-      centroids = ops.normalize((sums.double() * ops.FIXED_POINT_SCALE).float())
-      prev = labels
-      labels = ops.kmeans_estep(x, centroids.view(1, k, -1), xh=xh, xerr=xerr)
+      part = shard.local()
+      if exchange:
+        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+      running = part if running is None else running.add_(part)
+      shard.assign(running)
+    labels = shard.labels()
   return labels

@@ -284,6 +284,50 @@ def segment_reduce(x, labels, num_bins, mode, seg_offsets=None, max_seg_len=None
 FIXED_POINT_SCALE = 2.0 ** -36
 
 
+class DistKMeans:
+  """One shard of the row-sharded flat k-means, an iteration at a time (hsg_kmeans_dist_*): `local()` returns this
+  shard's exact int64 contribution to the [K,D] centroid sums (the full sums first, afterwards only the rows whose
+  label changed), the caller all-reduces it and adds it to its running sums, `assign(running)` runs the E-step.
+  The loop's state (labels, previous labels, sort tiles) lives in the workspace this object owns."""
+
+  def __init__(self, x, init_labels, kmax, xh=None, xerr=None, flags=_lib.KMEANS_AUTO):
+    _need_cuda(x, init_labels, xh, xerr)
+    self.x = _f32(x)
+    self.n, self.dim = self.x.shape
+    self.k = int(kmax)
+    self.init = _i64(init_labels).view(-1)
+    self.xh, self.xerr, self.flags = xh, xerr, flags
+    self.d16 = xh.shape[1] - XH_TAIL if xh is not None else 0
+    self.off = torch.tensor([0, self.n], dtype=torch.int64, device=self.x.device)
+    self.lib = _lib.load()
+    self.ws = _workspace(self.lib.hsg_kmeans_dist_workspace_bytes(self.n, self.dim, self.k), self.x.device)
+    self.first = True
+
+  def local(self):
+    out = torch.empty((self.k, self.dim), dtype=torch.int64, device=self.x.device)
+    with torch.cuda.device(self.x.device):
+      check(self.lib.hsg_kmeans_dist_local_i64(_ptr(self.x), self.n, self.dim, self.d16, _ptr(self.off), self.k,
+                                               int(self.first), _ptr(self.init), _ptr(out), _ptr(self.ws),
+                                               self.ws.numel(), _stream()), 'kmeans_dist_local')
+    self.first = False
+    return out
+
+  def assign(self, running_sums):
+    sums = running_sums.contiguous()
+    assert sums.dtype == torch.int64 and sums.numel() == self.k * self.dim
+    with torch.cuda.device(self.x.device):
+      check(self.lib.hsg_kmeans_dist_assign_f32(_ptr(self.x), self.n, self.dim, _ptr(self.xh), self.d16, _ptr(self.xerr),
+                                                _ptr(self.off), self.k, _ptr(sums), self.flags, _ptr(self.ws),
+                                                self.ws.numel(), _stream()), 'kmeans_dist_assign')
+
+  def labels(self):
+    out = torch.empty((self.n,), dtype=torch.int64, device=self.x.device)
+    with torch.cuda.device(self.x.device):
+      check(self.lib.hsg_kmeans_dist_labels_i64(self.n, self.dim, self.d16, self.k, _ptr(out), _ptr(self.ws),
+                                                self.ws.numel(), _stream()), 'kmeans_dist_labels')
+    return out
+
+
 def segment_sum_exact(x, labels, num_bins):
   """Exact bin sums as int64 fixed point (value = sum * FIXED_POINT_SCALE): independent of the row order and
   of how the rows are split over calls or GPUs (hsg_segment_sum_exact_i64).  x rows with |x| <= 1."""

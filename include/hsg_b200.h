@@ -255,6 +255,28 @@ HSG_API int hsg_segment_sum_exact_i64(const float* x, int64_t N, int dim, const 
                                       const int64_t* seg_base, int kmax, long long* sums_out,
                                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K1 over row shards: kmeans_with_initial_labels (common.py:67-97) on rows split across GPUs, as the reference's
+ *      flat k-means is used by hsg/models/embeddings/clusters.py:30-42 (BASELINE configs[4]); one iteration =
+ *        hsg_kmeans_dist_local_i64   this shard's exact int64 contribution to the [kmax,dim] centroid sums
+ *                                    (first != 0: the sums of init_labels; afterwards: only the rows whose label changed,
+ *                                    sum[new] += x, sum[old] -= x)
+ *        <caller: ncclAllReduce(sum, int64) over the shards; running += contribution>
+ *        hsg_kmeans_dist_assign_f32  centroids = normalise(running * 2^-36), E-step (same kernels and float64
+ *                                    re-decision as hsg_kmeans_f32); the new labels stay in the workspace
+ *      and hsg_kmeans_dist_labels_i64 copies the final labels out.  The workspace carries the loop's state and must be
+ *      left untouched between the calls (same N, dim, d16, kmax in all of them).  Integer sums make the centroids -- and
+ *      the labels -- bit-identical for every way of sharding the rows. */
+HSG_API size_t hsg_kmeans_dist_workspace_bytes(int64_t N, int dim, int kmax);
+HSG_API int hsg_kmeans_dist_local_i64(const float* x, int64_t N, int dim, int d16,
+                                      const int64_t* seg_offsets /* device {0,N} */, int kmax, int first,
+                                      const int64_t* init_labels, long long* sums_out /* [kmax,dim] */,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+HSG_API int hsg_kmeans_dist_assign_f32(const float* x, int64_t N, int dim, const void* xh, int d16, const float* xerr,
+                                       const int64_t* seg_offsets, int kmax, const long long* sums /* [kmax,dim] */,
+                                       int flags, void* workspace, size_t workspace_bytes, void* stream);
+HSG_API int hsg_kmeans_dist_labels_i64(int64_t N, int dim, int d16, int kmax, int64_t* labels_out,
+                                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K4: pixel-to-prototype NCE ("SegSort+") loss
  *      _calculate_log_likelihood (hsg/utils/segsort/loss.py:15-82).
  * e [N,dim], prototypes [P,dim], inst [N] (own prototype id), n_sets label

@@ -13,12 +13,15 @@ from hsg_b200.utils.segsort import common as S
 
 T = 20
 dev = torch.device('cuda:0')
-peak = 6539.2
+peak, tpeak = 6539.2, 1357.1
 pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')
 if os.path.exists(pk):
   peak = json.load(open(pk))['hbm_gbs']
-lines = ['# flat spherical k-means sweep (BASELINE configs[4]), 1 x B200, T=%d, HBM peak %.0f GB/s (measured copy)' % (T, peak),
-         '%9s %4s %5s %6s %10s %10s %8s %10s' % ('N', 'D', 'K', 'E-step', 'ms/iter', 'GB/s(alg)', 'frac', 'TFLOP/s')]
+  tpeak = json.load(open(pk)).get('bf16_tflops_sustained', tpeak)
+# which roof bounds a point: one fp16 pass costs 2NDK flop against N(4D+8) bytes, i.e. the tensor roof is the lower one
+# when K > peak_flops / peak_bytes * (4D+8) / (2D) ~ 425 at D=256; both fractions are printed
+lines = ['# flat spherical k-means sweep (BASELINE configs[4]), 1 x B200, T=%d, HBM peak %.0f GB/s (measured copy), tensor peak %.0f TFLOP/s (measured cuBLAS bf16, sustained)' % (T, peak, tpeak),
+         '%9s %4s %5s %6s %10s %10s %8s %10s %8s %7s' % ('N', 'D', 'K', 'E-step', 'ms/iter', 'GB/s(alg)', 'hbm', 'TFLOP/s', 'tensor', 'bound')]
 for nn in (100000, 1000000, 10000000):
   for d in (64, 256, 512):
     for k in (32, 256, 2048):
@@ -39,8 +42,10 @@ for nn in (100000, 1000000, 10000000):
       t1.record(); torch.cuda.synchronize()
       ms = t0.elapsed_time(t1) / T
       gbs = nn * (4.0 * d + 8) / ms / 1e6
-      lines.append('%9d %4d %5d %6s %10.3f %10.1f %8.3f %10.1f' % (nn, d, k, 'tc' if tc and nn >= 16384 else 'simt', ms, gbs,
-                                                                   gbs / peak, flops / ms / 1e9))
+      tfs = flops / ms / 1e9
+      bound = 'tensor' if tfs / tpeak > gbs / peak else 'hbm'
+      lines.append('%9d %4d %5d %6s %10.3f %10.1f %8.3f %10.1f %8.3f %7s' % (nn, d, k, 'tc' if tc and nn >= 16384 else 'simt', ms, gbs,
+                                                                            gbs / peak, tfs, tfs / tpeak, bound))
       del x, init
       torch.cuda.empty_cache()
 text = '\n'.join(lines)
