@@ -291,16 +291,26 @@ int nce_grad_tc_prepare(void* host_state, const float* e, const float* prototype
                         const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus,
                         float conc, void* workspace, cudaStream_t st);
 int nce_grad_tc(void* host_state, const float* stats, const float* w, float conc, int64_t i_begin, int64_t i_end,
-                float* G, int64_t ldg, cudaStream_t st);
+                float* G, int64_t ldg, __half* G2, const float* gscale, cudaStream_t st);
+const __half* nce_grad_tc_e2(void* host_state, float* scale);
+// dP = G^T E straight from the row-major fp16 copies (MN-major tcgen05 operands, split K) -- gemm_tc.cu
+bool gemm_tn_tc_supported(int N);
+int gemm_tn_ksplit(int64_t M, int64_t n_k);
+int gemm_tn_tc_split(const __half* a2, int64_t a_rows, int a_half, const __half* b2, int64_t b_rows, int b_half,
+                     int64_t b_row0, int64_t M, int N, int64_t n_k, int ksplit, float* part, const float* inv_scale,
+                     cudaStream_t st);
+int sum_splits(const float* part, int64_t n, int ksplit, float* out, cudaStream_t st);
 int absmax(const float* x, int64_t n, float* out, cudaStream_t st);
 
 // operand scales of the backward GEMMs: G is multiplied by sc[0] = 2^10 / (conc * n_sets * max|w|) before the
 // fp16 split (|G_ij| <= conc * sum_s |w_si|), E and P by 16; sc[1] = 1 / (16 sc[0]) undoes both
-__global__ void nce_bwd_scales_kernel(const float* __restrict__ wmax, float conc, int n_sets, float* __restrict__ sc) {
+__global__ void nce_bwd_scales_kernel(const float* __restrict__ wmax, float conc, int n_sets, float e2_scale,
+                                      float* __restrict__ sc) {
   const float bound = fabsf(conc) * n_sets * wmax[0];
   const float sa = bound > 0.f ? 1024.f / bound : 1.f;
   sc[0] = sa;
   sc[1] = 1.f / (16.f * sa);
+  sc[2] = 1.f / (e2_scale * sa);     // dP from the forward's fp16 copy of E (scaled by e2_scale)
 }
 
 struct BwdTcPlan {
@@ -314,23 +324,33 @@ struct BwdTcPlan {
   __half* Gt2;
   __half* Pt2;
   __half* Et2;
-  float* scal;     // [0] max|w|, [1] G scale, [2] output scale
+  float* scal;     // [0] max|w|, [1] G scale, [2] output scale (E, P scaled by 16), [3] output scale of the direct dP product
+  bool direct;     // G written as fp16 (hi | lo) by the G kernel; dP through the MN-major product (no fp32 G, no transposes)
+  float* part;     // [8][P, dim] K-split partial sums of dP
 };
 
-static void bwd_carve(Carver& c, BwdTcPlan& b, int64_t N, int64_t P, int dim, int n_sets, int64_t chunk, bool tc) {
+static void bwd_carve(Carver& c, BwdTcPlan& b, int64_t N, int64_t P, int dim, int n_sets, int64_t chunk, bool tc,
+                      bool g_tc = true) {
   b.on = tc;
   b.Pp = (P + 63) / 64 * 64;
   b.chunkp = (chunk + 63) / 64 * 64;
   b.ldg = tc ? b.Pp : P;
-  b.g_on = tc && nce_tc_supported(N, P, dim, n_sets);
-  b.G = c.take<float>((size_t)chunk * b.ldg);
+  b.g_on = tc && g_tc && nce_tc_supported(N, P, dim, n_sets);
+  b.direct = b.g_on && gemm_tn_tc_supported(dim);
+  b.G = b.direct ? nullptr : c.take<float>((size_t)chunk * b.ldg);
   b.fwd_ws = b.g_on ? c.take<char>(nce_tc_workspace_bytes(N, P, dim, n_sets)) : nullptr;
   if (!tc) return;
   b.G2 = c.take<__half>((size_t)chunk * 2 * b.Pp);
-  b.Gt2 = c.take<__half>((size_t)P * 2 * b.chunkp);
   b.Pt2 = c.take<__half>((size_t)dim * 2 * b.Pp);
-  b.Et2 = c.take<__half>((size_t)dim * 2 * b.chunkp);
   b.scal = c.take<float>(4);
+  if (b.direct) {
+    b.Gt2 = b.Et2 = nullptr;
+    b.part = c.take<float>((size_t)8 * P * dim);
+    return;
+  }
+  b.part = nullptr;
+  b.Gt2 = c.take<__half>((size_t)P * 2 * b.chunkp);
+  b.Et2 = c.take<__half>((size_t)dim * 2 * b.chunkp);
 }
 
 static bool bwd_tc_shape(int64_t P, int dim) {
@@ -338,8 +358,12 @@ static bool bwd_tc_shape(int64_t P, int dim) {
 }
 
 static int64_t nce_chunk_pixels(int64_t N, int64_t P) {
-  // keep the G chunk near 256 MB
-  int64_t c = (int64_t)(64ll << 20) / (P > 0 ? P : 1);
+  // G chunk of up to 2 GB (fp32; its two fp16 splits are as large again): the chunk's rows are the M of the dE GEMM
+  // (128-row tiles, one CTA each) and the K of the dP GEMM, so a chunk has to hold a few hundred tiles to fill
+  // 148 SMs -- at 256 MB and P = 12288 it held 43 (r1: 197 ms per 1M pixels)
+  int64_t c = (int64_t)(512ll << 20) / (P > 0 ? P : 1);
+  const int64_t wave = (int64_t)num_sms() * 128;          // rows of one wave of 128-row dE tiles
+  if (c > wave) c = c / wave * wave;
   c = c / NC_T * NC_T;
   if (c < NC_T) c = NC_T;
   if (c > N) c = ceil_div64(N, NC_T) * NC_T;
@@ -365,10 +389,13 @@ using namespace hsg;
 extern "C" {
 
 size_t hsg_nce_workspace_bytes(int64_t N, int64_t P, int dim, int n_sets) {
-  Carver cb(nullptr);
-  BwdTcPlan bp;
-  bwd_carve(cb, bp, N, P, dim, n_sets, nce_chunk_pixels(N, P), bwd_tc_shape(P, dim));
-  size_t need = cb.used() + 1024;                                                // backward: one G chunk (+ its fp16 splits)
+  size_t need = 0;
+  for (int g_tc = 0; g_tc < 2; ++g_tc) {                                         // backward: one G chunk (+ its fp16 splits),
+    Carver cb(nullptr);                                                          // with or without the tensor-core G kernel (tests)
+    BwdTcPlan bp;
+    bwd_carve(cb, bp, N, P, dim, n_sets, nce_chunk_pixels(N, P), bwd_tc_shape(P, dim), g_tc != 0);
+    if (cb.used() + 1024 > need) need = cb.used() + 1024;
+  }
   if (nce_tc_supported(N, P, dim, n_sets)) {
     const size_t tc = nce_tc_workspace_bytes(N, P, dim, n_sets);                 // forward: fp16 (hi,lo) copies
     if (tc > need) need = tc;
@@ -425,25 +452,40 @@ int hsg_nce_bwd_f32(const float* e, const float* prototypes, int64_t N, int64_t 
   const int64_t chunk = nce_chunk_pixels(N, P);
   Carver cw(workspace);
   BwdTcPlan b;
-  bwd_carve(cw, b, N, P, dim, n_sets, chunk, bwd_tc_shape(P, dim) && !(g_debug_flags & 4));
-  if (g_debug_flags & 8) b.g_on = false;
+  bwd_carve(cw, b, N, P, dim, n_sets, chunk, bwd_tc_shape(P, dim) && !(g_debug_flags & 4), !(g_debug_flags & 8));
   alignas(64) unsigned char tc_state[1024];
   HSG_REQUIRE(nce_grad_tc_host_state_bytes() <= sizeof(tc_state), HSG_E_UNSUPPORTED, "nce_bwd: host state");
   float* G = b.G;
+  const __half* e2 = nullptr;
+  int ksplit = 1;
   if (b.on) {
     // dE = G P and dP = G^T E on the tensor cores (three fp16 passes each, gemm_tc.cu)
-    if ((rc = absmax(w, (int64_t)n_sets * N, b.scal, st))) return rc;
-    nce_bwd_scales_kernel<<<1, 1, 0, st>>>(b.scal, concentration, n_sets, b.scal + 1);
-    HSG_LAUNCH_CHECK();
-    if ((rc = split_transpose(prototypes, dim, P, dim, b.Pp, 16.f, nullptr, b.Pt2, st))) return rc;
     if (b.g_on && (rc = nce_grad_tc_prepare(tc_state, e, prototypes, N, P, dim, inst, sem, psem, n_sets, group_plus_host,
                                             concentration, b.fwd_ws, st))) return rc;
+    float e2_scale = 1.f;
+    if (b.g_on) e2 = nce_grad_tc_e2(tc_state, &e2_scale);
+    if ((rc = absmax(w, (int64_t)n_sets * N, b.scal, st))) return rc;
+    nce_bwd_scales_kernel<<<1, 1, 0, st>>>(b.scal, concentration, n_sets, e2_scale, b.scal + 1);
+    HSG_LAUNCH_CHECK();
+    if ((rc = split_transpose(prototypes, dim, P, dim, b.Pp, 16.f, nullptr, b.Pt2, st))) return rc;
+    if (b.direct) HSG_CUDA(cudaMemsetAsync(b.part, 0, sizeof(float) * 8 * P * dim, st));
   }
   for (int64_t i0 = 0; i0 < N; i0 += chunk) {
     const int64_t i1 = i0 + chunk < N ? i0 + chunk : N;
     const int64_t m = i1 - i0;
+    if (b.direct) {
+      // G chunk as fp16 (hi | lo) rows straight from the accumulator, then both products read that one copy:
+      // dE[i0:i1] = G P (K-major A) and dP += G^T E[i0:i1] (MN-major A and B, K split over the SMs)
+      if ((rc = nce_grad_tc(tc_state, stats, w, concentration, i0, i1, nullptr, b.ldg, b.G2, b.scal + 1, st))) return rc;
+      if ((rc = gemm_tc_split(b.G2, b.Pt2, m, dim, (int)b.Pp, grad_e + i0 * dim, dim, b.scal + 2, 1.f, false, st))) return rc;
+      const int64_t n_k = ceil_div64(m, 64);
+      ksplit = gemm_tn_ksplit(P, ceil_div64(chunk < N ? chunk : N, 64));      // the same split for every chunk of the call
+      if (ksplit > n_k) ksplit = (int)n_k;
+      if ((rc = gemm_tn_tc_split(b.G2, m, (int)b.Pp, e2, N, dim, i0, P, dim, n_k, ksplit, b.part, b.scal + 3, st))) return rc;
+      continue;
+    }
     if (b.g_on) {
-      if ((rc = nce_grad_tc(tc_state, stats, w, concentration, i0, i1, G, b.ldg, st))) return rc;
+      if ((rc = nce_grad_tc(tc_state, stats, w, concentration, i0, i1, G, b.ldg, nullptr, nullptr, st))) return rc;
     } else {
       if (b.on && b.ldg != P) HSG_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * m * b.ldg, st));   // zero pad columns
       dim3 gg((unsigned)ceil_div64(m, NC_T), (unsigned)ceil_div64(P, NC_T));
@@ -475,6 +517,7 @@ int hsg_nce_bwd_f32(const float* e, const float* prototypes, int64_t N, int64_t 
     sgemm_kernel<true><<<g2, NC_THREADS, 0, st>>>(G, e + i0 * dim, grad_p, P, dim, m, 1);
     HSG_LAUNCH_CHECK();
   }
+  if (b.direct) return sum_splits(b.part, P * dim, 8, grad_p, st);      // unused splits stay zero
   return HSG_OK;
 }
 

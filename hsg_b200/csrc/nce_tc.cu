@@ -355,8 +355,10 @@ struct NceGradTcParams {
   const float* stats;        // [n_sets,N,4] num, den, own, flags (forward)
   const float* w;            // [n_sets,N] upstream gradient per pixel
   float conc;
-  float* G;                  // [i_end - i_begin, ldg]
+  float* G;                  // [i_end - i_begin, ldg] fp32, or NULL:
   int64_t ldg;               // multiple of 64, >= P; columns >= P are written as zeros
+  __half* G2;                // [i_end - i_begin, 2 * ldg] = fp16 (hi | lo) of G * (*gscale): the operand layout of the
+  const float* gscale;       //   two backward GEMMs, written straight from the accumulator (no fp32 round trip)
 };
 
 template <int NS>
@@ -528,7 +530,9 @@ nce_grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int nchunk = (max(n_store, 0) + 15) >> 4;
       const int own_rel = my_inst - nt * N2_BN;
       const int32_t* lab_tile = p.psem + (int64_t)nt * N2_BN;
-      float* grow = g.G + (pix - g.i_begin) * g.ldg + (int64_t)nt * N2_BN;
+      float* grow = g.G ? g.G + (pix - g.i_begin) * g.ldg + (int64_t)nt * N2_BN : nullptr;
+      __half* g2row = g.G2 ? g.G2 + (pix - g.i_begin) * 2 * g.ldg + (int64_t)nt * N2_BN : nullptr;
+      const float gsc = g.G2 ? *g.gscale : 1.f;
 
       mbar_wait(bar_tfull + 8 * grp, (seq >> 1) & 1);
       tc_fence_after();
@@ -562,10 +566,25 @@ nce_grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const float sv = col0 + j < n_valid ? ex2_approx(__uint_as_float(v[j])) : 0.f;
           gv[j] *= sv;
         }
-        if (inb) {
+        if (inb && grow) {
           float4* dst = reinterpret_cast<float4*>(grow + col0);
 #pragma unroll
           for (int w4 = 0; w4 < 4; ++w4) dst[w4] = make_float4(gv[4 * w4], gv[4 * w4 + 1], gv[4 * w4 + 2], gv[4 * w4 + 3]);
+        }
+        if (inb && g2row) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float a = gv[2 * j] * gsc, b = gv[2 * j + 1] * gsc;
+            const __half2 h = __floats2half2_rn(a, b);
+            const __half2 l = __floats2half2_rn(a - __low2float(h), b - __high2float(h));
+            hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+          uint4* dh = reinterpret_cast<uint4*>(g2row + col0);
+          uint4* dl = reinterpret_cast<uint4*>(g2row + g.ldg + col0);
+          dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
       }
       tc_fence_before();
@@ -605,6 +624,8 @@ struct NceTcSetup {
   NceTcParams p;
   CUtensorMap ma, mb;
   size_t smem;
+  const __half* e2;          // [N, 2 D] fp16 (hi | lo) of t * e
+  float t;                   // operand scale sqrt(|c| log2 e)
 };
 
 // fp16 (hi|lo) copies of both operands, int32 labels, tensor maps: everything the pair kernels read
@@ -632,6 +653,8 @@ static int nce_tc_setup(NceTcSetup& u, const float* e, const float* prototypes, 
   nce_labels32_kernel<<<(unsigned)ceil_div64(Ppad * n_sets, 256), 256, 0, st>>>(psem, P, Ppad, n_sets, psem32, INT_MIN + 1);
   HSG_LAUNCH_CHECK();
 
+  u.e2 = ah;
+  u.t = t;
   NceTcParams& p = u.p;
   p.N = N; p.P = P; p.D = dim; p.n_sets = n_sets; p.inst = inst32; p.sem = sem32; p.psem = psem32;
   p.Ppad = Ppad; p.per_pixel = nullptr; p.stats = nullptr;
@@ -691,12 +714,19 @@ int nce_grad_tc_prepare(void* host_state, const float* e, const float* prototype
   return nce_tc_setup(*setup_slot(host_state), e, prototypes, N, P, dim, inst, sem, psem, n_sets, plus, conc, workspace, st);
 }
 
+const __half* nce_grad_tc_e2(void* host_state, float* scale) {
+  *scale = setup_slot(host_state)->t;
+  return setup_slot(host_state)->e2;
+}
+
 int nce_grad_tc(void* host_state, const float* stats, const float* w, float conc, int64_t i_begin, int64_t i_end,
-                float* G, int64_t ldg, cudaStream_t st) {
+                float* G, int64_t ldg, __half* G2, const float* gscale, cudaStream_t st) {
   NceTcSetup& u = *setup_slot(host_state);
   HSG_REQUIRE(ldg % 64 == 0 && ldg >= u.p.P, HSG_E_INVALID, "nce_grad_tc: ldg=%lld", (long long)ldg);
+  HSG_REQUIRE(G || (G2 && gscale), HSG_E_INVALID, "nce_grad_tc: no output");
   NceGradTcParams g;
   g.f = u.p; g.i_begin = i_begin; g.i_end = i_end; g.stats = stats; g.w = w; g.conc = conc; g.G = G; g.ldg = ldg;
+  g.G2 = G2; g.gscale = gscale;
   const int64_t items = ceil_div64(i_end - i_begin, 2 * NT_BM) * (u.p.Ppad / N2_BN);
   int64_t grid = num_sms() & ~1;
   if (grid > 2 * items) grid = 2 * items;
