@@ -20,6 +20,8 @@
 // is > 0 else own, den = neg + num, l = -log(num/den).
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 #include <float.h>
 #include <limits.h>
 
@@ -359,7 +361,11 @@ struct NceGradTcParams {
   int64_t ldg;               // multiple of 64, >= P; columns >= P are written as zeros
   __half* G2;                // [i_end - i_begin, 2 * ldg] = fp16 (hi | lo) of G * (*gscale): the operand layout of the
   const float* gscale;       //   two backward GEMMs, written straight from the accumulator (no fp32 round trip)
+  int exp_flags;             // timing experiments (HSG_NCE_EXP), 0 in production: 1 = no stores, 2 = direct (uncoalesced) stores
+  uint32_t stg_off;          // staging area of the coalesced G2 stores, bytes from the aligned base (0 = none)
 };
+constexpr int NG_STG_ROW = 80;                       // bytes per staged row: 32 halves + 16 bytes of padding (conflict-free)
+constexpr int NG_STG_WARP = 2 * 32 * NG_STG_ROW;     // hi and lo blocks of one warp: 32 rows x 32 columns each
 
 template <int NS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_THREADS, 1)
@@ -497,6 +503,9 @@ nce_grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int my_inst = -1;
     int64_t pix = 0;
     bool inb = false;
+    // the operand scale of the fp16 copy rides in the per-pixel coefficients (one multiply per pixel and label set
+    // instead of one per element); the fp32 G and the fp16 G2 are never requested together
+    const float gsc0 = g.G2 ? *g.gscale : 1.f;
     for (int64_t it = it0; it < it1; ++it, ++seq) {
       const int64_t pt = it / n_ntiles;
       const int nt = (int)(it - pt * n_ntiles);
@@ -515,7 +524,7 @@ nce_grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const float num = st[0], den = st[1];
             const int fl = (int)st[3];
             const bool use = fl & 1, own_same = fl & 2;
-            const float ws = g.conc * g.w[(int64_t)s * p.N + pix];
+            const float ws = gsc0 * g.conc * g.w[(int64_t)s * p.N + pix];
             const float inv_den = 1.f / den, dlt = inv_den - 1.f / num;
             ca[s] = ws * inv_den;
             cb[s] = use ? ws * dlt : 0.f;
@@ -532,50 +541,80 @@ nce_grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int32_t* lab_tile = p.psem + (int64_t)nt * N2_BN;
       float* grow = g.G ? g.G + (pix - g.i_begin) * g.ldg + (int64_t)nt * N2_BN : nullptr;
       __half* g2row = g.G2 ? g.G2 + (pix - g.i_begin) * 2 * g.ldg + (int64_t)nt * N2_BN : nullptr;
-      const float gsc = g.G2 ? *g.gscale : 1.f;
+      // Coalesced G2 stores.  A thread owns one pixel row, so a direct 16-byte store of a warp touches 32 different
+      // lines: the load/store unit, not the tensor pipe, paced this kernel (r2: 1.15 ms per chunk, 0.4 ms with the
+      // stores removed).  Each warp stages 32 rows x 32 columns of hi and of lo in shared memory (row pitch 80 bytes:
+      // conflict-free both ways) and writes them out 8 rows x 64 contiguous bytes per instruction.
+      const bool staged = g2row && g.stg_off && !(g.exp_flags & 2);
+      uint8_t* stg = smem_raw + (base - smem_u32(smem_raw)) + g.stg_off + (warp - 4) * NG_STG_WARP;
+      const int64_t row0_local = pix - lane - g.i_begin;          // first row of this warp inside the chunk
+      const int64_t rows_left = g.i_end - (pix - lane);           // rows of this warp that exist
+      auto flush = [&](int col_first, int ncols) {                // ncols = 16 or 32 staged columns starting at col_first
+        __syncwarp();
+        const int sub = lane & 3, rsel = lane >> 2;
+        if (sub * 8 < ncols) {
+#pragma unroll
+          for (int it4 = 0; it4 < 4; ++it4) {
+            const int rr = it4 * 8 + rsel;
+            if (rr < rows_left) {
+              __half* dst = g.G2 + (row0_local + rr) * 2 * g.ldg + (int64_t)nt * N2_BN + col_first + sub * 8;
+              const uint4 h = *reinterpret_cast<const uint4*>(stg + rr * NG_STG_ROW + sub * 16);
+              const uint4 l = *reinterpret_cast<const uint4*>(stg + 32 * NG_STG_ROW + rr * NG_STG_ROW + sub * 16);
+              *reinterpret_cast<uint4*>(dst) = h;
+              *reinterpret_cast<uint4*>(dst + g.ldg) = l;
+            }
+          }
+        }
+        __syncwarp();
+      };
 
       mbar_wait(bar_tfull + 8 * grp, (seq >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + grp * N2_BN + ((uint32_t)(32 * q) << 16);
-#pragma unroll 1
-      for (int c = 0; c < nchunk; ++c) {
+      // chunk c + 1's TMEM load (and label loads) are in flight while chunk c is turned into G (r2: without the
+      // overlap this kernel ran its tensor pipe at 28 %, the slowest of the three backward kernels)
+      auto process = [&](EpiChunk<NS>& cur, EpiChunk<NS>& nxt, int c) {
         const int col0 = c * 16;
-        uint32_t v[16];
-        tc_ld16(trow + col0, v);
-        int4 lab[NS][4];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) epi_labels<NS>(lab[s], lab_tile + col0, p.Ppad, s);
         tc_ld_wait();
+        if (c + 1 < nchunk) epi_issue<NS>(nxt, trow + col0 + 16, lab_tile + col0 + 16, p.Ppad);
         float gv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) gv[j] = 0.f;
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
+          if constexpr (NS > 2) epi_labels<NS>(cur.lab[0], lab_tile + col0, p.Ppad, s);
+          const int4 (&lab)[4] = cur.lab[NS <= 2 ? s : 0];
 #pragma unroll
           for (int w4 = 0; w4 < 4; ++w4) {
-            gv[4 * w4 + 0] += lab[s][w4].x == my_sem[s] ? cb[s] : ca[s];
-            gv[4 * w4 + 1] += lab[s][w4].y == my_sem[s] ? cb[s] : ca[s];
-            gv[4 * w4 + 2] += lab[s][w4].z == my_sem[s] ? cb[s] : ca[s];
-            gv[4 * w4 + 3] += lab[s][w4].w == my_sem[s] ? cb[s] : ca[s];
+            gv[4 * w4 + 0] += lab[w4].x == my_sem[s] ? cb[s] : ca[s];
+            gv[4 * w4 + 1] += lab[w4].y == my_sem[s] ? cb[s] : ca[s];
+            gv[4 * w4 + 2] += lab[w4].z == my_sem[s] ? cb[s] : ca[s];
+            gv[4 * w4 + 3] += lab[w4].w == my_sem[s] ? cb[s] : ca[s];
           }
         }
+        // the epilogue is ALU-bound (r2: tensor pipe 28 %): the own-prototype column and the padding columns are
+        // handled off the common path, and the operand scale of G2 is folded into the coefficients
         const int rel = own_rel - col0;
+        if ((unsigned)rel < 16u) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (j == rel) gv[j] = c_own;
-          const float sv = col0 + j < n_valid ? ex2_approx(__uint_as_float(v[j])) : 0.f;
-          gv[j] *= sv;
+          for (int j = 0; j < 16; ++j) if (j == rel) gv[j] = c_own;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gv[j] *= ex2_approx(__uint_as_float(cur.v[j]));
+        if (col0 + 16 > n_valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (col0 + j >= n_valid) gv[j] = 0.f;
         }
         if (inb && grow) {
           float4* dst = reinterpret_cast<float4*>(grow + col0);
 #pragma unroll
           for (int w4 = 0; w4 < 4; ++w4) dst[w4] = make_float4(gv[4 * w4], gv[4 * w4 + 1], gv[4 * w4 + 2], gv[4 * w4 + 3]);
         }
-        if (inb && g2row) {
+        if (inb && g2row && !(g.exp_flags & 1)) {
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float a = gv[2 * j] * gsc, b = gv[2 * j + 1] * gsc;
+            const float a = gv[2 * j], b = gv[2 * j + 1];
             const __half2 h = __floats2half2_rn(a, b);
             const __half2 l = __floats2half2_rn(a - __low2float(h), b - __high2float(h));
             hi[j] = *reinterpret_cast<const uint32_t*>(&h);
@@ -583,9 +622,21 @@ nce_grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           uint4* dh = reinterpret_cast<uint4*>(g2row + col0);
           uint4* dl = reinterpret_cast<uint4*>(g2row + g.ldg + col0);
+          if (staged) {
+            dh = reinterpret_cast<uint4*>(stg + lane * NG_STG_ROW + (c & 1) * 32);
+            dl = reinterpret_cast<uint4*>(stg + 32 * NG_STG_ROW + lane * NG_STG_ROW + (c & 1) * 32);
+          }
           dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
           dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
+        if (staged && !(g.exp_flags & 1) && ((c & 1) || c + 1 == nchunk)) flush((c & ~1) * 16, (c & 1) ? 32 : 16);
+      };
+      EpiChunk<NS> cha, chb;
+      if (nchunk > 0) epi_issue<NS>(cha, trow, lab_tile, p.Ppad);
+#pragma unroll 1
+      for (int c = 0; c < nchunk; c += 2) {
+        process(cha, chb, c);
+        if (c + 1 < nchunk) process(chb, cha, c + 1);
       }
       tc_fence_before();
       __syncwarp();
@@ -624,6 +675,7 @@ struct NceTcSetup {
   NceTcParams p;
   CUtensorMap ma, mb;
   size_t smem;
+  size_t fixed;              // shared memory next to the prototype ring
   const __half* e2;          // [N, 2 D] fp16 (hi | lo) of t * e
   float t;                   // operand scale sqrt(|c| log2 e)
 };
@@ -668,6 +720,7 @@ static int nce_tc_setup(NceTcSetup& u, const float* e, const float* prototypes, 
   HSG_REQUIRE(nstb >= 2, HSG_E_UNSUPPORTED, "nce: shared memory budget");
   p.nstb = nstb;
   u.smem = 1024 + fixed + (size_t)nstb * NT_SLAB;
+  u.fixed = fixed;
   int rc;
   if ((rc = encode_2d_f16(&u.ma, ah, (uint64_t)N, (uint64_t)2 * dim, NT_BK, NT_BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = encode_2d_f16(&u.mb, bh, (uint64_t)Ppad, (uint64_t)2 * dim, NT_BK, NT_BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
@@ -723,14 +776,28 @@ int nce_grad_tc(void* host_state, const float* stats, const float* w, float conc
                 float* G, int64_t ldg, __half* G2, const float* gscale, cudaStream_t st) {
   NceTcSetup& u = *setup_slot(host_state);
   HSG_REQUIRE(ldg % 64 == 0 && ldg >= u.p.P, HSG_E_INVALID, "nce_grad_tc: ldg=%lld", (long long)ldg);
-  HSG_REQUIRE(G || (G2 && gscale), HSG_E_INVALID, "nce_grad_tc: no output");
+  HSG_REQUIRE((G != nullptr) != (G2 != nullptr && gscale != nullptr), HSG_E_INVALID, "nce_grad_tc: exactly one of G, G2");
   NceGradTcParams g;
   g.f = u.p; g.i_begin = i_begin; g.i_end = i_end; g.stats = stats; g.w = w; g.conc = conc; g.G = G; g.ldg = ldg;
   g.G2 = G2; g.gscale = gscale;
+  static const int exp_env = getenv("HSG_NCE_EXP") ? atoi(getenv("HSG_NCE_EXP")) : 0;
+  g.exp_flags = exp_env;
   const int64_t items = ceil_div64(i_end - i_begin, 2 * NT_BM) * (u.p.Ppad / N2_BN);
   int64_t grid = num_sms() & ~1;
   if (grid > 2 * items) grid = 2 * items;
-  const size_t smem = u.smem;
+  size_t smem = u.smem;
+  g.stg_off = 0;
+  if (G2) {
+    // staging area of the coalesced stores (8 epilogue warps), paid for with stages of the prototype ring
+    const size_t stg = 8 * (size_t)NG_STG_WARP;
+    int nstb = (int)((227 * 1024 - 1024 - 1024 - u.fixed - stg) / NT_SLAB);
+    if (nstb > 8) nstb = 8;
+    if (nstb >= 2) {
+      g.f.nstb = nstb;
+      g.stg_off = (uint32_t)(u.fixed + (size_t)nstb * NT_SLAB);
+      smem = 1024 + u.fixed + (size_t)nstb * NT_SLAB + stg;
+    }
+  }
 #define HSG_NCE_LAUNCH(NS)                                                                                   \
   do {                                                                                                       \
     HSG_CUDA(cudaFuncSetAttribute(nce_grad_tc2_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
