@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(256) runsum_combine_kernel(const RunSums r, in
 // sums are added in warp order -- a fixed order, the accuracy class of the general path.
 template <int NV>
 __device__ __forceinline__ void mstep_small_bin(const float* __restrict__ x, int dim, int64_t b, int64_t e, int key,
-                                                const int32_t* __restrict__ keys, float* __restrict__ out_row,
+                                                const int32_t* keys, float* out_row,
                                                 double (*part)[NV * 32]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t len = e - b;
@@ -528,24 +528,50 @@ __device__ __forceinline__ void mstep_small_bin(const float* __restrict__ x, int
 #pragma unroll
   for (int m = 0; m < NV; ++m) { acc[m] = 0.0; run[m] = 0.f; }
   int in_run = 0;
-  for (int64_t i0 = wb; i0 < we; i0 += 32) {
-    const int64_t i = i0 + lane;
-    unsigned hit = __ballot_sync(FULL, i < we && keys[i] == key);
+  for (int64_t g0 = wb; g0 < we; g0 += 128) {
+   int kq[4];                                               // four groups of 32 keys in flight
+#pragma unroll
+   for (int q4 = 0; q4 < 4; ++q4) {
+     const int64_t i = g0 + 32 * q4 + lane;
+     kq[q4] = i < we ? __ldcg(keys + i) : -1;               // L2: another SM may have written it (persistent kernel)
+   }
+#pragma unroll
+   for (int q4 = 0; q4 < 4; ++q4) {
+    const int64_t i0 = g0 + 32 * q4;
+    unsigned hit = __ballot_sync(FULL, kq[q4] == key);
     while (hit) {
-      const int j = __ffs(hit) - 1;
+      // two members' rows in flight (the loop is a chain of L2 round trips); added in index order as before
+      const int j0 = __ffs(hit) - 1;
       hit &= hit - 1;
-      const float* row = x + (i0 + j) * dim;
+      const int j1 = hit ? __ffs(hit) - 1 : -1;
+      if (j1 >= 0) hit &= hit - 1;
+      const float* row0 = x + (i0 + j0) * dim;
+      const float* row1 = x + (i0 + (j1 >= 0 ? j1 : j0)) * dim;
+      float v0[NV], v1[NV];
 #pragma unroll
       for (int m = 0; m < NV; ++m) {
         const int d = lane + 32 * m;
-        if (d < dim) run[m] += row[d];
+        v0[m] = d < dim ? row0[d] : 0.f;
+        v1[m] = (d < dim && j1 >= 0) ? row1[d] : 0.f;
       }
+#pragma unroll
+      for (int m = 0; m < NV; ++m) run[m] += v0[m];
       if (++in_run == 32) {
 #pragma unroll
         for (int m = 0; m < NV; ++m) { acc[m] += (double)run[m]; run[m] = 0.f; }
         in_run = 0;
       }
+      if (j1 >= 0) {
+#pragma unroll
+        for (int m = 0; m < NV; ++m) run[m] += v1[m];
+        if (++in_run == 32) {
+#pragma unroll
+          for (int m = 0; m < NV; ++m) { acc[m] += (double)run[m]; run[m] = 0.f; }
+          in_run = 0;
+        }
+      }
     }
+   }
   }
 #pragma unroll
   for (int m = 0; m < NV; ++m) part[warp][lane + 32 * m] = acc[m] + (double)run[m];
@@ -584,6 +610,256 @@ __global__ void __launch_bounds__(256) mstep_small_kernel(const float* __restric
 }
 
 constexpr int64_t KM_SMALL_MAX_SEG = 16384;    // rows per segment up to which the one-launch M-step is used
+
+// ---------------------------------------------------------------- the whole loop in ONE launch (launch-bound regime)
+// Training shapes (12 x 28x28 pixels, D = 128, K = 16, T = 15: SURVEY 3.1) spend their time between kernels: 54 launches,
+// 0.76 ms per call with the one-launch M-step above.  Here every iteration of every image runs inside one cooperative
+// kernel: keys from the initial labels | (M-step | E-step) x T | labels, separated by grid barriers; the data (5 MB)
+// stays in L2.  Same arithmetic as the multi-launch path, so the same labels bit for bit: the M-step is
+// mstep_small_bin, the E-step the fp32 tile product of estep_simt_kernel, and a pixel whose top-2 gap is inside the
+// rigorous fp32 bound is re-decided on the spot by the float64 scan of estep_fixup_kernel (same summation order).
+// Anything another SM wrote during the kernel (keys, centroids) is read through L2 (ld.global.cg).
+struct SmallArgs {
+  EStepArgs a;                 // a.centroids is written here (M-step) and read (E-step)
+  float* centroids;
+  const int64_t* init_labels;
+  int64_t* labels_out;
+  float* centroids_out;        // may be NULL
+  int iterations;
+  float thr;
+  unsigned* bar;               // [1] zeroed before the launch
+  int exp_flags;               // timing experiments (HSG_SMALL_EXP), 0 in production: 1 no M-step, 2 no E-step
+  int64_t max_seg_len;         // longest segment: sub-tiles beyond it are empty in every tile
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    while (v < target) {
+      __nanosleep(64);                                     // a few hundred pollers on one address slow the arrivals down
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// One item = 64 pixels of one image against all of its centroids.  The whole [64 x dim] pixel tile and (up to 64 of)
+// the centroids are staged in shared memory with ONE round of loads -- an item is a chain of L2 round trips, not a
+// throughput problem (r2: the 32-dim chunks of estep_simt_kernel cost 5 dependent rounds per item, 18 us per phase).
+// NJ = centroid columns per thread (K <= 16: one).
+struct SmallTileSmem {
+  float best_v[ES_TP], second_v[ES_TP];
+  int best_i[ES_TP];
+};
+
+template <int NV, int NJ>
+__device__ __forceinline__ void estep_small_tile(const EStepArgs& a, int ti, int sub, float thr, SmallTileSmem& sm,
+                                                 float* __restrict__ Xs, float* __restrict__ Cs, int dp) {
+  const int64_t p0 = a.tiles.begin[ti] + (int64_t)sub * ES_TP;
+  const int64_t pe = a.tiles.end[ti];
+  if (p0 >= pe) return;                                    // block-uniform
+  const int np = (int)min((int64_t)ES_TP, pe - p0);
+  const int seg = a.tiles.seg[ti];
+  const int K = a.seg_k ? a.seg_k[seg] : a.kmax;
+  const float* cbase = a.centroids + (int64_t)seg * a.kmax * a.dim;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int ld = dp + 1;
+  constexpr int CK = 16 * NJ;                              // centroid rows staged per block
+  __syncthreads();                                         // the previous item's readers are done with the arrays
+  if (tid < ES_TP) { sm.best_v[tid] = -FLT_MAX; sm.second_v[tid] = -FLT_MAX; sm.best_i[tid] = 0x7fffffff; }
+  // pixel rows: asynchronous 4-byte copies, all in flight together (read-only data: L1 is fine)
+  const int wrp = tid >> 5, ln = tid & 31;
+  for (int row = wrp; row < ES_TP; row += ES_THREADS / 32) {
+    for (int d = ln; d < dp; d += 32) {
+      float* dst = Xs + row * ld + d;
+      if (row < np && d < a.dim) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(a.x + (p0 + row) * a.dim + d) : "memory");
+      } else {
+        *dst = 0.f;
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int kb = 0; kb < K; kb += CK) {
+    if (kb > 0) __syncthreads();                           // the previous block's products are done with Cs
+    // centroid rows through L2 (another SM wrote them in the M-step phase): every load of a row pair issued first
+    for (int row = wrp; row < CK; row += 2 * (ES_THREADS / 32)) {
+      float v0[NV], v1[NV];
+      const int k0 = kb + row, k1 = k0 + ES_THREADS / 32;
+#pragma unroll
+      for (int m = 0; m < NV; ++m) {
+        const int d = ln + 32 * m;
+        v0[m] = (k0 < K && d < a.dim) ? __ldcg(cbase + (int64_t)k0 * a.dim + d) : 0.f;
+        v1[m] = (k1 < K && d < a.dim && row + ES_THREADS / 32 < CK) ? __ldcg(cbase + (int64_t)k1 * a.dim + d) : 0.f;
+      }
+#pragma unroll
+      for (int m = 0; m < NV; ++m) {
+        const int d = ln + 32 * m;
+        if (d < dp) {
+          Cs[row * ld + d] = v0[m];
+          if (row + ES_THREADS / 32 < CK) Cs[(row + ES_THREADS / 32) * ld + d] = v1[m];
+        }
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    float acc[4][NJ];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int dd = 0; dd < dp; ++dd) {
+      float xa[4], cb[NJ];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xa[i] = Xs[(ty + 16 * i) * ld + dd];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) cb[j] = Cs[(tx + 16 * j) * ld + dd];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(xa[i], cb[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float bv = -FLT_MAX, sv = -FLT_MAX;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int k = kb + tx + 16 * j;
+        if (k < K) merge_best(bv, bi, sv, acc[i][j], k, -FLT_MAX);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULL, bv, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        const float osv = __shfl_xor_sync(FULL, sv, o);
+        merge_best(bv, bi, sv, ov, oi, osv);
+      }
+      if (tx == 0) {
+        const int px = ty + 16 * i;
+        float rb = sm.best_v[px], rs = sm.second_v[px];
+        int ri = sm.best_i[px];
+        merge_best(rb, ri, rs, bv, bi, sv);
+        sm.best_v[px] = rb; sm.second_v[px] = rs; sm.best_i[px] = ri;
+      }
+    }
+  }
+  __syncthreads();
+  // labels; near-ties by the float64 scan of every cluster (estep_fixup_kernel's rule and summation order)
+  const int lane = tid & 31;
+  for (int px = tid >> 5; px < np; px += ES_THREADS / 32) {
+    const int64_t pix = p0 + px;
+    int bi = sm.best_i[px];
+    if (sm.best_v[px] - sm.second_v[px] <= thr) {          // warp-uniform
+      const float* xrow = a.x + pix * a.dim;
+      float xr[NV];
+#pragma unroll
+      for (int m = 0; m < NV; ++m) { const int d = lane + 32 * m; xr[m] = d < a.dim ? xrow[d] : 0.f; }
+      double bv = -DBL_MAX;
+      bi = 0x7fffffff;
+      for (int k0 = 0; k0 < K; k0 += 4) {                  // four centroid rows in flight: K/4 L2 round trips, not K
+        float cv[4][NV];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float* cr = cbase + (int64_t)min(k0 + u, K - 1) * a.dim;
+#pragma unroll
+          for (int m = 0; m < NV; ++m) { const int d = lane + 32 * m; cv[u][m] = d < a.dim ? __ldcg(cr + d) : 0.f; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          double s = 0.0;
+#pragma unroll
+          for (int m = 0; m < NV; ++m) if (lane + 32 * m < a.dim) s = fma((double)xr[m], (double)cv[u][m], s);
+          s = warp_sum(s);
+          const int k = k0 + u;
+          if (k < K && (s > bv || (s == bv && k < bi))) { bv = s; bi = k; }
+        }
+      }
+    }
+    if (lane == 0) a.keys_out[pix] = seg * a.kmax + bi;
+  }
+}
+
+template <int NV, int NJ>
+__global__ void __launch_bounds__(ES_THREADS) kmeans_small_persistent_kernel(const SmallArgs s) {
+  // dynamic shared memory: the M-step's float64 partials [8][NV*32], or the E-step's pixel tile [64][dp+1] and
+  // centroid block [16 NJ][dp+1]
+  extern __shared__ __align__(16) unsigned char raw[];
+  __shared__ SmallTileSmem tsm;
+  double (*part)[NV * 32] = reinterpret_cast<double (*)[NV * 32]>(raw);
+  const int dp = (s.a.dim + 31) / 32 * 32;
+  float* Xs = reinterpret_cast<float*>(raw);
+  float* Cs = Xs + ES_TP * (dp + 1);
+  const EStepArgs& a = s.a;
+  unsigned target = 0;
+  const int n_tiles = *a.tiles.count;
+  const int n_sub = (int)((min(a.tiles.tile, s.max_seg_len) + ES_TP - 1) / ES_TP);      // non-empty 64-pixel items per tile
+  const int64_t bins = (int64_t)a.S * a.kmax;
+
+  for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {                   // keys from the initial labels
+    const int seg = a.tiles.seg[ti];
+    for (int64_t i = a.tiles.begin[ti] + threadIdx.x; i < a.tiles.end[ti]; i += blockDim.x) {
+      int64_t k = s.init_labels[i];
+      k = k < 0 ? 0 : (k >= a.kmax ? a.kmax - 1 : k);
+      a.keys_out[i] = seg * a.kmax + (int)k;
+    }
+  }
+  grid_barrier(s.bar, target);
+  for (int it = 0; it < s.iterations; ++it) {
+    for (int64_t bin = blockIdx.x; bin < bins && !(s.exp_flags & 1); bin += gridDim.x) {
+      const int seg = (int)(bin / a.kmax);
+      mstep_small_bin<NV>(a.x, a.dim, a.seg_offsets[seg], a.seg_offsets[seg + 1], (int)bin, a.keys_out,
+                          s.centroids + bin * a.dim, part);
+    }
+    grid_barrier(s.bar, target);
+    for (int64_t w = blockIdx.x; w < (int64_t)n_tiles * n_sub && !(s.exp_flags & 2); w += gridDim.x)
+      estep_small_tile<NV, NJ>(a, (int)(w / n_sub), (int)(w % n_sub), s.thr, tsm, Xs, Cs, dp);
+    grid_barrier(s.bar, target);
+  }
+  for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {                   // labels out
+    const int seg = a.tiles.seg[ti];
+    for (int64_t i = a.tiles.begin[ti] + threadIdx.x; i < a.tiles.end[ti]; i += blockDim.x)
+      s.labels_out[i] = (int64_t)(__ldcg(a.keys_out + i) - seg * a.kmax);
+  }
+  if (s.centroids_out) {
+    const int64_t n = bins * a.dim;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      s.centroids_out[i] = __ldcg(s.centroids + i);
+  }
+}
+
+// returns HSG_OK and sets *done when the persistent kernel took the call
+template <int NV, int NJ>
+static int launch_small_persistent(const SmallArgs& s, int64_t work, cudaStream_t st, bool* done) {
+  const int dp = (s.a.dim + 31) / 32 * 32;
+  size_t smem = (size_t)(ES_TP + 16 * NJ) * (dp + 1) * sizeof(float);
+  if (smem < sizeof(double) * 8 * NV * 32) smem = sizeof(double) * 8 * NV * 32;
+  if (smem > 200 * 1024) return HSG_OK;
+  HSG_CUDA(cudaFuncSetAttribute(kmeans_small_persistent_kernel<NV, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  HSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kmeans_small_persistent_kernel<NV, NJ>, ES_THREADS, smem));
+  if (per_sm < 1) return HSG_OK;
+  static const int per_env = getenv("HSG_SMALL_CTAS") ? atoi(getenv("HSG_SMALL_CTAS")) : 2;     // tuning knob
+  if (per_sm > per_env) per_sm = per_env;
+  int64_t grid = (int64_t)num_sms() * per_sm;
+  if (grid > work) grid = work;
+  if (grid < 1) grid = 1;
+  HSG_CUDA(cudaMemsetAsync(s.bar, 0, sizeof(unsigned), st));
+  void* args[] = {(void*)&s};
+  HSG_CUDA(cudaLaunchCooperativeKernel((const void*)kmeans_small_persistent_kernel<NV, NJ>, dim3((unsigned)grid),
+                                       dim3(ES_THREADS), args, smem, st));
+  HSG_LAUNCH_CHECK();
+  *done = true;
+  return HSG_OK;
+}
 
 // one M-step of the k-means loop: full pass on the first iteration, afterwards delta or full
 // as decided on the device
@@ -739,6 +1015,25 @@ static int kmeans_impl(const float* x, int64_t N, int dim, const void* xh, int d
   // launch-bound regime: one-launch M-step (it also clears the re-decision counters)
   const bool small = !incremental && !(flags & HSG_KMEANS_FULL_MSTEP) && max_seg_len <= KM_SMALL_MAX_SEG && dim <= 32 * 9 &&
                      (int64_t)S * kmax <= (1 << 20);
+  static const bool no_persistent = getenv("HSG_KMEANS_NO_PERSISTENT") != nullptr;       // A/B switch for profiling only
+  if (small && !runs && iterations > 0 && !no_persistent && (!use_tc || kmax <= 64)) {
+    // launch-bound regime: the whole loop in one cooperative launch (fp32 CUDA-core E-step: at K <= 64 the products
+    // of such a call are a few GFLOP, the launches were the cost)
+    SmallArgs sa;
+    sa.a = ea; sa.centroids = p.centroids; sa.init_labels = init_labels; sa.labels_out = labels_out;
+    sa.centroids_out = centroids_out; sa.iterations = iterations;
+    sa.thr = 2.f * (dim + 2) * 5.9604645e-8f * 1.02f + 1e-7f;             // estep_simt's bound
+    sa.bar = reinterpret_cast<unsigned*>(p.fix.count);
+    static const int small_exp = getenv("HSG_SMALL_EXP") ? atoi(getenv("HSG_SMALL_EXP")) : 0;
+    sa.exp_flags = small_exp;
+    sa.max_seg_len = max_seg_len;
+    const int64_t work = max((int64_t)S * kmax, ceil_div64(N, ES_TP) + S);
+    bool done = false;
+    if (dim <= 32 * 5) rc = kmax <= 16 ? launch_small_persistent<5, 1>(sa, work, st, &done) : launch_small_persistent<5, 4>(sa, work, st, &done);
+    else rc = kmax <= 16 ? launch_small_persistent<9, 1>(sa, work, st, &done) : launch_small_persistent<9, 4>(sa, work, st, &done);
+    if (rc) return rc;
+    if (done) return HSG_OK;
+  }
   for (int it = 0; it < iterations; ++it) {
     if ((rc = km_mstep(p, x, seg_offsets, it, incremental, st, runs, small))) return rc;
     if ((rc = run_estep(ea, p, use_tc, st, small && !(it == 0 && runs)))) return rc;   // the small M-step cleared the counters

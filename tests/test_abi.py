@@ -73,10 +73,32 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     _lib.load()
 
 
-@pytest.mark.skipif(not os.path.isdir('/root/reference/hsg'), reason='reference tree only exists in the build container')
-def test_patch_rebinds_the_reference_operators(lib):
+def _reference_root():
+  """The unmodified reference: baseline/_ref (travels to the GPU box with the snapshot), else the build container's tree."""
   import sys
-  sys.path.insert(0, '/root/reference')
+  sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+  import refenv
+  if refenv.available():
+    return refenv.activate()
+  return '/root/reference' if os.path.isdir('/root/reference/hsg') else None
+
+
+@pytest.mark.skipif(_reference_root() is None, reason='no reference tree (baseline/_ref or /root/reference)')
+def test_patch_rebinds_the_reference_operators(lib):
+  _check_patch_rebinds()
+
+
+@pytest.mark.gpu
+def test_patch_rebinds_the_reference_operators_on_the_gpu_box(lib):
+  """the same check inside the `-m gpu` run of the GPU box, against baseline/_ref (it was skipped there)"""
+  assert _reference_root() is not None, 'baseline/_ref did not travel with the snapshot'
+  _check_patch_rebinds()
+
+
+def _check_patch_rebinds():
+  import sys
+  root = _reference_root()
+  sys.path.insert(0, root)
   try:
     import hsg.utils.segsort.common as ref_common
     import hsg.utils.segsort.loss as ref_loss
@@ -138,4 +160,4 @@ def test_patch_rebinds_the_reference_operators(lib):
     assert ref_head.Segsort.__dict__['predictions'] is retrieval_orig
     assert ref_others.load_memory_banks.__module__ == 'hsg.utils.segsort.others'
   finally:
-    sys.path.remove('/root/reference')
+    sys.path.remove(root)
