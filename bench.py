@@ -394,41 +394,62 @@ def run_ours(args):
   # ---- end to end: pinned host input, H2D + loss read-back inside the timed region
   e2e = None
   if not args.no_e2e:
+    # the pinned staging buffer should live on the NUMA node the GPU hangs off (first touch under the binding): a
+    # remote node caps the upload near 43 GB/s, i.e. 227 ms for the 9.87 GB of a step -- longer than the step's compute
+    saved_affinity = os.sched_getaffinity(0) if world == 1 else None
+    if world == 1:
+      numa_node = bind_to_gpu_numa_node(torch, local_rank)
     host = torch.empty(embs[0].shape, dtype=torch.float32, pin_memory=True)
     host.copy_(embs[0])
     copy_stream = torch.cuda.Stream(device=device)
-    landed = [torch.cuda.Event(), torch.cuda.Event()]
+    landed = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    started = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
 
     def upload(i):
       # every step's input crosses PCIe inside the timed region; the copy of step i+1
       # runs on a side stream while step i computes (ordinary input prefetch)
       with torch.cuda.stream(copy_stream):
+        started[i % 2].record(copy_stream)
         embs[i % 2].copy_(host, non_blocking=True)
         landed[i % 2].record(copy_stream)
+
+    c_events = []
 
     def e2e_step(i, last):
       torch.cuda.current_stream().wait_event(landed[i % 2])
       if not last:
         upload(i + 1)                     # buffer (i+1)%2 is free: step i-1 was read back already
+      c_events.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+      c_events[-1][0].record()
       with torch.no_grad():
         loss, _ = hot_path(torch, S, L, MU, embs[i % 2], args, world, group)
+      c_events[-1][1].record()
       return float(loss)                  # device -> host read of the result
 
     upload(0)
     e2e_step(0, True)
+    upload(0)                             # prime the pipeline: the input of the first timed step
     barrier()
     t0 = time.perf_counter()
     e_steps = max(2, args.steps)
-    upload(0)
+    # steady state of a prefetching input pipeline: K steps and K uploads inside the clock -- every step (the last one
+    # too) starts the upload of the step that follows it, and the clock stops once that last copy has landed
     for i in range(e_steps):
-      e2e_step(i, i == e_steps - 1)
+      e2e_step(i, False)
+    landed[e_steps % 2].synchronize()
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
     if world > 1:
       torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
     e2e = {'value': world * n_pix * e_steps / float(dt), 'unit': 'pixel-embeddings/s',
            'h2d_bytes_per_step': int(host.numel() * 4), 'd2h_bytes_per_step': 4, 'steps': e_steps,
-           'host_numa_node_rank0': numa_node}
+           'host_numa_node_rank0': numa_node,
+           'h2d_ms_per_step_rank0': started[(e_steps - 1) % 2].elapsed_time(landed[(e_steps - 1) % 2]),
+           # GPU time of each timed step's kernels
+           'compute_ms_per_step_rank0': [round(a.elapsed_time(b), 2) for a, b in c_events[-e_steps:]],
+           'note': 'steady state of an input-prefetching loop: the upload of step i+1 overlaps the compute of step i; K steps and K uploads are inside the clock (the pipeline is primed before it starts, the last step uploads the batch that would follow and the clock waits for it); a step cannot be shorter than its upload'}
+    if saved_affinity is not None:
+      os.sched_setaffinity(0, saved_affinity)           # the CPU baseline below uses every host core
 
   # ---- the same step through the reference signatures only (what patch() installs), single GPU
   ref_sig_ms = None
