@@ -502,11 +502,11 @@ def run_ours(args):
   # DRAM bytes of one k-means iteration from the committed ncu pass (only for the default workload)
   default_cfg = (args.images, args.size, args.dim, args.grid, args.iters, args.dist) == (48, 448, 256, 16, 10, 'iid')
   traffic, traffic_src = None, None
-  tpath = os.path.join(ROOT, 'profiles', 'r1_kmeans_traffic.json')
+  tpath = os.path.join(ROOT, 'profiles', 'r2_kmeans_traffic.json')
   if default_cfg and os.path.exists(tpath):
     with open(tpath) as f:
       traffic = json.load(f)['kmeans_dram_bytes_per_step'] / args.iters
-    traffic_src = ('profiles/r1_kmeans_traffic.json: ncu dram read+write of every kernel of the k-means loop over one '
+    traffic_src = ('profiles/r2_kmeans_traffic.json: ncu dram read+write of every kernel of the k-means loop over one '
                    'step, divided by the %d iterations (the incremental M-step re-reads only the rows that moved)' % args.iters)
   achieved = alg_bytes / (kmeans_ms * 1e-3) / 1e9 if kmeans_ms > 0 else 0.0
   roofline_kmeans = {'kernel': 'spherical k-means iteration (all kernels of the loop: delta list, sort, gather, combine, '
@@ -525,7 +525,7 @@ def run_ours(args):
   peak_tf = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
   nce_traffic = None
   if default_cfg and world == 1:
-    nce_traffic = 10.415e9          # profiles/r1_nce_fwd_tc.txt: dram read + write of the kernel (ncu --set full)
+    nce_traffic = 10.415e9          # profiles/r1_nce_fwd_tc.txt (ncu --set full) = profiles/r2_launches.txt source pass: dram read + write of the kernel
   roofline = {'kernel': 'NCE forward (nce_fwd_tc2_kernel + its fp16 operand split; %.0f %% of the step)'
                         % (100.0 * nce_ms / (ms / args.steps)),
               'bound': 'tensor', 'achieved': nce_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': nce_tf / peak_tf,

@@ -36,6 +36,8 @@ def launches(src, dst):
   lines = [l for l in open(src) if l.startswith('"')]
   agg = collections.OrderedDict()
   for row in csv.DictReader(lines):
+    if not row['Metric Name'].startswith('gpu__time_duration'):      # the pass may carry other metrics (DRAM bytes)
+      continue
     v = float(row['Metric Value'].replace(',', ''))
     u = row['Metric Unit']
     v = v / 1e6 if u in ('nsecond', 'ns') else v / 1e3 if u in ('usecond', 'us') else v
@@ -71,7 +73,8 @@ def kernel(src, dst):
       f.write('%-82s %18.4f %s\n' % ('traffic = dram read + write', tot / 1e9, 'Gbyte'))
 
 
-KMEANS_KERNELS = ('estep_tc_kernel', 'estep_simt_kernel', 'estep_fixup_kernel', 'gather_sum_kernel', 'combine64_kernel',
+KMEANS_KERNELS = ('estep_tc_kernel', 'estep_tc1_kernel', 'estep_tc2_kernel', 'estep_simt_kernel', 'estep_fixup_kernel',
+                  'estep_fixup8_kernel', 'gather_sum_kernel', 'combine64_kernel', 'runsum_combine_kernel',
                   'hist_kernel', 'scan_kernel', 'scatter_kernel', 'delta_count_kernel', 'delta_scan_kernel',
                   'delta_compact_kernel', 'tc_convert_kernel', 'build_tiles_kernel')
 
@@ -83,9 +86,14 @@ def traffic(src, dst):
   lines = [l for l in open(src) if l.startswith('"')]
   scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
   per = collections.OrderedDict()
-  for row in csv.DictReader(lines):
+  rows = [r for r in csv.DictReader(lines) if r['Metric Name'].startswith('dram__bytes')]
+  # the prototype pooling after the loop is the same full-pass gather kernel: its launch (the last non-delta
+  # gather of the step) is not part of the k-means loop
+  full_ids = [int(r['ID']) for r in rows if 'gather_sum_kernel' in r['Kernel Name'] and ', 0>' in r['Kernel Name'].replace('(int)', '')]
+  pool_id = max(full_ids) if full_ids else -1
+  for row in rows:
     name = row['Kernel Name'].split('(')[0].split('::')[-1].split('<')[0]
-    if name not in KMEANS_KERNELS:
+    if name not in KMEANS_KERNELS or int(row['ID']) == pool_id:
       continue
     v = float(row['Metric Value'].replace(',', '')) * scale.get(row['Metric Unit'], 1.0)
     d = per.setdefault(name, {'launches': 0, 'bytes': 0.0})
