@@ -256,7 +256,17 @@ def test_nce_forward_backward(golden):
     (pp * t(w)).sum().backward()
     row_ref = np.abs(g['de']).max(1, keepdims=True)
     assert np.all(np.abs(n(e.grad) - g['de']) <= row_ref * (1e-5 + 2e-6 * kappa) + 1e-12)
-    assert np.abs(n(p.grad) - g['dp']).max() <= 1e-3 * np.abs(g['dp']).max()
+    # Derived, not asserted: against the reference's OWN formula run in float64 on these inputs
+    # (oracle/gen_golden_f64.py), ours may be off by 1e-5 or by twice what the reference's fp32 run is off --
+    # on KAT3 that is 4e-3 for dE and 3.7e-4 for dP (the `sum_same S - own` cancellation), on the fallback case 4e-7
+    f64 = golden('gradients_f64')
+    for mine, key in ((n(pp), 'per_pixel'), (n(e.grad), 'de'), (n(p.grad), 'dp')):
+      exact = f64[name + '__' + key]
+      scale = np.abs(exact).max()
+      err_ref = np.abs(g[key] - exact).max() / scale
+      err_ours = np.abs(mine - exact).max() / scale
+      print('%s %s: ours %.2e, reference fp32 %.2e from the float64 value (max-norm relative)' % (name, key, err_ours, err_ref))
+      assert err_ours <= max(1e-5, 2.0 * err_ref), (name, key, err_ours, err_ref)
   g = golden('nce_kat3')
   loss = L.SegSortLoss(16)(t(g['e']), t(g['sem']), t(g['inst']), t(g['protos']), t(g['psem']))
   assert abs(float(loss) - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))    # scalar loss, 1e-5 rel
@@ -385,26 +395,30 @@ def test_hsg_losses_one_pass(golden):
              'finehrchy_nd_prototype_grouping_centroid': t(g['cent_t_fine']),
              'coarsehrchy_nd_prototype_grouping_centroid': t(g['cent_t_coarse'])}
   img, hr, cl, acc = head.losses(me, datas, targets)
-  close(n(img), g['img_sim_loss'], rtol=2e-5)
-  close(n(hr), g['hrchy_group_loss'], rtol=2e-5)
-  close(n(cl), g['clustering_loss'], rtol=2e-5)
   assert abs(float(acc) - float(g['accuracy'])) < 1e-6
   (img + hr + cl).backward()
-  close(n(emb.grad), g['demb'], rtol=2e-4, atol=1e-7)
-  close(n(protos.grad), g['dprotos'], rtol=2e-4, atol=1e-7)
-  close(n(cent_f.grad), g['dcent_fine'], rtol=2e-4, atol=1e-7)
-  close(n(cent_c.grad), g['dcent_coarse'], rtol=2e-4, atol=1e-7)
-  close(n(nd_f.grad), g['dnd_fine'], rtol=2e-4, atol=1e-8)
-  close(n(nd_c.grad), g['dnd_coarse'], rtol=2e-4, atol=1e-8)
+  # Tolerances derived from the reference itself: every value and gradient is compared with the reference's
+  # own method run in float64 on these inputs (oracle/gen_golden_f64.py); ours may be off by 1e-5 (max-norm relative)
+  # or by twice what the reference's fp32 run is off (4.5e-5 for the embedding gradient, 1.2e-5 for the prototypes')
+  f64 = golden('gradients_f64')
+  for mine, key in ((n(img), 'img_sim_loss'), (n(hr), 'hrchy_group_loss'), (n(cl), 'clustering_loss'),
+                    (n(emb.grad), 'demb'), (n(protos.grad), 'dprotos'), (n(cent_f.grad), 'dcent_fine'),
+                    (n(cent_c.grad), 'dcent_coarse'), (n(nd_f.grad), 'dnd_fine'), (n(nd_c.grad), 'dnd_coarse')):
+    exact = f64['hsg_losses__' + key]
+    scale = max(np.abs(exact).max(), 1e-300)
+    err_ref = np.abs(np.asarray(g[key], np.float64) - exact).max() / scale
+    err_ours = np.abs(np.asarray(mine, np.float64) - exact).max() / scale
+    print('Hsg.losses %s: ours %.2e, reference fp32 %.2e from the float64 value (max-norm relative)' % (key, err_ours, err_ref))
+    assert err_ours <= max(1e-5, 2.0 * err_ref), (key, err_ours, err_ref)
   # only one of the terms switched on, and a term with its own concentration (separate pass)
   me.fine_hrchy_loss = None
   me.coarse_hrchy_loss = L.SegSortLoss(10)
   me.dmon_loss = me.centroid_cont_loss = None
   img2, hr2, cl2, _ = head.losses(me, datas, targets)
   assert cl2 is None
-  close(n(img2), g['img_sim_loss'], rtol=2e-5)
+  close(n(img2), g['img_sim_loss'], rtol=1e-5)
   want = o_loss.segsort_loss(g['emb'], g['coarse_map'][g['cidx']], g['cidx'], g['protos'], g['coarse_map'], 10) * 0.1
-  close(n(hr2), want, rtol=2e-5)
+  close(n(hr2), want, rtol=1e-5)
 
 
 def test_dmon_knn_graph_and_loss(golden):
