@@ -268,16 +268,32 @@ class _SegmentReduce(torch.autograd.Function):
     return gx, None, None, None, None, None, None, None
 
 
+MAX_BINS_PER_SEGMENT = 49152      # SR_MAX_KEYS (csrc/segreduce.cuh): shared-memory histogram of one segment's keys
+
+
 def segment_reduce(x, labels, num_bins, mode, seg_offsets=None, max_seg_len=None, seg_base=None, kmax=None):
   """out[k] = finish(sum of rows of x with label k); differentiable in x."""
   _need_cuda(x, labels, seg_offsets, seg_base)
   x2 = x.reshape(-1, x.shape[-1])
   labels = _i64(labels).reshape(-1)
-  if (kmax if kmax is not None else num_bins) > 49152:
-    raise _lib.HsgError('segment_reduce: more than 49152 bins per segment; pass seg_offsets/seg_base '
-                        '(ids made by segment_by_kmeans are ranked by image)')
   if x2.shape[0] == 0:
     return torch.zeros((num_bins, x2.shape[1]), dtype=torch.float32, device=x.device)
+  if seg_offsets is None and num_bins > MAX_BINS_PER_SEGMENT:
+    # The reference takes any number of labels (calculate_prototypes_from_labels over the dense prototype ids of a
+    # whole batch: 48 x 256 x regions).  The kernels histogram at most 49152 bins per segment, so consecutive blocks
+    # of 49152 label ids become the segments.  Ids made by segment_by_kmeans are ranked by image -- the rows are already
+    # grouped by block and nothing moves; otherwise the rows are gathered into block order first (sums do not depend on it).
+    block = labels // MAX_BINS_PER_SEGMENT
+    n_blocks = (int(num_bins) + MAX_BINS_PER_SEGMENT - 1) // MAX_BINS_PER_SEGMENT
+    if not bool((block[1:] >= block[:-1]).all()):
+      perm = torch.argsort(block, stable=True)
+      x2, labels, block = x2.index_select(0, perm), labels.index_select(0, perm), block.index_select(0, perm)
+    counts = torch.bincount(block, minlength=n_blocks)
+    seg_offsets = torch.cat([counts.new_zeros(1), torch.cumsum(counts, 0)])
+    seg_base = torch.arange(n_blocks, dtype=torch.int64, device=x.device) * MAX_BINS_PER_SEGMENT
+    max_seg_len, kmax = int(counts.max()), MAX_BINS_PER_SEGMENT
+  elif (kmax if kmax is not None else num_bins) > MAX_BINS_PER_SEGMENT:
+    raise _lib.HsgError('segment_reduce: more than 49152 bins per segment')
   return _SegmentReduce.apply(x2, labels, int(num_bins), mode, seg_offsets, max_seg_len, seg_base, kmax)
 
 

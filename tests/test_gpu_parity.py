@@ -240,6 +240,30 @@ def test_estep_random_is_exact_float64_argmax(S):
   assert 0 < int(nre[0]) < nn // 10
 
 
+def test_pooling_with_more_than_49152_labels(S):
+  """the reference-signature pooling takes any number of labels (the flat path refused > 49152 bins):
+  ids ranked by block (as segment_by_kmeans makes them) and in arbitrary row order, values and gradient."""
+  rng = np.random.RandomState(3)
+  nn, d, p = 150000, 20, 120000
+  x = rng.randn(nn, d).astype(np.float32)
+  lab = np.sort(rng.randint(0, p, nn)).astype(np.int64)
+  lab[-1] = p - 1
+  want = o_ops.calculate_prototypes_from_labels(x, lab, p)
+  for order in (np.arange(nn), rng.permutation(nn)):
+    xt = t(x[order]).requires_grad_(True)
+    got = S.calculate_prototypes_from_labels(xt, t(lab[order]), p)
+    assert got.shape == (p, d)
+    close(n(got), want, rtol=1e-5, atol=1e-6)
+    wgt = t(rng.randn(p, d).astype(np.float32))
+    (got * wgt).sum().backward()
+    xr = torch.from_numpy(x[order]).double().requires_grad_(True)
+    sums = torch.zeros(p, d, dtype=torch.float64).index_add_(0, torch.from_numpy(lab[order]), xr)
+    ref = sums / sums.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    (ref * wgt.double().cpu()).sum().backward()
+    scale = float(xr.grad.abs().max())
+    assert np.abs(n(xt.grad) - xr.grad.numpy()).max() <= 1e-5 * scale
+
+
 def test_nce_forward_backward(golden):
   from hsg_b200.utils.segsort import loss as L
   for name, conc in (('nce_kat3', 16), ('nce_fallback', 10)):
