@@ -275,7 +275,7 @@ int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, in
                const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus, float conc,
                float* per_pixel, float* stats, void* workspace, cudaStream_t st);
 int g_debug_flags = 0;   // tests: bit 0 keeps the NCE forward on the fp32 CUDA-core kernel, bit 2 the backward GEMMs,
-                         // bit 3 the backward's G chunk
+                         // bit 3 the backward's G chunk; bit 6: backward chunks of 4096 pixels
 
 // fp32-grade tensor-core GEMM on pre-split fp16 (hi|lo) operands (gemm_tc.cu)
 bool gemm_tc_supported(int N, int K);
@@ -362,6 +362,7 @@ static int64_t nce_chunk_pixels(int64_t N, int64_t P) {
   // (128-row tiles, one CTA each) and the K of the dP GEMM, so a chunk has to hold a few hundred tiles to fill
   // 148 SMs -- at 256 MB and P = 12288 it held 43 (r1: 197 ms per 1M pixels)
   int64_t c = (int64_t)(512ll << 20) / (P > 0 ? P : 1);
+  if (g_debug_flags & 64) c = 4096;                       // tests: several chunks (and a ragged last one) at small sizes
   const int64_t wave = (int64_t)num_sms() * 128;          // rows of one wave of 128-row dE tiles
   if (c > wave) c = c / wave * wave;
   c = c / NC_T * NC_T;

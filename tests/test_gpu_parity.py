@@ -816,6 +816,40 @@ def test_nce_backward_tensor_core_gemms_vs_float64():
   assert max(errs[4]) < 1e-4, errs
 
 
+def test_nce_backward_over_several_chunks_vs_float64():
+  """The backward walks the pixels in chunks (one fp16 copy of G per chunk, dP accumulated over the chunks through the
+  K-split partial sums of the MN-major product): five chunks with a ragged last one, against the float64 closed form."""
+  from hsg_b200 import ops, _lib
+  rng = np.random.RandomState(29)
+  nn, pp, d, conc = 20000, 333, 128, 4.0
+  e = o_ops.normalize_embedding(rng.randn(nn, d).astype(np.float32))
+  inst = rng.randint(0, pp, nn).astype(np.int64)
+  protos = o_ops.calculate_prototypes_from_labels(e, inst, pp)
+  psem = np.stack([rng.randint(0, 12, pp), rng.randint(0, 40, pp)]).astype(np.int64)
+  sem = np.stack([psem[0][inst], psem[1][inst]])
+  w = (rng.rand(2, nn).astype(np.float32) + 0.1) / nn
+  want_e, want_p = np.zeros((nn, d)), np.zeros((pp, d))
+  for s in range(2):
+    de, dp = o_loss.segsort_loss_backward(e, sem[s], inst, protos, psem[s], conc, w[s])
+    want_e += de
+    want_p += dp
+  lib = _lib.load()
+  grads = {}
+  for flags in (64, 0):
+    lib.hsg_debug_set_flags(flags)
+    try:
+      et, pt = t(e).requires_grad_(True), t(protos).requires_grad_(True)
+      ll = ops.nce_log_likelihood(et, t(inst), t(sem), pt, t(psem), conc, ['segsort+', 'segsort+'])
+      (ll * t(w)).sum().backward()
+      torch.cuda.synchronize()
+    finally:
+      lib.hsg_debug_set_flags(0)
+    grads[flags] = (n(et.grad), n(pt.grad))
+    assert np.linalg.norm(grads[flags][0] - want_e) / np.linalg.norm(want_e) < 1e-5
+    assert np.linalg.norm(grads[flags][1] - want_p) / np.linalg.norm(want_p) < 1e-5
+  assert np.array_equal(grads[64][0], grads[0][0])          # dE rows do not depend on the chunking
+
+
 # ---------------------------------------------------------------- clustering transformer (fused attention)
 def _load_transformer(g):
   from hsg_b200.models.embeddings.transformer_clusters import TransformerClustering
