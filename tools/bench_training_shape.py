@@ -19,13 +19,16 @@ for (b, d, hw, grid, iters) in ((12, 128, 28, 4, 15), (32, 128, 14, 4, 15), (16,
   t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   lib = _lib.load()
   n0 = lib.hsg_launch_count()
+  import time
   t0.record()
   reps = 20
+  h0 = time.perf_counter()
   for _ in range(reps):
     S.segment_by_kmeans(emb, None, [grid, grid], iterations=iters)
+  h1 = time.perf_counter()
   t1.record(); torch.cuda.synchronize()
-  print('segment_by_kmeans %2d x %dx%d, D=%d, K=%d, T=%d: %.3f ms per call, %d kernel launches of the library, cluster-id checksum %d'
-        % (b, hw, hw, d, grid * grid, iters, t0.elapsed_time(t1) / reps, (lib.hsg_launch_count() - n0) // reps, check))
+  print('segment_by_kmeans %2d x %dx%d, D=%d, K=%d, T=%d: %.3f ms per call (host side %.3f ms), %d kernel launches of the library, cluster-id checksum %d'
+        % (b, hw, hw, d, grid * grid, iters, t0.elapsed_time(t1) / reps, (h1 - h0) * 1e3 / reps, (lib.hsg_launch_count() - n0) // reps, check))
 
 # the k-means call alone (one C call: prep, relabel and the Python around them excluded)
 print('hsg_kmeans_f32 alone:')
