@@ -185,19 +185,20 @@ def make_embeddings(torch, args, device, seed):
 def hot_path(torch, S, L, MU, emb, args, world, group):
   """The reference-facing call sequence for one batch (what train.py does between the
   embedding model and the loss, restricted to the operators of the path)."""
-  ex = S.segment_by_kmeans_ex(emb, None, [args.grid, args.grid], iterations=args.iters,
-                              count_prototypes=True)
+  ex = S.segment_by_kmeans_ex(emb, None, [args.grid, args.grid], iterations=args.iters)
   x, ids, bat = ex['embeddings'], ex['cluster_indices'], ex['batch_indices']
+  # the prototype count stays on the device from here to the loss (empty clusters are dropped by the relabel
+  # kernel, so it is data-dependent): pooling, exchange and NCE work on fixed-capacity arrays -- no host read
   protos = S.pool_prototypes(ex)
-  pbatch = ex['proto_batch']
+  pbatch, count = ex['proto_batch'], ex['num_prototypes_device']
   if world > 1:       # all-gather of the prototypes (replaces hsg/models/utils.py:127-217)
-    res = MU.exchange_prototypes(ids, protos, protos, pbatch, pbatch, pbatch, group,
-                                 capacity=ex['num_images'] * ex['slots_per_image'])
-    protos, pbatch, ids = res[0], res[2], res[5]
+    res = MU.exchange_prototypes_counted(ids, protos, protos, pbatch, pbatch, pbatch, count,
+                                         ex['num_images'] * ex['slots_per_image'], group)
+    protos, pbatch, ids, count = res[0], res[2], res[5], res[6]
   # two label sets in one pass over E x P: image-level positives ("img_sim",
   # hsg/models/predictions/hsg.py:97-110) and prototype-level positives
   pid = torch.arange(protos.shape[0], device=emb.device, dtype=torch.int64)
-  losses = L.segsort_loss_multi(x, ids, [bat, ids], protos, [pbatch, pid], args.concentration)
+  losses = L.segsort_loss_multi(x, ids, [bat, ids], protos, [pbatch, pid], args.concentration, num_prototypes=count)
   return losses[0] + losses[1], x.shape[0]
 
 

@@ -73,6 +73,12 @@ SIGNATURES = {
     'hsg_nce_fwd_f32': (_i, [_p, _p, _l, _l, _i, _p, _p, _p, _i, _p, _f, _p, _p, _p, _z, _p]),
     'hsg_nce_bwd_f32': (_i, [_p, _p, _l, _l, _i, _p, _p, _p, _i, _p, _f, _p, _p, _p, _p,
                              _p, _z, _p]),
+    'hsg_nce_fwd_counted_f32': (_i, [_p, _p, _l, _l, _p, _i, _p, _p, _p, _i, _p, _f, _p, _p, _p, _z, _p]),
+    'hsg_nce_bwd_counted_f32': (_i, [_p, _p, _l, _l, _p, _i, _p, _p, _p, _i, _p, _f, _p, _p, _p, _p,
+                                     _p, _z, _p]),
+    'hsg_exchange_record_bytes': (_z, [_l, _i, _i]),
+    'hsg_exchange_pack': (_i, [_p, _p, _p, _p, _p, _p, _l, _i, _i, _p, _p]),
+    'hsg_exchange_unpack': (_i, [_p, _i, _i, _l, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     'hsg_mha_workspace_bytes': (_z, [_i, _i, _i, _i]),
     'hsg_mha_fwd_workspace_bytes': (_z, [_i, _i, _i, _i, _i]),
     'hsg_mha_fwd_f32': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, ctypes.c_ulonglong, _p, _p, _p, _z, _p]),

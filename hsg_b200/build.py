@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libhsgb200.so')
 STAMP = os.path.join(HERE, 'build', 'stamp')
 
-SOURCES = ['abi.cu', 'prep.cu', 'segreduce.cu', 'kmeans.cu', 'tc_estep.cu', 'nce.cu', 'nce_tc.cu', 'gemm_tc.cu', 'relabel.cu', 'attention.cu', 'attention_tc.cu', 'attention_bwd_tc.cu', 'graph.cu', 'topk.cu', 'syncbn.cu']
+SOURCES = ['abi.cu', 'prep.cu', 'segreduce.cu', 'kmeans.cu', 'tc_estep.cu', 'nce.cu', 'nce_tc.cu', 'gemm_tc.cu', 'relabel.cu', 'attention.cu', 'attention_tc.cu', 'attention_bwd_tc.cu', 'graph.cu', 'topk.cu', 'syncbn.cu', 'exchange.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
     '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr',

@@ -69,6 +69,7 @@ struct NceArgs {
   const float* e;
   const float* p;
   int64_t N, P;
+  const int64_t* P_dev;  // optional device-side count of valid prototypes (<= P, the capacity of the arrays)
   int dim;
   const int64_t* inst;
   const int64_t* sem;    // [n_sets,N]
@@ -104,7 +105,8 @@ __global__ void __launch_bounds__(NC_THREADS) nce_fwd_kernel(const NceArgs a, fl
     for (int s = 0; s < NS; ++s) { pos[s][i] = 0.f; neg[s][i] = 0.f; }
   }
 
-  for (int64_t j0 = 0; j0 < a.P; j0 += NC_T) {
+  const int64_t P_eff = a.P_dev ? max((int64_t)0, min(a.P, *a.P_dev)) : a.P;
+  for (int64_t j0 = 0; j0 < P_eff; j0 += NC_T) {
     float acc[4][4];
     tile_dots(a.e, a.N, i0, a.p, a.P, j0, a.dim, As, Bs, acc);   // begins with __syncthreads()
     if (tid < NC_T) {
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(NC_THREADS) nce_fwd_kernel(const NceArgs a, fl
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int64_t pj = j0 + tx + 16 * j;
-      if (pj >= a.P) continue;
+      if (pj >= P_eff) continue;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float sv = expf(acc[i][j] * a.conc);
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(NC_THREADS) nce_fwd_kernel(const NceArgs a, fl
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         const int64_t inst = my_inst[i];
-        const bool own_same = inst >= 0 && inst < a.P && a.psem[(int64_t)s * a.P + inst] == my_sem[s][i];
+        const bool own_same = inst >= 0 && inst < P_eff && a.psem[(int64_t)s * a.P + inst] == my_sem[s][i];
         float num = own[i];
         float flags = own_same ? 2.f : 0.f;
         if (a.plus[s]) {
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(NC_THREADS) nce_grad_kernel(const NceArgs a, c
   const int64_t j0 = (int64_t)blockIdx.y * NC_T;
   float acc[4][4];
   tile_dots(a.e, i_end, i0, a.p, a.P, j0, a.dim, As, Bs, acc);
+  const int64_t P_eff = a.P_dev ? max((int64_t)0, min(a.P, *a.P_dev)) : a.P;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t pix = i0 + ty + 16 * i;
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(NC_THREADS) nce_grad_kernel(const NceArgs a, c
     for (int j = 0; j < 4; ++j) {
       const int64_t pj = j0 + tx + 16 * j;
       if (pj >= a.P) continue;
+      if (pj >= P_eff) { G[(pix - i_begin) * ldg + pj] = 0.f; continue; }
       const float sv = expf(acc[i][j] * a.conc);
       float coef = 0.f;
 #pragma unroll
@@ -273,7 +277,7 @@ bool nce_tc_supported(int64_t N, int64_t P, int dim, int n_sets);
 size_t nce_tc_workspace_bytes(int64_t N, int64_t P, int dim, int n_sets);
 int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, int dim, const int64_t* inst,
                const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus, float conc,
-               float* per_pixel, float* stats, void* workspace, cudaStream_t st);
+               float* per_pixel, float* stats, void* workspace, cudaStream_t st, const int64_t* P_dev);
 int g_debug_flags = 0;   // tests: bit 0 keeps the NCE forward on the fp32 CUDA-core kernel, bit 2 the backward GEMMs,
                          // bit 3 the backward's G chunk; bit 6: backward chunks of 4096 pixels
 
@@ -289,7 +293,7 @@ int split_transpose(const float* src, int64_t ld, int64_t R, int C, int64_t Rp, 
 size_t nce_grad_tc_host_state_bytes();
 int nce_grad_tc_prepare(void* host_state, const float* e, const float* prototypes, int64_t N, int64_t P, int dim,
                         const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus,
-                        float conc, void* workspace, cudaStream_t st);
+                        float conc, void* workspace, cudaStream_t st, const int64_t* P_dev);
 int nce_grad_tc(void* host_state, const float* stats, const float* w, float conc, int64_t i_begin, int64_t i_end,
                 float* G, int64_t ldg, __half* G2, const float* gscale, cudaStream_t st);
 const __half* nce_grad_tc_e2(void* host_state, float* scale);
@@ -373,11 +377,11 @@ static int64_t nce_chunk_pixels(int64_t N, int64_t P) {
 
 static int fill_args(NceArgs& a, const float* e, const float* p, int64_t N, int64_t P, int dim,
                      const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets,
-                     const int32_t* plus, float conc) {
+                     const int32_t* plus, float conc, const int64_t* P_dev) {
   HSG_REQUIRE(N >= 0 && P > 0 && dim > 0, HSG_E_INVALID, "nce: bad shape N=%lld P=%lld dim=%d", (long long)N, (long long)P, dim);
   HSG_REQUIRE(n_sets >= 1 && n_sets <= NC_MAX_SETS, HSG_E_UNSUPPORTED, "nce: %d label sets (1..%d)", n_sets, NC_MAX_SETS);
   HSG_REQUIRE(N == 0 || (e && p && inst && sem && psem && plus), HSG_E_INVALID, "nce: null pointer");
-  a.e = e; a.p = p; a.N = N; a.P = P; a.dim = dim; a.inst = inst; a.sem = sem; a.psem = psem;
+  a.e = e; a.p = p; a.N = N; a.P = P; a.P_dev = P_dev; a.dim = dim; a.inst = inst; a.sem = sem; a.psem = psem;
   a.n_sets = n_sets; a.conc = conc;
   for (int s = 0; s < NC_MAX_SETS; ++s) a.plus[s] = s < n_sets ? plus[s] : 0;
   return HSG_OK;
@@ -413,8 +417,17 @@ int hsg_nce_fwd_f32(const float* e, const float* prototypes, int64_t N, int64_t 
                     const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets,
                     const int32_t* group_plus_host, float concentration, float* per_pixel_out,
                     float* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return hsg_nce_fwd_counted_f32(e, prototypes, N, P, nullptr, dim, inst, sem, psem, n_sets, group_plus_host, concentration,
+                                 per_pixel_out, stats_out, workspace, workspace_bytes, stream);
+}
+
+int hsg_nce_fwd_counted_f32(const float* e, const float* prototypes, int64_t N, int64_t P,
+                            const int64_t* num_prototypes_dev, int dim,
+                            const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets,
+                            const int32_t* group_plus_host, float concentration, float* per_pixel_out,
+                            float* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
   NceArgs a;
-  int rc = fill_args(a, e, prototypes, N, P, dim, inst, sem, psem, n_sets, group_plus_host, concentration);
+  int rc = fill_args(a, e, prototypes, N, P, dim, inst, sem, psem, n_sets, group_plus_host, concentration, num_prototypes_dev);
   if (rc) return rc;
   if (N == 0) return HSG_OK;
   HSG_REQUIRE(per_pixel_out, HSG_E_INVALID, "nce_fwd: null output");
@@ -424,7 +437,7 @@ int hsg_nce_fwd_f32(const float* e, const float* prototypes, int64_t N, int64_t 
   if (!(g_debug_flags & 1) && nce_tc_supported(N, P, dim, n_sets) && workspace &&
       workspace_bytes >= nce_tc_workspace_bytes(N, P, dim, n_sets))
     return nce_fwd_tc(e, prototypes, N, P, dim, inst, sem, psem, n_sets, group_plus_host, concentration,
-                      per_pixel_out, stats_out, workspace, st);
+                      per_pixel_out, stats_out, workspace, st, num_prototypes_dev);
   switch (n_sets) {
     case 1: nce_fwd_kernel<1><<<grid, NC_THREADS, 0, st>>>(a, per_pixel_out, stats_out); break;
     case 2: nce_fwd_kernel<2><<<grid, NC_THREADS, 0, st>>>(a, per_pixel_out, stats_out); break;
@@ -440,8 +453,18 @@ int hsg_nce_bwd_f32(const float* e, const float* prototypes, int64_t N, int64_t 
                     const int32_t* group_plus_host, float concentration, const float* stats,
                     const float* w, float* grad_e, float* grad_p, void* workspace,
                     size_t workspace_bytes, void* stream) {
+  return hsg_nce_bwd_counted_f32(e, prototypes, N, P, nullptr, dim, inst, sem, psem, n_sets, group_plus_host, concentration,
+                                 stats, w, grad_e, grad_p, workspace, workspace_bytes, stream);
+}
+
+int hsg_nce_bwd_counted_f32(const float* e, const float* prototypes, int64_t N, int64_t P,
+                            const int64_t* num_prototypes_dev, int dim,
+                            const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets,
+                            const int32_t* group_plus_host, float concentration, const float* stats,
+                            const float* w, float* grad_e, float* grad_p, void* workspace,
+                            size_t workspace_bytes, void* stream) {
   NceArgs a;
-  int rc = fill_args(a, e, prototypes, N, P, dim, inst, sem, psem, n_sets, group_plus_host, concentration);
+  int rc = fill_args(a, e, prototypes, N, P, dim, inst, sem, psem, n_sets, group_plus_host, concentration, num_prototypes_dev);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   HSG_REQUIRE(grad_p && (N == 0 || (grad_e && stats && w)), HSG_E_INVALID, "nce_bwd: null pointer");
@@ -462,7 +485,7 @@ int hsg_nce_bwd_f32(const float* e, const float* prototypes, int64_t N, int64_t 
   if (b.on) {
     // dE = G P and dP = G^T E on the tensor cores (three fp16 passes each, gemm_tc.cu)
     if (b.g_on && (rc = nce_grad_tc_prepare(tc_state, e, prototypes, N, P, dim, inst, sem, psem, n_sets, group_plus_host,
-                                            concentration, b.fwd_ws, st))) return rc;
+                                            concentration, b.fwd_ws, st, num_prototypes_dev))) return rc;
     float e2_scale = 1.f;
     if (b.g_on) e2 = nce_grad_tc_e2(tc_state, &e2_scale);
     if ((rc = absmax(w, (int64_t)n_sets * N, b.scal, st))) return rc;

@@ -36,6 +36,8 @@ constexpr int NT_MAX_SETS = 4;
 
 struct NceTcParams {
   int64_t N, P;
+  const int64_t* P_dev;     // optional: the number of valid prototypes lives on the device (<= P, the capacity of the
+                            // arrays); rows and labels beyond it are never counted -- no host read before the launch
   int D;                    // 64, 128 or 256
   int n_sets;
   int plus[NT_MAX_SETS];
@@ -154,6 +156,7 @@ nce_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int nslab = p.D / NT_BK;                       // slabs per half (hi or lo)
+  const int64_t P_eff = p.P_dev ? max((int64_t)0, min(p.P, *p.P_dev)) : p.P;
   const uint32_t sA = base;                            // [2*nslab] slabs: eh_0.., el_0..
   const uint32_t sB = sA + 2 * nslab * NT_SLAB;        // ring of nstb slabs
   const uint32_t sMisc = sB + p.nstb * NT_SLAB;
@@ -280,8 +283,8 @@ nce_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
       for (int nt = 0; nt < n_ntiles; ++nt, ++seq) {
         if ((int)(seq & 1) != g) continue;
-        const int n_valid = (int)min((int64_t)N2_BN, p.P - (int64_t)nt * N2_BN);
-        const int nchunk = (n_valid + 15) >> 4;
+        const int n_valid = (int)min((int64_t)N2_BN, P_eff - (int64_t)nt * N2_BN);
+        const int nchunk = (max(n_valid, 1) + 15) >> 4;                  // a tile beyond a device-side count still drains once
         const int own_rel = my_inst - nt * N2_BN;                        // column of the own prototype in this tile
         const int32_t* lab_tile = p.psem + (int64_t)nt * N2_BN;
 
@@ -320,7 +323,7 @@ nce_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
           const float pp = pos[s] + row[2 * s], nn = neg[s] + row[2 * s + 1];
-          const bool own_same = my_inst >= 0 && my_inst < p.P && p.psem[(int64_t)s * p.Ppad + my_inst] == my_sem[s];
+          const bool own_same = my_inst >= 0 && my_inst < P_eff && p.psem[(int64_t)s * p.Ppad + my_inst] == my_sem[s];
           float num = own, flags = own_same ? 2.f : 0.f;
           if (p.plus[s]) {
             const float ps2 = __fsub_rn(pp, own);            // loss.py:64-66: sum over the class, then subtract own
@@ -375,6 +378,7 @@ nce_grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int nslab = p.D / NT_BK;
+  const int64_t P_eff = p.P_dev ? max((int64_t)0, min(p.P, *p.P_dev)) : p.P;
   const uint32_t sA = base;
   const uint32_t sB = sA + 2 * nslab * NT_SLAB;
   const uint32_t sMisc = sB + p.nstb * NT_SLAB;
@@ -534,7 +538,7 @@ nce_grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
       if ((int)(seq & 1) != grp) continue;
-      const int n_valid = (int)min((int64_t)N2_BN, p.P - (int64_t)nt * N2_BN);
+      const int n_valid = (int)min((int64_t)N2_BN, P_eff - (int64_t)nt * N2_BN);
       const int n_store = (int)min((int64_t)N2_BN, g.ldg - (int64_t)nt * N2_BN);      // columns of G that exist
       const int nchunk = (max(n_store, 0) + 15) >> 4;
       const int own_rel = my_inst - nt * N2_BN;
@@ -681,7 +685,7 @@ struct NceTcSetup {
 };
 
 // fp16 (hi|lo) copies of both operands, int32 labels, tensor maps: everything the pair kernels read
-static int nce_tc_setup(NceTcSetup& u, const float* e, const float* prototypes, int64_t N, int64_t P, int dim,
+static int nce_tc_setup(NceTcSetup& u, const int64_t* P_dev, const float* e, const float* prototypes, int64_t N, int64_t P, int dim,
                         const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus,
                         float conc, void* workspace, cudaStream_t st) {
   const int64_t Ppad = nce_ppad(P);
@@ -708,7 +712,7 @@ static int nce_tc_setup(NceTcSetup& u, const float* e, const float* prototypes, 
   u.e2 = ah;
   u.t = t;
   NceTcParams& p = u.p;
-  p.N = N; p.P = P; p.D = dim; p.n_sets = n_sets; p.inst = inst32; p.sem = sem32; p.psem = psem32;
+  p.N = N; p.P = P; p.P_dev = P_dev; p.D = dim; p.n_sets = n_sets; p.inst = inst32; p.sem = sem32; p.psem = psem32;
   p.Ppad = Ppad; p.per_pixel = nullptr; p.stats = nullptr;
   for (int s = 0; s < NT_MAX_SETS; ++s) p.plus[s] = s < n_sets ? plus[s] : 0;
   const int nslab = dim / NT_BK;
@@ -729,9 +733,9 @@ static int nce_tc_setup(NceTcSetup& u, const float* e, const float* prototypes, 
 
 int nce_fwd_tc(const float* e, const float* prototypes, int64_t N, int64_t P, int dim, const int64_t* inst,
                const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus, float conc,
-               float* per_pixel, float* stats, void* workspace, cudaStream_t st) {
+               float* per_pixel, float* stats, void* workspace, cudaStream_t st, const int64_t* P_dev) {
   NceTcSetup u;
-  int rc = nce_tc_setup(u, e, prototypes, N, P, dim, inst, sem, psem, n_sets, plus, conc, workspace, st);
+  int rc = nce_tc_setup(u, P_dev, e, prototypes, N, P, dim, inst, sem, psem, n_sets, plus, conc, workspace, st);
   if (rc) return rc;
   NceTcParams& p = u.p;
   p.per_pixel = per_pixel; p.stats = stats;
@@ -763,8 +767,8 @@ size_t nce_grad_tc_host_state_bytes() { return sizeof(NceTcSetup); }
 
 int nce_grad_tc_prepare(void* host_state, const float* e, const float* prototypes, int64_t N, int64_t P, int dim,
                         const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets, const int32_t* plus,
-                        float conc, void* workspace, cudaStream_t st) {
-  return nce_tc_setup(*setup_slot(host_state), e, prototypes, N, P, dim, inst, sem, psem, n_sets, plus, conc, workspace, st);
+                        float conc, void* workspace, cudaStream_t st, const int64_t* P_dev) {
+  return nce_tc_setup(*setup_slot(host_state), P_dev, e, prototypes, N, P, dim, inst, sem, psem, n_sets, plus, conc, workspace, st);
 }
 
 const __half* nce_grad_tc_e2(void* host_state, float* scale) {

@@ -219,6 +219,57 @@ def exchange_prototypes(local_ids, prototypes, prototypes_with_loc, proto_sem, p
   return out[0], out[1], out[2], out[3], out[4], local_ids + sum(sizes[:rank])
 
 
+class _CountedPrototypeExchange(torch.autograd.Function):
+  """The prototype exchange with every count on the device: pack (one launch) -> ONE all-gather -> unpack (one
+  launch).  Inputs and outputs are fixed-capacity arrays; the number of valid rows travels in the records and
+  comes back as a device scalar for the NCE (ops.nce_log_likelihood(num_prototypes=...)).  No size exchange, no
+  host read, no per-rank torch.cat.  Backward: one all-reduce of the two float gradients, then this rank's rows."""
+
+  @staticmethod
+  def forward(ctx, prototypes, prototypes_with_loc, proto_sem, proto_inst, proto_batch, num_prototypes, capacity, group):
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    cap = int(capacity)
+    d, d2 = prototypes.shape[1], prototypes_with_loc.shape[1]
+    record = ops.exchange_pack(prototypes, prototypes_with_loc, proto_sem, proto_inst, proto_batch, num_prototypes, cap)
+    gathered = torch.empty((world * record.numel(),), dtype=torch.uint8, device=record.device)
+    dist.all_gather_into_tensor(gathered, record, group=group)
+    protos, protos_loc, sem, inst, batch, total, offset = ops.exchange_unpack(gathered, world, rank, cap, d, d2)
+    ctx.group, ctx.cap, ctx.rows_in = group, cap, (prototypes.shape[0], prototypes_with_loc.shape[0])
+    ctx.save_for_backward(offset, num_prototypes.reshape(-1)[:1].long())
+    ctx.mark_non_differentiable(sem, inst, batch, total, offset)
+    return protos, protos_loc, sem, inst, batch, total, offset
+
+  @staticmethod
+  def backward(ctx, gp, gpl, *_unused):
+    offset, count = ctx.saved_tensors
+    slot = torch.arange(ctx.cap, device=offset.device)
+    keep = (slot < count).unsqueeze(1)
+    out = []
+    for g, rows_in in zip((gp, gpl), ctx.rows_in):
+      if g is None:
+        out.append(None)
+        continue
+      g = g.contiguous()
+      dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+      mine = g.index_select(0, (offset + slot).clamp_(max=g.shape[0] - 1)) * keep
+      if rows_in > ctx.cap:
+        mine = torch.cat([mine, mine.new_zeros((rows_in - ctx.cap, mine.shape[1]))], 0)
+      out.append(mine)
+    return out[0], out[1], None, None, None, None, None, None
+
+
+def exchange_prototypes_counted(local_ids, prototypes, prototypes_with_loc, proto_sem, proto_inst, proto_batch,
+                                num_prototypes, capacity, group=None):
+  """exchange_prototypes for a step whose prototype count lives on the device (segment_by_kmeans_ex without
+  count_prototypes, pool_prototypes at capacity).  Returns (prototypes, prototypes_with_loc, sem, inst, batch,
+  shifted local ids, total) where the arrays have world*capacity rows -- the valid ones first, in rank order
+  (the reference's global order, hsg/models/utils.py:172-213) -- and `total` is the device-side number of valid
+  rows, to be handed to segsort_loss_multi(num_prototypes=total)."""
+  res = _CountedPrototypeExchange.apply(prototypes, prototypes_with_loc, proto_sem, proto_inst, proto_batch,
+                                        num_prototypes, int(capacity), group)
+  return res[0], res[1], res[2], res[3], res[4], local_ids + res[6], res[5]
+
+
 def dist_gather_clustering_and_update_prototypes(embeddings, embeddings_with_loc, cluster_indices,
                                                  batch_indices, semantic_labels, instance_labels,
                                                  group=None):

@@ -370,7 +370,7 @@ def segment_sum_exact(x, labels, num_bins):
 class _Nce(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, e, protos, inst, sem, psem, plus, conc):
+  def forward(ctx, e, protos, inst, sem, psem, plus, conc, count=None):
     e2 = _f32(e)
     p2 = _f32(protos)
     n, dim = e2.shape
@@ -383,10 +383,12 @@ class _Nce(torch.autograd.Function):
     lib = _lib.load()
     ws = _workspace(lib.hsg_nce_workspace_bytes(n, p, dim, n_sets), dev)
     with torch.cuda.device(dev):
-      check(lib.hsg_nce_fwd_f32(_ptr(e2), _ptr(p2), n, p, dim, _ptr(inst), _ptr(sem), _ptr(psem),
-                                n_sets, plus_arr, float(conc), _ptr(out), _ptr(stats), _ptr(ws), ws.numel(),
-                                _stream()), 'nce_fwd')
+      check(lib.hsg_nce_fwd_counted_f32(_ptr(e2), _ptr(p2), n, p, _ptr(count) if count is not None else None, dim,
+                                        _ptr(inst), _ptr(sem), _ptr(psem),
+                                        n_sets, plus_arr, float(conc), _ptr(out), _ptr(stats), _ptr(ws), ws.numel(),
+                                        _stream()), 'nce_fwd')
     ctx.save_for_backward(e2, p2, inst, sem, psem, stats)
+    ctx.count = count
     ctx.plus = [int(v) for v in plus]
     ctx.conc = float(conc)
     return out
@@ -404,18 +406,21 @@ class _Nce(torch.autograd.Function):
     ws = _workspace(lib.hsg_nce_workspace_bytes(n, p, dim, n_sets), e2.device)
     plus_arr = (ctypes.c_int32 * n_sets)(*ctx.plus)
     with torch.cuda.device(e2.device):
-      check(lib.hsg_nce_bwd_f32(_ptr(e2), _ptr(p2), n, p, dim, _ptr(inst), _ptr(sem), _ptr(psem), n_sets,
-                                plus_arr, ctx.conc, _ptr(stats), _ptr(w), _ptr(ge), _ptr(gp), _ptr(ws),
-                                ws.numel(), _stream()), 'nce_bwd')
-    return ge, gp, None, None, None, None, None
+      check(lib.hsg_nce_bwd_counted_f32(_ptr(e2), _ptr(p2), n, p, _ptr(ctx.count) if ctx.count is not None else None,
+                                        dim, _ptr(inst), _ptr(sem), _ptr(psem), n_sets,
+                                        plus_arr, ctx.conc, _ptr(stats), _ptr(w), _ptr(ge), _ptr(gp), _ptr(ws),
+                                        ws.numel(), _stream()), 'nce_bwd')
+    return ge, gp, None, None, None, None, None, None
 
 
 def nce_log_likelihood(embeddings, instance_labels, semantic_label_sets, prototypes,
-                       prototype_semantic_label_sets, concentration, group_modes):
+                       prototype_semantic_label_sets, concentration, group_modes, num_prototypes=None):
   """Per-pixel negative log-likelihood for several label sets in one pass.
 
   semantic_label_sets [n_sets,N], prototype_semantic_label_sets [n_sets,P];
-  returns [n_sets,N] float32, differentiable in embeddings and prototypes."""
+  returns [n_sets,N] float32, differentiable in embeddings and prototypes.
+  num_prototypes: optional int64 device tensor [1] -- only the first num_prototypes rows of `prototypes` (and of the
+  label sets) exist; the rest is capacity (no host read of the count: hsg_nce_fwd_counted_f32)."""
   _need_cuda(embeddings, prototypes, instance_labels, semantic_label_sets, prototype_semantic_label_sets)
   e = embeddings.reshape(-1, embeddings.shape[-1])
   p = prototypes.reshape(-1, prototypes.shape[-1])
@@ -426,7 +431,11 @@ def nce_log_likelihood(embeddings, instance_labels, semantic_label_sets, prototy
   assert sem.shape[0] == psem.shape[0] == len(plus)
   if e.shape[0] == 0:
     return torch.zeros((sem.shape[0], 0), dtype=torch.float32, device=e.device)
-  return _Nce.apply(e, p, inst, sem, psem, plus, concentration)
+  count = None
+  if num_prototypes is not None:
+    count = _i64(num_prototypes).reshape(-1)[:1]
+    _need_cuda(count)
+  return _Nce.apply(e, p, inst, sem, psem, plus, concentration, count)
 
 
 # ---------------------------------------------------------------- K2 relabel
@@ -441,9 +450,11 @@ def relabel(batch, cluster, label, batch_base, num_images, kmax, label_values):
   t = num_images * kmax * nl
   cap = min(t, max(n, 1))
   ids = torch.empty((n,), dtype=torch.int64, device=dev)
-  pl = torch.empty((cap,), dtype=torch.int64, device=dev)
-  pb = torch.empty((cap,), dtype=torch.int64, device=dev)
-  pc = torch.empty((cap,), dtype=torch.int64, device=dev)
+  # slots beyond n_protos keep these fills: proto_batch stays sorted (searchsorted over the whole buffer is valid
+  # without knowing the count on the host), labels / clusters match nothing
+  pl = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+  pb = torch.full((cap,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
+  pc = torch.full((cap,), -1, dtype=torch.int64, device=dev)
   npro = torch.empty((1,), dtype=torch.int64, device=dev)
   lib = _lib.load()
   ws = _workspace(lib.hsg_relabel_workspace_bytes(num_images, kmax, nl), dev)
@@ -452,6 +463,44 @@ def relabel(batch, cluster, label, batch_base, num_images, kmax, label_values):
                               kmax, _ptr(label_values), nl, _ptr(ids), _ptr(pl), _ptr(pb), _ptr(pc),
                               _ptr(npro), _ptr(ws), ws.numel(), _stream()), 'relabel')
   return ids, pl, pb, pc, npro
+
+
+# ---------------------------------------------------------------- a13 prototype exchange records
+def exchange_record_bytes(capacity, dim, dim_loc):
+  return int(_lib.load().hsg_exchange_record_bytes(int(capacity), int(dim), int(dim_loc)))
+
+
+def exchange_pack(prototypes, prototypes_with_loc, sem, inst, batch, num_prototypes, capacity):
+  """This rank's fixed-capacity record (uint8 tensor) for the one all-gather of the prototype exchange; the count
+  is read on the device (include/hsg_b200.h: hsg_exchange_pack)."""
+  _need_cuda(prototypes, prototypes_with_loc, sem, inst, batch, num_prototypes)
+  p, pl = _f32(prototypes.detach()), _f32(prototypes_with_loc.detach())
+  cap = int(capacity)
+  if min(p.shape[0], pl.shape[0], sem.numel(), inst.numel(), batch.numel()) < cap:
+    raise ValueError('exchange_pack: inputs hold fewer than capacity=%d rows' % cap)
+  rec = torch.empty((exchange_record_bytes(cap, p.shape[1], pl.shape[1]),), dtype=torch.uint8, device=p.device)
+  with torch.cuda.device(p.device):
+    check(_lib.load().hsg_exchange_pack(_ptr(p), _ptr(pl), _ptr(_i64(sem)), _ptr(_i64(inst)), _ptr(_i64(batch)),
+                                        _ptr(_i64(num_prototypes)), cap, p.shape[1], pl.shape[1], _ptr(rec), _stream()),
+          'exchange_pack')
+  return rec
+
+
+def exchange_unpack(gathered, world, rank, capacity, dim, dim_loc):
+  """(prototypes, prototypes_with_loc, sem, inst, batch, total [1], offset [1]) from the `world` gathered records:
+  world*capacity rows, valid ones first in rank order (hsg_exchange_unpack)."""
+  _need_cuda(gathered)
+  dev = gathered.device
+  rows = int(world) * int(capacity)
+  protos = torch.empty((rows, dim), dtype=torch.float32, device=dev)
+  protos_loc = torch.empty((rows, dim_loc), dtype=torch.float32, device=dev)
+  sem, inst, batch = (torch.empty((rows,), dtype=torch.int64, device=dev) for _ in range(3))
+  total, offset = (torch.empty((1,), dtype=torch.int64, device=dev) for _ in range(2))
+  with torch.cuda.device(dev):
+    check(_lib.load().hsg_exchange_unpack(_ptr(gathered), int(world), int(rank), int(capacity), int(dim), int(dim_loc),
+                                          _ptr(protos), _ptr(protos_loc), _ptr(sem), _ptr(inst), _ptr(batch),
+                                          _ptr(total), _ptr(offset), _stream()), 'exchange_unpack')
+  return protos, protos_loc, sem, inst, batch, total, offset
 
 
 # ---------------------------------------------------------------- f3 top-k retrieval

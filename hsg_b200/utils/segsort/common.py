@@ -239,12 +239,13 @@ def pool_prototypes(ex, embeddings=None):
   """calculate_prototypes_from_labels(embeddings, cluster_indices) for the output
   of segment_by_kmeans_ex, using the image structure (ids are ranked by image) so
   the reduction needs no global sort.  Differentiable in the embeddings."""
-  if 'num_prototypes' not in ex:
-    raise ValueError('pool_prototypes needs segment_by_kmeans_ex(..., count_prototypes=True)')
   x = ex['embeddings'] if embeddings is None else embeddings
+  # without the host-side count (count_prototypes=False) the result has one row per SLOT of the step
+  # (ex['proto_batch'].shape[0]); rows beyond ex['num_prototypes_device'] are zero -- no host read
+  num = ex['num_prototypes'] if 'num_prototypes' in ex else int(ex['proto_batch'].shape[0])
   dev = x.device
   images = torch.arange(ex['num_images'], device=dev, dtype=torch.int64) + ex['batch_base']
   seg_base = torch.searchsorted(ex['proto_batch'], images).contiguous()   # first prototype id of each image
-  return ops.segment_reduce(x, ex['cluster_indices'], ex['num_prototypes'], REDUCE_NORMALIZE,
+  return ops.segment_reduce(x, ex['cluster_indices'], num, REDUCE_NORMALIZE,
                             seg_offsets=ex['seg_offsets'], max_seg_len=ex['max_seg_len'],
                             seg_base=seg_base, kmax=ex['slots_per_image'])

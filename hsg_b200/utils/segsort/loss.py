@@ -48,14 +48,15 @@ class SegSortLoss(_Loss):
 
 def segsort_loss_multi(embeddings, instance_labels, semantic_label_sets, prototypes,
                        prototype_semantic_label_sets, concentration, group_modes=None,
-                       reduction='mean'):
+                       reduction='mean', num_prototypes=None):
   """One pass over E x P for several (semantic_labels, prototype_semantic_labels)
   pairs.  Returns a list with one loss per set (same values as calling
-  SegSortLoss once per set)."""
+  SegSortLoss once per set).  num_prototypes (int64 device tensor [1], optional): only that many leading rows of
+  `prototypes` exist -- the count stays on the device (pool_prototypes / exchange_prototypes_counted)."""
   sem = torch.stack([s.reshape(-1) for s in semantic_label_sets], 0)
   psem = torch.stack([s.reshape(-1) for s in prototype_semantic_label_sets], 0)
   if group_modes is None:
     group_modes = ['segsort+'] * sem.shape[0]
   ll = ops.nce_log_likelihood(embeddings, instance_labels, sem, prototypes, psem, concentration,
-                              group_modes)
+                              group_modes, num_prototypes=num_prototypes)
   return [_reduce(ll[s].reshape(-1, 1), reduction) for s in range(sem.shape[0])]

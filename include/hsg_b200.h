@@ -302,6 +302,42 @@ HSG_API int hsg_nce_bwd_f32(const float* e, const float* prototypes, int64_t N, 
                     const int32_t* group_plus_host, float concentration,
                     const float* stats, const float* w, float* grad_e, float* grad_p,
                     void* workspace, size_t workspace_bytes, void* stream);
+/* The same two calls with the number of valid prototypes on the DEVICE: P is the capacity of the prototype arrays,
+ * *num_prototypes_dev (<= P; NULL = P) the rows that count.  Rows and labels beyond it contribute to no sum and
+ * receive a zero gradient, so a step whose prototype count is only known on the device (empty clusters dropped by
+ * hsg_relabel_i64, prototypes all-gathered by hsg_exchange_*) needs no host read between k-means and the loss.
+ */
+HSG_API int hsg_nce_fwd_counted_f32(const float* e, const float* prototypes, int64_t N, int64_t P,
+                    const int64_t* num_prototypes_dev, int dim,
+                    const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets,
+                    const int32_t* group_plus_host, float concentration,
+                    float* per_pixel_out, float* stats_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+HSG_API int hsg_nce_bwd_counted_f32(const float* e, const float* prototypes, int64_t N, int64_t P,
+                    const int64_t* num_prototypes_dev, int dim,
+                    const int64_t* inst, const int64_t* sem, const int64_t* psem, int n_sets,
+                    const int32_t* group_plus_host, float concentration,
+                    const float* stats, const float* w, float* grad_e, float* grad_p,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a13: prototype exchange around ONE all-gather, no host read
+ *      (replaces the gather + cat + unique of hsg/models/utils.py:127-217 for one-process-per-GPU launches;
+ *       the library holds no communicator: the caller all-gathers the records, e.g. ncclAllGather /
+ *       torch.distributed.all_gather_into_tensor).
+ * pack:   record [hsg_exchange_record_bytes(capacity, dim, dim_loc)] = this rank's count (read from the device,
+ *         clamped to capacity), prototypes [capacity,dim], prototypes_with_loc [capacity,dim_loc] and the three
+ *         label vectors [capacity]; rows beyond the count are written as zeros / -1.
+ * unpack: gathered = the `world` records in rank order.  Outputs have world*capacity rows: the valid rows of rank 0,
+ *         then rank 1, ... (the reference's global prototype order), the rest zeros / -1; *total_out = number of
+ *         valid rows, *offset_out = valid rows of the ranks below `rank` (add it to this rank's pixel -> prototype ids).
+ */
+HSG_API size_t hsg_exchange_record_bytes(int64_t capacity, int dim, int dim_loc);
+HSG_API int hsg_exchange_pack(const float* prototypes, const float* prototypes_with_loc, const int64_t* sem,
+                    const int64_t* inst, const int64_t* batch, const int64_t* num_prototypes_dev,
+                    int64_t capacity, int dim, int dim_loc, void* record, void* stream);
+HSG_API int hsg_exchange_unpack(const void* gathered, int world, int rank, int64_t capacity, int dim, int dim_loc,
+                    float* prototypes_out, float* prototypes_with_loc_out, int64_t* sem_out, int64_t* inst_out,
+                    int64_t* batch_out, int64_t* total_out, int64_t* offset_out, void* stream);
 
 /* ---- K5: fused attention core of the clustering transformer
  *      (nn.MultiheadAttention slow path used by hsg/models/heads/transformer.py:235,300,304:

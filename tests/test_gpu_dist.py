@@ -49,6 +49,19 @@ def _worker(rank, world, port, out_dir):
   ok = all(torch.equal(u.detach(), v.detach()) for u, v in zip(a, b))
   (b[0] * (rank + 1.0)).sum().backward()
   grad_ok = torch.allclose(protos.grad, torch.full_like(protos.grad, 3.0))
+  # counted exchange (counts on the device, fixed capacity): the valid rows equal the packed exchange
+  cap = 16
+  pad = lambda t, fill: torch.cat([t.detach(), torch.full((cap - n_p,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=dev)], 0)
+  protos_c = pad(protos, 7.0).requires_grad_(True)          # rows beyond the count hold junk on purpose
+  count = torch.tensor([n_p], device=dev)
+  c = MU.exchange_prototypes_counted(ids, protos_c, pad(ploc, 7.0), pad(sem, 3), pad(inst, 3), pad(bat, 3), count, cap)
+  total = int(c[6])
+  ok = ok and total == b[0].shape[0] and c[0].shape[0] == world * cap
+  ok = ok and all(torch.equal(u.detach()[:total], v.detach()) for u, v in zip(c[:5], b[:5]))
+  ok = ok and torch.equal(c[5], b[5]) and bool((c[0][total:] == 0).all()) and bool((c[2][total:] == -1).all())
+  (c[0] * (rank + 1.0)).sum().backward()
+  grad_ok = grad_ok and torch.allclose(protos_c.grad[:n_p], torch.full_like(protos_c.grad[:n_p], 3.0)) and \
+      bool((protos_c.grad[n_p:] == 0).all())
   np.save(os.path.join(out_dir, 'ok%d.npy' % rank), np.asarray([ok, grad_ok]))
   dist.destroy_process_group()
 

@@ -1333,3 +1333,59 @@ def test_inference_prototype_bank_and_retrieval(golden, tmp_path):
   assert pred.dtype == torch.int64 and topk.shape == (g['pred'].shape[0], 20)
   assert np.array_equal(n(pred), g['pred']) and np.array_equal(n(topk), g['topk'])
   assert inference.nearest_neighbor_labels({}, bank_p, bank_l) == (None, None)  # reference :70-84
+
+
+def test_nce_with_a_device_side_prototype_count():
+  """hsg_nce_fwd/bwd_counted_f32: the prototype arrays are capacity-sized, the number of valid rows is a device
+  scalar (no host read between k-means and the loss).  Loss and gradients must equal the call on the sliced
+  arrays -- whatever the rows beyond the count hold -- on the tensor-core path (D = 64) and the CUDA-core one
+  (D = 48), with the count inside a prototype tile, on a tile boundary, and leaving whole tiles empty."""
+  from hsg_b200.utils.segsort import loss as L
+  rng = np.random.RandomState(77)
+  for d, npix, p_valid, cap in ((64, 700, 300, 1000), (64, 300, 256, 900), (48, 500, 37, 200), (256, 260, 100, 101)):
+    e = o_ops.normalize_embedding(rng.randn(npix, d).astype(np.float32))
+    pr = o_ops.normalize_embedding(rng.randn(cap, d).astype(np.float32))
+    pr[p_valid:] = 3.0 * rng.randn(cap - p_valid, d)                       # junk beyond the count
+    inst = rng.randint(0, p_valid, npix).astype(np.int64)
+    psem = [rng.randint(0, 5, cap).astype(np.int64), np.arange(cap, dtype=np.int64)]
+    sem = [psem[0][inst].copy(), inst.copy()]
+    sem[0][::7] = (sem[0][::7] + 1) % 5
+    count = torch.tensor([p_valid], device='cuda')
+    outs = []
+    for counted in (False, True):
+      et, pt = t(e).requires_grad_(True), t(pr if counted else pr[:p_valid]).requires_grad_(True)
+      ps = [t(a if counted else a[:p_valid]) for a in psem]
+      losses = L.segsort_loss_multi(et, t(inst), [t(a) for a in sem], pt, ps, 12.0,
+                                    num_prototypes=count if counted else None)
+      (losses[0] + 0.5 * losses[1]).backward()
+      outs.append((float(losses[0]), float(losses[1]), n(et.grad), n(pt.grad)))
+    ref, got = outs
+    assert abs(got[0] - ref[0]) <= 1e-6 * abs(ref[0]) and abs(got[1] - ref[1]) <= 1e-6 * abs(ref[1]), (d, got[:2], ref[:2])
+    close(got[2], ref[2], rtol=1e-5, atol=1e-8)
+    close(got[3][:p_valid], ref[3], rtol=1e-5, atol=1e-8)
+    assert np.all(got[3][p_valid:] == 0)
+
+
+def test_prototype_exchange_records_roundtrip_on_one_gpu():
+  """hsg_exchange_pack / hsg_exchange_unpack (the two launches around the one all-gather of the counted exchange):
+  three ranks emulated on one GPU; the unpacked arrays are the valid rows in rank order, zeros / -1 after them,
+  total and this rank's offset on the device."""
+  from hsg_b200 import ops
+  g = torch.Generator().manual_seed(3)
+  cap, d, d2, counts = 9, 10, 13, [4, 0, 9]
+  recs, parts = [], []
+  for r, c in enumerate(counts):
+    pr, pl = torch.randn(cap, d, generator=g).cuda(), torch.randn(cap, d2, generator=g).cuda()
+    lab = [torch.randint(0, 50, (cap,), generator=g).cuda() for _ in range(3)]
+    recs.append(ops.exchange_pack(pr, pl, lab[0], lab[1], lab[2], torch.tensor([c]).cuda(), cap))
+    parts.append([pr[:c], pl[:c]] + [a[:c] for a in lab])
+  assert recs[0].numel() == ops.exchange_record_bytes(cap, d, d2)
+  gathered = torch.cat(recs)
+  for rank in range(3):
+    out = ops.exchange_unpack(gathered, 3, rank, cap, d, d2)
+    total = int(out[5])
+    assert total == sum(counts) and int(out[6]) == sum(counts[:rank])
+    for j in range(5):
+      want = torch.cat([q[j] for q in parts], 0)
+      assert torch.equal(out[j][:total], want)
+      assert bool((out[j][total:] == (0 if j < 2 else -1)).all()) and out[j].shape[0] == 3 * cap
