@@ -36,6 +36,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 constexpr int PROF_MAX = 8192;
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
+static bool g_prof_coarse = false;   // hsg_profile_enable(2): one range per library call, not per kernel group
 static int g_prof_n = 0;
 static int g_prof_phase[PROF_MAX];
 static cudaEvent_t g_prof_ev[PROF_MAX][2];
@@ -47,6 +48,7 @@ ProfSuppress::~ProfSuppress() { --g_prof_suppress; }
 
 ProfRange::ProfRange(int phase, cudaStream_t stream) : slot(-1), st(stream) {
   if (!g_prof_on || g_prof_suppress) return;
+  if (g_prof_coarse && ((phase >= PROF_MSTEP_SORT && phase <= PROF_ESTEP_FIXUP) || phase == PROF_CONVERT)) return;
   std::lock_guard<std::mutex> lock(g_prof_mu);
   if (!g_prof_on || g_prof_n >= PROF_MAX) return;
   slot = g_prof_n++;
@@ -72,6 +74,7 @@ long long hsg_launch_count(void) { return hsg::g_launches.load(); }
 int hsg_profile_enable(int on) {
   std::lock_guard<std::mutex> lock(hsg::g_prof_mu);
   hsg::g_prof_on = on != 0;
+  hsg::g_prof_coarse = on == 2;
   if (on) hsg::g_prof_n = 0;
   return HSG_OK;
 }

@@ -52,7 +52,7 @@ void count_launch();
 // of CUDA events on the launching stream around a phase when enabled
 enum ProfPhase { PROF_PREP = 0, PROF_MSTEP_SORT, PROF_MSTEP_GATHER, PROF_MSTEP_COMBINE,
                  PROF_ESTEP, PROF_ESTEP_FIXUP, PROF_RELABEL, PROF_POOL, PROF_NCE_FWD,
-                 PROF_NCE_BWD, PROF_CONVERT, PROF_NUM };
+                 PROF_NCE_BWD, PROF_CONVERT, PROF_KMEANS /* one whole hsg_kmeans_* call */, PROF_NUM };
 struct ProfSuppress {   // inner ranges are skipped while one of these is alive (per thread)
   ProfSuppress();
   ~ProfSuppress();

@@ -994,6 +994,7 @@ static int kmeans_impl(const float* x, int64_t N, int dim, const void* xh, int d
   rc = decide_tc(flags, dim, xh, d16, xerr, kmax, &use_tc);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfRange prof_call(PROF_KMEANS, st);
   Carver c(workspace);
   KmPlan p;
   km_carve(c, p, N, dim, S, kmax, max_seg_len, d16);

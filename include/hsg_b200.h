@@ -71,7 +71,10 @@ HSG_API int hsg_device_sms(void);
  * so far (process-wide), and optional CUDA-event timing of the phases of the
  * path on the launching stream (phase ids: 0 prep, 1 M-step sort, 2 M-step
  * gather, 3 M-step combine, 4 E-step, 5 E-step float64 re-decision, 6 relabel,
- * 7 pooling, 8 NCE fwd, 9 NCE bwd, 10 centroid fp16 conversion). */
+ * 7 pooling, 8 NCE fwd, 9 NCE bwd, 10 centroid fp16 conversion, 11 one whole
+ * hsg_kmeans_* call).  on = 1: every phase; on = 2: coarse -- phases 1-5 and 10
+ * are not recorded (two events per k-means call instead of ~200: the events
+ * themselves cost ~2 us each on the stream). */
 HSG_API long long hsg_launch_count(void);
 HSG_API int hsg_profile_enable(int on);
 HSG_API int hsg_profile_collect(double* total_ms_host, long long* counts_host, int n_phases);
