@@ -179,19 +179,32 @@ __global__ void __launch_bounds__(SCATTER_WARPS * 32) scatter_kernel(
   __syncwarp();
   const int64_t b = t.begin[ti], e = t.end[ti];
   const unsigned lt = (1u << lane) - 1u;
-  for (int64_t base = b; base < e; base += 32) {
-    const int64_t i = base + lane;
-    const bool valid = i < e;
-    const int kl = valid ? keys[i] - kbase : -1 - lane;
-    const unsigned m = __match_any_sync(FULL, kl);
-    uint32_t pos = 0;
-    if (valid) pos = cur[kl] + __popc(m & lt);
-    __syncwarp();
-    if (valid) {
-      perm[so + pos] = (uint32_t)(i - so);
-      if ((m & lt) == 0) cur[kl] += __popc(m);   // lowest lane of the group advances the cursor
+  // the placement is serial per tile (one warp walks it in order), so the key loads are issued eight steps
+  // ahead: the walk was a chain of 64 dependent load latencies per tile
+  constexpr int AHEAD = 8;
+  for (int64_t base0 = b; base0 < e; base0 += 32 * AHEAD) {
+    int kk[AHEAD];
+#pragma unroll
+    for (int u = 0; u < AHEAD; ++u) {
+      const int64_t i = base0 + 32 * u + lane;
+      kk[u] = i < e ? keys[i] - kbase : -1 - lane;
     }
-    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < AHEAD; ++u) {
+      const int64_t i = base0 + 32 * u + lane;
+      if (base0 + 32 * u >= e) break;            // warp-uniform
+      const bool valid = i < e;
+      const int kl = kk[u];
+      const unsigned m = __match_any_sync(FULL, kl);
+      uint32_t pos = 0;
+      if (valid) pos = cur[kl] + __popc(m & lt);
+      __syncwarp();
+      if (valid) {
+        perm[so + pos] = (uint32_t)(i - so);
+        if ((m & lt) == 0) cur[kl] += __popc(m);   // lowest lane of the group advances the cursor
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -364,6 +377,7 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_kernel(
 // a full pass SETS sums = sum of the float pieces, a delta pass ADDS the float64 pieces of the
 // signed entries.  Member counts are carried exactly, so a cluster that lost every member is
 // reset to an exact zero sum (the reference's empty cluster: zero centroid).
+template <int NV>
 __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine64_kernel(
     int64_t bins, int dim, const int64_t* __restrict__ bin_start, const int32_t* __restrict__ bin_count,
     const float* __restrict__ pieces, const double* __restrict__ p64, const int32_t* __restrict__ piece_cnt,
@@ -378,28 +392,57 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine64_kernel(
   const int64_t r0 = start / SR_RUN, r1 = cnt > 0 ? (start + cnt - 1) / SR_RUN : r0 - 1;
   int mem = cnt;
   if (delta) {
-    mem = members[key];
-    for (int64_t r = r0; r <= r1; ++r) mem += piece_cnt[r + key];
+    // member count: lanes read the pieces' counts in parallel, integer sum (order-free)
+    int c = 0;
+    for (int64_t r = r0 + lane; r <= r1; r += 32) c += piece_cnt[r + key];
+    mem = members[key] + warp_sum(c);
   }
   if (lane == 0) members[key] = mem;
   double* sk = sums + key * dim;
-  float* o = out + key * dim;
-  float ss = 0.f;
-  for (int d = lane; d < dim; d += 32) {
-    double a = delta ? sk[d] : 0.0;
-    if (delta) {
-      for (int64_t r = r0; r <= r1; ++r) a += p64[(r + key) * dim + d];
-    } else {
-      for (int64_t r = r0; r <= r1; ++r) a += (double)pieces[(r + key) * dim + d];
+  // the whole row lives in registers: every run contributes NV independent loads (the kernel used to be a chain
+  // of dependent load latencies, 30-50 us per launch whatever the batch size); pieces are added in run order
+  double a[NV];
+#pragma unroll
+  for (int m = 0; m < NV; ++m) {
+    const int d = lane + 32 * m;
+    a[m] = (delta && d < dim) ? sk[d] : 0.0;
+  }
+  if (delta) {
+#pragma unroll 2
+    for (int64_t r = r0; r <= r1; ++r) {
+      const double* src = p64 + (r + key) * dim + lane;
+#pragma unroll
+      for (int m = 0; m < NV; ++m)
+        if (lane + 32 * m < dim) a[m] += src[32 * m];
     }
-    if (mem == 0) a = 0.0;
-    sk[d] = a;
-    const float f = (float)a;
-    o[d] = f;
-    ss = fmaf(f, f, ss);
+  } else {
+#pragma unroll 2
+    for (int64_t r = r0; r <= r1; ++r) {
+      const float* src = pieces + (r + key) * dim + lane;
+#pragma unroll
+      for (int m = 0; m < NV; ++m)
+        if (lane + 32 * m < dim) a[m] += (double)src[32 * m];
+    }
+  }
+  float f[NV];
+  float ss = 0.f;
+#pragma unroll
+  for (int m = 0; m < NV; ++m) {
+    const int d = lane + 32 * m;
+    if (mem == 0) a[m] = 0.0;
+    f[m] = (float)a[m];
+    if (d < dim) {
+      sk[d] = a[m];
+      ss = fmaf(f[m], f[m], ss);
+    }
   }
   const float n = safe_norm(warp_sum(ss));
-  for (int d = lane; d < dim; d += 32) o[d] = o[d] / n;
+  float* o = out + key * dim;
+#pragma unroll
+  for (int m = 0; m < NV; ++m) {
+    const int d = lane + 32 * m;
+    if (d < dim) o[d] = f[m] / n;
+  }
 }
 
 // ---------------------------------------------------------------- delta list (incremental k-means M-step)
@@ -682,8 +725,14 @@ int sr_combine_exact(const SegReducePlan& p, int64_t P, const int64_t* seg_base,
 int sr_combine64(const SegReducePlan& p, const float* pieces_full, const double* pieces_delta,
                  const int32_t* delta_flag, double* sums, int32_t* members, float* out, cudaStream_t st, Gate gate) {
   ProfRange prof(PROF_MSTEP_COMBINE, st);
-  combine64_kernel<<<(unsigned)ceil_div64(p.bins, COMBINE_WARPS), COMBINE_WARPS * 32, 0, st>>>(
-      p.bins, p.dim, p.bin_start, p.bin_count, pieces_full, pieces_delta, p.piece_cnt, delta_flag, sums, members, out, gate);
+  const unsigned grid = (unsigned)ceil_div64(p.bins, COMBINE_WARPS);
+#define HSG_COMBINE64(NV) combine64_kernel<NV><<<grid, COMBINE_WARPS * 32, 0, st>>>( \
+      p.bins, p.dim, p.bin_start, p.bin_count, pieces_full, pieces_delta, p.piece_cnt, delta_flag, sums, members, out, gate)
+  if (p.dim <= 32 * 3) HSG_COMBINE64(3);
+  else if (p.dim <= 32 * 5) HSG_COMBINE64(5);
+  else if (p.dim <= 32 * 9) HSG_COMBINE64(9);
+  else HSG_COMBINE64(20);
+#undef HSG_COMBINE64
   HSG_LAUNCH_CHECK();
   return HSG_OK;
 }
