@@ -861,6 +861,331 @@ static int launch_small_persistent(const SmallArgs& s, int64_t work, cudaStream_
   return HSG_OK;
 }
 
+// ---------------------------------------------------------------- the whole loop inside one thread-block cluster per image
+// At the training shapes an image is small enough to LIVE in shared memory: 28x28 rows of 130 floats are 408 KB,
+// an eighth of that per CTA of an 8-CTA cluster.  Images are independent, so nothing has to cross the cluster: the
+// rows are loaded once, and every iteration is  partial sums (local) | cluster barrier | centroids (distributed
+// shared memory) | cluster barrier | assignment (local)  -- hardware barriers of ~1 us instead of grid barriers through
+// L2, no traffic between iterations at all, no co-residency requirement (clusters queue like ordinary CTAs).
+// The arithmetic is that of mstep_small_bin / estep_small_tile: CTA r of the cluster owns exactly the row range that
+// warp r of the one-bin-per-CTA M-step sums (members in index order, fp32 runs of 32 folded into float64, the eight
+// partials added in rank order), the products are the same fmaf chains and a near-tie takes the same float64 scan,
+// so the labels are bit-identical to the other paths.
+constexpr int KC_RANKS = 8;             // CTAs per cluster = row ranges per segment (portable cluster size)
+
+__device__ __forceinline__ uint32_t kc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t kc_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t kc_mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void kc_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double kc_ld_f64(uint32_t caddr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(caddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float kc_lds(uint32_t saddr) {      // explicit shared-space load: a generic pointer into shared
+  float v;                                                     // memory costs an S2R of the cluster window base per access
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void kc_st_f32(uint32_t caddr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(caddr), "f"(v) : "memory");
+}
+
+struct ClusterKmArgs {
+  const float* x;              // [N,dim]
+  int dim, kmax, S;
+  const int64_t* seg_offsets;
+  const int32_t* seg_k;        // may be NULL
+  const int64_t* init_labels;
+  int64_t* labels_out;
+  float* centroids_out;        // may be NULL: [S,kmax,dim]
+  int iterations;
+  float thr;
+  int per_max;                 // rows per CTA the shared-memory carve-up was sized for
+  int exp_flags;               // timing experiments (HSG_CLUSTER_EXP), 0 in production: 1 no partial sums, 2 no centroids, 4 no assignment
+};
+
+__host__ __device__ inline int64_t kc_rows_per_rank(int64_t len) { return ((len + 7) / 8 + 31) / 32 * 32; }
+
+// shared-memory carve-up (floats unless noted), the same in every CTA of a launch:
+//   XT  [dp][ldr]      the rows of this rank, TRANSPOSED (ldr = rows + 1, odd): the products read consecutive rows of one
+//                      feature (a broadcast per row group), the partial sums and the float64 scan read a row across
+//                      features -- lane stride ldr, conflict-free because it is odd
+//   Cs  [CK][ld]       centroids, row-major (float64 scan; written by the ranks that finish them)
+//   CT  [dp][CK]       centroids transposed (products)
+//   part[kmax][NV*32]  float64 partial sums of every bin over this rank's rows
+//   keys[rows], best_v/second_v/best_i[KC_TILE]
+constexpr int KC_TILE = 128;            // rows per pass of the products: 32 row groups x 4 rows, 8 column groups x 2 NJ columns
+
+template <int NV, int NJ>
+struct KcLayout {
+  int dp, ld, ldr, rows_pad;
+  size_t xt, cs, ct, part, keys, best, total;        // byte offsets
+  __host__ __device__ KcLayout(int dim, int kmax, int per) {
+    constexpr int CK = 16 * NJ;
+    dp = (dim + 31) / 32 * 32; ld = dp + 1;
+    rows_pad = (per + 3) / 4 * 4;
+    ldr = rows_pad + 1;
+    xt = 0;
+    cs = xt + sizeof(float) * (size_t)dp * ldr;
+    ct = cs + sizeof(float) * (size_t)CK * ld;
+    part = (ct + sizeof(float) * (size_t)dp * CK + 15) & ~(size_t)15;
+    keys = part + sizeof(double) * (size_t)kmax * NV * 32;
+    best = keys + sizeof(int) * (size_t)rows_pad;
+    total = best + 3 * sizeof(float) * KC_TILE + 16;
+  }
+};
+
+template <int NV, int NJ>
+__global__ void __launch_bounds__(ES_THREADS) kmeans_cluster_kernel(const ClusterKmArgs s) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  constexpr int CK = 16 * NJ;
+  const KcLayout<NV, NJ> L(s.dim, s.kmax, s.per_max);
+  const int dp = L.dp, ld = L.ld, ldr = L.ldr;
+  float* XT = reinterpret_cast<float*>(raw + L.xt);
+  float* Cs = reinterpret_cast<float*>(raw + L.cs);
+  float* CT = reinterpret_cast<float*>(raw + L.ct);
+  double* part = reinterpret_cast<double*>(raw + L.part);
+  int* keys = reinterpret_cast<int*>(raw + L.keys);
+  float* best_v = reinterpret_cast<float*>(raw + L.best);
+  float* second_v = best_v + KC_TILE;
+  int* best_i = reinterpret_cast<int*>(second_v + KC_TILE);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = kc_rank();
+  const int seg = blockIdx.x / KC_RANKS;
+  const int64_t b = s.seg_offsets[seg], e = s.seg_offsets[seg + 1];
+  const int64_t per = kc_rows_per_rank(e - b);
+  const int64_t wb = min(e, b + (int64_t)rank * per), we = min(e, wb + per);
+  const int nrows = (int)(we - wb);
+  const int K = s.seg_k ? s.seg_k[seg] : s.kmax;
+
+  // ---- the rows of this rank, once: coalesced global reads (a warp per row), transposed into XT
+  for (int i = tid; i < dp * ldr; i += ES_THREADS) XT[i] = 0.f;
+  for (int i = tid; i < CK * ld; i += ES_THREADS) Cs[i] = 0.f;
+  __syncthreads();
+  for (int row0 = 0; row0 < nrows; row0 += 4 * (ES_THREADS / 32)) {
+    float v[4][NV];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int row = row0 + warp + (ES_THREADS / 32) * u;
+#pragma unroll
+      for (int m = 0; m < NV; ++m) {
+        const int d = lane + 32 * m;
+        v[u][m] = (row < nrows && d < s.dim) ? s.x[(wb + row) * s.dim + d] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int row = row0 + warp + (ES_THREADS / 32) * u;
+      if (row < nrows) {
+#pragma unroll
+        for (int m = 0; m < NV; ++m) {
+          const int d = lane + 32 * m;
+          if (d < s.dim) XT[(size_t)d * ldr + row] = v[u][m];
+        }
+      }
+    }
+  }
+  for (int r = tid; r < L.rows_pad; r += ES_THREADS) {
+    int64_t k = r < nrows ? s.init_labels[wb + r] : -1;
+    if (r < nrows) k = k < 0 ? 0 : (k >= s.kmax ? s.kmax - 1 : k);
+    keys[r] = (int)k;
+  }
+  __syncthreads();
+
+  const uint32_t part_s = kc_smem_u32(part), cs_s = kc_smem_u32(Cs), xt_s = kc_smem_u32(XT);
+  const int tx = tid & 7, ty = tid >> 3;
+  for (int it = 0; it < s.iterations; ++it) {
+    // ---- partial sums of this rank's rows, one warp per bin (mstep_small_bin's warp loop)
+    for (int k = warp; k < s.kmax && !(s.exp_flags & 1); k += ES_THREADS / 32) {
+      double acc[NV];
+      float run[NV];
+#pragma unroll
+      for (int m = 0; m < NV; ++m) { acc[m] = 0.0; run[m] = 0.f; }
+      int in_run = 0;
+      for (int g0 = 0; g0 < nrows; g0 += 32) {
+        unsigned hit = __ballot_sync(FULL, g0 + lane < nrows && keys[g0 + lane] == k);
+        if (s.exp_flags & 8) hit = 0;
+        while (hit) {
+          // four members' rows in flight (the loop is a chain of shared-memory latencies); added in index order
+          int jj[4];
+          float v[4][NV];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            jj[u] = hit ? __ffs(hit) - 1 : -1;
+            hit &= hit - 1;
+            const uint32_t col = xt_s + 4u * (uint32_t)(lane * ldr + g0 + (jj[u] >= 0 ? jj[u] : 0));
+#pragma unroll
+            for (int m = 0; m < NV; ++m) {
+              // unconditional loads (a conditional asm load becomes a branch): an absent member re-reads row g0 and is
+              // not added; feature blocks beyond dp (inside the shared-memory window) are zeroed by the select
+              const float t = kc_lds(col + 128u * (uint32_t)(min(32 * m, dp - 32) / 32 * ldr));
+              v[u][m] = 32 * m < dp ? t : 0.f;                       // features dim..dp-1 hold zeros
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (jj[u] >= 0) {
+#pragma unroll
+              for (int m = 0; m < NV; ++m) run[m] += v[u][m];
+              if (++in_run == 32) {
+#pragma unroll
+                for (int m = 0; m < NV; ++m) { acc[m] += (double)run[m]; run[m] = 0.f; }
+                in_run = 0;
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < NV; ++m) part[(size_t)k * NV * 32 + lane + 32 * m] = acc[m] + (double)run[m];
+    }
+    kc_sync();
+    // ---- centroids: bin k is finished by rank k % 8 (partials in rank order) and written into every rank's copy
+    for (int k = (int)rank + KC_RANKS * warp; k < s.kmax && !(s.exp_flags & 2); k += KC_RANKS * (ES_THREADS / 32)) {
+      float f[NV];
+      float ss = 0.f;
+#pragma unroll
+      for (int m = 0; m < NV; ++m) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < KC_RANKS; ++w)
+          a += kc_ld_f64(kc_mapa(part_s + (uint32_t)(((size_t)k * NV * 32 + lane + 32 * m) * sizeof(double)), w));
+        f[m] = (float)a;
+        if (lane + 32 * m < s.dim) ss = fmaf(f[m], f[m], ss);
+      }
+      const float n = safe_norm(warp_sum(ss));
+#pragma unroll
+      for (int m = 0; m < NV; ++m) {
+        const int d = lane + 32 * m;
+        if (d < s.dim) {
+          const float c = f[m] / n;
+          if (k < CK) {
+#pragma unroll
+            for (int w = 0; w < KC_RANKS; ++w) kc_st_f32(kc_mapa(cs_s + (uint32_t)(((size_t)k * ld + d) * sizeof(float)), w), c);
+          }
+          if (s.centroids_out && it == s.iterations - 1) s.centroids_out[((int64_t)seg * s.kmax + k) * s.dim + d] = c;
+        }
+      }
+    }
+    kc_sync();
+    for (int i = tid; i < dp * CK; i += ES_THREADS) CT[i] = Cs[(size_t)(i % CK) * ld + i / CK];      // local transpose
+    __syncthreads();
+    // ---- assignment of this rank's rows, 128 at a time: thread (ty, tx) = rows 4 ty .. 4 ty + 3, columns 16 j + 2 tx, + 1
+    // (the same fmaf chain over the features as estep_small_tile, so the same products)
+    for (int r0 = 0; r0 < nrows && !(s.exp_flags & 4); r0 += KC_TILE) {
+      const int np = min(KC_TILE, nrows - r0);
+      float acc[4][2 * NJ];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2 * NJ; ++j) acc[i][j] = 0.f;
+      const float* xp = XT + min(r0 + 4 * ty, L.rows_pad - 4);      // row groups beyond the rank's rows recompute the last one
+      const float* cp = CT + 2 * tx;
+#pragma unroll 4
+      for (int dd = 0; dd < dp; ++dd) {
+        const float* xq = xp + (size_t)dd * ldr;
+        const float xs[4] = {xq[0], xq[1], xq[2], xq[3]};
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const float2 cb = *reinterpret_cast<const float2*>(cp + (size_t)dd * CK + 16 * j);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[i][2 * j] = fmaf(xs[i], cb.x, acc[i][2 * j]);
+            acc[i][2 * j + 1] = fmaf(xs[i], cb.y, acc[i][2 * j + 1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float bv = -FLT_MAX, sv = -FLT_MAX;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < 2 * NJ; ++j) {
+          const int k = 16 * (j >> 1) + 2 * tx + (j & 1);
+          if (k < K) merge_best(bv, bi, sv, acc[i][j], k, -FLT_MAX);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(FULL, bv, o);
+          const int oi = __shfl_xor_sync(FULL, bi, o);
+          const float osv = __shfl_xor_sync(FULL, sv, o);
+          merge_best(bv, bi, sv, ov, oi, osv);
+        }
+        if (tx == 0) {
+          const int px = 4 * ty + i;
+          best_v[px] = bv; second_v[px] = sv; best_i[px] = bi;
+        }
+      }
+      __syncthreads();
+      for (int px = warp; px < np; px += ES_THREADS / 32) {
+        int bi = best_i[px];
+        if (best_v[px] - second_v[px] <= s.thr) {            // warp-uniform: the float64 scan of every cluster
+          float xr[NV];
+#pragma unroll
+          for (int m = 0; m < NV; ++m) { const int d = lane + 32 * m; xr[m] = d < s.dim ? XT[(size_t)d * ldr + r0 + px] : 0.f; }
+          double bv = -DBL_MAX;
+          bi = 0x7fffffff;
+          for (int k = 0; k < K; ++k) {
+            double sum = 0.0;
+#pragma unroll
+            for (int m = 0; m < NV; ++m)
+              if (lane + 32 * m < s.dim) sum = fma((double)xr[m], (double)Cs[(size_t)k * ld + lane + 32 * m], sum);
+            sum = warp_sum(sum);
+            if (sum > bv || (sum == bv && k < bi)) { bv = sum; bi = k; }
+          }
+        }
+        if (lane == 0) keys[r0 + px] = bi;
+      }
+      __syncthreads();
+    }
+  }
+  for (int r = tid; r < nrows; r += ES_THREADS) s.labels_out[wb + r] = (int64_t)keys[r];
+  kc_sync();                    // no CTA leaves while another may still read its partials
+}
+
+template <int NV, int NJ>
+static int launch_cluster_kmeans(const ClusterKmArgs& s, int64_t max_seg_len, cudaStream_t st, bool* done) {
+  const int per = (int)kc_rows_per_rank(max_seg_len);
+  const size_t smem = KcLayout<NV, NJ>(s.dim, s.kmax, per).total;
+  if (smem > 220 * 1024) return HSG_OK;
+  auto kern = kmeans_cluster_kernel<NV, NJ>;
+  HSG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(s.S * KC_RANKS));
+  cfg.blockDim = dim3(ES_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = KC_RANKS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess || clusters < 1) {
+    cudaGetLastError();
+    return HSG_OK;              // no room for such a cluster on this device: the caller takes another path
+  }
+  ClusterKmArgs a = s;
+  a.per_max = per;
+  HSG_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  HSG_LAUNCH_CHECK();
+  *done = true;
+  return HSG_OK;
+}
+
 // one M-step of the k-means loop: full pass on the first iteration, afterwards delta or full
 // as decided on the device
 static int km_mstep(KmPlan& p, const float* x, const int64_t* seg_offsets, int it, bool incremental,
@@ -1017,6 +1342,22 @@ static int kmeans_impl(const float* x, int64_t N, int dim, const void* xh, int d
   const bool small = !incremental && !(flags & HSG_KMEANS_FULL_MSTEP) && max_seg_len <= KM_SMALL_MAX_SEG && dim <= 32 * 9 &&
                      (int64_t)S * kmax <= (1 << 20);
   static const bool no_persistent = getenv("HSG_KMEANS_NO_PERSISTENT") != nullptr;       // A/B switch for profiling only
+  static const bool no_cluster = getenv("HSG_KMEANS_NO_CLUSTER") != nullptr;              // A/B switch for profiling only
+  if (small && !runs && iterations > 0 && !no_cluster && (!use_tc || kmax <= 64) && kmax <= 64 && S <= (1 << 20)) {
+    // an image per thread-block cluster, resident in shared memory for all iterations
+    ClusterKmArgs ca;
+    ca.x = x; ca.dim = dim; ca.kmax = kmax; ca.S = S; ca.seg_offsets = seg_offsets; ca.seg_k = seg_k;
+    ca.init_labels = init_labels; ca.labels_out = labels_out; ca.centroids_out = centroids_out;
+    ca.iterations = iterations; ca.per_max = 0;
+    static const int cluster_exp = getenv("HSG_CLUSTER_EXP") ? atoi(getenv("HSG_CLUSTER_EXP")) : 0;
+    ca.exp_flags = cluster_exp;
+    ca.thr = 2.f * (dim + 2) * 5.9604645e-8f * 1.02f + 1e-7f;             // estep_simt's bound
+    bool done = false;
+    if (dim <= 32 * 5) rc = kmax <= 16 ? launch_cluster_kmeans<5, 1>(ca, max_seg_len, st, &done) : launch_cluster_kmeans<5, 4>(ca, max_seg_len, st, &done);
+    else rc = kmax <= 16 ? launch_cluster_kmeans<9, 1>(ca, max_seg_len, st, &done) : launch_cluster_kmeans<9, 4>(ca, max_seg_len, st, &done);
+    if (rc) return rc;
+    if (done) return HSG_OK;
+  }
   if (small && !runs && iterations > 0 && !no_persistent && (!use_tc || kmax <= 64)) {
     // launch-bound regime: the whole loop in one cooperative launch (fp32 CUDA-core E-step: at K <= 64 the products
     // of such a call are a few GFLOP, the launches were the cost)

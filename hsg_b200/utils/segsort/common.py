@@ -125,6 +125,9 @@ class _PrepOutputs(torch.autograd.Function):
     return gemb, None, None, None, None, None, None
 
 
+_LOC_CACHE = {}
+
+
 def _grid_init(num_clusters, hw, device):
   key = (int(num_clusters[0]), int(num_clusters[1]), int(hw[0]), int(hw[1]), str(device))
   hit = _GRID_CACHE.get(key)
@@ -159,7 +162,13 @@ def segment_by_kmeans_ex(embeddings, labels=None, num_clusters=[5, 5], cluster_i
   dev = embeddings.device
 
   if local_features is None:                                              # :313-317
-    loc = (generate_location_features((h, w), dev, 'float') - 0.5).contiguous()
+    # the same read-only map for every call of a given size: seven small torch launches otherwise, a third of the
+    # host time of a training-shape call
+    key = (h, w, str(dev))
+    loc = _LOC_CACHE.get(key)
+    if loc is None:
+      loc = (generate_location_features((h, w), dev, 'float') - 0.5).contiguous()
+      _LOC_CACHE[key] = loc
     loc_stride = 0
   else:
     lf = local_features
