@@ -248,7 +248,15 @@ def _check_gradients(r, title, per_tensor=True):
   d_ulp = float(np.median(moved)) if moved else 0.0
   print('reference with its inputs moved by one ulp (%d comparable runs): median distance to the unperturbed runs %.3e'
         % (len(r['perturbed']), d_ulp))
-  assert d_ours <= max(1e-5, SPREAD_FACTOR * max(d_ref, d_ulp)), (d_ours, d_ref, d_ulp)
+  # The distribution is bimodal, not just wide: a near-tie flipping inside a train-mode BatchNorm batch of 8 tokens puts
+  # a run into one of two modes.  When the reference's five runs split 4-1 the median run<->run distance is the small
+  # in-mode one; the patched step -- bit-reproducible, so always in the same mode -- is then either at that distance or at
+  # the cross-mode one from the median run (one full-suite run in six landed there).  A deviation the reference shows
+  # against ITSELF cannot count against the patched step, so the largest self-distance observed is admitted as it is
+  # (no factor on it).
+  d_self_max = max(pair + moved)
+  print('largest distance of the reference to itself (repeats and one-ulp runs): %.3e' % d_self_max)
+  assert d_ours <= max(1e-5, SPREAD_FACTOR * max(d_ref, d_ulp), d_self_max), (d_ours, d_ref, d_ulp, d_self_max)
 
 
 def test_patched_step_runs_native_kernels(stage1):
