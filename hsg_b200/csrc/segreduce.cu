@@ -332,6 +332,109 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_sum_kernel(
   if (cur >= 0) flush();
 }
 
+// ---------------------------------------------------------------- delta gather, lean inner loop
+// gather_sum_kernel<NV, 1> spends ~116 instructions per entry (r2 ncu: 127 M for 1.09 M entries, 2 IPC: the pass is
+// issue-bound, not DRAM-bound): a select and an address computation per element, a 64-bit shuffle pair per entry,
+// register copies around the bin-change branch.  Same work, same order of additions, for rows of 32*NVF + tail floats
+// (the D+2 rows of k-means): the (row, sign) of an entry travels as one 32-bit word, the full vectors load
+// unconditionally at immediate offsets, and the sign is a +-1.0 factor of a float64 FMA (acc + (-1)(double)v is the
+// same rounding as acc + (double)(-v)), so an element costs load + convert + FMA.
+template <int NVF>
+__global__ void __launch_bounds__(GATHER_WARPS * 32) gather_delta_lean_kernel(
+    const float* __restrict__ x, int dim, const int64_t* __restrict__ off, int S,
+    const int32_t* __restrict__ keys, const uint32_t* __restrict__ perm,
+    double* __restrict__ pieces, int32_t* __restrict__ piece_cnt, Gate gate,
+    const int64_t* __restrict__ eoff, const uint32_t* __restrict__ erow) {
+  constexpr int NV = NVF + 1;
+  if (gate.closed()) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t run = (int64_t)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
+  const int64_t j0 = run * SR_RUN;
+  const int64_t M = eoff[S];
+  if (j0 >= M) return;
+  const int n = (int)min((int64_t)SR_RUN, M - j0);
+  const bool tail_on = 32 * NVF + lane < dim;
+  const float* xl = x + lane;
+
+  uint32_t rs[2];          // global row (< 2^31) | remove bit
+  int key[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int64_t j = j0 + h * 32 + lane;
+    rs[h] = 0; key[h] = -1;
+    if (j < j0 + n) {
+      const int s = upper_bound_i64(eoff, S + 1, j) - 1;
+      const int64_t e = eoff[s] + perm[j];
+      const uint32_t r = erow[e];
+      rs[h] = (uint32_t)(off[s] + (int64_t)(r & 0x7fffffffu)) | (r & 0x80000000u);
+      key[h] = keys[e];
+    }
+  }
+
+  double acc[NV];
+#pragma unroll
+  for (int m = 0; m < NV; ++m) acc[m] = 0.0;
+  int cur = -1, cnt = 0;
+  auto flush = [&]() {
+    const int64_t id = run + cur;
+    double* dst = pieces + id * dim + lane;
+#pragma unroll
+    for (int m = 0; m < NVF; ++m) dst[32 * m] = acc[m];
+    if (tail_on) dst[32 * NVF] = acc[NVF];
+    if (lane == 0) piece_cnt[id] = cnt;
+  };
+
+  constexpr int U = 4;
+  for (int e0 = 0; e0 < n; e0 += U) {
+    float v[U][NV];
+    uint32_t rr[U];
+    int kk[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u;
+      rr[u] = __shfl_sync(FULL, e < 32 ? rs[0] : rs[1], e & 31);
+      kk[u] = __shfl_sync(FULL, e < 32 ? key[0] : key[1], e & 31);
+      if (e < n) {
+        const float* row = xl + (size_t)(rr[u] & 0x7fffffffu) * dim;
+#pragma unroll
+        for (int m = 0; m < NVF; ++m) v[u][m] = ld_stream(row + 32 * m);
+        v[u][NVF] = tail_on ? ld_stream(row + 32 * NVF) : 0.f;
+      }
+    }
+    // the usual batch: four entries of the bin that is already open -- straight-line code, the accumulators stay where
+    // they are (with the bin-change branch inside, the compiler copies all 18 accumulator registers per entry)
+    if (e0 + U <= n && kk[0] == cur && kk[1] == cur && kk[2] == cur && kk[3] == cur) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool neg = rr[u] >> 31;
+        const double sg = neg ? -1.0 : 1.0;
+        cnt += neg ? -1 : 1;
+#pragma unroll
+        for (int m = 0; m < NV; ++m) acc[m] = fma((double)v[u][m], sg, acc[m]);
+      }
+      continue;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (e0 + u < n) {
+        if (kk[u] != cur) {
+          if (cur >= 0) flush();
+          cur = kk[u];
+          cnt = 0;
+#pragma unroll
+          for (int m = 0; m < NV; ++m) acc[m] = 0.0;
+        }
+        const bool neg = rr[u] >> 31;
+        const double sg = neg ? -1.0 : 1.0;
+        cnt += neg ? -1 : 1;
+#pragma unroll
+        for (int m = 0; m < NV; ++m) acc[m] = fma((double)v[u][m], sg, acc[m]);
+      }
+    }
+  }
+  if (cur >= 0) flush();
+}
+
 // ---------------------------------------------------------------- combine
 constexpr int COMBINE_WARPS = 8;
 
@@ -678,6 +781,18 @@ int sr_sort_and_sum_gated(const SegReducePlan& p, const float* x, const int64_t*
   HSG_LAUNCH_CHECK();
   }
   ProfRange prof(PROF_MSTEP_GATHER, st);
+  static const bool no_lean = getenv("HSG_GATHER_NO_LEAN") != nullptr;       // A/B switch for profiling only
+  if (eoff && !p.exact && !no_lean && p.dim % 32 != 0 && (p.dim / 32 == 2 || p.dim / 32 == 4 || p.dim / 32 == 8)) {
+    const unsigned grid = (unsigned)ceil_div64(ceil_div64(p.N, SR_RUN), GATHER_WARPS);
+    double* p64 = reinterpret_cast<double*>(p.pieces);
+    switch (p.dim / 32) {
+      case 2: gather_delta_lean_kernel<2><<<grid, GATHER_WARPS * 32, 0, st>>>(x, p.dim, off, p.S, p.keys, p.perm, p64, p.piece_cnt, gate, eoff, erow); break;
+      case 4: gather_delta_lean_kernel<4><<<grid, GATHER_WARPS * 32, 0, st>>>(x, p.dim, off, p.S, p.keys, p.perm, p64, p.piece_cnt, gate, eoff, erow); break;
+      default: gather_delta_lean_kernel<8><<<grid, GATHER_WARPS * 32, 0, st>>>(x, p.dim, off, p.S, p.keys, p.perm, p64, p.piece_cnt, gate, eoff, erow); break;
+    }
+    HSG_LAUNCH_CHECK();
+    return HSG_OK;
+  }
   if (p.exact) return eoff ? gather_dispatch<3>(p, x, off, gate, eoff, erow, st)
                            : gather_dispatch<2>(p, x, off, gate, nullptr, nullptr, st);
   return eoff ? gather_dispatch<1>(p, x, off, gate, eoff, erow, st)
