@@ -26,6 +26,24 @@ _PACK = 1 << 31   # order-preserving packing of (semantic, instance) pairs
 
 
 # ---------------------------------------------------------------- local stage (per GPU)
+_RELABEL_TABLE_LIMIT = 1 << 28   # relabel.cu: presence table of num_images * kmax * n_label_values entries
+
+
+def _rank_triples_by_sort(batch_indices, cluster_indices, packed):
+  """Sort-based ranking of the distinct (batch, cluster, label) triples for the shapes whose presence table
+  would not fit (many images x many dense cluster ids x many instance labels): two `torch.unique` passes on the
+  device, which is what the reference itself does (utils.py:181-194, segsort/common.py:82-86).  Same ids and
+  the same lexicographic order as the table path.  Returns (ids, proto_label, proto_batch, n)."""
+  cdiv = cluster_indices.max() + 1
+  groups, g = torch.unique(batch_indices * cdiv + cluster_indices, return_inverse=True)
+  label_values, l = torch.unique(packed, return_inverse=True)
+  nl = label_values.numel()
+  keys, ids = torch.unique(g * nl + l, return_inverse=True)
+  proto_label = label_values[keys % nl]
+  proto_batch = torch.div(groups[torch.div(keys, nl, rounding_mode='floor')], cdiv, rounding_mode='floor')
+  return ids, proto_label, proto_batch, keys.numel()
+
+
 def _local_rank_and_pool(embeddings, embeddings_with_loc, cluster_indices, batch_indices,
                          semantic_labels, instance_labels):
   """Dense ids of the distinct (batch, cluster, sem, inst) tuples on this GPU
@@ -37,9 +55,12 @@ def _local_rank_and_pool(embeddings, embeddings_with_loc, cluster_indices, batch
   b0, b1 = int(batch_indices.min()), int(batch_indices.max())
   kmax = int(cluster_indices.max()) + 1
   label_values = torch.unique(packed)
-  ids, pl, pb, _, npro = ops.relabel(batch_indices.long().contiguous(), cluster_indices.long().contiguous(),
-                                     packed.contiguous(), b0, b1 - b0 + 1, kmax, label_values)
-  n = int(npro)
+  if (b1 - b0 + 1) * kmax * label_values.numel() >= _RELABEL_TABLE_LIMIT:
+    ids, pl, pb, n = _rank_triples_by_sort(batch_indices.long(), cluster_indices.long(), packed)
+  else:
+    ids, pl, pb, _, npro = ops.relabel(batch_indices.long().contiguous(), cluster_indices.long().contiguous(),
+                                       packed.contiguous(), b0, b1 - b0 + 1, kmax, label_values)
+    n = int(npro)
   protos = ops.segment_reduce(embeddings, ids, n, REDUCE_NORMALIZE)
   protos_loc = ops.segment_reduce(embeddings_with_loc, ids, n, REDUCE_NORMALIZE)
   pl = pl[:n]

@@ -78,3 +78,28 @@ def test_prototype_exchange_matches_reference_gather(tmp_path):
   s0 = np.load(os.path.join(str(tmp_path), 'sums0.npy'))
   s1 = np.load(os.path.join(str(tmp_path), 'sums1.npy'))
   assert np.array_equal(s0, s1)
+
+
+def test_sorted_triple_ranking_matches_reference_order():
+  """The sort-based ranking that takes over when the presence table of the relabel kernel would not fit
+  (hsg_b200/models/utils.py: _rank_triples_by_sort) gives the ids, labels and batch indices of the reference's
+  two `unique` passes (hsg/models/utils.py:181-197, restated in oracle/protos.py)."""
+  import sys
+  sys.path.insert(0, ROOT)
+  from hsg_b200.models import utils as mu
+  from oracle import protos as o_protos
+  rng = np.random.RandomState(235)
+  n = 4000
+  bidx = np.sort(rng.randint(3, 9, n)).astype(np.int64)             # images 3..8, rank-major
+  cidx = (bidx - 3) * 7 + rng.randint(0, 7, n)                      # dense per-GPU cluster ids, some unused
+  sem = rng.randint(0, 5, n).astype(np.int64)
+  inst = rng.randint(0, 300, n).astype(np.int64)
+  emb = rng.randn(n, 4).astype(np.float32)
+  ref = o_protos.gather_clustering_and_update_prototypes([emb], [emb], [cidx], [bidx], [sem], [inst])
+  packed = torch.from_numpy(sem) * mu._PACK + torch.from_numpy(inst)
+  ids, pl, pb, cnt = mu._rank_triples_by_sort(torch.from_numpy(bidx), torch.from_numpy(cidx), packed)
+  assert cnt == ref[2].shape[0]
+  np.testing.assert_array_equal(ids.numpy(), ref[5][0])
+  np.testing.assert_array_equal((pl // mu._PACK).numpy(), ref[2])
+  np.testing.assert_array_equal((pl % mu._PACK).numpy(), ref[3])
+  np.testing.assert_array_equal(pb.numpy(), ref[4])
