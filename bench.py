@@ -529,6 +529,14 @@ def run_ours(args):
                      'traffic_source': traffic_src,
                      'algorithmic_bytes_per_launch': alg_bytes, 'ms_per_launch': kmeans_ms,
                      'share_of_step': kmeans_ms * args.iters / (ms / args.steps)}
+  # SURVEY 8d asks for both roofs per point: 2*N*D'*K flops per iteration against the sustained tensor figure.
+  # One fp16 pass over D'+padding columns is executed (the screening product; ties go to float64), so this is
+  # the smaller fraction at K = 256 -- but it is the E-step's own limiter (tensor pipe 58 % busy).
+  km_flops = 2.0 * n_pix * dp * args.grid ** 2
+  km_tf = km_flops / (kmeans_ms * 1e-3) / 1e12 if kmeans_ms > 0 else 0.0
+  km_peak_tf = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
+  roofline_kmeans['tensor'] = {'achieved': km_tf, 'peak': km_peak_tf, 'unit': 'TFLOP/s', 'frac': km_tf / km_peak_tf,
+                               'algorithmic_flops_per_launch': km_flops}
   # the dominant kernel of the step by time: the NCE forward (tcgen05, CTA pairs).  Algorithmic flops
   # 2*N*P*D; the kernel executes three fp16 passes of them to reach fp32-grade similarities.
   p_glob = world * args.images * args.grid ** 2

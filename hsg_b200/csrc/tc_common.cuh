@@ -71,6 +71,27 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// Warp-convergent issue: the whole warp executes the surrounding loop and one elected lane issues.  Inside an
+// `if (lane == 0)` branch the compiler cannot keep the descriptors in uniform registers and wraps every
+// tcgen05.mma / commit in an ELECT + R2UR.BROADCAST retry loop (~70 issue cycles per MMA); with convergent
+// control flow and warp-uniform operands the instruction issues straight from uniform registers.
+__device__ __forceinline__ void tc_mma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar) : "memory");
+}
+// a value the compiler may treat as warp-uniform (it is: loaded from a warp-uniform address)
+__device__ __forceinline__ int uniform_i32(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"

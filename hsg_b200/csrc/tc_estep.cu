@@ -66,9 +66,10 @@ struct TcParams {
 
 __device__ __forceinline__ bool item_rows(const TcParams& p, long long item, int count, int& seg,
                                           int64_t& row0, int& np) {
-  const int ti = (int)(item / p.sub);
+  const int sh = 31 - __clz(p.sub);                   // sub-tiles per tile: a power of two (checked on the host)
+  const int ti = (int)(item >> sh);
   if (ti >= count) return false;
-  const int64_t b = p.tiles.begin[ti] + (int64_t)(item % p.sub) * TC_BM;
+  const int64_t b = p.tiles.begin[ti] + (int64_t)((int)item & (p.sub - 1)) * TC_BM;
   const int64_t e = p.tiles.end[ti];
   if (b >= e) return false;
   seg = p.tiles.seg[ti];
@@ -553,13 +554,18 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loop and an elected lane issues (tc_mma_f16_elect): r2 timeline -- the issuing
+    // thread was busy 90 % of a 3 950-cycle tile while the tensor pipe needs 2 176, because every MMA and commit
+    // issued from inside a lane-0 branch went through an ELECT + R2UR.BROADCAST retry loop.
+    {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.kpad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0, cur_seg = -1, acc = 0, tl = 0;
       uint32_t phase = 0, bcount = 0, tl_phase = 0, acc_phase0 = 0, acc_phase1 = 0;
       for (long long item = i_begin; item < i_end; item += i_step) {
-        int seg, np; int64_t row0;
-        if (!item_rows(p, item, count, seg, row0, np)) continue;
+        int seg = 0, np; int64_t row0;
+        const bool have = item_rows(p, item, count, seg, row0, np);
+        if (!uniform_i32(have ? 1 : 0)) continue;             // the table entries come from warp-uniform addresses
+        seg = uniform_i32(seg);
         if (seg != cur_seg) {
           mbar_wait(bar_bfull, bcount & 1);
           ++bcount;
@@ -580,18 +586,18 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           if (!(p.exp_flags & 32)) {                       // timing experiment (32): the data path without the products
 #pragma unroll
             for (int k4 = 0; k4 < TC_BK / 16; ++k4)
-              tc_mma_f16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (j | k4) ? 1u : 0u);
+              tc_mma_f16_elect(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (j | k4) ? 1u : 0u);
           }
-          tc_commit(bar_empty + 8 * stage);
+          tc_commit_elect(bar_empty + 8 * stage);
           if (++stage == p.nst) { stage = 0; phase ^= 1; }
         }
         mbar_wait(bar_tlfull + 8 * tl, tl_phase);
         tc_fence_after();
         if (!(p.exp_flags & (1 | 32)))
-          tc_mma_f16(d_tmem, umma_desc(sAT + tl * TC_TAIL_BYTES, 256, 6), umma_desc(sBT, 256, 6), idesc, 1u);
-        tc_commit(bar_tlempty + 8 * tl);
+          tc_mma_f16_elect(d_tmem, umma_desc(sAT + tl * TC_TAIL_BYTES, 256, 6), umma_desc(sBT, 256, 6), idesc, 1u);
+        tc_commit_elect(bar_tlempty + 8 * tl);
         if (++tl == 2) { tl = 0; tl_phase ^= 1; }
-        tc_commit(bar_tfull + 8 * acc);
+        tc_commit_elect(bar_tfull + 8 * acc);
         if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
         acc ^= 1;
       }
@@ -603,17 +609,29 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int g = e >> 2;                          // accumulator / tile parity
     const int r = 32 * q + lane;                   // accumulator row = pixel within the tile
     const int kpad = p.kpad;
-    int cur_seg = -1, seq = 0;
+    // The loop is software-pipelined by one tile: the next tile's rows, its error bound (a global load whose
+    // latency the sweep used to wait for) and the centroid error are fetched while the list slots of this tile
+    // are still on their way back from the atomic.
+    int seq = 0;
     uint32_t acc_phase = 0;
-    float cerrmax = 0.f;
-    for (long long item = i_begin; item < i_end; item += i_step) {
-      int seg, np; int64_t row0;
-      if (!item_rows(p, item, count, seg, row0, np)) continue;
-      if (((seq++) & 1) != g) continue;
-      if (seg != cur_seg) { cerrmax = p.cerr_max[seg]; cur_seg = seg; }
+    long long item = i_begin;
+    auto next_tile = [&](int& seg_, int64_t& row0_, int& np_) -> bool {     // the next tile of this warp group
+      while (item < i_end) {
+        const long long it = item;
+        item += i_step;
+        if (!item_rows(p, it, count, seg_, row0_, np_)) continue;
+        if (((seq++) & 1) != g) continue;
+        return true;
+      }
+      return false;
+    };
+    int seg = 0, np = 0; int64_t row0 = 0;
+    bool have = next_tile(seg, row0, np);
+    float xe = 0.f, cerrmax = 0.f;
+    if (have) { xe = r < np ? p.xerr[row0 + r] : 0.f; cerrmax = p.cerr_max[seg]; }
+    while (have) {
       const int64_t pix = row0 + r;
       const bool inb = r < np;
-      const float xe = inb ? p.xerr[pix] : 0.f;
       const float thr = 2.f * (xe * 1.001f + cerrmax * 1.001f + TC1_EPS_CONST);
 
       long long c0 = timing ? clock64() : 0;
@@ -667,59 +685,68 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (lane == 0) mbar_arrive(bar_tempty + 8 * g);
       acc_phase ^= 1;
       if (timing) t_wait1 += clock64() - c0;          // sweep
-      if (p.exp_flags & 64) continue;                 // timing experiment: no labels, no list
-
-      const float t_final = run - thr;
-      int cnt = 0, first = 0;
+      const bool post = !(p.exp_flags & 64);          // timing experiment (64): no labels, no list
+      unsigned amb_mask = 0;
+      int slot_base = 0, cnt = 0;
+      bool amb = false;
+      if (post) {
+        const float t_final = run - thr;
+        int first = 0;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t hits = (c * 32 < kpad && cm[c] >= t_final) ? ~mk[c] : 0u;
-        mk[c] = hits;
-        if (cnt == 0 && hits) first = c * 32 + __clz(hits);
-        cnt += __popc(hits);
-      }
-      bool amb = inb && cnt > 1;
-      if (inb) p.keys_out[pix] = seg * p.kmax + first;
-      // Ambiguous rows.  The kernel is paced by the tensor pipe and this warp idles ~2/3 of a tile period, so up
-      // to TC1_INLINE rows per warp and tile are settled right here (same rule as estep_fixup: float64 dot
-      // products of the fp32 row with the fp32 centroids of the listed candidates, fixed order, ties to the
-      // lowest index); the rest -- the bulk of the first two iterations -- goes to the list as before.
-      if (p.x32) {
-        unsigned todo = __ballot_sync(FULL, amb && cnt <= FIX_MAX_CAND);
-        for (int n_in = 0; todo && n_in < TC1_INLINE; ++n_in) {
-          const int src = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const int64_t apix = __shfl_sync(FULL, pix, src);
-          const float* xrow = p.x32 + apix * p.dim32;
-          const float* cbase = p.c32 + (int64_t)seg * p.kmax * p.dim32;
-          float xr[9];
-#pragma unroll
-          for (int m = 0; m < 9; ++m) { const int d = lane + 32 * m; xr[m] = d < p.dim32 ? ld_stream(xrow + d) : 0.f; }
-          double bv = -DBL_MAX;
-          int bi = 0x7fffffff;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint32_t hits = __shfl_sync(FULL, mk[c], src);
-            while (hits) {
-              const int jb = __clz(hits);
-              hits &= ~(0x80000000u >> jb);
-              const int k = c * 32 + jb;
-              const float* cr = cbase + (int64_t)min(k, p.kmax - 1) * p.dim32;
-              double sacc = 0.0;
-#pragma unroll
-              for (int m = 0; m < 9; ++m) { const int d = lane + 32 * m; if (d < p.dim32) sacc = fma((double)xr[m], (double)cr[d], sacc); }
-              sacc = warp_sum(sacc);
-              if (k < p.kmax && (sacc > bv || (sacc == bv && k < bi))) { bv = sacc; bi = k; }
-            }
-          }
-          if (lane == src) { p.keys_out[pix] = seg * p.kmax + bi; amb = false; }
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t hits = (c * 32 < kpad && cm[c] >= t_final) ? ~mk[c] : 0u;
+          mk[c] = hits;
+          if (cnt == 0 && hits) first = c * 32 + __clz(hits);
+          cnt += __popc(hits);
         }
+        amb = inb && cnt > 1;
+        if (inb) p.keys_out[pix] = seg * p.kmax + first;
+        // Ambiguous rows, optional in-kernel re-decision (HSG_ESTEP_INLINE; off by default: measured slower): up
+        // to TC1_INLINE rows per warp and tile are settled right here (same rule as estep_fixup: float64 dot
+        // products of the fp32 row with the fp32 centroids of the listed candidates, fixed order, ties to the
+        // lowest index); the rest goes to the list.
+        if (p.x32) {
+          unsigned todo = __ballot_sync(FULL, amb && cnt <= FIX_MAX_CAND);
+          for (int n_in = 0; todo && n_in < TC1_INLINE; ++n_in) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t apix = __shfl_sync(FULL, pix, src);
+            const float* xrow = p.x32 + apix * p.dim32;
+            const float* cbase = p.c32 + (int64_t)seg * p.kmax * p.dim32;
+            float xr[9];
+#pragma unroll
+            for (int m = 0; m < 9; ++m) { const int d = lane + 32 * m; xr[m] = d < p.dim32 ? ld_stream(xrow + d) : 0.f; }
+            double bv = -DBL_MAX;
+            int bi = 0x7fffffff;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              uint32_t hits = __shfl_sync(FULL, mk[c], src);
+              while (hits) {
+                const int jb = __clz(hits);
+                hits &= ~(0x80000000u >> jb);
+                const int k = c * 32 + jb;
+                const float* cr = cbase + (int64_t)min(k, p.kmax - 1) * p.dim32;
+                double sacc = 0.0;
+#pragma unroll
+                for (int m = 0; m < 9; ++m) { const int d = lane + 32 * m; if (d < p.dim32) sacc = fma((double)xr[m], (double)cr[d], sacc); }
+                sacc = warp_sum(sacc);
+                if (k < p.kmax && (sacc > bv || (sacc == bv && k < bi))) { bv = sacc; bi = k; }
+              }
+            }
+            if (lane == src) { p.keys_out[pix] = seg * p.kmax + bi; amb = false; }
+          }
+        }
+        // one atomic per warp for the list slots (the counter is a single address shared by every SM); its
+        // result is not needed before the next tile's loads below are on their way
+        amb_mask = __ballot_sync(FULL, amb);
+        if (amb_mask && lane == 0) slot_base = atomicAdd(p.fix.count, __popc(amb_mask));
       }
-      // one atomic per warp for the list slots (the counter is a single address shared by every SM)
-      const unsigned amb_mask = __ballot_sync(FULL, amb);
+      // the next tile of this warp group: rows and error bounds (in flight during the list writes and the wait)
+      int nseg = 0, nnp = 0; int64_t nrow0 = 0;
+      const bool nhave = next_tile(nseg, nrow0, nnp);
+      float nxe = 0.f, ncm = 0.f;
+      if (nhave) { nxe = r < nnp ? p.xerr[nrow0 + r] : 0.f; ncm = p.cerr_max[nseg]; }
       if (amb_mask) {
-        int slot_base = 0;
-        if (lane == 0) slot_base = atomicAdd(p.fix.count, __popc(amb_mask));
         slot_base = __shfl_sync(FULL, slot_base, 0);
         if (amb) {
           const int slot = slot_base + __popc(amb_mask & ((1u << lane) - 1u));
@@ -746,6 +773,7 @@ estep_tc1_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           }
         }
       }
+      seg = nseg; row0 = nrow0; np = nnp; xe = nxe; cerrmax = ncm; have = nhave;
     }
   }
 
@@ -1198,6 +1226,7 @@ int estep_tc(const EStepArgs& a, const TcState& t, cudaStream_t st) {
   p.d16 = t.d16; p.kmax = a.kmax; p.kpad = t.kpad; p.kpad_total = t.kpad_total; p.n_pass = t.n_pass; p.pass = 0;
   p.st_val = t.st_val; p.st_tile = t.st_tile; p.xerr = t.xerr; p.cerr_max = t.cerr_max;
   p.tiles = a.tiles; p.sub = (int)(a.tiles.tile / TC_BM); p.items = (long long)a.tiles.bound * p.sub;
+  HSG_REQUIRE(p.sub > 0 && (p.sub & (p.sub - 1)) == 0, HSG_E_INVALID, "tensor-core E-step: tile of %lld rows", (long long)a.tiles.tile);
   p.keys_out = a.keys_out; p.fix = a.fix; p.dbg_sims = g_tc_debug_sims; p.xh = t.xh; p.pf_dist = 0; p.exp_flags = 0; p.dbg_clk = g_tc_debug_clk;
   static const bool no_inline = getenv("HSG_ESTEP_INLINE") == nullptr;      // opt-in: measured 2x SLOWER
   p.x32 = (a.dim <= 288 && !no_inline) ? a.x : nullptr; p.c32 = a.centroids; p.dim32 = a.dim;
