@@ -44,11 +44,11 @@ struct AttnBwdTcParams {
 __device__ __forceinline__ void mma3(uint32_t tmem, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc,
                                      bool fresh) {
 #pragma unroll
-  for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16(tmem, ah + 2 * k4, bh + 2 * k4, idesc, (fresh && k4 == 0) ? 0u : 1u);
+  for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16_elect(tmem, ah + 2 * k4, bh + 2 * k4, idesc, (fresh && k4 == 0) ? 0u : 1u);
 #pragma unroll
-  for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16(tmem, al + 2 * k4, bh + 2 * k4, idesc, 1u);
+  for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16_elect(tmem, al + 2 * k4, bh + 2 * k4, idesc, 1u);
 #pragma unroll
-  for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16(tmem, ah + 2 * k4, bl + 2 * k4, idesc, 1u);
+  for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16_elect(tmem, ah + 2 * k4, bl + 2 * k4, idesc, 1u);
 }
 
 // hi / lo fp16 halves of 16 values -> the two slabs of a (hi, lo) operand, row r, columns [16*c16, 16*c16 + 16) of a slab
@@ -104,16 +104,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   const uint32_t t_s = tmem_base, t_dp = tmem_base + 256, t_dq = tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(bar_in, 4 * AC_SLAB + 4 * k_bytes);
-      tma_load_2d(sQ, &tmap_q, 0, bh * p.L + row0, bar_in);
-      tma_load_2d(sQ + AC_SLAB, &tmap_q, AC_HD, bh * p.L + row0, bar_in);
-      tma_load_2d(sDO, &tmap_do, 0, bh * p.L + row0, bar_in);
-      tma_load_2d(sDO + AC_SLAB, &tmap_do, AC_HD, bh * p.L + row0, bar_in);
-      tma_load_2d(sK, &tmap_k, 0, bh * p.S, bar_in);
-      tma_load_2d(sK + k_bytes, &tmap_k, AC_HD, bh * p.S, bar_in);
-      tma_load_2d(sV, &tmap_v, 0, bh * p.S, bar_in);
-      tma_load_2d(sV + k_bytes, &tmap_v, AC_HD, bh * p.S, bar_in);
+    {   // the whole warp walks this role, an elected lane issues (tc_common.cuh: tc_mma_f16_elect)
+      mbar_expect_tx_elect(bar_in, 4 * AC_SLAB + 4 * k_bytes);
+      tma_load_2d_elect(sQ, &tmap_q, 0, bh * p.L + row0, bar_in);
+      tma_load_2d_elect(sQ + AC_SLAB, &tmap_q, AC_HD, bh * p.L + row0, bar_in);
+      tma_load_2d_elect(sDO, &tmap_do, 0, bh * p.L + row0, bar_in);
+      tma_load_2d_elect(sDO + AC_SLAB, &tmap_do, AC_HD, bh * p.L + row0, bar_in);
+      tma_load_2d_elect(sK, &tmap_k, 0, bh * p.S, bar_in);
+      tma_load_2d_elect(sK + k_bytes, &tmap_k, AC_HD, bh * p.S, bar_in);
+      tma_load_2d_elect(sV, &tmap_v, 0, bh * p.S, bar_in);
+      tma_load_2d_elect(sV + k_bytes, &tmap_v, AC_HD, bh * p.S, bar_in);
       mbar_wait(bar_in, 0);
       tc_fence_after();
       {
@@ -122,14 +122,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
              umma_desc(sK + k_bytes, 1024, 2), idesc, true);
         mma3(t_dp, umma_desc(sDO, 1024, 2), umma_desc(sDO + AC_SLAB, 1024, 2), umma_desc(sV, 1024, 2),
              umma_desc(sV + k_bytes, 1024, 2), idesc, true);
-        tc_commit(bar_s);
+        tc_commit_elect(bar_s);
       }
       // the phase-1 operands are dead once the products have completed: bring K^T into their place
       mbar_wait(bar_s, 0);
-      mbar_expect_tx(bar_t, 2 * nks * AC_TSLAB);
+      mbar_expect_tx_elect(bar_t, 2 * nks * AC_TSLAB);
       for (int ks = 0; ks < nks; ++ks) {
-        tma_load_2d(base + oKT + ks * AC_TSLAB, &tmap_kt, ks * 64, bh * AC_HD, bar_t);
-        tma_load_2d(base + oKT + (nks + ks) * AC_TSLAB, &tmap_kt, p.Sp + ks * 64, bh * AC_HD, bar_t);
+        tma_load_2d_elect(base + oKT + ks * AC_TSLAB, &tmap_kt, ks * 64, bh * AC_HD, bar_t);
+        tma_load_2d_elect(base + oKT + (nks + ks) * AC_TSLAB, &tmap_kt, p.Sp + ks * 64, bh * AC_HD, bar_t);
       }
       mbar_wait(bar_p, 0);
       mbar_wait(bar_t, 0);
@@ -140,7 +140,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           mma3(t_dq, umma_desc(base + oDS + ks * AC_SLAB, 1024, 2), umma_desc(base + oDS + (nks + ks) * AC_SLAB, 1024, 2),
                umma_desc(base + oKT + ks * AC_TSLAB, 1024, 2), umma_desc(base + oKT + (nks + ks) * AC_TSLAB, 1024, 2),
                idesc, ks == 0);
-        tc_commit(bar_o);
+        tc_commit_elect(bar_o);
       }
     }
   } else if (warp >= 2) {
@@ -257,7 +257,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
   const uint32_t t_s = tmem_base, t_dp = tmem_base + 128, t_dk = tmem_base + 256, t_dv = tmem_base + 320;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // the whole warp walks this role, an elected lane issues (tc_common.cuh: tc_mma_f16_elect)
       for (int half = 0; half < halves; ++half) {
         const uint32_t ph = half & 1;
         const int l0 = half * AC_BM;
@@ -266,15 +266,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
         const uint32_t oDS = 0, oPD = 2u * nls * AC_SLAB, oQT = 4u * nls * AC_SLAB, oDOT = oQT + 2u * nls * AC_TSLAB;
         // the previous half's second products still read the shared memory the loads below overwrite
         if (half > 0) mbar_wait(bar_o, ph ^ 1u);
-        mbar_expect_tx(bar_in, 4 * AC_SLAB + 4 * q_bytes);
-        tma_load_2d(sK, &tmap_k, 0, bh * p.S + key0, bar_in);
-        tma_load_2d(sK + AC_SLAB, &tmap_k, AC_HD, bh * p.S + key0, bar_in);
-        tma_load_2d(sV, &tmap_v, 0, bh * p.S + key0, bar_in);
-        tma_load_2d(sV + AC_SLAB, &tmap_v, AC_HD, bh * p.S + key0, bar_in);
-        tma_load_2d(sQ, &tmap_q, 0, bh * p.L + l0, bar_in);
-        tma_load_2d(sQ + q_bytes, &tmap_q, AC_HD, bh * p.L + l0, bar_in);
-        tma_load_2d(sDO, &tmap_do, 0, bh * p.L + l0, bar_in);
-        tma_load_2d(sDO + q_bytes, &tmap_do, AC_HD, bh * p.L + l0, bar_in);
+        mbar_expect_tx_elect(bar_in, 4 * AC_SLAB + 4 * q_bytes);
+        tma_load_2d_elect(sK, &tmap_k, 0, bh * p.S + key0, bar_in);
+        tma_load_2d_elect(sK + AC_SLAB, &tmap_k, AC_HD, bh * p.S + key0, bar_in);
+        tma_load_2d_elect(sV, &tmap_v, 0, bh * p.S + key0, bar_in);
+        tma_load_2d_elect(sV + AC_SLAB, &tmap_v, AC_HD, bh * p.S + key0, bar_in);
+        tma_load_2d_elect(sQ, &tmap_q, 0, bh * p.L + l0, bar_in);
+        tma_load_2d_elect(sQ + q_bytes, &tmap_q, AC_HD, bh * p.L + l0, bar_in);
+        tma_load_2d_elect(sDO, &tmap_do, 0, bh * p.L + l0, bar_in);
+        tma_load_2d_elect(sDO + q_bytes, &tmap_do, AC_HD, bh * p.L + l0, bar_in);
         mbar_wait(bar_in, ph);
         tc_fence_after();
         {
@@ -283,16 +283,16 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
                umma_desc(sQ + q_bytes, 1024, 2), idesc, true);
           mma3(t_dp, umma_desc(sV, 1024, 2), umma_desc(sV + AC_SLAB, 1024, 2), umma_desc(sDO, 1024, 2),
                umma_desc(sDO + q_bytes, 1024, 2), idesc, true);
-          tc_commit(bar_s);
+          tc_commit_elect(bar_s);
         }
         // the phase-1 operands are dead once the products have completed: bring Q^T, dO^T into their place
         mbar_wait(bar_s, ph);
-        mbar_expect_tx(bar_t, 4 * nls * AC_TSLAB);
+        mbar_expect_tx_elect(bar_t, 4 * nls * AC_TSLAB);
         for (int ls = 0; ls < nls; ++ls) {
-          tma_load_2d(base + oQT + ls * AC_TSLAB, &tmap_qt, l0 + ls * 64, bh * AC_HD, bar_t);
-          tma_load_2d(base + oQT + (nls + ls) * AC_TSLAB, &tmap_qt, p.Lp + l0 + ls * 64, bh * AC_HD, bar_t);
-          tma_load_2d(base + oDOT + ls * AC_TSLAB, &tmap_dot, l0 + ls * 64, bh * AC_HD, bar_t);
-          tma_load_2d(base + oDOT + (nls + ls) * AC_TSLAB, &tmap_dot, p.Lp + l0 + ls * 64, bh * AC_HD, bar_t);
+          tma_load_2d_elect(base + oQT + ls * AC_TSLAB, &tmap_qt, l0 + ls * 64, bh * AC_HD, bar_t);
+          tma_load_2d_elect(base + oQT + (nls + ls) * AC_TSLAB, &tmap_qt, p.Lp + l0 + ls * 64, bh * AC_HD, bar_t);
+          tma_load_2d_elect(base + oDOT + ls * AC_TSLAB, &tmap_dot, l0 + ls * 64, bh * AC_HD, bar_t);
+          tma_load_2d_elect(base + oDOT + (nls + ls) * AC_TSLAB, &tmap_dot, p.Lp + l0 + ls * 64, bh * AC_HD, bar_t);
         }
         mbar_wait(bar_p, ph);
         mbar_wait(bar_t, ph);
@@ -308,7 +308,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
                  umma_desc(base + oDOT + ls * AC_TSLAB, 1024, 2), umma_desc(base + oDOT + (nls + ls) * AC_TSLAB, 1024, 2),
                  idesc, fresh);
           }
-          tc_commit(bar_o);
+          tc_commit_elect(bar_o);
         }
       }
     }

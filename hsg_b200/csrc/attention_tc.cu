@@ -130,27 +130,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_vt, const AttnTcPara
   const uint32_t t_s = tmem_base, t_o = tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // the whole warp walks this role, an elected lane issues (tc_common.cuh: tc_mma_f16_elect)
       // ---- S = Q K^T (three passes)
       {
         const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Sp >> 3) << 17) | ((uint32_t)(AC_BM >> 4) << 24);
         const uint64_t qh = umma_desc(sQ, 1024, 2), ql = umma_desc(sQ + AC_SLAB, 1024, 2);
         const uint64_t kh = umma_desc(sK, 1024, 2), kl = umma_desc(sK + k_bytes, 1024, 2);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16(t_s, qh + 2 * k4, kh + 2 * k4, idesc, k4 ? 1u : 0u);
+        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16_elect(t_s, qh + 2 * k4, kh + 2 * k4, idesc, k4 ? 1u : 0u);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16(t_s, ql + 2 * k4, kh + 2 * k4, idesc, 1u);
+        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16_elect(t_s, ql + 2 * k4, kh + 2 * k4, idesc, 1u);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16(t_s, qh + 2 * k4, kl + 2 * k4, idesc, 1u);
-        tc_commit(bar_s);
+        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16_elect(t_s, qh + 2 * k4, kl + 2 * k4, idesc, 1u);
+        tc_commit_elect(bar_s);
       }
       // ---- the Q / K bytes are free once S is complete: V^T slabs of the first ring round
       mbar_wait(bar_s, 0);
       auto load_v = [&](int ks) {
         const uint32_t slot = (uint32_t)(ks & 1);
-        mbar_expect_tx(bar_v + 8 * slot, 2 * v_slab);
-        tma_load_2d(sV + slot * 2 * v_slab, &tmap_vt, ks * 64, bh * AC_HD, bar_v + 8 * slot);
-        tma_load_2d(sV + slot * 2 * v_slab + v_slab, &tmap_vt, p.Sp + ks * 64, bh * AC_HD, bar_v + 8 * slot);
+        mbar_expect_tx_elect(bar_v + 8 * slot, 2 * v_slab);
+        tma_load_2d_elect(sV + slot * 2 * v_slab, &tmap_vt, ks * 64, bh * AC_HD, bar_v + 8 * slot);
+        tma_load_2d_elect(sV + slot * 2 * v_slab + v_slab, &tmap_vt, p.Sp + ks * 64, bh * AC_HD, bar_v + 8 * slot);
       };
       for (int ks = 0; ks < nring; ++ks) load_v(ks);
       // ---- O += P_ks V_ks (three passes) as the slabs of probabilities arrive
@@ -163,13 +163,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_vt, const AttnTcPara
         const uint64_t pdh = umma_desc(sP + slot * 2 * AC_SLAB, 1024, 2), pdl = umma_desc(sP + slot * 2 * AC_SLAB + AC_SLAB, 1024, 2);
         const uint64_t vh = umma_desc(sV + slot * 2 * v_slab, 1024, 2), vl = umma_desc(sV + slot * 2 * v_slab + v_slab, 1024, 2);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16(t_o, pdh + 2 * k4, vh + 2 * k4, idesc, (ks || k4) ? 1u : 0u);
+        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16_elect(t_o, pdh + 2 * k4, vh + 2 * k4, idesc, (ks || k4) ? 1u : 0u);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16(t_o, pdl + 2 * k4, vh + 2 * k4, idesc, 1u);
+        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16_elect(t_o, pdl + 2 * k4, vh + 2 * k4, idesc, 1u);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16(t_o, pdh + 2 * k4, vl + 2 * k4, idesc, 1u);
-        tc_commit(bar_free + 8 * slot);
-        if (ks == nks - 1) tc_commit(bar_o);
+        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16_elect(t_o, pdh + 2 * k4, vl + 2 * k4, idesc, 1u);
+        tc_commit_elect(bar_free + 8 * slot);
+        if (ks == nks - 1) tc_commit_elect(bar_o);
         if (ks >= 1 && ks + 1 < nks) {            // the slot of slab ks-1 is free once its products are done: V^T of slab ks+1
           mbar_wait(bar_free + 8 * (slot ^ 1u), (uint32_t)((ks - 1) >> 1) & 1u);
           load_v(ks + 1);

@@ -74,7 +74,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int n_k = p.K / GT_BK;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // the whole warp walks the loop, an elected lane issues the copies
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -82,17 +82,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int ks = 0; ks < n_k; ++ks) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t s0 = base + stage * stage_bytes;
-          mbar_expect_tx(bar_full + 8 * stage, 2 * a_bytes + 2 * b_bytes);
-          tma_load_2d(s0, &tmap_a, ks * GT_BK, row0, bar_full + 8 * stage);                       // A hi
-          tma_load_2d(s0 + a_bytes, &tmap_a, p.K + ks * GT_BK, row0, bar_full + 8 * stage);       // A lo
-          tma_load_2d(s0 + b_off, &tmap_b, ks * GT_BK, 0, bar_full + 8 * stage);                  // B hi
-          tma_load_2d(s0 + b_off + b_stride, &tmap_b, p.K + ks * GT_BK, 0, bar_full + 8 * stage); // B lo
+          mbar_expect_tx_elect(bar_full + 8 * stage, 2 * a_bytes + 2 * b_bytes);
+          tma_load_2d_elect(s0, &tmap_a, ks * GT_BK, row0, bar_full + 8 * stage);                       // A hi
+          tma_load_2d_elect(s0 + a_bytes, &tmap_a, p.K + ks * GT_BK, row0, bar_full + 8 * stage);       // A lo
+          tma_load_2d_elect(s0 + b_off, &tmap_b, ks * GT_BK, 0, bar_full + 8 * stage);                  // B hi
+          tma_load_2d_elect(s0 + b_off + b_stride, &tmap_b, p.K + ks * GT_BK, 0, bar_full + 8 * stage); // B lo
           if (++stage == p.nst) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the whole warp walks the loop, an elected lane issues (tc_common.cuh: tc_mma_f16_elect)
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(GT_BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, seq = 0;
@@ -111,15 +111,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t ah = umma_desc(s0, 1024, 2), al = umma_desc(s0 + a_bytes, 1024, 2);
           const uint64_t bh = umma_desc(s0 + b_off, 1024, 2), bl = umma_desc(s0 + b_off + b_stride, 1024, 2);
 #pragma unroll
-          for (int k4 = 0; k4 < GT_BK / 16; ++k4) { tc_mma_f16(d_tmem, ah + 2 * k4, bh + 2 * k4, idesc, first ? 0u : 1u); first = 0; }
+          for (int k4 = 0; k4 < GT_BK / 16; ++k4) { tc_mma_f16_elect(d_tmem, ah + 2 * k4, bh + 2 * k4, idesc, first ? 0u : 1u); first = 0; }
 #pragma unroll
-          for (int k4 = 0; k4 < GT_BK / 16; ++k4) tc_mma_f16(d_tmem, al + 2 * k4, bh + 2 * k4, idesc, 1u);
+          for (int k4 = 0; k4 < GT_BK / 16; ++k4) tc_mma_f16_elect(d_tmem, al + 2 * k4, bh + 2 * k4, idesc, 1u);
 #pragma unroll
-          for (int k4 = 0; k4 < GT_BK / 16; ++k4) tc_mma_f16(d_tmem, ah + 2 * k4, bl + 2 * k4, idesc, 1u);
-          tc_commit(bar_empty + 8 * stage);
+          for (int k4 = 0; k4 < GT_BK / 16; ++k4) tc_mma_f16_elect(d_tmem, ah + 2 * k4, bl + 2 * k4, idesc, 1u);
+          tc_commit_elect(bar_empty + 8 * stage);
           if (++stage == p.nst) { stage = 0; phase ^= 1; }
         }
-        tc_commit(bar_tfull + 8 * acc);
+        tc_commit_elect(bar_tfull + 8 * acc);
        }
       }
     }
@@ -241,7 +241,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int64_t items = n_tiles * p.ksplit;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // the whole warp walks the loop, an elected lane issues the copies
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
@@ -253,22 +253,22 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t s0 = base + stage * stage_bytes;
           const uint32_t bar = bar_full + 8 * stage;
-          mbar_expect_tx(bar, stage_bytes);
+          mbar_expect_tx_elect(bar, stage_bytes);
           const int row = (int)(kk * GT_BK);
           for (int h = 0; h < 2; ++h) {
-            tma_load_2d(s0 + h * BOX, &tmap_a, col0 + 64 * h, row, bar);                          // A hi
-            tma_load_2d(s0 + a_bytes + h * BOX, &tmap_a, p.a_lo_col + col0 + 64 * h, row, bar);   // A lo
+            tma_load_2d_elect(s0 + h * BOX, &tmap_a, col0 + 64 * h, row, bar);                          // A hi
+            tma_load_2d_elect(s0 + a_bytes + h * BOX, &tmap_a, p.a_lo_col + col0 + 64 * h, row, bar);   // A lo
           }
           for (int h = 0; h < nb; ++h) {
-            tma_load_2d(s0 + 2 * a_bytes + h * BOX, &tmap_b, 64 * h, (int)p.b_row0 + row, bar);                        // B hi
-            tma_load_2d(s0 + 2 * a_bytes + b_bytes + h * BOX, &tmap_b, p.b_lo_col + 64 * h, (int)p.b_row0 + row, bar); // B lo
+            tma_load_2d_elect(s0 + 2 * a_bytes + h * BOX, &tmap_b, 64 * h, (int)p.b_row0 + row, bar);                        // B hi
+            tma_load_2d_elect(s0 + 2 * a_bytes + b_bytes + h * BOX, &tmap_b, p.b_lo_col + 64 * h, (int)p.b_row0 + row, bar); // B lo
           }
           if (++stage == p.nst) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the whole warp walks the loop, an elected lane issues (tc_common.cuh: tc_mma_f16_elect)
       // D = f32, A = B = f16, BOTH MN-major (bits 15, 16)
       const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(GT_BM >> 4) << 24);
       int stage = 0;
@@ -292,15 +292,15 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint64_t bh = umma_desc_mn(s0 + 2 * a_bytes, BOX, 1024), bl = umma_desc_mn(s0 + 2 * a_bytes + b_bytes, BOX, 1024);
             // one K = 16 step = two 8-row groups = 2048 bytes = 128 descriptor units
 #pragma unroll
-            for (int k4 = 0; k4 < GT_BK / 16; ++k4) { tc_mma_f16(d_tmem, ah + 128 * k4, bh + 128 * k4, idesc, first ? 0u : 1u); first = 0; }
+            for (int k4 = 0; k4 < GT_BK / 16; ++k4) { tc_mma_f16_elect(d_tmem, ah + 128 * k4, bh + 128 * k4, idesc, first ? 0u : 1u); first = 0; }
 #pragma unroll
-            for (int k4 = 0; k4 < GT_BK / 16; ++k4) tc_mma_f16(d_tmem, al + 128 * k4, bh + 128 * k4, idesc, 1u);
+            for (int k4 = 0; k4 < GT_BK / 16; ++k4) tc_mma_f16_elect(d_tmem, al + 128 * k4, bh + 128 * k4, idesc, 1u);
 #pragma unroll
-            for (int k4 = 0; k4 < GT_BK / 16; ++k4) tc_mma_f16(d_tmem, ah + 128 * k4, bl + 128 * k4, idesc, 1u);
-            tc_commit(bar_empty + 8 * stage);
+            for (int k4 = 0; k4 < GT_BK / 16; ++k4) tc_mma_f16_elect(d_tmem, ah + 128 * k4, bl + 128 * k4, idesc, 1u);
+            tc_commit_elect(bar_empty + 8 * stage);
             if (++stage == p.nst) { stage = 0; phase ^= 1; }
           }
-          tc_commit(bar_tfull + 8 * acc);
+          tc_commit_elect(bar_tfull + 8 * acc);
         }
       }
     }

@@ -200,23 +200,23 @@ nce_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    {   // the whole warp walks the loop, an elected lane issues the copies
       const uint32_t l_afull = mapa_cluster(bar_afull, 0);
       const uint32_t l_bfull = mapa_cluster(bar_bfull, 0);
       int stage = 0;
       uint32_t phase = 0, a_round = 0;
       for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs, ++a_round) {
         mbar_wait(bar_aempty, (a_round & 1) ^ 1);               // previous pixel tile fully consumed
-        if (leader) mbar_expect_tx(bar_afull, 2 * 2 * nslab * NT_SLAB);     // both CTAs' rows
+        if (leader) mbar_expect_tx_elect(bar_afull, 2 * 2 * nslab * NT_SLAB);     // both CTAs' rows
         const int row0 = (int)(pt * 2 * NT_BM + rank * NT_BM);
         for (int j = 0; j < 2 * nslab; ++j)
-          tma_load_2d_pair(sA + j * NT_SLAB, &tmap_a, j * NT_BK, row0, l_afull);
+          tma_load_2d_pair_elect(sA + j * NT_SLAB, &tmap_a, j * NT_BK, row0, l_afull);
         for (int nt = 0; nt < n_ntiles; ++nt) {
           const int prow0 = nt * N2_BN + (int)rank * NT_BN;
           for (int j = 0; j < 2 * nslab; ++j) {                  // ph_0.., then pl_0..
             mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
-            if (leader) mbar_expect_tx(bar_bfull + 8 * stage, 2 * NT_SLAB);
-            tma_load_2d_pair(sB + stage * NT_SLAB, &tmap_b, j * NT_BK, prow0, l_bfull + 8 * stage);
+            if (leader) mbar_expect_tx_elect(bar_bfull + 8 * stage, 2 * NT_SLAB);
+            tma_load_2d_pair_elect(sB + stage * NT_SLAB, &tmap_b, j * NT_BK, prow0, l_bfull + 8 * stage);
             if (++stage == p.nstb) { stage = 0; phase ^= 1; }
           }
         }
@@ -224,7 +224,8 @@ nce_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader only) =====================
-    if (lane == 0 && leader) {
+    // the whole warp walks the loop, an elected lane issues (tc_common.cuh: tc_mma_f16_elect)
+    if (uniform_i32(leader ? 1 : 0)) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(N2_BN >> 3) << 17) | ((uint32_t)((2 * NT_BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, a_round = 0, seq = 0;
@@ -249,16 +250,16 @@ nce_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               const uint64_t ad = umma_desc(sA + (ps * nslab + js) * NT_SLAB, 1024, 2);
 #pragma unroll
               for (int k4 = 0; k4 < NT_BK / 16; ++k4) {
-                tc_mma_f16_pair(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, first ? 0u : 1u);   // +32 bytes per K=16 step
+                tc_mma_f16_pair_elect(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, first ? 0u : 1u);   // +32 bytes per K=16 step
                 first = 0;
               }
             }
-            tc_commit_pair(bar_bempty + 8 * stage);
+            tc_commit_pair_elect(bar_bempty + 8 * stage);
             if (++stage == p.nstb) { stage = 0; phase ^= 1; }
           }
-          tc_commit_pair(bar_tfull + 8 * acc);
+          tc_commit_pair_elect(bar_tfull + 8 * acc);
         }
-        tc_commit_pair(bar_aempty);                                // arrives when every MMA of this pixel tile retired
+        tc_commit_pair_elect(bar_aempty);                                // arrives when every MMA of this pixel tile retired
       }
     }
   } else if (warp >= 4) {
@@ -424,7 +425,7 @@ nce_grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    {   // the whole warp walks the loop, an elected lane issues the copies
       const uint32_t l_afull = mapa_cluster(bar_afull, 0);
       const uint32_t l_bfull = mapa_cluster(bar_bfull, 0);
       int stage = 0;
@@ -435,25 +436,26 @@ nce_grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int nt = (int)(it - pt * n_ntiles);
         if (pt != cur_pt) {
           mbar_wait(bar_aempty, (a_round & 1) ^ 1);
-          if (leader) mbar_expect_tx(bar_afull, 2 * 2 * nslab * NT_SLAB);
+          if (leader) mbar_expect_tx_elect(bar_afull, 2 * 2 * nslab * NT_SLAB);
           const int row0 = (int)(g.i_begin + pt * 2 * NT_BM + rank * NT_BM);
           for (int j = 0; j < 2 * nslab; ++j)
-            tma_load_2d_pair(sA + j * NT_SLAB, &tmap_a, j * NT_BK, row0, l_afull);
+            tma_load_2d_pair_elect(sA + j * NT_SLAB, &tmap_a, j * NT_BK, row0, l_afull);
           cur_pt = pt;
           ++a_round;
         }
         const int prow0 = nt * N2_BN + (int)rank * NT_BN;
         for (int j = 0; j < 2 * nslab; ++j) {
           mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
-          if (leader) mbar_expect_tx(bar_bfull + 8 * stage, 2 * NT_SLAB);
-          tma_load_2d_pair(sB + stage * NT_SLAB, &tmap_b, j * NT_BK, prow0, l_bfull + 8 * stage);
+          if (leader) mbar_expect_tx_elect(bar_bfull + 8 * stage, 2 * NT_SLAB);
+          tma_load_2d_pair_elect(sB + stage * NT_SLAB, &tmap_b, j * NT_BK, prow0, l_bfull + 8 * stage);
           if (++stage == p.nstb) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader only) =====================
-    if (lane == 0 && leader) {
+    // the whole warp walks the loop, an elected lane issues (tc_common.cuh: tc_mma_f16_elect)
+    if (uniform_i32(leader ? 1 : 0)) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(N2_BN >> 3) << 17) | ((uint32_t)((2 * NT_BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, a_round = 0, seq = 0;
@@ -482,16 +484,16 @@ nce_grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint64_t ad = umma_desc(sA + (ps * nslab + js) * NT_SLAB, 1024, 2);
 #pragma unroll
             for (int k4 = 0; k4 < NT_BK / 16; ++k4) {
-              tc_mma_f16_pair(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, first ? 0u : 1u);
+              tc_mma_f16_pair_elect(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, first ? 0u : 1u);
               first = 0;
             }
           }
-          tc_commit_pair(bar_bempty + 8 * stage);
+          tc_commit_pair_elect(bar_bempty + 8 * stage);
           if (++stage == p.nstb) { stage = 0; phase ^= 1; }
         }
-        tc_commit_pair(bar_tfull + 8 * acc);
+        tc_commit_pair_elect(bar_tfull + 8 * acc);
         // last item of this pixel tile (in this pair's slice): its rows may be replaced once these MMAs retire
-        if (it + 1 == it1 || (it + 1) / n_ntiles != pt) tc_commit_pair(bar_aempty);
+        if (it + 1 == it1 || (it + 1) / n_ntiles != pt) tc_commit_pair_elect(bar_aempty);
       }
     }
   } else if (warp >= 4) {
