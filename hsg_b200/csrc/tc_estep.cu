@@ -184,16 +184,16 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    {   // the whole warp walks the loop, an elected lane issues (tc_common.cuh: tc_mma_f16_elect)
+    // (lane-0 issue kept here: the multi-pass shapes are starved by their 16 re-reads of the pixel copy, and the
+    // convergent elected-lane form of the other kernels measured 1.8x SLOWER at D = 512, K = 2048)
+    if (lane == 0) {
       // instruction descriptor: D=f32, A=B=f16, both K-major, N=kpad, M=128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.kpad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0, cur_seg = -1, acc = 0, tl = 0;
       uint32_t phase = 0, bcount = 0, tl_phase = 0, acc_phase0 = 0, acc_phase1 = 0;
       for (long long item = i_begin; item < i_end; ++item) {
-        int seg = 0, np; int64_t row0;
-        const bool have = item_rows(p, item, count, seg, row0, np);
-        if (!uniform_i32(have ? 1 : 0)) continue;
-        seg = uniform_i32(seg);
+        int seg, np; int64_t row0;
+        if (!item_rows(p, item, count, seg, row0, np)) continue;
         if (seg != cur_seg) {
           mbar_wait(bar_bfull, bcount & 1);
           ++bcount;
@@ -209,17 +209,17 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           const uint64_t bd = umma_desc(sB + j * slab_b_bytes, 1024, 2);
 #pragma unroll
           for (int k4 = 0; k4 < TC_BK / 16; ++k4)                       // +32 bytes per K=16 step
-            tc_mma_f16_elect(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (j | k4) ? 1u : 0u);
-          tc_commit_elect(bar_empty + 8 * stage);
+            tc_mma_f16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (j | k4) ? 1u : 0u);
+          tc_commit(bar_empty + 8 * stage);
           if (++stage == p.nst) { stage = 0; phase ^= 1; }
         }
         // tail slab: split location features + padding marker (one K=16 MMA)
         mbar_wait(bar_tlfull + 8 * tl, tl_phase);
         tc_fence_after();
-        tc_mma_f16_elect(d_tmem, umma_desc(sAT + tl * TC_TAIL_BYTES, 256, 6), umma_desc(sBT, 256, 6), idesc, 1u);
-        tc_commit_elect(bar_tlempty + 8 * tl);
+        tc_mma_f16(d_tmem, umma_desc(sAT + tl * TC_TAIL_BYTES, 256, 6), umma_desc(sBT, 256, 6), idesc, 1u);
+        tc_commit(bar_tlempty + 8 * tl);
         if (++tl == 2) { tl = 0; tl_phase ^= 1; }
-        tc_commit_elect(bar_tfull + 8 * acc);
+        tc_commit(bar_tfull + 8 * acc);
         if (acc) acc_phase1 ^= 1; else acc_phase0 ^= 1;
         acc ^= 1;
       }
