@@ -184,8 +184,8 @@ estep_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // (lane-0 issue kept here: the multi-pass shapes are starved by their 16 re-reads of the pixel copy, and the
-    // convergent elected-lane form of the other kernels measured 1.8x SLOWER at D = 512, K = 2048)
+    // (lane-0 issue kept here: the multi-pass shapes are bound by the float64 re-decision and their re-reads of the
+    // pixel copy; the convergent elected-lane form of the other kernels measured the same within 2 %)
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=f16, both K-major, N=kpad, M=128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.kpad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
