@@ -161,3 +161,37 @@ def _check_patch_rebinds():
     assert ref_others.load_memory_banks.__module__ == 'hsg.utils.segsort.others'
   finally:
     sys.path.remove(root)
+
+
+def test_tensor_core_issue_is_free_of_retry_loops(lib):
+  """SASS guard (no GPU needed: cuobjdump reads the built library).  A tcgen05.mma issued from inside an
+  `if (lane == 0)` branch is wrapped by the compiler in an ELECT + R2UR.BROADCAST + BRA.U.ANY retry loop
+  (~70 issue cycles per MMA): that, not the tensor pipe, paced the E-step until round 2.  Every
+  tensor-core kernel except the multi-pass E-step issues from a convergent warp through an elected lane now; this
+  test keeps it that way: no UTCHMMA whose next instruction is the retry branch."""
+  import shutil
+  import subprocess
+  tool = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+  if not os.path.exists(tool):
+    pytest.skip('cuobjdump not available')
+  sass = subprocess.run([tool, '-sass', _lib.LIB_PATH], stdout=subprocess.PIPE, text=True, check=True).stdout
+  name, instrs, per_fn = None, [], {}
+  for line in sass.splitlines():
+    m = re.search(r'Function : (\S+)', line)
+    if m:
+      name = m.group(1)
+      per_fn[name] = instrs = []
+      continue
+    m = re.match(r'\s+/\*[0-9a-f]{4,}\*/\s+(.*?);', line)
+    if m and name:
+      instrs.append(m.group(1).strip())
+  checked = 0
+  for fn, ins in per_fn.items():
+    if not any('UTCHMMA' in i for i in ins) or 'estep_tc_kernel' in fn:      # multi-pass kernel: lane-0 issue kept
+      continue
+    checked += 1
+    for k, i in enumerate(ins):
+      if 'UTCHMMA' in i:
+        nxt = ins[k + 1] if k + 1 < len(ins) else ''
+        assert 'BRA.U.ANY' not in nxt, '%s: tcgen05.mma inside a uniform-register retry loop again' % fn
+  assert checked >= 10, 'expected the tensor-core kernels in the library (found %d)' % checked
