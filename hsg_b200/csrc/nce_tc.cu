@@ -195,7 +195,10 @@ nce_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   const int64_t n_ptiles = (p.N + 2 * NT_BM - 1) / (2 * NT_BM);     // pair tiles of 256 pixels
-  const int n_ntiles = (int)(p.Ppad / N2_BN);
+  // prototype tiles: with a device-side count only the tiles that hold valid prototypes are visited (every role
+  // reads the same count, so producer, issuer and epilogue agree); at least one, so the pipeline protocol is the same
+  const int n_ntiles_cap = (int)(p.Ppad / N2_BN);
+  const int n_ntiles = p.P_dev ? max(1, min(n_ntiles_cap, (int)((P_eff + N2_BN - 1) / N2_BN))) : n_ntiles_cap;
   const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
   if (warp == 0) {
