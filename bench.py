@@ -705,7 +705,7 @@ def run_reference(args):
       'metric': 'pixel-embeddings/sec spherical-kmeans+NCE (448^2, D=256, K=256)',
       'value': value, 'unit': 'pixel-embeddings/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', '1')),
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
-      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': 'configs[1] sampled: see cpu_baseline.sample', 'images_per_gpu': args.images,
                  'embedding_grid': [args.size, args.size], 'dim': args.dim, 'k': args.grid ** 2,
                  'iterations': args.iters, 'full_batch_pixels': n_pix},
